@@ -1,0 +1,216 @@
+/*
+ * letkf_b200.h -- C ABI of the B200-native LETKF analysis hot path.
+ *
+ * Drop-in boundary for the SCALE-LETKF analysis path.  The reference has no FFI:
+ * the boundary today is two Fortran module procedures,
+ *     letkf_core(ne,nobs,nobsl,hdxb,rdiag,rloc,dep,parm_infl,trans,transm,pao,
+ *                rdiag_wloc,infl_update,depd,transmd)      common/common_letkf.f90:52
+ *     das_letkf(gues3d,gues2d,anal3d,anal2d)               scale/letkf/letkf_tools.f90:50
+ * plus the module state das_letkf reads (grid coordinates, namelist scalars, the
+ * bucket-sorted observation tables built by set_letkf_obs, scale/letkf/letkf_obs.f90:78)
+ * and the member<->grid transposes scatter/gather_grd_mpi_alltoall
+ * (scale/common/common_mpi_scale.f90:1279,1340).
+ *
+ * Every entry point below replaces one of those; the Fortran ISO_C_BINDING stub
+ * a maintainer adds is in scale_letkf_b200/fortran/letkf_b200_iface.f90 and
+ * INTEGRATION.md.  All arrays are Fortran column-major, fp64 (REAL(r_size),
+ * common/common.f90:18-24) and default 32-bit INTEGER.  Functions return 0 on
+ * success and a negative LETKF_B200_E* code otherwise; the library never calls
+ * exit()/abort() (the reference STOPs, common/common_mtx.f90:61-64).
+ *
+ * There is no CPU fallback: every compute entry point runs CUDA kernels built
+ * for sm_100a and returns LETKF_B200_ECUDA when no device is usable.
+ */
+#ifndef LETKF_B200_H
+#define LETKF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LETKF_B200_NOBTYPE 24       /* nobtype, scale/common/common_nml.f90:22 */
+#define LETKF_B200_NID_OBS 16       /* nid_obs, scale/common/common_nml.f90:21 */
+#define LETKF_B200_NID_VARLOCAL 9   /* nid_obs_varlocal, common_obs_scale.f90:43 */
+#define LETKF_B200_MAX_NV 16        /* upper bound on nv3d+nv2d (11+0 in the reference) */
+#define LETKF_B200_MAX_MEMBER 128   /* k limit of the one-CTA-per-point solver */
+
+/* status codes */
+#define LETKF_B200_OK 0
+#define LETKF_B200_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define LETKF_B200_ECUDA (-2)    /* CUDA runtime error or no device          */
+#define LETKF_B200_ESTATE (-3)   /* call order (grid/obs not set)            */
+#define LETKF_B200_EEIGEN (-4)   /* eigensolve failed at >=1 point (reference: STOP 2) */
+#define LETKF_B200_ENOMEM (-5)
+
+/* where the caller's array arguments live */
+#define LETKF_B200_MEM_HOST 0
+#define LETKF_B200_MEM_DEVICE 1
+
+/*
+ * Namelist + module scalars das_letkf reads, names 1:1 with
+ * scale/common/common_nml.f90 (PARAM_ENSEMBLE :40-46, PARAM_LETKF :109-142,
+ * PARAM_LETKF_OBS :160-218, PARAM_LETKF_VAR_LOCAL :221-229, PARAM_LETKF_RADAR :264).
+ * Arrays indexed by report type are 0-based here (type 22 'PHARAD' = index 21).
+ * letkf_b200_config_defaults() fills the reference defaults;
+ * letkf_b200_config_resolve() applies the "negative inherits element 1" rules of
+ * read_nml_letkf_obs (common_nml.f90:741-775).
+ */
+typedef struct letkf_b200_config {
+  /* ensemble */
+  int32_t MEMBER;                /* k */
+  int32_t DET_RUN;               /* 0/1: deterministic member in slot MEMBER+2 */
+  /* grid (single sorting mesh over the whole horizontal plane, PRC 1x1 view) */
+  int32_t nlon, nlat, nlev;      /* = nlong, nlatg, nlev */
+  int32_t nv3d, nv2d;
+  int32_t IHALO, JHALO;
+  double DX, DY;
+  int32_t iv3d_p, iv3d_q, iv3d_qg; /* 1-based variable indices, common_scale.f90:45-51 */
+  /* PARAM_LETKF */
+  double INFL_MUL, INFL_MUL_MIN;
+  int32_t INFL_MUL_ADAPTIVE;
+  int32_t RELAX_TO_INFLATED_PRIOR;
+  double RELAX_ALPHA, RELAX_ALPHA_SPREAD;
+  double Q_UPDATE_TOP, Q_SPRD_MAX, BOUNDARY_BUFFER_WIDTH;
+  /* PARAM_LETKF_OBS */
+  double HORI_LOCAL[LETKF_B200_NOBTYPE];
+  double VERT_LOCAL[LETKF_B200_NOBTYPE];
+  double HORI_LOCAL_RADAR_OBSNOREF, HORI_LOCAL_RADAR_VR, VERT_LOCAL_RADAR_VR;
+  double VERT_LOCAL_RAIN_BASE;
+  int32_t MAX_NOBS_PER_GRID[LETKF_B200_NOBTYPE];
+  int32_t MAX_NOBS_PER_GRID_CRITERION;
+  double OBS_MIN_SPACING[LETKF_B200_NOBTYPE];
+  double OBS_SORT_GRID_SPACING[LETKF_B200_NOBTYPE];
+  /* PARAM_LETKF_VAR_LOCAL: VAR_LOCAL[iv][n]; iv: 0 UV,1 T,2 Q,3 PS,4 RAIN,5 TC,6 RADAR_REF,7 RADAR_VR,8 H08 */
+  double VAR_LOCAL[LETKF_B200_NID_VARLOCAL][LETKF_B200_MAX_NV];
+  /* PARAM_LETKF_RADAR */
+  double RADAR_ZMAX;
+  /* letkf_obs.f90:27-28 -- default-REAL literals widened to double; carried as data */
+  double dist_zero_fac, dist_zero_fac_square;
+  int32_t reserved[8];
+} letkf_b200_config;
+
+/* One combined observation type (elm_u, typ) and its sorting mesh:
+ * letkf_obs.f90:33-41 (ctype tables) and :47-65 (obs_grid_type). */
+typedef struct letkf_b200_ctype_info {
+  int32_t elm, elm_u, typ;       /* raw element id, uid_obs(elm) 1..16, report type 1..24 */
+  int32_t ngrd_i, ngrd_j, ngrdsch_i, ngrdsch_j, ngrdext_i, ngrdext_j;
+  int32_t tot_ext;               /* obs of this ctype                                   */
+  int32_t ac_begin;              /* ac_ext(0,1): sorted index of this ctype's first obs  */
+  int32_t n_merge;               /* letkf_tools.f90:167-192; 0 = merged into a master    */
+  double hori_loc, vert_loc, grdspc_i, grdspc_j;
+} letkf_b200_ctype_info;
+
+/* QC-passed observations in their original (unsorted) order: the fields of
+ * obs(:)%{elm,typ,lev,dat,err,ri,rj} and obsda%{val,ensval} (common_obs_scale.f90:98-133)
+ * that das_letkf/obs_local read.  ensval is ensval(nensobs,nobs), member fastest,
+ * already in perturbation form; row MEMBER+1 (DET_RUN) holds y - H(x_det). */
+typedef struct letkf_b200_obs {
+  int32_t nobs, nensobs;
+  const int32_t *elm, *typ;
+  const double *ri, *rj, *lev, *dat, *err, *val;
+  const double *ensval;
+} letkf_b200_obs;
+
+typedef struct letkf_b200_handle letkf_b200_handle;
+
+/* ---- lifetime / configuration -------------------------------------------- */
+void letkf_b200_config_defaults(letkf_b200_config *cfg);
+void letkf_b200_config_resolve(letkf_b200_config *cfg);
+int letkf_b200_create(const letkf_b200_config *cfg, int device, letkf_b200_handle **out);
+int letkf_b200_destroy(letkf_b200_handle *h);
+const char *letkf_b200_last_error(const letkf_b200_handle *h);
+/* run all subsequent work of this handle on a caller-owned cudaStream_t (NULL = default) */
+int letkf_b200_set_stream(letkf_b200_handle *h, void *cuda_stream);
+
+/* ---- letkf_core twin (common/common_letkf.f90:52) -------------------------
+ * Batched: point i uses hdxb + i*nobs*ne (column-major (nobs,ne), rows 1..nobsl[i]),
+ * rdiag/rloc/dep/depd + i*nobs, parm_infl[i]; writes trans + i*ne*ne (column-major),
+ * transm/transmd + i*ne, pao + i*ne*ne.  transm, pao, depd, transmd may be NULL
+ * (Fortran OPTIONAL absent); when transm is NULL the mean weight is added to every
+ * column of trans (:218-226).  npts = 1 reproduces one reference call. */
+int letkf_b200_core_batch(letkf_b200_handle *h, int ne, int nobs, int npts,
+                          const int32_t *nobsl, const double *hdxb, const double *rdiag,
+                          const double *rloc, const double *dep, double *parm_infl,
+                          double *trans, double *transm, double *pao, int rdiag_wloc,
+                          int infl_update, const double *depd, double *transmd,
+                          int mem_space);
+
+/* ---- module state das_letkf reads ----------------------------------------- */
+/* rig1(nij1), rjg1(nij1), hgt1(nij1,nlev): common_mpi_scale.f90:40-42,303-308 */
+int letkf_b200_set_grid(letkf_b200_handle *h, int nij1, const double *rig1,
+                        const double *rjg1, const double *hgt1, int mem_space);
+/* Twin of the bucket-sort half of set_letkf_obs (letkf_obs.f90:308-342 ctype table,
+ * :660-695 mesh, :747-805 counting sort, :922-976 extended prefix sums).  Host arrays. */
+int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs);
+int letkf_b200_obs_info(const letkf_b200_handle *h, int32_t *nobstotal, int32_t *nctype);
+int letkf_b200_get_ctype(const letkf_b200_handle *h, int ic, letkf_b200_ctype_info *out);
+/* ac_ext(0:ngrdext_i, 1:ngrdext_j) of ctype ic, column-major, chained across ctypes */
+int letkf_b200_get_ac_ext(const letkf_b200_handle *h, int ic, int32_t *ac_ext);
+/* sorted position -> original obs index (0-based): the order of obsda_sort */
+int letkf_b200_get_sorted_index(const letkf_b200_handle *h, int32_t *sorted_to_orig);
+
+/* ---- obs_local twin (letkf_tools.f90:1325) ---------------------------------
+ * For npts points (ri,rj,rlev=mean pressure,rz=height) and model variable nvar
+ * (1-based, 0 = no variable localisation): writes nobsl[i] and, when not NULL, the
+ * selected sorted-obs indices (0-based) idx + i*max_out, rdiag/rloc + i*max_out.
+ * Order of the list is unspecified (the reference's is quickselect order). */
+int letkf_b200_obs_local(letkf_b200_handle *h, int npts, const double *ri, const double *rj,
+                         const double *rlev, const double *rz, int nvar, int32_t *nobsl,
+                         int32_t *idx, double *rdiag, double *rloc, int max_out,
+                         int mem_space);
+
+/* ---- das_letkf twin (letkf_tools.f90:50) ----------------------------------- */
+typedef struct letkf_b200_das_args {
+  double *gues3d;        /* (nij1,nlev,nens,nv3d) INOUT: destroyed -> perturbations, slot MEMBER+1 = mean */
+  double *gues2d;        /* (nij1,nens,nv2d) or NULL when nv2d == 0 */
+  double *anal3d;        /* (nij1,nlev,nens,nv3d) OUT: slots 1..MEMBER (+ mmdet) */
+  double *anal2d;
+  double *infl3d;        /* optional (nij1,nlev,nv3d) work3d: in = inflation field when INFL_MUL<=0,
+                            out = adaptively updated field when INFL_MUL_ADAPTIVE; NULL = INFL_MUL */
+  double *rtps_infl_out; /* optional (nij1,nlev,nv3d): work3da, RELAX_SPREAD_OUT (letkf_tools.f90:271-276) */
+  int32_t *nobsl_out;    /* optional (nij1,nlev): local obs count of variable group 1 (NOBS_OUT) */
+  const double *logp;    /* optional (nij1,nlev): log(mean pressure) precomputed by the host libm so that
+                            selection thresholds are bit-identical to a CPU run; NULL = device log() */
+  int32_t mem_space;     /* LETKF_B200_MEM_HOST: arrays are host memory (H2D/D2H inside the call) */
+  int32_t reserved;
+} letkf_b200_das_args;
+int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *args);
+/* counters of the last das call: points analysed, points solved (nobsl>0), eigensolve failures */
+int letkf_b200_das_stats(const letkf_b200_handle *h, int64_t *npoints, int64_t *nsolved,
+                         int64_t *nfail, int64_t *nobsl_sum);
+/* CUDA-event time (ms) of the dominant kernel in the last das call (bench roofline) */
+int letkf_b200_das_kernel_ms(const letkf_b200_handle *h, float *analysis_ms, int *launches);
+
+/* ---- ensmean_grd twin (common_scale.f90:1513) ------------------------------ */
+int letkf_b200_ensmean_grd(letkf_b200_handle *h, int mem, int nens, int nij, double *v3d,
+                           double *v2d, int mem_space);
+
+/* ---- member<->grid transposes (common_mpi_scale.f90:1279-1476) --------------
+ * pack:   v3dg(nlev,nlon,nlat,nv3d), v2dg(nlon,nlat,nv2d) of ONE member ->
+ *         bufs(nij1max,nlevall,np) with the cyclic column deal of grd_to_buf (:1428)
+ * unpack: bufr(nij1max,nlevall,mcount) received from the member owners ->
+ *         v3d(1:nij1,:,mstart:mend,:), v2d(1:nij1,mstart:mend,:)
+ * and the two reverse directions for gather_grd_mpi_alltoall.  The exchange between
+ * pack and unpack is an NCCL all-to-all issued by the caller on the same stream.
+ * Device pointers only. */
+int letkf_b200_grd_to_buf(letkf_b200_handle *h, int np, const double *v3dg, const double *v2dg,
+                          double *bufs);
+int letkf_b200_buf_to_ens(letkf_b200_handle *h, int np, int myrank_e, int nens, int mstart,
+                          int mend, const double *bufr, double *v3d, double *v2d);
+int letkf_b200_ens_to_buf(letkf_b200_handle *h, int np, int myrank_e, int nens, int mstart,
+                          int mend, const double *v3d, const double *v2d, double *bufs);
+int letkf_b200_buf_to_grd(letkf_b200_handle *h, int np, const double *bufr, double *v3dg,
+                          double *v2dg);
+/* nij1 / nij1max of rank myrank_e among np ranks (set_common_mpi_grid :264-283) */
+int letkf_b200_nij1(const letkf_b200_handle *h, int np, int myrank_e, int32_t *nij1,
+                    int32_t *nij1max);
+
+/* library build info (arch string, e.g. "sm_100a") */
+const char *letkf_b200_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LETKF_B200_H */

@@ -1,0 +1,95 @@
+/*
+ * letkf_oracle.h -- CPU restatement of the SCALE-LETKF analysis hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the shipped product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may build, load or call it, and there only as the checker / CPU baseline.
+ *
+ * PARITY UNPINNED: the reference (Fortran 90 + MPI + SCALE-RM) cannot be compiled in
+ * this environment (no Fortran front-end, no MPI, SCALE-RM/NetCDF not vendored) and its
+ * tree holds no golden vectors, KATs or fixtures for this path (its only test diffs log
+ * statistics against files outside the repository, scale/run/test.sh:274-302).  The
+ * oracle is therefore pinned by analytic known answers, algebraic invariants and an
+ * independent LAPACK (scipy.linalg.eigh) cross-check -- see tests/ and DESIGN.md.
+ *
+ * Every function cites the reference file:line it follows (paths relative to the
+ * reference root).  Arrays are Fortran column-major.
+ */
+#ifndef LETKF_ORACLE_H
+#define LETKF_ORACLE_H
+
+#include "../include/letkf_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* EISPACK restatements, common/netlibrs.f */
+double oracle_pythag(double a, double b);                                   /* :1-20   */
+void oracle_tred2(int nm, int n, const double *a, double *d, double *e, double *z); /* :520-683 */
+int oracle_tql2(int nm, int n, double *d, double *e, double *z);            /* :215-384 */
+int oracle_rs(int nm, int n, const double *a, double *w, double *z);        /* :21-79 (matz != 0) */
+/* common/common_mtx.f90:41-99; returns nrank_eff, or -1 (rs failed) / -2 (no positive eigenvalue) */
+int oracle_mtx_eigen(int n, const double *a, double *eival, double *eivec);
+/* common/common_letkf.f90:52-257; optional arguments may be NULL; returns 0 or the mtx_eigen error */
+int oracle_letkf_core(int ne, int nobs, int nobsl, const double *hdxb, const double *rdiag,
+                      const double *rloc, const double *dep, double *parm_infl, double *trans,
+                      double *transm, double *pao, int rdiag_wloc, int infl_update,
+                      const double *depd, double *transmd);
+/* batched driver over oracle_letkf_core with the layout of letkf_b200_core_batch */
+int oracle_core_batch(int ne, int nobs, int npts, const int32_t *nobsl, const double *hdxb,
+                      const double *rdiag, const double *rloc, const double *dep,
+                      double *parm_infl, double *trans, double *transm, double *pao,
+                      int rdiag_wloc, int infl_update, const double *depd, double *transmd,
+                      int nthreads);
+/* common/common_sort.f90:341-369 / :404-432.  A is 1-based through X (X holds 1-based
+ * indices into A, as in Fortran); left/right/K are 1-based positions in X. */
+void oracle_quickselect_arg(const double *A, int32_t *X, int left, int right, int K);
+void oracle_quickselect_desc_arg(const double *A, int32_t *X, int left, int right, int K);
+
+/* stateful twin of the module state (set_letkf_obs / set_common_mpi_grid / das_letkf) */
+typedef struct oracle_state oracle_state;
+oracle_state *oracle_create(const letkf_b200_config *cfg);
+void oracle_destroy(oracle_state *s);
+/* quirk != 0 reproduces ij_obsgrd's use of ngrd_i for the j index (letkf_obs.f90:1200) */
+void oracle_set_quirks(oracle_state *s, int ij_obsgrd_quirk);
+int oracle_set_obs(oracle_state *s, const letkf_b200_obs *obs);   /* letkf_obs.f90:308-342,660-976 */
+int oracle_set_grid(oracle_state *s, int nij1, const double *rig1, const double *rjg1,
+                    const double *hgt1);
+int oracle_obs_info(const oracle_state *s, int32_t *nobstotal, int32_t *nctype);
+int oracle_get_ctype(const oracle_state *s, int ic, letkf_b200_ctype_info *out);
+int oracle_get_ac_ext(const oracle_state *s, int ic, int32_t *ac_ext);
+int oracle_get_sorted_index(const oracle_state *s, int32_t *sorted_to_orig);
+/* letkf_tools.f90:1325-1759 for a batch of points (srch_q0 starts at 1 for each point);
+ * brute != 0 replaces the bucket search by an O(nobs) scan of every observation
+ * (semantic definition used by test_search_semantic_vs_bruteforce). */
+int oracle_obs_local(oracle_state *s, int npts, const double *ri, const double *rj,
+                     const double *rlev, const double *rz, int nvar, int32_t *nobsl,
+                     int32_t *idx, double *rdiag, double *rloc, int max_out, int brute);
+/* letkf_tools.f90:50-932 (live path :130-230, :289-693).  point_mask (nij1,nlev) optional:
+ * only points with mask != 0 are analysed (bounded CPU-baseline samples); others untouched. */
+int oracle_das_letkf(oracle_state *s, double *gues3d, double *gues2d, double *anal3d,
+                     double *anal2d, double *infl3d, double *rtps_infl_out,
+                     int32_t *nobsl_out, const uint8_t *point_mask, int nthreads,
+                     int64_t *npoints, int64_t *nsolved);
+/* scale/common/common_scale.f90:1513-1552 */
+void oracle_ensmean_grd(int mem, int nens, int nij, int nlev, int nv3d, int nv2d, double *v3d,
+                        double *v2d);
+/* scale/common/common_mpi_scale.f90:264-283, 1428-1476, 1279-1396 (pack/unpack halves) */
+void oracle_nij1(int nlon, int nlat, int np, int myrank_e, int32_t *nij1, int32_t *nij1max);
+void oracle_grd_to_buf(int nlon, int nlat, int nlev, int nv3d, int nv2d, int np,
+                       const double *v3dg, const double *v2dg, double *bufs);
+void oracle_buf_to_ens(int nlon, int nlat, int nlev, int nv3d, int nv2d, int np, int myrank_e,
+                       int nens, int mstart, int mend, const double *bufr, double *v3d,
+                       double *v2d);
+void oracle_ens_to_buf(int nlon, int nlat, int nlev, int nv3d, int nv2d, int np, int myrank_e,
+                       int nens, int mstart, int mend, const double *v3d, const double *v2d,
+                       double *bufs);
+void oracle_buf_to_grd(int nlon, int nlat, int nlev, int nv3d, int nv2d, int np,
+                       const double *bufr, double *v3dg, double *v2dg);
+int oracle_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,141 @@
+"""ctypes view of include/letkf_b200.h (structs, constants, prototypes, loader).
+
+The structures mirror `letkf_b200_config`, `letkf_b200_obs`, `letkf_b200_ctype_info` and
+`letkf_b200_das_args` field for field; the names are the reference's namelist / module
+names (scale/common/common_nml.f90:19-330, scale/letkf/letkf_obs.f90:33-65).
+
+There is no CPU fallback: `load_library()` raises if the CUDA shared library has not been
+built (run `python -c "import __graft_entry__ as g; g.build()"`).
+"""
+import ctypes as C
+import os
+
+NOBTYPE = 24
+NID_OBS = 16
+NID_VARLOCAL = 9
+MAX_NV = 16
+MAX_MEMBER = 128
+
+OK, EINVAL, ECUDA, ESTATE, EEIGEN, ENOMEM = 0, -1, -2, -3, -4, -5
+MEM_HOST, MEM_DEVICE = 0, 1
+
+# raw observation element ids (scale/common/common_obs_scale.f90:45-77)
+ID_U, ID_V, ID_T, ID_TV, ID_Q, ID_RH = 2819, 2820, 3073, 3074, 3330, 3331
+ID_PS, ID_RAIN = 14593, 19999
+ID_RADAR_REF, ID_RADAR_REF_ZERO, ID_RADAR_VR, ID_RADAR_PRH = 4001, 4004, 4002, 4003
+# report types (1-based index into obtypelist, common_obs_scale.f90:84-89)
+TYP_ADPUPA, TYP_ADPSFC, TYP_PHARAD = 1, 8, 22
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("MEMBER", C.c_int32), ("DET_RUN", C.c_int32),
+        ("nlon", C.c_int32), ("nlat", C.c_int32), ("nlev", C.c_int32),
+        ("nv3d", C.c_int32), ("nv2d", C.c_int32),
+        ("IHALO", C.c_int32), ("JHALO", C.c_int32),
+        ("DX", C.c_double), ("DY", C.c_double),
+        ("iv3d_p", C.c_int32), ("iv3d_q", C.c_int32), ("iv3d_qg", C.c_int32),
+        ("INFL_MUL", C.c_double), ("INFL_MUL_MIN", C.c_double),
+        ("INFL_MUL_ADAPTIVE", C.c_int32), ("RELAX_TO_INFLATED_PRIOR", C.c_int32),
+        ("RELAX_ALPHA", C.c_double), ("RELAX_ALPHA_SPREAD", C.c_double),
+        ("Q_UPDATE_TOP", C.c_double), ("Q_SPRD_MAX", C.c_double),
+        ("BOUNDARY_BUFFER_WIDTH", C.c_double),
+        ("HORI_LOCAL", C.c_double * NOBTYPE), ("VERT_LOCAL", C.c_double * NOBTYPE),
+        ("HORI_LOCAL_RADAR_OBSNOREF", C.c_double), ("HORI_LOCAL_RADAR_VR", C.c_double),
+        ("VERT_LOCAL_RADAR_VR", C.c_double), ("VERT_LOCAL_RAIN_BASE", C.c_double),
+        ("MAX_NOBS_PER_GRID", C.c_int32 * NOBTYPE), ("MAX_NOBS_PER_GRID_CRITERION", C.c_int32),
+        ("OBS_MIN_SPACING", C.c_double * NOBTYPE), ("OBS_SORT_GRID_SPACING", C.c_double * NOBTYPE),
+        ("VAR_LOCAL", (C.c_double * MAX_NV) * NID_VARLOCAL),
+        ("RADAR_ZMAX", C.c_double),
+        ("dist_zero_fac", C.c_double), ("dist_zero_fac_square", C.c_double),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
+class CtypeInfo(C.Structure):
+    _fields_ = [
+        ("elm", C.c_int32), ("elm_u", C.c_int32), ("typ", C.c_int32),
+        ("ngrd_i", C.c_int32), ("ngrd_j", C.c_int32),
+        ("ngrdsch_i", C.c_int32), ("ngrdsch_j", C.c_int32),
+        ("ngrdext_i", C.c_int32), ("ngrdext_j", C.c_int32),
+        ("tot_ext", C.c_int32), ("ac_begin", C.c_int32), ("n_merge", C.c_int32),
+        ("hori_loc", C.c_double), ("vert_loc", C.c_double),
+        ("grdspc_i", C.c_double), ("grdspc_j", C.c_double),
+    ]
+
+
+class Obs(C.Structure):
+    _fields_ = [
+        ("nobs", C.c_int32), ("nensobs", C.c_int32),
+        ("elm", C.c_void_p), ("typ", C.c_void_p),
+        ("ri", C.c_void_p), ("rj", C.c_void_p), ("lev", C.c_void_p),
+        ("dat", C.c_void_p), ("err", C.c_void_p), ("val", C.c_void_p),
+        ("ensval", C.c_void_p),
+    ]
+
+
+class DasArgs(C.Structure):
+    _fields_ = [
+        ("gues3d", C.c_void_p), ("gues2d", C.c_void_p),
+        ("anal3d", C.c_void_p), ("anal2d", C.c_void_p),
+        ("infl3d", C.c_void_p), ("rtps_infl_out", C.c_void_p),
+        ("nobsl_out", C.c_void_p), ("logp", C.c_void_p),
+        ("mem_space", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libletkf_b200.so")
+_lib = None
+
+_vp, _i, _ip = C.c_void_p, C.c_int, C.POINTER(C.c_int32)
+PROTOTYPES = {
+    # name: (restype, argtypes) -- one entry per symbol declared in include/letkf_b200.h
+    "letkf_b200_config_defaults": (None, [C.POINTER(Config)]),
+    "letkf_b200_config_resolve": (None, [C.POINTER(Config)]),
+    "letkf_b200_create": (_i, [C.POINTER(Config), _i, C.POINTER(_vp)]),
+    "letkf_b200_destroy": (_i, [_vp]),
+    "letkf_b200_last_error": (C.c_char_p, [_vp]),
+    "letkf_b200_set_stream": (_i, [_vp, _vp]),
+    "letkf_b200_core_batch": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _i, _i, _vp, _vp, _i]),
+    "letkf_b200_set_grid": (_i, [_vp, _i, _vp, _vp, _vp, _i]),
+    "letkf_b200_set_obs": (_i, [_vp, C.POINTER(Obs)]),
+    "letkf_b200_obs_info": (_i, [_vp, _ip, _ip]),
+    "letkf_b200_get_ctype": (_i, [_vp, _i, C.POINTER(CtypeInfo)]),
+    "letkf_b200_get_ac_ext": (_i, [_vp, _i, _vp]),
+    "letkf_b200_get_sorted_index": (_i, [_vp, _vp]),
+    "letkf_b200_obs_local": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i]),
+    "letkf_b200_das_letkf": (_i, [_vp, C.POINTER(DasArgs)]),
+    "letkf_b200_das_stats": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "letkf_b200_das_kernel_ms": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "letkf_b200_ensmean_grd": (_i, [_vp, _i, _i, _i, _vp, _vp, _i]),
+    "letkf_b200_grd_to_buf": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "letkf_b200_buf_to_ens": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "letkf_b200_ens_to_buf": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "letkf_b200_buf_to_grd": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "letkf_b200_nij1": (_i, [_vp, _i, _i, _ip, _ip]),
+    "letkf_b200_build_info": (C.c_char_p, []),
+}
+
+
+def load_library(path=None):
+    """dlopen libletkf_b200.so and attach prototypes.  Raises if the library is missing:
+    the product has no CPU path."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} not found: the CUDA extension is not built and there is no CPU fallback. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` at the repo root.")
+    lib = C.CDLL(p)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)   # AttributeError => header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib

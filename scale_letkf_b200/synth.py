@@ -1,0 +1,234 @@
+"""Seeded synthetic inputs for the BASELINE.json configs.
+
+Everything the reference would read from NetCDF / observation files is replaced by
+numpy `PCG64` draws with fixed seeds (20260101 + config number).  The same arrays feed
+the CPU oracle and the CUDA library, so parity tests compare like with like.
+
+Layouts follow the reference: state `gues3d(nij1, nlev, nens, nv3d)` Fortran order
+(scale/letkf/letkf_tools.f90:54-57), observation `ensval(nensobs, nobs)` member fastest
+(scale/common/common_obs_scale.f90:130), grid coordinates `rig1 = i + IHALO`
+(scale/common/common_mpi_scale.f90:303-308).
+"""
+import numpy as np
+
+from . import capi
+from .config import default_config, resolve_config
+
+SEED0 = 20260101
+
+
+def rng(config_no, extra=0):
+    return np.random.Generator(np.random.PCG64(SEED0 + config_no + 1000 * extra))
+
+
+# ----------------------------------------------------------------------------- C1
+def make_core_batch(ne=20, npts=10000, nobs=100, seed_no=1, det=False, infl=1.0):
+    """BASELINE config 1: independent letkf_core problems, p ~ U{0..nobs} (p = 0 and p = 1
+    forced for the first two points), rows of hdxb have zero member-mean
+    (scale/letkf/letkf_obs.f90:474-489), rloc = exp(-ndist/2), rdiag = err^2/rloc."""
+    g = rng(seed_no)
+    nobsl = g.integers(0, nobs + 1, size=npts).astype(np.int32)
+    if npts >= 2:
+        nobsl[0], nobsl[1] = 0, 1
+    hdxb = g.standard_normal((npts, ne, nobs))
+    hdxb -= hdxb.mean(axis=1, keepdims=True)
+    ndist = g.uniform(0.0, 13.33, size=(npts, nobs))
+    rloc = np.exp(-0.5 * ndist)
+    rdiag = 1.0 / rloc
+    dep = 2.0 * g.standard_normal((npts, nobs))
+    depd = 2.0 * g.standard_normal((npts, nobs)) if det else None
+    parm_infl = np.full(npts, infl)
+    return dict(ne=ne, nobs=nobs, npts=npts, nobsl=nobsl, hdxb=hdxb, rdiag=rdiag, rloc=rloc,
+                dep=dep, depd=depd, parm_infl=parm_infl)
+
+
+# ----------------------------------------------------------------------------- grids
+def z_levels(nlev, zbot=100.0, ztop=28000.0):
+    """stretched model-level heights (m)"""
+    s = np.linspace(0.0, 1.0, nlev)
+    return zbot + (ztop - zbot) * (0.35 * s + 0.65 * s * s)
+
+
+def pressure_of_z(z):
+    return 1.0e5 * np.exp(-z / 7500.0)
+
+
+def column_deal(nlon, nlat, nprocs_e=1, myrank_e=0):
+    """cyclic column deal of grd_to_buf (common_mpi_scale.f90:1428-1440): local column i
+    (1-based) of e-rank m is global j = (m-1) + np*(i-1), ilon = mod(j,nlon)+1."""
+    j = np.arange(myrank_e, nlon * nlat, nprocs_e)
+    ilon = j % nlon + 1
+    ilat = (j - ilon + 1) // nlon + 1
+    return ilon, ilat
+
+
+def make_grid(cfg, nprocs_e=1, myrank_e=0, topo_amp=0.0, seed_no=0):
+    ilon, ilat = column_deal(cfg.nlon, cfg.nlat, nprocs_e, myrank_e)
+    rig1 = (ilon + cfg.IHALO).astype(np.float64)
+    rjg1 = (ilat + cfg.JHALO).astype(np.float64)
+    z = z_levels(cfg.nlev)
+    topo = topo_amp * (0.5 + 0.5 * np.sin(2 * np.pi * ilon / cfg.nlon) * np.cos(2 * np.pi * ilat / cfg.nlat))
+    decay = np.linspace(1.0, 0.0, cfg.nlev)
+    hgt1 = np.asfortranarray(z[None, :] + topo[:, None] * decay[None, :])
+    return rig1, rjg1, hgt1
+
+
+_VAR_SCALE = np.array([3.0, 3.0, 0.3, 1.0, 80.0, 8e-4, 1e-4, 1e-4, 1e-4, 1e-4, 1e-4])
+_VAR_MEAN = np.array([10.0, 2.0, 0.0, 280.0, 0.0, 5e-3, 1e-4, 1e-4, 1e-4, 1e-4, 1e-4])
+
+
+def make_state(cfg, rig1, rjg1, hgt1, seed_no=0, xp=np, device=None, gen=None):
+    """Background ensemble gues3d(nij1,nlev,nens,nv3d): smooth mean + N(0, sigma_v) member
+    noise; variable iv3d_p is a hydrostatic pressure (Pa) so vertical localisation in ln p
+    is realistic.  Slot MEMBER+1 (mean) and MEMBER+2 (DET_RUN) are filled like
+    ensmean_grd would (the caller may recompute the mean through the library)."""
+    nij1, nlev = hgt1.shape
+    k = cfg.MEMBER
+    nens = k + 2 if cfg.DET_RUN else k + 1
+    nv3d = cfg.nv3d
+    if xp is np:
+        g = rng(seed_no, 7)
+        gues = np.empty((nij1, nlev, nens, nv3d), order="F")
+        pz = pressure_of_z(hgt1)
+        for n in range(nv3d):
+            sc, mu = _VAR_SCALE[n % 11], _VAR_MEAN[n % 11]
+            base = mu + sc * np.sin(0.07 * rig1)[:, None] * np.cos(0.05 * rjg1)[:, None] * np.ones((1, nlev))
+            if n + 1 == cfg.iv3d_p:
+                base = pz + 50.0 * np.sin(0.03 * rig1)[:, None]
+            noise = sc * g.standard_normal((nij1, nlev, k))
+            gues[:, :, :k, n] = base[:, :, None] + noise
+            if cfg.DET_RUN:
+                gues[:, :, k + 1, n] = base + sc * g.standard_normal((nij1, nlev))
+            m = gues[:, :, 0, n].copy()
+            for mm in range(1, k):
+                m += gues[:, :, mm, n]
+            gues[:, :, k, n] = m / k
+        return gues
+    # torch path (device-resident synthetic state for the full-size bench)
+    import torch
+    rig = torch.as_tensor(rig1, device=device)
+    rjg = torch.as_tensor(rjg1, device=device)
+    hg = torch.as_tensor(np.ascontiguousarray(hgt1.T), device=device)   # (nlev, nij1)
+    # memory order of Fortran (nij1,nlev,nens,nv3d) == C order (nv3d,nens,nlev,nij1)
+    gues = torch.empty((nv3d, nens, nlev, nij1), dtype=torch.float64, device=device)
+    pz = 1.0e5 * torch.exp(-hg / 7500.0)
+    for n in range(nv3d):
+        sc, mu = float(_VAR_SCALE[n % 11]), float(_VAR_MEAN[n % 11])
+        base = mu + sc * (torch.sin(0.07 * rig) * torch.cos(0.05 * rjg))[None, :].expand(nlev, nij1)
+        if n + 1 == cfg.iv3d_p:
+            base = pz + 50.0 * torch.sin(0.03 * rig)[None, :]
+        gues[n, :k] = torch.randn((k, nlev, nij1), dtype=torch.float64, device=device, generator=gen)
+        gues[n, :k].mul_(sc).add_(base[None])
+        if cfg.DET_RUN:
+            gues[n, k + 1] = base + sc * torch.randn((nlev, nij1), dtype=torch.float64, device=device, generator=gen)
+        gues[n, k] = gues[n, :k].mean(dim=0)
+    return gues
+
+
+def _finish_obs(g, elm, typ, ri, rj, lev, dat, err, k, det, ens_sigma):
+    nobs = len(elm)
+    nensobs = k + 1 if det else k
+    ens = g.standard_normal((nobs, nensobs)) * np.asarray(ens_sigma)[:, None]
+    ens[:, :k] -= ens[:, :k].mean(axis=1, keepdims=True)   # perturbation form, zero member mean
+    val = 2.0 * np.asarray(ens_sigma) * g.standard_normal(nobs)
+    perm = g.permutation(nobs)   # arrival order is not sorted in the reference either
+    return dict(elm=np.asarray(elm, np.int32)[perm], typ=np.asarray(typ, np.int32)[perm],
+                ri=np.asarray(ri)[perm], rj=np.asarray(rj)[perm], lev=np.asarray(lev)[perm],
+                dat=np.asarray(dat)[perm], err=np.asarray(err)[perm], val=val[perm],
+                ensval=np.ascontiguousarray(ens[perm]))
+
+
+def make_sonde_obs(cfg, nsonde, nsfc, nlevobs=25, seed_no=2):
+    """Config-2 style conventional obs: `nsonde` soundings at continuous random positions x
+    `nlevobs` pressure levels x {U,V,T,Q} as ADPUPA(1), plus `nsfc` surface-pressure obs as
+    ADPSFC(8)."""
+    g = rng(seed_no, 3)
+    k, det = cfg.MEMBER, bool(cfg.DET_RUN)
+    lo_i, hi_i = cfg.IHALO + 0.5, cfg.nlon + cfg.IHALO + 0.5
+    lo_j, hi_j = cfg.JHALO + 0.5, cfg.nlat + cfg.JHALO + 0.5
+    sri = g.uniform(lo_i, hi_i, nsonde)
+    srj = g.uniform(lo_j, hi_j, nsonde)
+    plev = np.exp(np.linspace(np.log(1.0e5), np.log(5.0e3), nlevobs))
+    elms = [capi.ID_U, capi.ID_V, capi.ID_T, capi.ID_Q]
+    errs = {capi.ID_U: 2.0, capi.ID_V: 2.0, capi.ID_T: 1.0, capi.ID_Q: 1.0e-3}
+    elm, typ, ri, rj, lev, dat, err, sig = [], [], [], [], [], [], [], []
+    for s in range(nsonde):
+        for p in plev * np.exp(g.uniform(-0.02, 0.02, nlevobs)):
+            for e in elms:
+                elm.append(e); typ.append(capi.TYP_ADPUPA); ri.append(sri[s]); rj.append(srj[s])
+                lev.append(p); dat.append(0.0); err.append(errs[e]); sig.append(errs[e] * 1.2)
+    for s in range(nsfc):
+        elm.append(capi.ID_PS); typ.append(capi.TYP_ADPSFC)
+        ri.append(g.uniform(lo_i, hi_i)); rj.append(g.uniform(lo_j, hi_j))
+        lev.append(10.0); dat.append(1.0e5 + 1500.0 * g.standard_normal()); err.append(100.0)
+        sig.append(120.0)
+    return _finish_obs(g, elm, typ, ri, rj, lev, dat, err, k, det, sig)
+
+
+def make_radar_obs(cfg, radius_m=60.0e3, zmin=500.0, zmax=11000.0, dz=500.0, mesh_m=500.0,
+                   jitter_m=200.0, frac_ref=0.5, seed_no=3, center=None):
+    """Config-3 style phased-array radar obs (type 22 PHARAD): positions on a `mesh_m` mesh
+    with +-`jitter_m` uniform jitter (so that equal-distance ties have measure zero, SURVEY
+    H2) inside a cylinder; each position is REF (4001) or RE0 (4004), and REF positions
+    also carry a Doppler velocity VR (4002)."""
+    g = rng(seed_no, 5)
+    k, det = cfg.MEMBER, bool(cfg.DET_RUN)
+    cx = (cfg.nlon * 0.5 + cfg.IHALO + 0.5) if center is None else center[0]
+    cy = (cfg.nlat * 0.5 + cfg.JHALO + 0.5) if center is None else center[1]
+    nx = int(radius_m / mesh_m)
+    xs = np.arange(-nx, nx + 1) * mesh_m
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    m = (X * X + Y * Y) <= radius_m * radius_m
+    X, Y = X[m], Y[m]
+    zs = np.arange(zmin, zmax + 0.5 * dz, dz)
+    elm, typ, ri, rj, lev, dat, err, sig = [], [], [], [], [], [], [], []
+    for z in zs:
+        n = X.size
+        x = X + g.uniform(-jitter_m, jitter_m, n)
+        y = Y + g.uniform(-jitter_m, jitter_m, n)
+        zz = z + g.uniform(-0.2 * dz, 0.2 * dz, n)
+        r_i = cx + x / cfg.DX
+        r_j = cy + y / cfg.DY
+        ok = (r_i > cfg.IHALO + 0.5) & (r_i < cfg.nlon + cfg.IHALO + 0.5) & \
+             (r_j > cfg.JHALO + 0.5) & (r_j < cfg.nlat + cfg.JHALO + 0.5)
+        r_i, r_j, zz = r_i[ok], r_j[ok], zz[ok]
+        n = r_i.size
+        is_ref = g.uniform(size=n) < frac_ref
+        e = np.where(is_ref, capi.ID_RADAR_REF, capi.ID_RADAR_REF_ZERO)
+        elm += list(e); typ += [capi.TYP_PHARAD] * n; ri += list(r_i); rj += list(r_j)
+        lev += list(zz); dat += list(np.where(is_ref, 30.0, 5.0)); err += [5.0] * n; sig += [6.0] * n
+        nv = int(is_ref.sum())
+        elm += [capi.ID_RADAR_VR] * nv; typ += [capi.TYP_PHARAD] * nv
+        ri += list(r_i[is_ref]); rj += list(r_j[is_ref]); lev += list(zz[is_ref])
+        dat += [0.0] * nv; err += [3.0] * nv; sig += [3.5] * nv
+    return _finish_obs(g, elm, typ, ri, rj, lev, dat, err, k, det, sig)
+
+
+# ----------------------------------------------------------------------------- named configs
+def config_c2(nlon=256, nlat=256, nlev=60, member=50, **kw):
+    """BASELINE config 2: 15 km mesh, sonde/surface obs, R-localisation, RTPS 0.95."""
+    c = default_config(MEMBER=member, nlon=nlon, nlat=nlat, nlev=nlev, DX=15000.0, DY=15000.0,
+                       RELAX_ALPHA_SPREAD=0.95, INFL_MUL=1.0)
+    c.HORI_LOCAL[0] = 200.0e3
+    c.VERT_LOCAL[0] = 0.4
+    c.MAX_NOBS_PER_GRID[0] = 0
+    for key, v in kw.items():
+        setattr(c, key, v)
+    return resolve_config(c)
+
+
+def config_c3(nlon=256, nlat=256, nlev=60, member=100, max_nobs=500, **kw):
+    """BASELINE config 3 / 5: 500 m mesh, dense radar, settings of
+    scale/run/config/BDA_d4_500m_9p_bf30/config.nml.letkf:34,44,52-61,84."""
+    c = default_config(MEMBER=member, nlon=nlon, nlat=nlat, nlev=nlev, DX=500.0, DY=500.0,
+                       RELAX_ALPHA_SPREAD=0.95, INFL_MUL=1.0, BOUNDARY_BUFFER_WIDTH=15.0e3,
+                       RADAR_ZMAX=11.0e3)
+    c.HORI_LOCAL[0] = 4.0e3
+    c.VERT_LOCAL[0] = 0.3
+    c.VERT_LOCAL[21] = 2.0e3
+    c.HORI_LOCAL_RADAR_OBSNOREF = 2.0e3
+    c.MAX_NOBS_PER_GRID[0] = max_nobs
+    c.MAX_NOBS_PER_GRID_CRITERION = 1
+    for key, v in kw.items():
+        setattr(c, key, v)
+    return resolve_config(c)
