@@ -1,0 +1,230 @@
+"""Host-side mirror of the reference's operator interface for the analysis path.
+
+`LETKF` carries the module state the Fortran `das_letkf` reads (grid coordinates,
+bucket-sorted observation tables, namelist scalars) and exposes the reference's entry
+points under their own names:
+
+    letkf_core(...)      common/common_letkf.f90:52      (batched)
+    set_letkf_obs(obs)   scale/letkf/letkf_obs.f90:78    (bucket-sort half)
+    set_common_mpi_grid  scale/common/common_mpi_scale.f90:244 (rig1, rjg1, hgt1)
+    obs_local(...)       scale/letkf/letkf_tools.f90:1325
+    das_letkf(...)       scale/letkf/letkf_tools.f90:50
+    ensmean_grd(...)     scale/common/common_scale.f90:1513
+
+Every call goes through the C ABI of include/letkf_b200.h into CUDA kernels; numpy arrays
+are host buffers (copied H2D/D2H inside the call), torch CUDA tensors are used in place.
+There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+_ERR = {capi.EINVAL: "EINVAL", capi.ECUDA: "ECUDA", capi.ESTATE: "ESTATE", capi.EEIGEN: "EEIGEN",
+        capi.ENOMEM: "ENOMEM"}
+
+
+class LetkfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"letkf_b200 error {_ERR.get(code, code)}: {msg}")
+        self.code = code
+
+
+def _is_torch(x):
+    return x is not None and type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        return C.c_void_p(x.data_ptr())
+    return x.ctypes.data_as(C.c_void_p)
+
+
+class LETKF:
+    def __init__(self, cfg, device=0):
+        self.lib = capi.load_library()
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        r = self.lib.letkf_b200_create(C.byref(cfg), int(device), C.byref(self.h))
+        if r != 0:
+            self.h = None
+            raise LetkfError(r, "letkf_b200_create failed (no usable CUDA device?)")
+        self.device = device
+        self.nij1 = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.letkf_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, r, allow=()):
+        if r != 0 and r not in allow:
+            raise LetkfError(r, self.lib.letkf_b200_last_error(self.h).decode())
+        return r
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.lib.letkf_b200_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    # ---- letkf_core ---------------------------------------------------------------------
+    def letkf_core(self, ne, nobs, nobsl, hdxb, rdiag, rloc, dep, parm_infl, rdiag_wloc=True,
+                   infl_update=False, depd=None, want_transm=True, want_pao=True):
+        """Batched twin of letkf_core.  hdxb: (npts, ne, nobs) C-order (= per point the
+        Fortran hdxb(nobs, ne)); returns dict(trans (npts, ne, ne) column-major per point, ...)."""
+        npts = len(nobsl)
+        nobsl = np.ascontiguousarray(nobsl, dtype=np.int32)
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        hdxb, rdiag, rloc, dep = f(hdxb), f(rdiag), f(rloc), f(dep)
+        infl = np.array(parm_infl, dtype=np.float64).copy()
+        trans = np.zeros((npts, ne, ne))
+        transm = np.zeros((npts, ne)) if want_transm else None
+        pao = np.zeros((npts, ne, ne)) if want_pao else None
+        depd_ = f(depd) if depd is not None else None
+        transmd = np.zeros((npts, ne)) if depd is not None else None
+        r = self.lib.letkf_b200_core_batch(self.h, ne, nobs, npts, _ptr(nobsl), _ptr(hdxb), _ptr(rdiag),
+                                           _ptr(rloc), _ptr(dep), _ptr(infl), _ptr(trans), _ptr(transm),
+                                           _ptr(pao), int(rdiag_wloc), int(infl_update), _ptr(depd_),
+                                           _ptr(transmd), capi.MEM_HOST)
+        self._ck(r)
+        return dict(status=r, trans=trans, transm=transm, pao=pao, transmd=transmd, parm_infl=infl)
+
+    # ---- module state ---------------------------------------------------------------------
+    def set_common_mpi_grid(self, rig1, rjg1, hgt1):
+        """rig1, rjg1 (nij1,), hgt1 (nij1, nlev) Fortran order -- numpy or torch CUDA."""
+        self.nij1 = int(rig1.shape[0])
+        if _is_torch(rig1):
+            space = capi.MEM_DEVICE
+        else:
+            space = capi.MEM_HOST
+            rig1 = np.ascontiguousarray(rig1, dtype=np.float64)
+            rjg1 = np.ascontiguousarray(rjg1, dtype=np.float64)
+            hgt1 = np.asfortranarray(hgt1, dtype=np.float64)
+        self._ck(self.lib.letkf_b200_set_grid(self.h, self.nij1, _ptr(rig1), _ptr(rjg1), _ptr(hgt1), space))
+
+    def set_letkf_obs(self, obs):
+        """obs: dict(elm, typ, ri, rj, lev, dat, err, val, ensval (nobs, nensobs))."""
+        keep = {"elm": np.ascontiguousarray(obs["elm"], dtype=np.int32),
+                "typ": np.ascontiguousarray(obs["typ"], dtype=np.int32)}
+        for kf in ("ri", "rj", "lev", "dat", "err", "val", "ensval"):
+            keep[kf] = np.ascontiguousarray(obs[kf], dtype=np.float64)
+        o = capi.Obs()
+        o.nobs = keep["elm"].shape[0]
+        o.nensobs = keep["ensval"].shape[1] if keep["ensval"].ndim == 2 else 0
+        for kf, arr in keep.items():
+            setattr(o, kf, arr.ctypes.data)
+        self._ck(self.lib.letkf_b200_set_obs(self.h, C.byref(o)))
+
+    def obs_info(self):
+        a, b = C.c_int32(), C.c_int32()
+        self._ck(self.lib.letkf_b200_obs_info(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def ctype(self, ic):
+        info = capi.CtypeInfo()
+        self._ck(self.lib.letkf_b200_get_ctype(self.h, ic, C.byref(info)))
+        return info
+
+    def ac_ext(self, ic):
+        info = self.ctype(ic)
+        a = np.zeros((info.ngrdext_j, info.ngrdext_i + 1), dtype=np.int32)
+        self._ck(self.lib.letkf_b200_get_ac_ext(self.h, ic, _ptr(a)))
+        return a
+
+    def sorted_index(self):
+        n, _ = self.obs_info()
+        a = np.zeros(n, dtype=np.int32)
+        self._ck(self.lib.letkf_b200_get_sorted_index(self.h, _ptr(a)))
+        return a
+
+    # ---- obs_local --------------------------------------------------------------------------
+    def obs_local(self, ri, rj, rlev, rz, nvar, max_out):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        ri, rj, rlev, rz = f(ri), f(rj), f(rlev), f(rz)
+        npts = len(ri)
+        nobsl = np.zeros(npts, dtype=np.int32)
+        idx = np.full((npts, max_out), -1, dtype=np.int32)
+        rdiag = np.zeros((npts, max_out))
+        rloc = np.zeros((npts, max_out))
+        self._ck(self.lib.letkf_b200_obs_local(self.h, npts, _ptr(ri), _ptr(rj), _ptr(rlev), _ptr(rz), nvar,
+                                               _ptr(nobsl), _ptr(idx), _ptr(rdiag), _ptr(rloc), max_out,
+                                               capi.MEM_HOST))
+        return nobsl, idx, rdiag, rloc
+
+    # ---- das_letkf --------------------------------------------------------------------------
+    def das_letkf(self, gues3d, anal3d=None, gues2d=None, anal2d=None, infl3d=None, want_rtps=False,
+                  want_nobsl=False, logp=None, copy_back_gues=True, allow_eigen_fail=False):
+        """gues3d (nij1, nlev, nens, nv3d) Fortran order (numpy) or the same memory as a torch
+        CUDA tensor of shape (nv3d, nens, nlev, nij1).  INOUT: destroyed -> perturbations."""
+        dev = _is_torch(gues3d)
+        a = capi.DasArgs()
+        nlev, nv3d = self.cfg.nlev, self.cfg.nv3d
+        if dev:
+            import torch
+            assert gues3d.is_contiguous()
+            if anal3d is None:
+                anal3d = torch.empty_like(gues3d)
+            rtps = torch.empty((nv3d, nlev, self.nij1), dtype=torch.float64, device=gues3d.device) if want_rtps else None
+            nobsl = torch.empty((nlev, self.nij1), dtype=torch.int32, device=gues3d.device) if want_nobsl else None
+            a.mem_space = capi.MEM_DEVICE
+        else:
+            assert gues3d.flags.f_contiguous and gues3d.dtype == np.float64
+            if anal3d is None:
+                anal3d = np.zeros_like(gues3d, order="F")
+            if gues2d is not None and anal2d is None:
+                anal2d = np.zeros_like(gues2d, order="F")
+            rtps = np.zeros((self.nij1, nlev, nv3d), order="F") if want_rtps else None
+            nobsl = np.zeros((self.nij1, nlev), dtype=np.int32, order="F") if want_nobsl else None
+            a.mem_space = capi.MEM_HOST
+        a.gues3d, a.anal3d = _ptr(gues3d), _ptr(anal3d)
+        a.gues2d, a.anal2d = _ptr(gues2d), _ptr(anal2d)
+        a.infl3d, a.rtps_infl_out, a.nobsl_out, a.logp = _ptr(infl3d), _ptr(rtps), _ptr(nobsl), _ptr(logp)
+        a.reserved = 0 if copy_back_gues else 1
+        r = self._ck(self.lib.letkf_b200_das_letkf(self.h, C.byref(a)),
+                     allow=(capi.EEIGEN,) if allow_eigen_fail else ())
+        st = [C.c_int64() for _ in range(4)]
+        self.lib.letkf_b200_das_stats(self.h, *[C.byref(s) for s in st])
+        ms, nl = C.c_float(), C.c_int()
+        self.lib.letkf_b200_das_kernel_ms(self.h, C.byref(ms), C.byref(nl))
+        return dict(status=r, anal3d=anal3d, anal2d=anal2d, rtps=rtps, nobsl=nobsl, npoints=st[0].value,
+                    nsolved=st[1].value, nfail=st[2].value, nobsl_sum=st[3].value, kernel_ms=ms.value,
+                    launches=nl.value)
+
+    def ensmean_grd(self, v3d, v2d=None):
+        """Fill slot MEMBER+1 with the member mean (in place)."""
+        k = self.cfg.MEMBER
+        nens = k + 2 if self.cfg.DET_RUN else k + 1
+        if _is_torch(v3d):
+            nij = v3d.shape[-1]
+            space = capi.MEM_DEVICE
+        else:
+            nij = v3d.shape[0]
+            space = capi.MEM_HOST
+        self._ck(self.lib.letkf_b200_ensmean_grd(self.h, k, nens, nij, _ptr(v3d), _ptr(v2d), space))
+
+    # ---- transposes (device pointers; the all-to-all between them is the caller's NCCL call) --
+    def nij1_of(self, nprocs_e, myrank_e):
+        a, b = C.c_int32(), C.c_int32()
+        self._ck(self.lib.letkf_b200_nij1(self.h, nprocs_e, myrank_e, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def grd_to_buf(self, nprocs_e, v3dg, v2dg, bufs):
+        self._ck(self.lib.letkf_b200_grd_to_buf(self.h, nprocs_e, _ptr(v3dg), _ptr(v2dg), _ptr(bufs)))
+
+    def buf_to_grd(self, nprocs_e, bufr, v3dg, v2dg):
+        self._ck(self.lib.letkf_b200_buf_to_grd(self.h, nprocs_e, _ptr(bufr), _ptr(v3dg), _ptr(v2dg)))
+
+    def buf_to_ens(self, nprocs_e, myrank_e, nens, mstart, mend, bufr, v3d, v2d):
+        self._ck(self.lib.letkf_b200_buf_to_ens(self.h, nprocs_e, myrank_e, nens, mstart, mend, _ptr(bufr),
+                                                _ptr(v3d), _ptr(v2d)))
+
+    def ens_to_buf(self, nprocs_e, myrank_e, nens, mstart, mend, v3d, v2d, bufs):
+        self._ck(self.lib.letkf_b200_ens_to_buf(self.h, nprocs_e, myrank_e, nens, mstart, mend, _ptr(v3d),
+                                                _ptr(v2d), _ptr(bufs)))

@@ -1,0 +1,185 @@
+// aux_kernels.cuh -- HBM-bound helper kernels: device-side bucket sort of observations
+// (twin of set_letkf_obs' counting sort, scale/letkf/letkf_obs.f90:747-805, :922-976),
+// ensmean_grd (scale/common/common_scale.f90:1513) and the pack/unpack halves of the
+// member<->grid transposes (scale/common/common_mpi_scale.f90:1279-1476).
+#pragma once
+#include "search.cuh"
+
+namespace letkf {
+
+// ---- bucket sort ----------------------------------------------------------------------------
+// key[n] = global bucket id of observation n: boff(ic) + (j-1)*ngrdext_i + (i-1), with (i, j)
+// from ij_obsgrd (letkf_obs.f90:1187-1204) clamped to the subdomain (:758-761) and shifted
+// by ngrdsch into the extended mesh (:936-940).
+__global__ void bucket_key_kernel(const SearchTables *T, int nobs, const int *__restrict__ ic_of,
+                                  const double *__restrict__ ri, const double *__restrict__ rj,
+                                  int *__restrict__ key, int *__restrict__ count) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nobs) return;
+  const CtypeDev &c = T->ct[ic_of[n]];
+  int i = obsgrd_index(ri[n], T->IHALO, c.ngrd_i, T->nlon, 0);
+  int j = obsgrd_index(rj[n], T->JHALO, c.ngrd_j, T->nlat, 0);
+  i = min(max(i, 1), c.ngrd_i) + c.ngrdsch_i;
+  j = min(max(j, 1), c.ngrd_j) + c.ngrdsch_j;
+  const int b = c.boff + (j - 1) * c.ngrdext_i + (i - 1);
+  key[n] = b;
+  atomicAdd(&count[b], 1);
+}
+
+// single-CTA exclusive scan (setup path; nb up to a few million buckets)
+__global__ void exclusive_scan_kernel(const int *__restrict__ count, int *__restrict__ start, int nb) {
+  __shared__ int red[kMaxWarps];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < nb ? count[i] : 0;
+    int tot;
+    const int ex = block_excl_scan_i(v, red, tot);
+    const int carry = carry_s;
+    if (i < nb) start[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) start[nb] = carry_s;
+}
+
+__global__ void bucket_scatter_kernel(int nobs, const int *__restrict__ key, const int *__restrict__ start,
+                                      int *__restrict__ fill, int *__restrict__ tmp) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nobs) return;
+  const int b = key[n];
+  tmp[start[b] + atomicAdd(&fill[b], 1)] = n;
+}
+
+// restore arrival order inside each bucket (stable counting sort): rank = #entries of the
+// same bucket with a smaller original index.
+__global__ void bucket_rank_kernel(int nobs, const int *__restrict__ key, const int *__restrict__ start,
+                                   const int *__restrict__ tmp, int *__restrict__ sorted_to_orig) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nobs) return;
+  const int me = tmp[s];
+  const int b = key[me];
+  const int b0 = start[b], b1 = start[b + 1];
+  int rank = 0;
+  for (int e = b0; e < b1; ++e) rank += (tmp[e] < me);
+  sorted_to_orig[b0 + rank] = me;
+}
+
+__global__ void obs_gather_kernel(int nobs, int nensobs, int ldens, const int *__restrict__ s2o,
+                                  const double *__restrict__ ri, const double *__restrict__ rj,
+                                  const double *__restrict__ vc, const double *__restrict__ err,
+                                  const double *__restrict__ val, const double *__restrict__ ensval,
+                                  ObsRec *__restrict__ rec, double *__restrict__ sval,
+                                  double *__restrict__ sens) {
+  const int s = blockIdx.x;
+  if (s >= nobs) return;
+  const int n = s2o[s];
+  if (threadIdx.x == 0) {
+    ObsRec r;
+    r.ri = ri[n];
+    r.rj = rj[n];
+    r.vc = vc[n];
+    r.err = err[n];
+    rec[s] = r;
+    sval[s] = val[n];
+  }
+  for (int m = threadIdx.x; m < ldens; m += blockDim.x)
+    sens[(size_t)s * ldens + m] = m < nensobs ? ensval[(size_t)n * nensobs + m] : 0.0;
+}
+
+__global__ void fill_kernel(double *__restrict__ p, size_t n, double v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---- ensmean_grd ----------------------------------------------------------------------------
+// slot mem+1 = (x_1 + x_2 + ... + x_mem) / mem, summed in member order like the reference.
+__global__ void ensmean_kernel(int mem, int nens, size_t sl, int nvar, double *__restrict__ v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sl * nvar) return;
+  const size_t n = i / sl, p = i - n * sl;
+  double *b = v + p + n * (size_t)nens * sl;
+  double a = b[0];
+  for (int m = 1; m < mem; ++m) a += b[(size_t)m * sl];
+  b[(size_t)mem * sl] = a / (double)mem;
+}
+
+// ---- transposes -----------------------------------------------------------------------------
+struct TransposeDims {
+  int nlon, nlat, nlev, nv3d, nv2d, np, nij1max, nlevall;
+};
+__device__ __forceinline__ int nij1_of(const TransposeDims &d, int rank) {
+  const int r = (d.nlon * d.nlat) % d.np;
+  return rank < r ? d.nij1max : d.nij1max - 1;
+}
+// grd_to_buf over all levels/variables of one member: bufs(nij1max, nlevall, np)
+__global__ void grd_to_buf_kernel(TransposeDims d, const double *__restrict__ v3dg,
+                                  const double *__restrict__ v2dg, double *__restrict__ bufs) {
+  const size_t total = (size_t)d.nij1max * d.nlevall * d.np;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % d.nij1max);
+    const size_t t = idx / d.nij1max;
+    const int jl = (int)(t % d.nlevall), m = (int)(t / d.nlevall);
+    double v = -9.99e33;   // undef (common/common.f90:38) in the padding row
+    if (i < nij1_of(d, m)) {
+      const int j = m + d.np * i;
+      const int ilon = j % d.nlon, ilat = j / d.nlon;
+      if (jl < d.nlev * d.nv3d) {
+        const int n = jl / d.nlev, k = jl - n * d.nlev;
+        v = v3dg[k + (size_t)d.nlev * (ilon + (size_t)d.nlon * (ilat + (size_t)d.nlat * n))];
+      } else {
+        const int n = jl - d.nlev * d.nv3d;
+        v = v2dg[ilon + (size_t)d.nlon * (ilat + (size_t)d.nlat * n)];
+      }
+    }
+    bufs[idx] = v;
+  }
+}
+__global__ void buf_to_grd_kernel(TransposeDims d, const double *__restrict__ bufr,
+                                  double *__restrict__ v3dg, double *__restrict__ v2dg) {
+  const size_t total = (size_t)d.nij1max * d.nlevall * d.np;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % d.nij1max);
+    const size_t t = idx / d.nij1max;
+    const int jl = (int)(t % d.nlevall), m = (int)(t / d.nlevall);
+    if (i >= nij1_of(d, m)) continue;
+    const int j = m + d.np * i;
+    const int ilon = j % d.nlon, ilat = j / d.nlon;
+    if (jl < d.nlev * d.nv3d) {
+      const int n = jl / d.nlev, k = jl - n * d.nlev;
+      v3dg[k + (size_t)d.nlev * (ilon + (size_t)d.nlon * (ilat + (size_t)d.nlat * n))] = bufr[idx];
+    } else {
+      const int n = jl - d.nlev * d.nv3d;
+      v2dg[ilon + (size_t)d.nlon * (ilat + (size_t)d.nlat * n)] = bufr[idx];
+    }
+  }
+}
+// bufr(nij1max, nlevall, mcount) -> v3d(nij1, nlev, nens, nv3d), v2d(nij1, nens, nv2d) slots mstart..mend
+__global__ void buf_to_ens_kernel(TransposeDims d, int nij1, int nens, int mstart, int mcount,
+                                  const double *__restrict__ bufr, double *__restrict__ v3d,
+                                  double *__restrict__ v2d, int reverse) {
+  const size_t total = (size_t)nij1 * d.nlevall * mcount;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % nij1);
+    const size_t t = idx / nij1;
+    const int jl = (int)(t % d.nlevall), mm = (int)(t / d.nlevall);
+    const size_t bi = i + (size_t)d.nij1max * (jl + (size_t)d.nlevall * mm);
+    const int m = mstart - 1 + mm;
+    double *p;
+    if (jl < d.nlev * d.nv3d) {
+      const int n = jl / d.nlev, k = jl - n * d.nlev;
+      p = v3d + i + (size_t)nij1 * (k + (size_t)d.nlev * (m + (size_t)nens * n));
+    } else {
+      const int n = jl - d.nlev * d.nv3d;
+      p = v2d + i + (size_t)nij1 * (m + (size_t)nens * n);
+    }
+    if (reverse) const_cast<double *>(bufr)[bi] = *p; else *p = bufr[bi];
+  }
+}
+
+}  // namespace letkf

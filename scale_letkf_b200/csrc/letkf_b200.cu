@@ -1,0 +1,882 @@
+// letkf_b200.cu -- C ABI of the B200-native LETKF analysis path (include/letkf_b200.h).
+// Host side: handle, configuration, observation tables, kernel launches.  No CPU compute
+// path exists: every entry point that produces numbers launches sm_100a kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/letkf_b200.h"
+#include "aux_kernels.cuh"
+#include "das_kernel.cuh"
+
+using namespace letkf;
+
+namespace {
+
+const int ELEM_UID[LETKF_B200_NID_OBS] = {2819, 2820, 3073, 3074, 3330, 3331, 14593, 19999,
+                                          4001, 4004, 4002, 4003, 8800, 99991, 99992, 99993};
+const int ID_PS = 14593, ID_RAIN = 19999, ID_REF = 4001, ID_RE0 = 4004, ID_VR = 4002;
+
+int uid_obs(int elm) {   // common_obs_scale.f90:171-211
+  for (int i = 0; i < LETKF_B200_NID_OBS; ++i)
+    if (ELEM_UID[i] == elm) return i + 1;
+  return -1;
+}
+int uid_obs_varlocal(int elm) {   // common_obs_scale.f90:216-242
+  switch (elm) {
+    case 2819: case 2820: return 1;
+    case 3073: case 3074: return 2;
+    case 3330: case 3331: return 3;
+    case 14593: return 4;
+    case 19999: return 5;
+    case 99991: case 99992: case 99993: return 6;
+    case 4001: case 4004: case 4003: return 7;
+    case 4002: return 8;
+    case 8800: return 9;
+    default: return -1;
+  }
+}
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+}  // namespace
+
+struct letkf_b200_handle {
+  letkf_b200_config cfg;
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // grid
+  int nij1 = 0;
+  DevBuf<double> rig1, rjg1, hgt1;
+  // observations
+  bool obs_set = false;
+  int nobstotal = 0, nctype = 0, nensobs = 0, ldens = 0, nbuckets = 0;
+  SearchTables tables;
+  std::vector<letkf_b200_ctype_info> ctinfo;
+  std::vector<int> h_bstart, h_s2o;
+  bool radar_only = true;
+  int maxl = 1;
+  DevBuf<SearchTables> d_tables;
+  DevBuf<ObsRec> rec;
+  DevBuf<int> bstart, s2o;
+  DevBuf<double> sval, sens;
+  // variable localisation groups
+  int nvgroup = 1;
+  int vgroup[kMaxNV], vfirst[kMaxNV];
+  std::vector<double> h_vlfac;   // [nvar][nctype] factors for every variable (obs_local twin)
+  DevBuf<double> vlfac_groups, vlfac_one;
+  // scratch
+  DevBuf<int> l_iob;
+  DevBuf<double> l_rdiag, l_rloc;
+  DevBuf<unsigned long long> counters;
+  DevBuf<double> st_gues, st_anal, st_gues2, st_anal2, st_infl, st_rtps, st_logp;
+  DevBuf<int> st_nobsl;
+  DevBuf<double> cb[10];
+  DevBuf<int> cb_i;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // stats of the last das call
+  long long st_points = 0, st_solved = 0, st_fail = 0, st_nobs = 0;
+  float last_ms = 0.f;
+  int last_launches = 0;
+};
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+      return LETKF_B200_ECUDA;                                                           \
+    }                                                                                    \
+  } while (0)
+
+namespace {
+
+int fail(letkf_b200_handle *h, int code, const char *msg) {
+  h->err = msg;
+  return code;
+}
+
+// letkf_tools.f90:130-163 -- group variables with identical var_local rows
+void setup_var_groups(letkf_b200_handle *h) {
+  const letkf_b200_config &c = h->cfg;
+  const int nv = c.nv3d + c.nv2d;
+  int n2nc[kMaxNV], n2n[kMaxNV], n2nc_max = 1;
+  n2nc[0] = 1;
+  n2n[0] = 1;
+  for (int n = 2; n <= nv; ++n) {
+    bool found = false;
+    for (int i = 1; i <= n2nc_max; ++i) {
+      const int ref = n2nc[i - 1];   // as written in the reference (:146)
+      double md = 0.0;
+      for (int iv = 0; iv < LETKF_B200_NID_VARLOCAL; ++iv)
+        md = std::max(md, std::fabs(c.VAR_LOCAL[iv][ref - 1] - c.VAR_LOCAL[iv][n - 1]));
+      if (md < std::numeric_limits<double>::min()) {
+        n2nc[n - 1] = n2nc[i - 1];
+        n2n[n - 1] = n2n[n2nc[n - 1] - 1];
+        found = true;
+        break;
+      }
+    }
+    if (!found) {
+      ++n2nc_max;
+      n2nc[n - 1] = n2nc_max;
+      n2n[n - 1] = n;
+    }
+  }
+  h->nvgroup = n2nc_max;
+  for (int n = 0; n < nv; ++n) {
+    h->vgroup[n] = n2nc[n] - 1;
+    h->vfirst[n] = n2n[n] - 1;
+  }
+}
+
+template <int KC>
+int launch_das(letkf_b200_handle *h, DasParams &P) {
+  using SC = SizeClass<KC>;
+  const size_t smem = das_smem_bytes(P.k, SC::NT);
+  CK(cudaFuncSetAttribute(das_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, das_kernel<KC>, SC::NT, smem));
+  if (occ < 1) return fail(h, LETKF_B200_EINVAL, "das_kernel does not fit on an SM");
+  long long grid = (long long)occ * h->num_sms;
+  grid = std::min<long long>(grid, std::max<long long>(P.npoints_total, 1));
+  CK(h->l_iob.ensure((size_t)grid * P.lcap));
+  CK(h->l_rdiag.ensure((size_t)grid * P.lcap));
+  CK(h->l_rloc.ensure((size_t)grid * P.lcap));
+  P.l_iob = h->l_iob.p;
+  P.l_rdiag = h->l_rdiag.p;
+  P.l_rloc = h->l_rloc.p;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  das_kernel<KC><<<(unsigned)grid, SC::NT, smem, h->stream>>>(P);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->last_launches = 1;
+  return LETKF_B200_OK;
+}
+
+template <int KC>
+int launch_core(letkf_b200_handle *h, CoreParams &P) {
+  using SC = SizeClass<KC>;
+  const size_t smem = core_smem_bytes(P.ne);
+  CK(cudaFuncSetAttribute(core_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, core_kernel<KC>, SC::NT, smem));
+  if (occ < 1) return fail(h, LETKF_B200_EINVAL, "core_kernel does not fit on an SM");
+  const long long grid = std::min<long long>((long long)occ * h->num_sms, std::max(P.npts, 1));
+  core_kernel<KC><<<(unsigned)grid, SC::NT, smem, h->stream>>>(P);
+  CK(cudaGetLastError());
+  return LETKF_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *letkf_b200_build_info(void) { return "libletkf_b200 sm_100a fp64 (CUDA " __DATE__ ")"; }
+
+void letkf_b200_config_defaults(letkf_b200_config *c) {
+  // scale/common/common_nml.f90 defaults (:40-46, :109-142, :160-229, :264)
+  static const double min_spacing[LETKF_B200_NOBTYPE] = {
+      300.0e3, 100.0e3, 100.0e3, 150.0e3, 300.0e3, 150.0e3, 150.0e3, 100.0e3, 150.0e3, 150.0e3, 150.0e3, 150.0e3,
+      150.0e3, 150.0e3, 150.0e3, 150.0e3, 300.0e3, 150.0e3, 150.0e3, 150.0e3, 150.0e3, 1.0e3,   15.0e3,  1000.0e3};
+  std::memset(c, 0, sizeof(*c));
+  c->MEMBER = 3;
+  c->nv3d = 11;
+  c->IHALO = c->JHALO = 2;
+  c->DX = c->DY = 1.0;
+  c->iv3d_p = 5;
+  c->iv3d_q = 6;
+  c->iv3d_qg = 11;
+  c->INFL_MUL = 1.0;
+  c->INFL_MUL_MIN = -1.0;
+  c->Q_SPRD_MAX = -1.0;
+  for (int t = 0; t < LETKF_B200_NOBTYPE; ++t) {
+    c->HORI_LOCAL[t] = -1.0;
+    c->VERT_LOCAL[t] = -1.0;
+    c->MAX_NOBS_PER_GRID[t] = -1;
+    c->OBS_MIN_SPACING[t] = min_spacing[t];
+    c->OBS_SORT_GRID_SPACING[t] = -1.0;
+  }
+  c->HORI_LOCAL[0] = 500.0e3;
+  c->VERT_LOCAL[0] = 0.4;
+  c->VERT_LOCAL[21] = 1000.0;
+  c->MAX_NOBS_PER_GRID[0] = 0;
+  c->OBS_SORT_GRID_SPACING[0] = 0.0;
+  c->HORI_LOCAL_RADAR_OBSNOREF = c->HORI_LOCAL_RADAR_VR = c->VERT_LOCAL_RADAR_VR = -1.0;
+  c->VERT_LOCAL_RAIN_BASE = 85000.0;
+  c->MAX_NOBS_PER_GRID_CRITERION = 1;
+  for (int iv = 0; iv < LETKF_B200_NID_VARLOCAL; ++iv)
+    for (int n = 0; n < LETKF_B200_MAX_NV; ++n) c->VAR_LOCAL[iv][n] = 1.0;
+  c->RADAR_ZMAX = 99.0e3;
+  // letkf_obs.f90:27-28: default-REAL literals widened to double
+  c->dist_zero_fac = (double)3.651483717f;
+  c->dist_zero_fac_square = (double)13.33333333f;
+}
+
+void letkf_b200_config_resolve(letkf_b200_config *c) {   // common_nml.f90:741-775
+  for (int t = 1; t < LETKF_B200_NOBTYPE; ++t) {
+    if (c->HORI_LOCAL[t] < 0.0) c->HORI_LOCAL[t] = c->HORI_LOCAL[0];
+    if (c->VERT_LOCAL[t] < 0.0) c->VERT_LOCAL[t] = c->VERT_LOCAL[0];
+    if (c->MAX_NOBS_PER_GRID[t] < 0) c->MAX_NOBS_PER_GRID[t] = c->MAX_NOBS_PER_GRID[0];
+    if (c->OBS_MIN_SPACING[t] <= 0.0) c->OBS_MIN_SPACING[t] = c->OBS_MIN_SPACING[0];
+    if (c->OBS_SORT_GRID_SPACING[t] < 0.0) c->OBS_SORT_GRID_SPACING[t] = c->OBS_SORT_GRID_SPACING[0];
+  }
+  if (c->HORI_LOCAL_RADAR_OBSNOREF < 0.0) c->HORI_LOCAL_RADAR_OBSNOREF = c->HORI_LOCAL[21];
+  if (c->HORI_LOCAL_RADAR_VR < 0.0) c->HORI_LOCAL_RADAR_VR = c->HORI_LOCAL[21];
+  if (c->VERT_LOCAL_RADAR_VR < 0.0) c->VERT_LOCAL_RADAR_VR = c->VERT_LOCAL[21];
+}
+
+int letkf_b200_create(const letkf_b200_config *cfg, int device, letkf_b200_handle **out) {
+  if (!cfg || !out) return LETKF_B200_EINVAL;
+  *out = nullptr;
+  letkf_b200_handle *h = new letkf_b200_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  const letkf_b200_config &c = h->cfg;
+  auto bad = [&](const char *m) {
+    std::fprintf(stderr, "letkf_b200_create: %s\n", m);
+    delete h;
+    return LETKF_B200_EINVAL;
+  };
+  if (c.MEMBER < 2 || c.MEMBER > LETKF_B200_MAX_MEMBER) return bad("MEMBER must be in [2, 128] (tiled k>=1000 path not built yet)");
+  if (c.nv3d < 1 || c.nv3d + c.nv2d > kMaxNV - 2) return bad("nv3d + nv2d must be in [1, 14]");
+  if (c.nlon < 1 || c.nlat < 1 || c.nlev < 1) return bad("nlon/nlat/nlev must be positive");
+  if (c.MAX_NOBS_PER_GRID_CRITERION < 1 || c.MAX_NOBS_PER_GRID_CRITERION > 3) return bad("Unsupported MAX_NOBS_PER_GRID_CRITERION");
+  if (c.iv3d_p < 1 || c.iv3d_p > c.nv3d) return bad("iv3d_p out of range");
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    std::fprintf(stderr, "letkf_b200_create: cudaSetDevice(%d): %s (no CPU fallback exists)\n", device,
+                 cudaGetErrorString(e));
+    delete h;
+    return LETKF_B200_ECUDA;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    delete h;
+    return LETKF_B200_ECUDA;
+  }
+  h->num_sms = prop.multiProcessorCount;
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  if (h->counters.ensure(8) != cudaSuccess) {
+    delete h;
+    return LETKF_B200_ECUDA;
+  }
+  setup_var_groups(h);
+  *out = h;
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_destroy(letkf_b200_handle *h) {
+  if (!h) return LETKF_B200_OK;
+  cudaSetDevice(h->device);
+  h->rig1.release(); h->rjg1.release(); h->hgt1.release();
+  h->d_tables.release(); h->rec.release(); h->bstart.release(); h->s2o.release();
+  h->sval.release(); h->sens.release(); h->vlfac_groups.release(); h->vlfac_one.release();
+  h->l_iob.release(); h->l_rdiag.release(); h->l_rloc.release(); h->counters.release();
+  h->st_gues.release(); h->st_anal.release(); h->st_gues2.release(); h->st_anal2.release();
+  h->st_infl.release(); h->st_rtps.release(); h->st_logp.release(); h->st_nobsl.release();
+  for (auto &b : h->cb) b.release();
+  h->cb_i.release();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+  return LETKF_B200_OK;
+}
+
+const char *letkf_b200_last_error(const letkf_b200_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int letkf_b200_set_stream(letkf_b200_handle *h, void *s) {
+  if (!h) return LETKF_B200_EINVAL;
+  h->stream = (cudaStream_t)s;
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_set_grid(letkf_b200_handle *h, int nij1, const double *rig1, const double *rjg1,
+                        const double *hgt1, int mem_space) {
+  if (!h || nij1 < 1 || !rig1 || !rjg1 || !hgt1) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const cudaMemcpyKind kind = mem_space == LETKF_B200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CK(h->rig1.ensure(nij1));
+  CK(h->rjg1.ensure(nij1));
+  CK(h->hgt1.ensure((size_t)nij1 * h->cfg.nlev));
+  CK(cudaMemcpyAsync(h->rig1.p, rig1, sizeof(double) * nij1, kind, h->stream));
+  CK(cudaMemcpyAsync(h->rjg1.p, rjg1, sizeof(double) * nij1, kind, h->stream));
+  CK(cudaMemcpyAsync(h->hgt1.p, hgt1, sizeof(double) * (size_t)nij1 * h->cfg.nlev, kind, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->nij1 = nij1;
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
+  if (!h || !obs || obs->nobs < 0) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const letkf_b200_config &c = h->cfg;
+  const int nobs = obs->nobs;
+  const int need = c.DET_RUN ? c.MEMBER + 1 : c.MEMBER;
+  if (nobs > 0 && obs->nensobs < need) return fail(h, LETKF_B200_EINVAL, "nensobs < MEMBER (+1 with DET_RUN)");
+  h->obs_set = false;
+  // ---- ctype table (letkf_obs.f90:300-342) --------------------------------------------------
+  bool use[LETKF_B200_NID_OBS][LETKF_B200_NOBTYPE];
+  std::memset(use, 0, sizeof(use));
+  for (int n = 0; n < nobs; ++n) {
+    const int u = uid_obs(obs->elm[n]);
+    if (u < 1 || obs->typ[n] < 1 || obs->typ[n] > LETKF_B200_NOBTYPE) return fail(h, LETKF_B200_EINVAL, "unknown obs elm/typ");
+    use[u - 1][obs->typ[n] - 1] = true;
+  }
+  int ctype_elmtyp[LETKF_B200_NID_OBS][LETKF_B200_NOBTYPE];
+  std::memset(ctype_elmtyp, 0, sizeof(ctype_elmtyp));
+  SearchTables &T = h->tables;
+  std::memset(&T, 0, sizeof(T));
+  h->ctinfo.clear();
+  int nct = 0, boff = 0;
+  for (int ityp = 1; ityp <= LETKF_B200_NOBTYPE; ++ityp)
+    for (int ielm_u = 1; ielm_u <= LETKF_B200_NID_OBS; ++ielm_u) {
+      if (!use[ielm_u - 1][ityp - 1]) continue;
+      if (nct >= kMaxCtype) return fail(h, LETKF_B200_EINVAL, "too many combined obs types");
+      ctype_elmtyp[ielm_u - 1][ityp - 1] = nct + 1;
+      const int elm = ELEM_UID[ielm_u - 1];
+      CtypeDev &d = T.ct[nct];
+      letkf_b200_ctype_info info;
+      std::memset(&info, 0, sizeof(info));
+      d.hori_loc = (elm == ID_RE0) ? c.HORI_LOCAL_RADAR_OBSNOREF
+                   : (elm == ID_VR) ? c.HORI_LOCAL_RADAR_VR : c.HORI_LOCAL[ityp - 1];
+      d.vert_loc = (elm == ID_VR) ? c.VERT_LOCAL_RADAR_VR : c.VERT_LOCAL[ityp - 1];
+      // sorting mesh (letkf_obs.f90:660-695)
+      double target;
+      if (c.OBS_SORT_GRID_SPACING[ityp - 1] > 0) target = c.OBS_SORT_GRID_SPACING[ityp - 1];
+      else if (c.MAX_NOBS_PER_GRID[ityp - 1] > 0)
+        target = 0.1 * std::sqrt((double)c.MAX_NOBS_PER_GRID[ityp - 1]) * c.OBS_MIN_SPACING[ityp - 1];
+      else target = d.hori_loc * c.dist_zero_fac / 6.0;
+      d.ngrd_i = std::min((int)std::ceil(c.DX * (double)c.nlon / target), c.nlon);
+      d.ngrd_j = std::min((int)std::ceil(c.DY * (double)c.nlat / target), c.nlat);
+      d.grdspc_i = c.DX * (double)c.nlon / (double)d.ngrd_i;
+      d.grdspc_j = c.DY * (double)c.nlat / (double)d.ngrd_j;
+      d.ngrdsch_i = (int)std::ceil(d.hori_loc * c.dist_zero_fac / d.grdspc_i);
+      d.ngrdsch_j = (int)std::ceil(d.hori_loc * c.dist_zero_fac / d.grdspc_j);
+      d.ngrdext_i = d.ngrd_i + d.ngrdsch_i * 2;
+      d.ngrdext_j = d.ngrd_j + d.ngrdsch_j * 2;
+      d.boff = boff;
+      boff += d.ngrdext_i * d.ngrdext_j;
+      d.elm_u = ielm_u;
+      d.typ = ityp;
+      d.varlocal = uid_obs_varlocal(elm) - 1;
+      d.vconst = 0.0;
+      // vertical coordinate mode, same precedence as obs_local_cal (letkf_tools.f90:1852-1866)
+      if (d.vert_loc == 0.0) d.vmode = 0;
+      else if (elm == ID_PS) d.vmode = 1;
+      else if (elm == ID_RAIN) { d.vmode = 2; d.vconst = std::log(c.VERT_LOCAL_RAIN_BASE); }
+      else if (ityp == 22) d.vmode = 3;
+      else d.vmode = 1;
+      info.elm = elm; info.elm_u = ielm_u; info.typ = ityp;
+      info.ngrd_i = d.ngrd_i; info.ngrd_j = d.ngrd_j; info.ngrdsch_i = d.ngrdsch_i; info.ngrdsch_j = d.ngrdsch_j;
+      info.ngrdext_i = d.ngrdext_i; info.ngrdext_j = d.ngrdext_j;
+      info.hori_loc = d.hori_loc; info.vert_loc = d.vert_loc; info.grdspc_i = d.grdspc_i; info.grdspc_j = d.grdspc_j;
+      h->ctinfo.push_back(info);
+      ++nct;
+    }
+  h->nctype = nct;
+  h->nbuckets = boff;
+  T.nctype = nct;
+  T.criterion = c.MAX_NOBS_PER_GRID_CRITERION;
+  T.IHALO = c.IHALO; T.JHALO = c.JHALO; T.nlon = c.nlon; T.nlat = c.nlat;
+  T.DX = c.DX; T.DY = c.DY; T.dzf = c.dist_zero_fac; T.dzf2 = c.dist_zero_fac_square;
+  // ---- per-obs ctype and vertical coordinate (host libm: same log() as a CPU run) ---------------
+  std::vector<int> ic_of(nobs);
+  std::vector<double> vc(nobs);
+  for (int n = 0; n < nobs; ++n) {
+    const int ic = ctype_elmtyp[uid_obs(obs->elm[n]) - 1][obs->typ[n] - 1] - 1;
+    ic_of[n] = ic;
+    const CtypeDev &d = T.ct[ic];
+    if (d.vmode == 3) vc[n] = obs->lev[n];
+    else if (obs->elm[n] == ID_PS) vc[n] = std::log(obs->dat[n]);
+    else vc[n] = std::log(obs->lev[n]);
+  }
+  // ---- device bucket sort ------------------------------------------------------------------------
+  h->nensobs = obs->nensobs;
+  h->ldens = round_up(std::max(need, 1), 2);
+  h->nobstotal = nobs;
+  DevBuf<int> d_ic, d_key, d_count, d_fill, d_tmp;
+  DevBuf<double> d_ri, d_rj, d_vc, d_err, d_val, d_ens;
+  CK(h->d_tables.ensure(1));
+  CK(cudaMemcpyAsync(h->d_tables.p, &T, sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  CK(h->bstart.ensure((size_t)boff + 1));
+  CK(h->s2o.ensure(nobs));
+  CK(h->rec.ensure(nobs));
+  CK(h->sval.ensure(nobs));
+  CK(h->sens.ensure((size_t)nobs * h->ldens));
+  CK(d_count.ensure(boff + 1));
+  CK(d_fill.ensure(boff + 1));
+  CK(cudaMemsetAsync(d_count.p, 0, sizeof(int) * (boff + 1), h->stream));
+  CK(cudaMemsetAsync(d_fill.p, 0, sizeof(int) * (boff + 1), h->stream));
+  if (nobs > 0) {
+    CK(d_ic.ensure(nobs)); CK(d_key.ensure(nobs)); CK(d_tmp.ensure(nobs));
+    CK(d_ri.ensure(nobs)); CK(d_rj.ensure(nobs)); CK(d_vc.ensure(nobs)); CK(d_err.ensure(nobs));
+    CK(d_val.ensure(nobs)); CK(d_ens.ensure((size_t)nobs * obs->nensobs));
+    const size_t nb = sizeof(double) * nobs;
+    CK(cudaMemcpyAsync(d_ic.p, ic_of.data(), sizeof(int) * nobs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_ri.p, obs->ri, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_rj.p, obs->rj, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_vc.p, vc.data(), nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_err.p, obs->err, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_val.p, obs->val, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_ens.p, obs->ensval, nb * obs->nensobs, cudaMemcpyHostToDevice, h->stream));
+    const int tb = 256, gb = (nobs + tb - 1) / tb;
+    bucket_key_kernel<<<gb, tb, 0, h->stream>>>(h->d_tables.p, nobs, d_ic.p, d_ri.p, d_rj.p, d_key.p, d_count.p);
+    exclusive_scan_kernel<<<1, 256, 0, h->stream>>>(d_count.p, h->bstart.p, boff);
+    bucket_scatter_kernel<<<gb, tb, 0, h->stream>>>(nobs, d_key.p, h->bstart.p, d_fill.p, d_tmp.p);
+    bucket_rank_kernel<<<gb, tb, 0, h->stream>>>(nobs, d_key.p, h->bstart.p, d_tmp.p, h->s2o.p);
+    obs_gather_kernel<<<nobs, 64, 0, h->stream>>>(nobs, obs->nensobs, h->ldens, h->s2o.p, d_ri.p, d_rj.p, d_vc.p,
+                                                  d_err.p, d_val.p, d_ens.p, h->rec.p, h->sval.p, h->sens.p);
+    CK(cudaGetLastError());
+  } else {
+    exclusive_scan_kernel<<<1, 256, 0, h->stream>>>(d_count.p, h->bstart.p, boff);
+    CK(cudaGetLastError());
+  }
+  h->h_bstart.resize((size_t)boff + 1);
+  h->h_s2o.resize(nobs);
+  CK(cudaMemcpyAsync(h->h_bstart.data(), h->bstart.p, sizeof(int) * ((size_t)boff + 1), cudaMemcpyDeviceToHost, h->stream));
+  if (nobs > 0) CK(cudaMemcpyAsync(h->h_s2o.data(), h->s2o.p, sizeof(int) * nobs, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  d_ic.release(); d_key.release(); d_count.release(); d_fill.release(); d_tmp.release();
+  d_ri.release(); d_rj.release(); d_vc.release(); d_err.release(); d_val.release(); d_ens.release();
+  for (int ic = 0; ic < nct; ++ic) {
+    const CtypeDev &d = T.ct[ic];
+    const int b0 = h->h_bstart[d.boff], b1 = h->h_bstart[d.boff + d.ngrdext_i * d.ngrdext_j];
+    T.ct[ic].tot = b1 - b0;
+    h->ctinfo[ic].tot_ext = b1 - b0;
+    h->ctinfo[ic].ac_begin = b0;
+  }
+  // ---- merged obs-number budgets (letkf_tools.f90:167-192) -------------------------------------
+  std::vector<int> n_merge(nct, 1);
+  T.ngroup = 0;
+  int maxl = 0;
+  auto merge_id = [&](int ic) { return (T.ct[ic].typ == 22 && (T.ct[ic].elm_u == 9 || T.ct[ic].elm_u == 10)) ? 1 : 0; };
+  for (int ic = 0; ic < nct; ++ic) {
+    if (n_merge[ic] == 0) continue;
+    GroupDev &G = T.grp[T.ngroup++];
+    G.n = 1;
+    G.ic[0] = ic;
+    G.limit = c.MAX_NOBS_PER_GRID[T.ct[ic].typ - 1];
+    if (merge_id(ic) > 0)
+      for (int ic2 = ic + 1; ic2 < nct; ++ic2)
+        if (merge_id(ic2) == merge_id(ic)) {
+          if (G.n >= kMaxMerge) return fail(h, LETKF_B200_EINVAL, "too many merged obs types");
+          G.ic[G.n++] = ic2;
+          n_merge[ic] += 1;
+          n_merge[ic2] = 0;
+        }
+    int tot = 0;
+    for (int m = 0; m < G.n; ++m) tot += T.ct[G.ic[m]].tot;
+    maxl += (G.limit > 0) ? std::min(G.limit, tot) : tot;
+  }
+  for (int ic = 0; ic < nct; ++ic) h->ctinfo[ic].n_merge = n_merge[ic];
+  h->maxl = std::max(maxl, 1);
+  h->radar_only = true;   // letkf_tools.f90:197-203
+  for (int ic = 0; ic < nct; ++ic)
+    if (T.ct[ic].typ != 22) h->radar_only = false;
+  CK(cudaMemcpyAsync(h->d_tables.p, &T, sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  // ---- variable-localisation factors -------------------------------------------------------------
+  const int nv = c.nv3d + c.nv2d;
+  h->h_vlfac.assign((size_t)nv * std::max(nct, 1), 1.0);
+  for (int n = 0; n < nv; ++n)
+    for (int ic = 0; ic < nct; ++ic) h->h_vlfac[(size_t)n * nct + ic] = c.VAR_LOCAL[T.ct[ic].varlocal][n];
+  std::vector<double> vg((size_t)h->nvgroup * std::max(nct, 1), 1.0);
+  for (int n = nv - 1; n >= 0; --n)   // representative = first variable of each group
+    for (int ic = 0; ic < nct; ++ic) vg[(size_t)h->vgroup[n] * nct + ic] = h->h_vlfac[(size_t)n * nct + ic];
+  CK(h->vlfac_groups.ensure(vg.size()));
+  CK(cudaMemcpyAsync(h->vlfac_groups.p, vg.data(), sizeof(double) * vg.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->obs_set = true;
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_obs_info(const letkf_b200_handle *h, int32_t *nobstotal, int32_t *nctype) {
+  if (!h || !h->obs_set) return LETKF_B200_ESTATE;
+  if (nobstotal) *nobstotal = h->nobstotal;
+  if (nctype) *nctype = h->nctype;
+  return LETKF_B200_OK;
+}
+int letkf_b200_get_ctype(const letkf_b200_handle *h, int ic, letkf_b200_ctype_info *out) {
+  if (!h || !h->obs_set) return LETKF_B200_ESTATE;
+  if (ic < 0 || ic >= h->nctype || !out) return LETKF_B200_EINVAL;
+  *out = h->ctinfo[ic];
+  return LETKF_B200_OK;
+}
+int letkf_b200_get_ac_ext(const letkf_b200_handle *h, int ic, int32_t *ac) {
+  if (!h || !h->obs_set) return LETKF_B200_ESTATE;
+  if (ic < 0 || ic >= h->nctype || !ac) return LETKF_B200_EINVAL;
+  const CtypeDev &d = h->tables.ct[ic];
+  for (int j = 1; j <= d.ngrdext_j; ++j)
+    for (int i = 0; i <= d.ngrdext_i; ++i)
+      ac[i + (size_t)(j - 1) * (d.ngrdext_i + 1)] = h->h_bstart[d.boff + (j - 1) * d.ngrdext_i + i];
+  return LETKF_B200_OK;
+}
+int letkf_b200_get_sorted_index(const letkf_b200_handle *h, int32_t *s2o) {
+  if (!h || !h->obs_set) return LETKF_B200_ESTATE;
+  std::copy(h->h_s2o.begin(), h->h_s2o.end(), s2o);
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_obs_local(letkf_b200_handle *h, int npts, const double *ri, const double *rj, const double *rlev,
+                         const double *rz, int nvar, int32_t *nobsl, int32_t *idx, double *rdiag, double *rloc,
+                         int max_out, int mem_space) {
+  if (!h || npts < 0 || !nobsl) return LETKF_B200_EINVAL;
+  if (!h->obs_set) return fail(h, LETKF_B200_ESTATE, "set_obs has not been called");
+  const int nv = h->cfg.nv3d + h->cfg.nv2d;
+  if (nvar < 1 || nvar > nv) return fail(h, LETKF_B200_EINVAL, "nvar must be in [1, nv3d+nv2d]");
+  CK(cudaSetDevice(h->device));
+  const bool host = mem_space != LETKF_B200_MEM_DEVICE;
+  const int nct = std::max(h->nctype, 1);
+  CK(h->vlfac_one.ensure(nct));
+  CK(cudaMemcpyAsync(h->vlfac_one.p, h->h_vlfac.data() + (size_t)(nvar - 1) * h->nctype, sizeof(double) * h->nctype,
+                     cudaMemcpyHostToDevice, h->stream));
+  SearchParams P;
+  std::memset(&P, 0, sizeof(P));
+  std::vector<double> lp;
+  if (host) {
+    lp.resize(npts);
+    for (int i = 0; i < npts; ++i) lp[i] = std::log(rlev[i]);   // host libm
+    for (int b = 0; b < 4; ++b) CK(h->cb[b].ensure(npts));
+    CK(cudaMemcpyAsync(h->cb[0].p, ri, sizeof(double) * npts, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->cb[1].p, rj, sizeof(double) * npts, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->cb[2].p, lp.data(), sizeof(double) * npts, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->cb[3].p, rz, sizeof(double) * npts, cudaMemcpyHostToDevice, h->stream));
+    P.ri = h->cb[0].p; P.rj = h->cb[1].p; P.lp = h->cb[2].p; P.rz = h->cb[3].p;
+    CK(h->cb_i.ensure((size_t)npts * (1 + (idx ? max_out : 0))));
+    P.nobsl = h->cb_i.p;
+    P.idx = idx ? h->cb_i.p + npts : nullptr;
+    if (rdiag) { CK(h->cb[4].ensure((size_t)npts * max_out)); P.rdiag = h->cb[4].p; }
+    if (rloc) { CK(h->cb[5].ensure((size_t)npts * max_out)); P.rloc = h->cb[5].p; }
+  } else {
+    return fail(h, LETKF_B200_EINVAL, "obs_local: device mem_space not supported (host computes log p)");
+  }
+  const int grid = std::max(1, std::min(npts, h->num_sms * 8));
+  CK(h->l_iob.ensure((size_t)grid * h->maxl));
+  CK(h->l_rdiag.ensure((size_t)grid * h->maxl));
+  CK(h->l_rloc.ensure((size_t)grid * h->maxl));
+  CK(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  P.T = h->d_tables.p; P.rec = h->rec.p; P.bstart = h->bstart.p; P.vlfac = h->vlfac_one.p;
+  P.npts = npts; P.max_out = max_out;
+  P.l_iob = h->l_iob.p; P.l_rdiag = h->l_rdiag.p; P.l_rloc = h->l_rloc.p; P.lcap = h->maxl;
+  P.counters = h->counters.p;
+  if (npts > 0) {
+    search_kernel<<<grid, 128, 0, h->stream>>>(P);
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(nobsl, P.nobsl, sizeof(int) * npts, cudaMemcpyDeviceToHost, h->stream));
+  if (idx) CK(cudaMemcpyAsync(idx, P.idx, sizeof(int) * (size_t)npts * max_out, cudaMemcpyDeviceToHost, h->stream));
+  if (rdiag) CK(cudaMemcpyAsync(rdiag, P.rdiag, sizeof(double) * (size_t)npts * max_out, cudaMemcpyDeviceToHost, h->stream));
+  if (rloc) CK(cudaMemcpyAsync(rloc, P.rloc, sizeof(double) * (size_t)npts * max_out, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (idx)
+    for (int i = 0; i < npts; ++i)
+      if (nobsl[i] > max_out) return fail(h, LETKF_B200_EINVAL, "obs_local: max_out too small");
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
+  if (!h || !a || !a->gues3d || !a->anal3d) return LETKF_B200_EINVAL;
+  if (!h->obs_set) return fail(h, LETKF_B200_ESTATE, "set_obs has not been called");
+  if (h->nij1 < 1) return fail(h, LETKF_B200_ESTATE, "set_grid has not been called");
+  const letkf_b200_config &c = h->cfg;
+  if (c.nv2d > 0 && (!a->gues2d || !a->anal2d)) return fail(h, LETKF_B200_EINVAL, "gues2d/anal2d required when nv2d > 0");
+  if (c.INFL_MUL <= 0.0 && !a->infl3d) return fail(h, LETKF_B200_EINVAL, "INFL_MUL <= 0 needs the infl3d field");
+  CK(cudaSetDevice(h->device));
+  const int k = c.MEMBER, nens = c.DET_RUN ? k + 2 : k + 1;
+  const size_t sl = (size_t)h->nij1 * c.nlev;
+  const size_t n3 = sl * nens * c.nv3d, n2 = (size_t)h->nij1 * nens * c.nv2d, nf = sl * c.nv3d;
+  const bool host = a->mem_space != LETKF_B200_MEM_DEVICE;
+  DasParams P;
+  std::memset(&P, 0, sizeof(P));
+  if (host) {
+    CK(h->st_gues.ensure(n3));
+    CK(h->st_anal.ensure(n3));
+    CK(cudaMemcpyAsync(h->st_gues.p, a->gues3d, sizeof(double) * n3, cudaMemcpyHostToDevice, h->stream));
+    P.gues3d = h->st_gues.p;
+    P.anal3d = h->st_anal.p;
+    if (c.nv2d > 0) {
+      CK(h->st_gues2.ensure(n2));
+      CK(h->st_anal2.ensure(n2));
+      CK(cudaMemcpyAsync(h->st_gues2.p, a->gues2d, sizeof(double) * n2, cudaMemcpyHostToDevice, h->stream));
+      P.gues2d = h->st_gues2.p;
+      P.anal2d = h->st_anal2.p;
+    }
+    if (a->infl3d) {
+      CK(h->st_infl.ensure(nf));
+      if (c.INFL_MUL <= 0.0) CK(cudaMemcpyAsync(h->st_infl.p, a->infl3d, sizeof(double) * nf, cudaMemcpyHostToDevice, h->stream));
+      P.infl3d = h->st_infl.p;
+    }
+    if (a->rtps_infl_out) { CK(h->st_rtps.ensure(nf)); P.rtps_out = h->st_rtps.p; }
+    if (a->nobsl_out) { CK(h->st_nobsl.ensure(sl)); P.nobsl_out = h->st_nobsl.p; }
+    if (a->logp) {
+      CK(h->st_logp.ensure(sl));
+      CK(cudaMemcpyAsync(h->st_logp.p, a->logp, sizeof(double) * sl, cudaMemcpyHostToDevice, h->stream));
+      P.logp = h->st_logp.p;
+    }
+  } else {
+    P.gues3d = a->gues3d; P.anal3d = a->anal3d; P.gues2d = a->gues2d; P.anal2d = a->anal2d;
+    P.infl3d = a->infl3d; P.rtps_out = a->rtps_infl_out; P.nobsl_out = a->nobsl_out; P.logp = a->logp;
+  }
+  if (P.rtps_out) {   // work3da = 1 (letkf_tools.f90:271-276); skipped points keep 1
+    fill_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(P.rtps_out, nf, 1.0);
+    CK(cudaGetLastError());
+  }
+  if (P.nobsl_out) CK(cudaMemsetAsync(P.nobsl_out, 0, sizeof(int) * sl, h->stream));
+  P.k = k; P.nens = nens; P.nij1 = h->nij1; P.nlev = c.nlev; P.nv3d = c.nv3d; P.nv2d = c.nv2d; P.det = c.DET_RUN ? 1 : 0;
+  P.ld = ld_of(k); P.ldk = ldk_of(k); P.npairs = (k + 1) / 2; P.ncols = 2 * P.npairs;
+  P.rig1 = h->rig1.p; P.rjg1 = h->rjg1.p; P.hgt1 = h->hgt1.p;
+  P.T = h->d_tables.p; P.rec = h->rec.p; P.bstart = h->bstart.p; P.ensval = h->sens.p; P.val = h->sval.p; P.ldens = h->ldens;
+  P.nvgroup = h->nvgroup;
+  for (int n = 0; n < kMaxNV; ++n) { P.vgroup[n] = h->vgroup[n]; P.vfirst[n] = h->vfirst[n]; }
+  P.vlfac = h->vlfac_groups.p;
+  P.INFL_MUL = c.INFL_MUL; P.INFL_MUL_MIN = c.INFL_MUL_MIN; P.RELAX_ALPHA = c.RELAX_ALPHA;
+  P.RELAX_ALPHA_SPREAD = c.RELAX_ALPHA_SPREAD; P.Q_UPDATE_TOP = c.Q_UPDATE_TOP; P.Q_SPRD_MAX = c.Q_SPRD_MAX;
+  P.RELAX_TO_INFLATED_PRIOR = c.RELAX_TO_INFLATED_PRIOR; P.INFL_MUL_ADAPTIVE = c.INFL_MUL_ADAPTIVE;
+  P.infl_from_field = (c.INFL_MUL <= 0.0) ? 1 : 0;
+  P.iv3d_p = c.iv3d_p; P.iv3d_q = c.iv3d_q; P.iv3d_qg = c.iv3d_qg;
+  P.radar_only = h->radar_only ? 1 : 0;
+  P.zcut = c.RADAR_ZMAX + std::max(c.VERT_LOCAL[21], c.VERT_LOCAL_RADAR_VR) * c.dist_zero_fac;
+  P.BOUNDARY_BUFFER_WIDTH = c.BOUNDARY_BUFFER_WIDTH; P.DX = c.DX; P.DY = c.DY;
+  P.IHALO = c.IHALO; P.JHALO = c.JHALO; P.nlon = c.nlon; P.nlat = c.nlat;
+  P.lcap = h->maxl;
+  P.counters = h->counters.p;
+  P.npoints_total = (long long)sl;
+  P.max_sweeps = 30;
+  CK(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  int r;
+  if (k <= 20) r = launch_das<20>(h, P);
+  else if (k <= 52) r = launch_das<52>(h, P);
+  else if (k <= 64) r = launch_das<64>(h, P);
+  else if (k <= 100) r = launch_das<100>(h, P);
+  else r = launch_das<128>(h, P);
+  if (r != LETKF_B200_OK) return r;
+  if (host) {
+    CK(cudaMemcpyAsync(a->anal3d, P.anal3d, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+    // gues3d is INTENT(INOUT) "destroyed" in the reference; hand the perturbations back too so
+    // that callers relying on slots 1..k holding dX / slot k+1 the mean keep working.
+    if (!(a->reserved & 1))
+      CK(cudaMemcpyAsync(a->gues3d, P.gues3d, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+    if (c.nv2d > 0) {
+      CK(cudaMemcpyAsync(a->anal2d, P.anal2d, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
+      if (!(a->reserved & 1))
+        CK(cudaMemcpyAsync(a->gues2d, P.gues2d, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (a->infl3d) CK(cudaMemcpyAsync(a->infl3d, P.infl3d, sizeof(double) * nf, cudaMemcpyDeviceToHost, h->stream));
+    if (a->rtps_infl_out) CK(cudaMemcpyAsync(a->rtps_infl_out, P.rtps_out, sizeof(double) * nf, cudaMemcpyDeviceToHost, h->stream));
+    if (a->nobsl_out) CK(cudaMemcpyAsync(a->nobsl_out, P.nobsl_out, sizeof(int) * sl, cudaMemcpyDeviceToHost, h->stream));
+  }
+  unsigned long long cnt[8];
+  CK(cudaMemcpyAsync(cnt, h->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  h->st_points = (long long)cnt[1];
+  h->st_solved = (long long)cnt[2];
+  h->st_fail = (long long)cnt[3];
+  h->st_nobs = (long long)cnt[4];
+  if (cnt[5] > 0) return fail(h, LETKF_B200_ENOMEM, "local observation list overflow");
+  if (cnt[3] > 0) return fail(h, LETKF_B200_EEIGEN, "eigensolve failed at one or more grid points");
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_das_stats(const letkf_b200_handle *h, int64_t *npoints, int64_t *nsolved, int64_t *nfail,
+                         int64_t *nobsl_sum) {
+  if (!h) return LETKF_B200_EINVAL;
+  if (npoints) *npoints = h->st_points;
+  if (nsolved) *nsolved = h->st_solved;
+  if (nfail) *nfail = h->st_fail;
+  if (nobsl_sum) *nobsl_sum = h->st_nobs;
+  return LETKF_B200_OK;
+}
+int letkf_b200_das_kernel_ms(const letkf_b200_handle *h, float *ms, int *launches) {
+  if (!h) return LETKF_B200_EINVAL;
+  if (ms) *ms = h->last_ms;
+  if (launches) *launches = h->last_launches;
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_core_batch(letkf_b200_handle *h, int ne, int nobs, int npts, const int32_t *nobsl, const double *hdxb,
+                          const double *rdiag, const double *rloc, const double *dep, double *parm_infl, double *trans,
+                          double *transm, double *pao, int rdiag_wloc, int infl_update, const double *depd,
+                          double *transmd, int mem_space) {
+  if (!h || ne < 2 || ne > LETKF_B200_MAX_MEMBER || nobs < 0 || npts < 0) return LETKF_B200_EINVAL;
+  if (!nobsl || !hdxb || !rdiag || !rloc || !dep || !parm_infl || !trans) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const bool host = mem_space != LETKF_B200_MEM_DEVICE;
+  const size_t k2 = (size_t)ne * ne, no = (size_t)npts * nobs;
+  CoreParams P;
+  std::memset(&P, 0, sizeof(P));
+  if (host) {
+    for (int i = 0; i < npts; ++i)
+      if (nobsl[i] < 0 || nobsl[i] > nobs) return fail(h, LETKF_B200_EINVAL, "nobsl out of range");
+    CK(h->cb_i.ensure(npts));
+    CK(h->cb[0].ensure(no * ne)); CK(h->cb[1].ensure(no)); CK(h->cb[2].ensure(no)); CK(h->cb[3].ensure(no));
+    CK(h->cb[4].ensure(npts)); CK(h->cb[5].ensure(npts * k2));
+    CK(cudaMemcpyAsync(h->cb_i.p, nobsl, sizeof(int) * npts, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->cb[0].p, hdxb, sizeof(double) * no * ne, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->cb[1].p, rdiag, sizeof(double) * no, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->cb[2].p, rloc, sizeof(double) * no, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->cb[3].p, dep, sizeof(double) * no, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->cb[4].p, parm_infl, sizeof(double) * npts, cudaMemcpyHostToDevice, h->stream));
+    P.nobsl = h->cb_i.p; P.hdxb = h->cb[0].p; P.rdiag = h->cb[1].p; P.rloc = h->cb[2].p; P.dep = h->cb[3].p;
+    P.parm_infl = h->cb[4].p; P.trans = h->cb[5].p;
+    if (transm) { CK(h->cb[6].ensure((size_t)npts * ne)); P.transm = h->cb[6].p; }
+    if (pao) { CK(h->cb[7].ensure(npts * k2)); P.pao = h->cb[7].p; }
+    if (depd) {
+      CK(h->cb[8].ensure(no));
+      CK(cudaMemcpyAsync(h->cb[8].p, depd, sizeof(double) * no, cudaMemcpyHostToDevice, h->stream));
+      P.depd = h->cb[8].p;
+    }
+    if (transmd) { CK(h->cb[9].ensure((size_t)npts * ne)); P.transmd = h->cb[9].p; }
+  } else {
+    P.nobsl = nobsl; P.hdxb = hdxb; P.rdiag = rdiag; P.rloc = rloc; P.dep = dep; P.parm_infl = parm_infl;
+    P.trans = trans; P.transm = transm; P.pao = pao; P.depd = depd; P.transmd = transmd;
+  }
+  P.ne = ne; P.nobs = nobs; P.npts = npts;
+  P.ld = ld_of(ne); P.ldk = ldk_of(ne); P.npairs = (ne + 1) / 2; P.ncols = 2 * P.npairs;
+  P.rdiag_wloc = rdiag_wloc; P.infl_update = infl_update;
+  P.counters = h->counters.p;
+  P.max_sweeps = 30;
+  CK(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  if (npts > 0) {
+    int r;
+    if (ne <= 20) r = launch_core<20>(h, P);
+    else if (ne <= 52) r = launch_core<52>(h, P);
+    else if (ne <= 64) r = launch_core<64>(h, P);
+    else if (ne <= 100) r = launch_core<100>(h, P);
+    else r = launch_core<128>(h, P);
+    if (r != LETKF_B200_OK) return r;
+  }
+  if (host) {
+    CK(cudaMemcpyAsync(trans, P.trans, sizeof(double) * npts * k2, cudaMemcpyDeviceToHost, h->stream));
+    if (transm) CK(cudaMemcpyAsync(transm, P.transm, sizeof(double) * (size_t)npts * ne, cudaMemcpyDeviceToHost, h->stream));
+    if (pao) CK(cudaMemcpyAsync(pao, P.pao, sizeof(double) * npts * k2, cudaMemcpyDeviceToHost, h->stream));
+    if (transmd) CK(cudaMemcpyAsync(transmd, P.transmd, sizeof(double) * (size_t)npts * ne, cudaMemcpyDeviceToHost, h->stream));
+    if (infl_update) CK(cudaMemcpyAsync(parm_infl, P.parm_infl, sizeof(double) * npts, cudaMemcpyDeviceToHost, h->stream));
+  }
+  unsigned long long cnt[8];
+  CK(cudaMemcpyAsync(cnt, h->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (cnt[3] > 0) return fail(h, LETKF_B200_EEIGEN, "eigensolve failed at one or more points");
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_ensmean_grd(letkf_b200_handle *h, int mem, int nens, int nij, double *v3d, double *v2d, int mem_space) {
+  if (!h || mem < 1 || nens <= mem || nij < 1 || !v3d) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const letkf_b200_config &c = h->cfg;
+  const size_t sl = (size_t)nij * c.nlev, n3 = sl * nens * c.nv3d, n2 = (size_t)nij * nens * c.nv2d;
+  double *d3 = v3d, *d2 = v2d;
+  if (mem_space != LETKF_B200_MEM_DEVICE) {
+    CK(h->st_gues.ensure(n3));
+    CK(cudaMemcpyAsync(h->st_gues.p, v3d, sizeof(double) * n3, cudaMemcpyHostToDevice, h->stream));
+    d3 = h->st_gues.p;
+    if (c.nv2d > 0 && v2d) {
+      CK(h->st_gues2.ensure(n2));
+      CK(cudaMemcpyAsync(h->st_gues2.p, v2d, sizeof(double) * n2, cudaMemcpyHostToDevice, h->stream));
+      d2 = h->st_gues2.p;
+    }
+  }
+  {
+    const size_t tot = sl * c.nv3d;
+    ensmean_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(mem, nens, sl, c.nv3d, d3);
+  }
+  if (c.nv2d > 0 && d2) {
+    const size_t tot = (size_t)nij * c.nv2d;
+    ensmean_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(mem, nens, (size_t)nij, c.nv2d, d2);
+  }
+  CK(cudaGetLastError());
+  if (mem_space != LETKF_B200_MEM_DEVICE) {
+    CK(cudaMemcpyAsync(v3d, d3, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+    if (c.nv2d > 0 && v2d) CK(cudaMemcpyAsync(v2d, d2, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_nij1(const letkf_b200_handle *h, int np, int myrank_e, int32_t *nij1, int32_t *nij1max) {
+  if (!h || np < 1 || myrank_e < 0 || myrank_e >= np) return LETKF_B200_EINVAL;
+  const int tot = h->cfg.nlon * h->cfg.nlat;
+  const int i = tot % np;   // common_mpi_scale.f90:264-271
+  const int mx = (tot - i) / np + 1;
+  if (nij1max) *nij1max = mx;
+  if (nij1) *nij1 = myrank_e < i ? mx : mx - 1;
+  return LETKF_B200_OK;
+}
+
+static TransposeDims make_dims(const letkf_b200_handle *h, int np) {
+  TransposeDims d;
+  const letkf_b200_config &c = h->cfg;
+  d.nlon = c.nlon; d.nlat = c.nlat; d.nlev = c.nlev; d.nv3d = c.nv3d; d.nv2d = c.nv2d; d.np = np;
+  const int tot = c.nlon * c.nlat, i = tot % np;
+  d.nij1max = (tot - i) / np + 1;
+  d.nlevall = c.nlev * c.nv3d + c.nv2d;
+  return d;
+}
+
+int letkf_b200_grd_to_buf(letkf_b200_handle *h, int np, const double *v3dg, const double *v2dg, double *bufs) {
+  if (!h || np < 1 || !v3dg || !bufs) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const TransposeDims d = make_dims(h, np);
+  grd_to_buf_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(d, v3dg, v2dg, bufs);
+  CK(cudaGetLastError());
+  return LETKF_B200_OK;
+}
+int letkf_b200_buf_to_grd(letkf_b200_handle *h, int np, const double *bufr, double *v3dg, double *v2dg) {
+  if (!h || np < 1 || !v3dg || !bufr) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const TransposeDims d = make_dims(h, np);
+  buf_to_grd_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(d, bufr, v3dg, v2dg);
+  CK(cudaGetLastError());
+  return LETKF_B200_OK;
+}
+int letkf_b200_buf_to_ens(letkf_b200_handle *h, int np, int myrank_e, int nens, int mstart, int mend,
+                          const double *bufr, double *v3d, double *v2d) {
+  if (!h || np < 1 || !v3d || !bufr || mstart < 1 || mend < mstart || mend > nens) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const TransposeDims d = make_dims(h, np);
+  int32_t nij1;
+  letkf_b200_nij1(h, np, myrank_e, &nij1, nullptr);
+  buf_to_ens_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(d, nij1, nens, mstart, mend - mstart + 1, bufr, v3d, v2d, 0);
+  CK(cudaGetLastError());
+  return LETKF_B200_OK;
+}
+int letkf_b200_ens_to_buf(letkf_b200_handle *h, int np, int myrank_e, int nens, int mstart, int mend,
+                          const double *v3d, const double *v2d, double *bufs) {
+  if (!h || np < 1 || !v3d || !bufs || mstart < 1 || mend < mstart || mend > nens) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const TransposeDims d = make_dims(h, np);
+  int32_t nij1;
+  letkf_b200_nij1(h, np, myrank_e, &nij1, nullptr);
+  buf_to_ens_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(d, nij1, nens, mstart, mend - mstart + 1, bufs,
+                                                          const_cast<double *>(v3d), const_cast<double *>(v2d), 1);
+  CK(cudaGetLastError());
+  return LETKF_B200_OK;
+}
+
+}  // extern "C"
