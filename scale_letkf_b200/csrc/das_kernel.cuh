@@ -51,7 +51,7 @@ struct DasParams {
   int *l_iob;
   double *l_rdiag, *l_rloc;
   int lcap;
-  unsigned long long *counters;   // [0] work, [1] npoints, [2] nsolved, [3] nfail, [4] nobsl_sum, [5] overflow
+  unsigned long long *counters;   // [0] work, [1] npoints, [2] nsolved, [3] nfail, [4] nobsl_sum, [5] overflow, [6] Jacobi sweeps
   long long npoints_total;
   int max_sweeps;
 };
@@ -131,7 +131,7 @@ das_kernel(const DasParams P) {
 
   const size_t sl = (size_t)P.nij1 * P.nlev;
   const int ntiles = ((k + 3) / 4) * ((k + 3) / 4 + 1) / 2;
-  unsigned long long c_points = 0, c_solved = 0, c_fail = 0, c_nobs = 0, c_over = 0;
+  unsigned long long c_points = 0, c_solved = 0, c_fail = 0, c_nobs = 0, c_over = 0, c_sweeps = 0;
   double *xm = colsc, *xdet = colsc + kMaxNV, *varg = colsc + 2 * kMaxNV, *vara = colsc + 3 * kMaxNV;
   double *ssum = colsc + 4 * kMaxNV, *sdsum = colsc + 5 * kMaxNV, *inflv = colsc + 6 * kMaxNV;
   double *parmv = colsc + 7 * kMaxNV;
@@ -286,7 +286,7 @@ das_kernel(const DasParams P) {
         // ---- A = L L^T, one-sided Jacobi on L -> G = U S ------------------------------------------
         const bool ok = cholesky_lower(G, k, ld, ncols, piv);
         bool conv = false;
-        jacobi_onesided<SC::RJ>(G, k, ld, P.npairs, red, P.max_sweeps, &conv);
+        c_sweeps += (unsigned long long)jacobi_onesided<SC::RJ>(G, k, ld, P.npairs, red, P.max_sweeps, cdiag, &conv);
         column_norms(G, k, ld, ncols, lam);
         if (!ok || !conv) fail = true;
         double lmax = 0.0, lmin = 1.0e300;
@@ -312,47 +312,60 @@ das_kernel(const DasParams P) {
         gemm_gt_x(G, k, ld, ncols, Zs, Ts, nvb, kMaxNV);   // Ts[j][c] = (G^T X)_jc
         __syncthreads();
         // ---- per-column scalars: var_g, var_a = x^T Pa x, s = x^T Pa b, sd = x^T Pa bd --------
+        // shifted form: x^T Pa y = x.y / c0 + sum_j (1/lambda_j - 1/c0)/lambda_j (G^T x)_j (G^T y)_j
         {
           const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+          const double ic0 = 1.0 / cdiag;
           for (int c = warp; c < nc; c += nw) {
-            double vg_ = 0.0, va_ = 0.0, s_ = 0.0, sdv_ = 0.0;
+            double vg_ = 0.0, va_ = 0.0, s_ = 0.0, sdv_ = 0.0, xb_ = 0.0, xbd_ = 0.0;
             for (int a = lane; a < k; a += 32) {
               const double x = Xs[(size_t)a * kMaxNV + cols[c]];
               vg_ = fma(x, x, vg_);
+              xb_ = fma(x, Xs[(size_t)a * kMaxNV + kMaxNV - 2], xb_);
+              xbd_ = fma(x, Xs[(size_t)a * kMaxNV + kMaxNV - 1], xbd_);
             }
             for (int j = lane; j < ncols; j += 32) {
               const double l = lam[j];
               if (l > 0.0) {
-                const double il2 = 1.0 / (l * l);
+                const double w = (cdiag - l) / (l * cdiag) / l;
                 const double t = Ts[(size_t)j * kMaxNV + c];
-                va_ = fma(t * t, il2, va_);
-                s_ = fma(t * Ts[(size_t)j * kMaxNV + cb], il2, s_);
-                if (P.det) sdv_ = fma(t * Ts[(size_t)j * kMaxNV + cbd], il2, sdv_);
+                va_ = fma(t * t, w, va_);
+                s_ = fma(t * Ts[(size_t)j * kMaxNV + cb], w, s_);
+                if (P.det) sdv_ = fma(t * Ts[(size_t)j * kMaxNV + cbd], w, sdv_);
               }
             }
             vg_ = warp_sum(vg_);
             va_ = warp_sum(va_);
             s_ = warp_sum(s_);
             sdv_ = warp_sum(sdv_);
+            xb_ = warp_sum(xb_);
+            xbd_ = warp_sum(xbd_);
             if (lane == 0) {
               varg[c] = vg_;
-              vara[c] = va_;
-              ssum[c] = s_;
-              sdsum[c] = sdv_;
+              vara[c] = fma(vg_, ic0, va_);
+              ssum[c] = fma(xb_, ic0, s_);
+              sdsum[c] = P.det ? fma(xbd_, ic0, sdv_) : 0.0;
             }
           }
         }
         __syncthreads();
-        // U = D2 T for the variable columns, then Z = G U = W dx
+        // U = D2 T for the variable columns, then Z = sqrt(rho) dx + G U = W dx with
+        // D2_j = (sqrt((k-1)/lambda_j) - sqrt((k-1)/c0)) / lambda_j
         const double sk1 = sqrt((double)(k - 1));
+        const double fw0 = sk1 / sqrt(cdiag);
         for (int idx = tid; idx < ncols * nc; idx += blockDim.x) {
           const int j = idx / nc, c = idx - j * nc;
           const double l = lam[j];
-          const double d2 = (l > 0.0) ? sk1 / (l * sqrt(l)) : 0.0;
+          const double d2 = (l > 0.0) ? (sk1 / sqrt(l) - fw0) / l : 0.0;
           Ts[(size_t)j * kMaxNV + c] *= d2;
         }
         __syncthreads();
-        gemm_g_u(G, k, ld, ncols, Ts, Zs, (nc + 3) / 4, kMaxNV);   // Zs[m][c] = (W dx)_m
+        gemm_g_u(G, k, ld, ncols, Ts, Zs, (nc + 3) / 4, kMaxNV);   // Zs[m][c] = ((W - sqrt(rho) I) dx)_m
+        __syncthreads();
+        for (int idx = tid; idx < k * nc; idx += blockDim.x) {
+          const int a = idx / nc, c = idx - a * nc;
+          Zs[(size_t)a * kMaxNV + c] = fma(fw0, Xs[(size_t)a * kMaxNV + cols[c]], Zs[(size_t)a * kMaxNV + c]);
+        }
         __syncthreads();
       } else {
         // nobsl == 0 (common_letkf.f90:89-107): W = sqrt(infl) I, wbar = 0, Pa = infl/(k-1) I
@@ -456,6 +469,7 @@ das_kernel(const DasParams P) {
     atomicAdd(&P.counters[3], c_fail);
     atomicAdd(&P.counters[4], c_nobs);
     atomicAdd(&P.counters[5], c_over);
+    atomicAdd(&P.counters[6], c_sweeps);
   }
   (void)s_flag;
 }
@@ -633,9 +647,10 @@ core_kernel(const CoreParams P) {
       if (tid == 0) P.parm_infl[pt] = infl + gain * parm4;
     }
     __syncthreads();
+    const double c0 = (double)(k - 1) / infl;
     const bool ok = cholesky_lower(G, k, ld, ncols, piv);
     bool conv = false;
-    jacobi_onesided<SC::RJ>(G, k, ld, P.npairs, red, P.max_sweeps, &conv);
+    jacobi_onesided<SC::RJ>(G, k, ld, P.npairs, red, P.max_sweeps, c0, &conv);
     column_norms(G, k, ld, ncols, lam);
     double lmax = 0.0, lmin = 1.0e300;
     for (int j = 0; j < ncols; ++j)
@@ -645,7 +660,7 @@ core_kernel(const CoreParams P) {
       }
     if ((!ok || !conv || !(lmin >= lmax * 1.4901161193847656e-08)) && tid == 0)
       atomicAdd(&P.counters[3], 1ull);
-    // transm = Pa b = G diag(1/lambda^2) G^T b   (:169-195 restructured: Pa (Yr^T d))
+    // transm = Pa b = b/c0 + G diag((1/lambda - 1/c0)/lambda) G^T b   (:169-195 restructured: Pa (Yr^T d))
     for (int j = tid; j < ncols; j += blockDim.x) {
       const double *g = G + (size_t)j * ld;
       double s1 = 0.0, s2 = 0.0;
@@ -654,9 +669,9 @@ core_kernel(const CoreParams P) {
         s2 = fma(g[a], bdv[a], s2);
       }
       const double l = lam[j];
-      const double il2 = l > 0.0 ? 1.0 / (l * l) : 0.0;
-      tb[j] = s1 * il2;
-      tbd[j] = s2 * il2;
+      const double w = l > 0.0 ? (c0 - l) / (l * c0) / l : 0.0;
+      tb[j] = s1 * w;
+      tbd[j] = s2 * w;
     }
     __syncthreads();
     double wm = 0.0, wmd = 0.0;
@@ -666,15 +681,24 @@ core_kernel(const CoreParams P) {
         wm = fma(g, tb[j], wm);
         wmd = fma(g, tbd[j], wmd);
       }
+      wm += bv[tid] / c0;
+      wmd += bdv[tid] / c0;
+    }
+    __syncthreads();
+    if (tid < k) {
       if (transm) transm[tid] = wm;
       if (transmd) transmd[tid] = wmd;
       bv[tid] = wm;   // reused below when transm is absent
     }
     __syncthreads();
-    // pao = G D1 G^T, trans = G D2 G^T through the chunked SYRK (rows = scaled columns of G)
+    // pao = I/c0 - G D1 G^T, trans = sqrt(rho) I - G D2 G^T through the chunked SYRK (rows =
+    // scaled columns of G); D1 = (1/c0 - 1/lambda)/lambda >= 0, D2 = (f(c0) - f(lambda))/lambda >= 0,
+    // f = sqrt((k-1)/lambda)
+    const double fw0 = sqrt((double)(k - 1) / c0);
     for (int which = 0; which < 2; ++which) {
       double *out = which == 0 ? pao : trans;
       if (!out) continue;
+      const double dg = which == 0 ? 1.0 / c0 : fw0;
       gram_zero<R>(acc);
       for (int j0 = 0; j0 < ncols; j0 += kChunk) {
         const int nrows = min(kChunk, ncols - j0);
@@ -682,12 +706,27 @@ core_kernel(const CoreParams P) {
           const int o = idx / ldk, a = idx - o * ldk;
           const double l = lam[j0 + o];
           double sc = 0.0;
-          if (l > 0.0) sc = which == 0 ? 1.0 / l : sqrt(sqrt((double)(k - 1)) / (l * sqrt(l)));
+          if (l > 0.0) {
+            const double d = which == 0 ? (l - c0) / (l * c0) / l : (fw0 - sqrt((double)(k - 1) / l)) / l;
+            sc = d > 0.0 ? sqrt(d) : 0.0;
+          }
           Ys[idx] = (a < k) ? G[(size_t)(j0 + o) * ld + a] * sc : 0.0;
         }
         __syncthreads();
         gram_accumulate<R>(acc, Ys, nrows, ldk, ntiles);
         __syncthreads();
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int t = tid + r * blockDim.x;
+        if (t >= ntiles) continue;
+        int ta, tbb;
+        tile_coords(t, ta, tbb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            acc[r][i * 4 + j] = ((4 * ta + i == 4 * tbb + j) ? dg : 0.0) - acc[r][i * 4 + j];
       }
       if (which == 1 && !transm) {   // add the mean weight to every column (:218-226)
 #pragma unroll
@@ -696,7 +735,9 @@ core_kernel(const CoreParams P) {
           if (t >= ntiles) continue;
           int ta, tbb;
           tile_coords(t, ta, tbb);
+#pragma unroll
           for (int i = 0; i < 4; ++i)
+#pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int row = 4 * ta + i, col = 4 * tbb + j;
               if (row < k && col < k && row >= col) {

@@ -585,6 +585,10 @@ int letkf_b200_obs_local(letkf_b200_handle *h, int npts, const double *ri, const
   P.npts = npts; P.max_out = max_out;
   P.l_iob = h->l_iob.p; P.l_rdiag = h->l_rdiag.p; P.l_rloc = h->l_rloc.p; P.lcap = h->maxl;
   P.counters = h->counters.p;
+  // unused tail entries: idx = -1, rdiag = rloc = 0
+  if (P.idx) CK(cudaMemsetAsync(P.idx, 0xFF, sizeof(int) * (size_t)npts * max_out, h->stream));
+  if (P.rdiag) CK(cudaMemsetAsync(P.rdiag, 0, sizeof(double) * (size_t)npts * max_out, h->stream));
+  if (P.rloc) CK(cudaMemsetAsync(P.rloc, 0, sizeof(double) * (size_t)npts * max_out, h->stream));
   if (npts > 0) {
     search_kernel<<<grid, 128, 0, h->stream>>>(P);
     CK(cudaGetLastError());

@@ -7,9 +7,12 @@
 //   L V = U S                          one-sided (Hestenes) Jacobi on the Cholesky factor
 //                                      (Veselic-Hari): A = U S^2 U^T, no V accumulation
 // which replaces mtx_eigen / EISPACK rs (common/common_mtx.f90:41, common/netlibrs.f:21).
-// With G = U S (orthogonal columns g_j, lambda_j = |g_j|^2):
-//   Pa    = sum_j g_j g_j^T / lambda_j^2                 (common_letkf.f90:151-157)
-//   trans = sum_j g_j g_j^T sqrt(k-1) / lambda_j^1.5     (common_letkf.f90:199-206)
+// With G = U S (orthogonal columns g_j, lambda_j = |g_j|^2) and the known lowest eigenvalue
+// c0 = (k-1)/rho (A = c0 I + Yr^T Y), every f(A) is evaluated in shifted form
+//   f(A) = f(c0) I + sum_j (f(lambda_j) - f(c0)) g_j g_j^T / lambda_j
+//   Pa    : f = 1/lambda                                 (common_letkf.f90:151-157)
+//   trans : f = sqrt((k-1)/lambda)                       (common_letkf.f90:199-206)
+// so that columns inside the degenerate c0 cluster (p < k) drop out.
 // Only f(A) is ever used, so the eigenvector sign / order / basis inside degenerate
 // eigenspaces is immaterial (SURVEY.md section 8c "acceptance").
 #pragma once
@@ -152,7 +155,7 @@ __device__ __forceinline__ bool cholesky_lower(double *G, int k, int ld, int nco
 // Returns the number of sweeps used; *converged tells whether the stop rule was met.
 template <int RJ>
 __device__ __forceinline__ int jacobi_onesided(double *G, int k, int ld, int m, double *red,
-                                               int max_sweeps, bool *converged) {
+                                               int max_sweeps, double c0, bool *converged) {
   const int tid = threadIdx.x;
   const int j = tid >> 2, t = tid & 3;
   const bool act = j < m;
@@ -200,8 +203,14 @@ __device__ __forceinline__ int jacobi_onesided(double *G, int k, int ld, int m, 
       const double ab = a * b;
       if (ab > 0.0) {
         const double cosang = fabs(c) * rsqrt(ab);
-        maxc = fmax(maxc, cosang);
-        if (cosang > 1.0e-15) {
+        // Columns that both sit on the known lowest eigenvalue c0 = (k-1)/rho (exactly (k-p)-fold
+        // degenerate when p < k) carry weight f(lambda) - f(c0) ~ 0 in the shifted formulas of
+        // the consumers, so their mutual angle is irrelevant once it is small; rotating them
+        // would only re-diagonalise rounding noise inside the cluster (large-angle rotations,
+        // linear convergence).
+        const bool cluster = cosang < 1.0e-6 && fabs(a - c0) <= 1.0e-9 * c0 && fabs(b - c0) <= 1.0e-9 * c0;
+        if (!cluster) maxc = fmax(maxc, cosang);
+        if (!cluster && cosang > 1.0e-15) {
           const double zeta = (b - a) / (2.0 * c);
           const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
           const double cs = rsqrt(fma(tt, tt, 1.0));
@@ -229,9 +238,9 @@ __device__ __forceinline__ int jacobi_onesided(double *G, int k, int ld, int m, 
     }
     ++sweep;
     maxc = block_max(maxc, red);
-    // quadratic convergence: the rotations of a sweep whose largest |cos| was < 1e-7 leave
-    // off-diagonal cosines of order 1e-14.
-    if (maxc < 1.0e-7) {
+    // quadratic convergence: the rotations of a sweep whose largest |cos| was < 1e-8 leave
+    // off-diagonal cosines of order 1e-16 / (relative eigenvalue gap).
+    if (maxc < 1.0e-8) {
       *converged = true;
       break;
     }
