@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- analysed grid points/s of the LETKF analysis hot path (das_letkf twin).
+
+Workload (BASELINE.json configs[1], "C2"): SCALE-LETKF regional 256x256x60 grid, 50 members,
+synthetic sonde/surface observations, R-localisation, RTPS 0.95.  One "step" = one das_letkf
+over the whole domain: local-observation search + weight solve + relaxation + ensemble update
+of every (ij, lev) point.  With N ranks the horizontal domain is dealt to the ranks column by
+column exactly like the reference's e-rank deal (scale/common/common_mpi_scale.f90:264-283,
+1428-1440), every rank holds all observations, and there is no data-path collective
+(strong scaling: total work fixed).
+
+    python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
+    python bench.py --impl reference ...                     CPU restatement of the reference
+                                                             (oracle/, all host threads), rank 0
+
+Prints ONE JSON line (see the task contract): value = device-resident throughput,
+e2e = the same call through the C ABI with host buffers (H2D + D2H inside the timed region),
+roofline for the dominant kernel (das_kernel), cpu_baseline = oracle on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "analysed grid points/s"
+UNIT = "points/s"
+
+WORKLOADS = {
+    # name: (config factory kwargs, obs kwargs)
+    "c2": dict(kind="sonde", nlon=256, nlat=256, nlev=60, member=50, nsonde=50, nsfc=500,
+               desc="C2: 256x256x60, 50 members, sonde+surface obs, R-localisation, RTPS 0.95"),
+    "c2small": dict(kind="sonde", nlon=64, nlat=64, nlev=20, member=50, nsonde=50, nsfc=500,
+                    desc="C2 shape on a 64x64x20 grid (smoke-size)"),
+    "c3": dict(kind="radar", nlon=256, nlat=256, nlev=60, member=100, max_nobs=500,
+               desc="C3: 256x256x60 500 m mesh, 100 members, dense radar, MAX_NOBS_PER_GRID(22)=500"),
+    "c3small": dict(kind="radar", nlon=96, nlat=96, nlev=20, member=100, max_nobs=500,
+                    desc="C3 shape on a 96x96x20 grid"),
+}
+
+
+def make_workload(name, nprocs_e=1, myrank_e=0):
+    from scale_letkf_b200 import synth
+    w = WORKLOADS[name]
+    if w["kind"] == "sonde":
+        cfg = synth.config_c2(nlon=w["nlon"], nlat=w["nlat"], nlev=w["nlev"], member=w["member"])
+        obs = synth.make_sonde_obs(cfg, w["nsonde"], w["nsfc"], nlevobs=25, seed_no=2)
+    else:
+        cfg = synth.config_c3(nlon=w["nlon"], nlat=w["nlat"], nlev=w["nlev"], member=w["member"],
+                              max_nobs=w["max_nobs"])
+        rad = min(60.0e3, 0.47 * w["nlon"] * 500.0)
+        obs = synth.make_radar_obs(cfg, radius_m=rad, zmin=500.0, zmax=11000.0, dz=500.0, seed_no=3)
+    rig1, rjg1, hgt1 = synth.make_grid(cfg, nprocs_e=nprocs_e, myrank_e=myrank_e)
+    return cfg, obs, rig1, rjg1, hgt1
+
+
+def algorithmic_work(k, nv, npoints, nsolved, nobsl_sum):
+    """F(k,p) = 2pk^2 + 9k^3 + 4k^3 + (2pk + 2k^2) + nv(2k^2 + 2k^2) per
+    solved point, B(k,p) = 2 nv (k+1) 8 per analysed point + p (k+4) 8 per solved point."""
+    flops = nobsl_sum * (2.0 * k * k + 2.0 * k) + nsolved * (13.0 * k ** 3 + 2.0 * k * k + nv * 4.0 * k * k)
+    bytes_ = npoints * 2.0 * nv * (k + 1) * 8.0 + nobsl_sum * (k + 4) * 8.0
+    return flops, bytes_
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:   # NVML missing: report it, never fake clocks
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2.0)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def fp64_peak_live():
+    """FP64 FMA / DMMA peak measured live by tools/fp64_peak (MEASURED_PEAKS.json has no FP64
+    figure).  Falls back to the value recorded under profiles/ on the same pool."""
+    exe = os.path.join(ROOT, "tools", "fp64_peak")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout.strip()
+        j = json.loads(out.splitlines()[-1])
+        return max(j["fp64_fma_tflops"], j["fp64_dmma_tflops"]), "measured live (tools/fp64_peak.cu)"
+    except Exception:
+        return 36.6, "recorded (profiles/fp64_peak_r01.json)"
+
+
+# ---------------------------------------------------------------------------------------------
+class CpuSample:
+    """The oracle (CPU restatement of the reference algorithm, OpenMP over ij inside a level loop
+    like letkf_tools.f90:289-320) on a cyclic-deal sample of the workload's columns: every
+    `npe`-th column of the plane, all levels.  calibrate() sizes the sample for ~target_s."""
+
+    def __init__(self, name, nthreads=0):
+        from oracle import oracle_py
+        oracle_py.build()
+        self.name, self.w = name, WORKLOADS[name]
+        self.oracle_py = oracle_py
+        self.nth = nthreads or oracle_py.max_threads()
+        self.ncol = self.w["nlon"] * self.w["nlat"]
+
+    def _deal_width(self, target_cols):   # coprime with nlon: spreads the sample over the plane
+        npe = max(1, self.ncol // max(1, target_cols))
+        while npe > 1 and np.gcd(npe, self.w["nlon"]) != 1:
+            npe += 1
+        return npe
+
+    def prepare(self, npe):
+        from scale_letkf_b200 import synth
+        cfg, obs, rig1, rjg1, hgt1 = make_workload(self.name, nprocs_e=npe, myrank_e=npe // 3)
+        o = self.oracle_py.Oracle(cfg)
+        o.set_obs(obs)
+        o.set_grid(rig1, rjg1, hgt1)
+        self.o, self.npe = o, npe
+        self.gues0 = synth.make_state(cfg, rig1, rjg1, hgt1, seed_no=4)
+
+    def run(self):
+        g = self.gues0.copy(order="F")
+        t0 = time.perf_counter()
+        r = self.o.das_letkf(g, nthreads=self.nth)
+        dt = time.perf_counter() - t0
+        return r["npoints"], dt, r["nsolved"]
+
+    def calibrate(self, target_s, calib_points=1500):
+        self.prepare(self._deal_width(max(1, calib_points // self.w["nlev"])))
+        npts, dt, _ = self.run()
+        want_cols = max(1, int(npts / dt * target_s / self.w["nlev"]))
+        self.prepare(self._deal_width(min(want_cols, self.ncol)))
+
+    def describe(self, npts, nsolved, dt):
+        w = self.w
+        return (f"oracle das_letkf on every {self.npe}-th column of the {w['nlon']}x{w['nlat']} plane x "
+                f"{w['nlev']} levels = {npts} points ({nsolved} solved) per pass, {self.nth} OpenMP threads, "
+                f"{dt:.1f} s per pass")
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (C++ restatement under oracle/ -- the Fortran
+    original cannot be built here: no Fortran compiler, no MPI, SCALE-RM/NetCDF not vendored)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    name = args.workload
+    cs = CpuSample(name)
+    cs.calibrate(args.cpu_seconds / 4.0)
+    tot_pts, tot_s, nsolved, npts = 0, 0.0, 0, 0
+    for i in range(args.warmup + args.steps):
+        npts, dt, nsolved = cs.run()
+        if i >= args.warmup:
+            tot_pts += npts
+            tot_s += dt
+    value = tot_pts / tot_s
+    w = WORKLOADS[name]
+    desc = cs.describe(npts, nsolved, tot_s / max(args.steps, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "k": w["member"], "grid": [w["nlon"], w["nlat"], w["nlev"]],
+                   "step": "one pass over a bounded sample of the workload (see cpu_baseline.sample)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cs.nth, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=16.0, help="CPU baseline sample budget")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
+    ap.add_argument("--subsample", type=int, default=1,
+                    help="profiling aid: analyse only every S-th column of the plane (same per-point work)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import scale_letkf_b200 as sl
+    from scale_letkf_b200 import synth, capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    name = args.workload
+    w = WORKLOADS[name]
+    cfg, obs, rig1, rjg1, hgt1 = make_workload(name, nprocs_e=world * args.subsample, myrank_e=rank)
+    k, nv, nlev = cfg.MEMBER, cfg.nv3d, cfg.nlev
+    nij1 = len(rig1)
+    eng = sl.LETKF(cfg, device=local)
+    eng.set_letkf_obs(obs)
+    eng.set_common_mpi_grid(rig1, rjg1, hgt1)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(20260102 + rank)
+    gues0 = synth.make_state(cfg, rig1, rjg1, hgt1, xp=torch, device=dev, gen=gen)
+    gues = torch.empty_like(gues0)
+    anal = torch.empty_like(gues0)
+    state_bytes = gues0.numel() * 8
+
+    # ---- device-resident leg ------------------------------------------------------------------
+    def step():
+        gues.copy_(gues0)            # das_letkf destroys gues (INTENT(INOUT)); restore is untimed
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = eng.das_letkf(gues, anal3d=anal)
+        e1.record()
+        return e0, e1, out
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        evs.append(step())
+    barrier()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b, _ in evs]
+    kern_ms = [o["kernel_ms"] for _, _, o in evs]
+    out = evs[-1][2]
+    ph = np.array(out["phase_clocks"], dtype=np.float64)
+    phases = dict(zip(["load", "search", "gram", "factor", "eigen", "apply", "store", "sched"],
+                      (ph / max(ph.sum(), 1.0)).round(4).tolist()))
+    phases["solver_iterations_per_solve"] = out["solver_iterations"] / max(out["nsolved"], 1)
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms, float(sum(kern_ms))], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([out["npoints"], out["nsolved"], out["nobsl_sum"], out["launches"]], dtype=torch.float64,
+                       device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms, kernel_ms_sum = float(t[0]), float(t[1])
+    npoints, nsolved, nobsl_sum, launches = (float(x) for x in cnt)
+    value = npoints * args.steps / (total_ms * 1e-3)
+    ms_per_step = total_ms / args.steps
+
+    # ---- roofline of the dominant kernel (das_kernel; one launch per step per rank) -------------
+    peaks, peaks_src = measured_peaks()
+    flops, abytes = algorithmic_work(k, nv, npoints, nsolved, nobsl_sum)   # whole job, per step
+    kms = kernel_ms_sum / args.steps                                       # max-rank kernel time per launch
+    fp64_peak, fp64_src = fp64_peak_live() if rank == 0 else (36.6, "")
+    ach_tf = flops / world / (kms * 1e-3) * 1e-12                          # per GPU
+    ach_gbs = abytes / world / (kms * 1e-3) * 1e-9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "das_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(name)
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "das_kernel", "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": ach_tf / fp64_peak, "traffic": traffic,
+        "peak_source": fp64_src + "; MEASURED_PEAKS.json holds no FP64 figure",
+        "kernel_ms_per_launch": kms, "algorithmic_flops_per_launch": flops / world,
+        "algorithmic_bytes_per_launch": abytes / world,
+        "hbm": {"achieved": ach_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": ach_gbs / peaks.get("hbm_gbs"), "peak_source": peaks_src + " MEASURED_PEAKS.json"},
+    }
+
+    # ---- end-to-end leg: host buffers through the C ABI -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hg = torch.empty(gues0.shape, dtype=torch.float64, pin_memory=True)
+        hg.copy_(gues0)
+        ha = torch.empty(gues0.shape, dtype=torch.float64, pin_memory=True)
+        del gues0, gues, anal
+        torch.cuda.empty_cache()
+        g_np = hg.numpy().T      # (nij1, nlev, nens, nv3d) Fortran order view of the same memory
+        a_np = ha.numpy().T
+        nst = args.e2e_steps or args.steps
+        e2e_ms = []
+        for i in range(min(args.warmup, 2) + nst):
+            barrier()                # host gues3d is left untouched by the call (copy_back_gues=False)
+            t0 = time.perf_counter()
+            eng.das_letkf(g_np, anal3d=a_np, copy_back_gues=False)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) * 1e3
+            if i >= min(args.warmup, 2):
+                e2e_ms.append(dt)
+        te = torch.tensor([float(sum(e2e_ms))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": npoints * nst / (float(te[0]) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": state_bytes * world, "d2h_bytes_per_step": state_bytes * world,
+               "ms_per_step": float(te[0]) / nst, "steps": nst,
+               "api": "letkf_b200_das_letkf(mem_space=HOST) via scale_letkf_b200.LETKF.das_letkf; pinned host "
+                      "gues3d in, anal3d out (gues3d perturbations are not copied back)"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cs = CpuSample(name)
+        cs.calibrate(args.cpu_seconds)
+        npts_c, dt_c, nsolved_c = cs.run()
+        cpu = {"value": npts_c / dt_c, "unit": UNIT, "cores": cs.nth, "kind": "port",
+               "sample": cs.describe(npts_c, nsolved_c, dt_c)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "k": k, "grid": [w["nlon"], w["nlat"], w["nlev"]],
+                       "nobs": int(len(obs["elm"])), "mean_local_obs": nobsl_sum / max(nsolved, 1.0),
+                       "points": int(npoints), "solved_points": int(nsolved),
+                       "decomposition": f"cyclic column deal over {world} rank(s), obs replicated, no collective",
+                       "l2": "inputs (%.1f GB state per rank) far larger than the 126 MB L2" % (state_bytes / 1e9)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches / world) * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu,
+            "kernel_ms_per_step": kms, "phase_share_rank0": phases,
+        }
+        if args.subsample > 1:
+            line["config"]["subsample"] = f"every {args.subsample}-th column only (profiling aid, not a bench value)"
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -183,6 +183,12 @@ int letkf_b200_das_stats(const letkf_b200_handle *h, int64_t *npoints, int64_t *
 /* CUDA-event time (ms) of the dominant kernel in the last das call (bench roofline) */
 int letkf_b200_das_kernel_ms(const letkf_b200_handle *h, float *analysis_ms, int *launches);
 
+/* profiling aid: SM-clock cycles summed over CTAs (thread 0) per phase of the last das call --
+ * [0] load+perturbation, [1] local-obs search, [2] Gram, [3] factorisation, [4] eigen/f(A) iteration,
+ * [5] apply (G^T x, scalars, W dx), [6] relaxation+store, [7] scheduling -- and the total number of
+ * solver sweeps/iterations.  (The reference's equivalent is mpi_timer, common_mpi_scale.f90:1971.) */
+int letkf_b200_das_phase_clocks(const letkf_b200_handle *h, int64_t *clocks, int64_t *solver_iterations);
+
 /* ---- ensmean_grd twin (common_scale.f90:1513) ------------------------------ */
 int letkf_b200_ensmean_grd(letkf_b200_handle *h, int mem, int nens, int nij, double *v3d,
                            double *v2d, int mem_space);

@@ -193,9 +193,12 @@ class LETKF:
         self.lib.letkf_b200_das_stats(self.h, *[C.byref(s) for s in st])
         ms, nl = C.c_float(), C.c_int()
         self.lib.letkf_b200_das_kernel_ms(self.h, C.byref(ms), C.byref(nl))
+        ph = (C.c_int64 * 8)()
+        it = C.c_int64()
+        self.lib.letkf_b200_das_phase_clocks(self.h, ph, C.byref(it))
         return dict(status=r, anal3d=anal3d, anal2d=anal2d, rtps=rtps, nobsl=nobsl, npoints=st[0].value,
                     nsolved=st[1].value, nfail=st[2].value, nobsl_sum=st[3].value, kernel_ms=ms.value,
-                    launches=nl.value)
+                    launches=nl.value, phase_clocks=list(ph), solver_iterations=it.value)
 
     def ensmean_grd(self, v3d, v2d=None):
         """Fill slot MEMBER+1 with the member mean (in place)."""

@@ -110,6 +110,7 @@ PROTOTYPES = {
     "letkf_b200_das_stats": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "letkf_b200_das_kernel_ms": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "letkf_b200_das_phase_clocks": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "letkf_b200_ensmean_grd": (_i, [_vp, _i, _i, _i, _vp, _vp, _i]),
     "letkf_b200_grd_to_buf": (_i, [_vp, _i, _vp, _vp, _vp]),
     "letkf_b200_buf_to_ens": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -7,7 +7,7 @@
 
 namespace letkf {
 
-constexpr int kMaxThreads = 256;   // largest CTA any kernel here launches
+constexpr int kMaxThreads = 512;   // largest CTA any kernel here launches (das_ns_kernel<13>: 416)
 constexpr int kMaxWarps = kMaxThreads / 32;
 
 __device__ __forceinline__ double warp_sum(double v) {

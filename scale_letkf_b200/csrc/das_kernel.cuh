@@ -51,7 +51,7 @@ struct DasParams {
   int *l_iob;
   double *l_rdiag, *l_rloc;
   int lcap;
-  unsigned long long *counters;   // [0] work, [1] npoints, [2] nsolved, [3] nfail, [4] nobsl_sum, [5] overflow, [6] Jacobi sweeps
+  unsigned long long *counters;   // [0] work, [1] npoints, [2] nsolved, [3] nfail, [4] nobsl_sum, [5] overflow, [6] Jacobi sweeps, [8..15] phase clocks
   long long npoints_total;
   int max_sweeps;
 };
@@ -132,6 +132,14 @@ das_kernel(const DasParams P) {
   const size_t sl = (size_t)P.nij1 * P.nlev;
   const int ntiles = ((k + 3) / 4) * ((k + 3) / 4 + 1) / 2;
   unsigned long long c_points = 0, c_solved = 0, c_fail = 0, c_nobs = 0, c_over = 0, c_sweeps = 0;
+  // SM-clock cycles of this CTA per phase (thread 0): load, search, gram, cholesky, jacobi, apply, store
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tph = clock64();
+  auto phase = [&](int i) {
+    const long long now = clock64();
+    ph[i] += now - tph;
+    tph = now;
+  };
   double *xm = colsc, *xdet = colsc + kMaxNV, *varg = colsc + 2 * kMaxNV, *vara = colsc + 3 * kMaxNV;
   double *ssum = colsc + 4 * kMaxNV, *sdsum = colsc + 5 * kMaxNV, *inflv = colsc + 6 * kMaxNV;
   double *parmv = colsc + 7 * kMaxNV;
@@ -142,6 +150,7 @@ das_kernel(const DasParams P) {
     __syncthreads();
     const long long wp = s_work;
     if (wp >= P.npoints_total) break;
+    phase(7);
     const int il = (int)(wp / P.nij1), ij = (int)(wp - (long long)il * P.nij1);
     ++c_points;
     const int nvtot = P.nv3d + (il == 0 ? P.nv2d : 0);
@@ -185,6 +194,7 @@ das_kernel(const DasParams P) {
     }
     __syncthreads();
 
+    phase(0);
     auto store_anal = [&](int vv, int m, double v) {
       double *dst = (vv < P.nv3d) ? P.anal3d : P.anal2d;
       dst[gaddr(vv, m)] = v;
@@ -232,6 +242,7 @@ das_kernel(const DasParams P) {
         ++c_over;
       }
       const int p_use = nobsl < 0 ? 0 : nobsl;
+      phase(1);
       if (P.nobsl_out && vg == 0 && tid == 0) P.nobsl_out[pbase] = p_use;
       c_nobs += (unsigned long long)p_use;
       const int cb = nc, cbd = nc + 1;             // columns of b = Yr^T dep, bd = Yr^T depd
@@ -283,10 +294,13 @@ das_kernel(const DasParams P) {
           if (tid == 0) inflv[vtrig] = infl + gain * parm4;
         }
         __syncthreads();
+        phase(2);
         // ---- A = L L^T, one-sided Jacobi on L -> G = U S ------------------------------------------
         const bool ok = cholesky_lower(G, k, ld, ncols, piv);
+        phase(3);
         bool conv = false;
         c_sweeps += (unsigned long long)jacobi_onesided<SC::RJ>(G, k, ld, P.npairs, red, P.max_sweeps, cdiag, &conv);
+        phase(4);
         column_norms(G, k, ld, ncols, lam);
         if (!ok || !conv) fail = true;
         double lmax = 0.0, lmin = 1.0e300;
@@ -392,6 +406,7 @@ das_kernel(const DasParams P) {
         __syncthreads();
       }
       if (fail) ++c_fail;
+      phase(5);
 
       // ---- relaxation + update (letkf_tools.f90:457-513) --------------------------------------
       for (int idx = tid; idx < nc * k; idx += blockDim.x) {
@@ -460,6 +475,7 @@ das_kernel(const DasParams P) {
         }
       }
       __syncthreads();
+      phase(6);
     }
     if (solved_any) ++c_solved;
   }
@@ -470,6 +486,7 @@ das_kernel(const DasParams P) {
     atomicAdd(&P.counters[4], c_nobs);
     atomicAdd(&P.counters[5], c_over);
     atomicAdd(&P.counters[6], c_sweeps);
+    for (int i = 0; i < 8; ++i) atomicAdd(&P.counters[8 + i], (unsigned long long)ph[i]);
   }
   (void)s_flag;
 }

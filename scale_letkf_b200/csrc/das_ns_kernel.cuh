@@ -1,0 +1,394 @@
+// das_ns_kernel.cuh -- fused per-grid-point LETKF analysis kernel on the FP64 tensor cores (twin of
+// the main loop of das_letkf, scale/letkf/letkf_tools.f90:313-686), for MEMBER <= 104.
+//
+// Persistent CTAs (NB warps, one per 8-row block of the k x k matrices) pull (ij, ilev) points from
+// a global counter:
+//   relax_beta -> load members, form perturbations -> [per variable-localisation group]
+//   local-obs search -> DMMA Gram A = Yr^T Y from L2-resident obs rows -> interval-scaled coupled
+//   Newton-Schulz Z = sqrt(s) A^-1/2 (ns_solver.cuh) -> one skinny DMMA product Z [dX | b | bd]
+//   -> RTPP/RTPS relaxation -> xa = xmean + dX T -> store.
+// With t_c = A^-1/2 x_c:   dX W = sqrt(k-1) t_c,   x^T Pa y = t_x . t_y,   dX wbar = t_x . t_b,
+// so neither W nor Pa is formed and nothing k x k ever goes to HBM.
+#pragma once
+#include "das_kernel.cuh"
+#include "ns_solver.cuh"
+
+namespace letkf {
+
+template <int NB>
+__host__ __device__ inline size_t das_ns_smem_bytes() {
+  using C = NsCfg<NB>;
+  size_t d = 2 * (size_t)C::KP * C::LD;   // Y, Z (Z doubles as the obs-chunk staging area)
+  d += 2 * (size_t)kMaxNV * C::LD;        // Xall, Ts
+  d += 3 * (size_t)C::KP;                 // sw, sd, sdd
+  d += 8 * kMaxNV + 32 + 8;               // per-column scalars, reductions
+  return d * sizeof(double) + sizeof(SearchSmem) + 64;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(NsCfg<NB>::NT, NsCfg<NB>::MINB)
+das_ns_kernel(const DasParams P) {
+  using C = NsCfg<NB>;
+  constexpr int KP = C::KP, LD = C::LD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int k = P.k, nens = P.nens;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  double *Yb = reinterpret_cast<double *>(smem_raw);
+  double *Zb = Yb + (size_t)KP * LD;
+  double *Xall = Zb + (size_t)KP * LD;          // [kMaxNV][LD]: perturbations of variable vv; rows 14/15: b, bd
+  double *Ts = Xall + (size_t)kMaxNV * LD;      // [kMaxNV][LD]: Z Xall
+  double *sw = Ts + (size_t)kMaxNV * LD;
+  double *sd = sw + KP;
+  double *sdd = sd + KP;
+  double *colsc = sdd + KP;                     // [8][kMaxNV]
+  double *red = colsc + 8 * kMaxNV;
+  SearchSmem &S = *reinterpret_cast<SearchSmem *>((reinterpret_cast<uintptr_t>(red + 40) + 15) & ~(uintptr_t)15);
+  __shared__ long long s_work;
+
+  LocalList L;
+  L.cap = P.lcap;
+  L.iob = P.l_iob + (size_t)blockIdx.x * P.lcap;
+  L.rdiag = P.l_rdiag + (size_t)blockIdx.x * P.lcap;
+  L.rloc = P.l_rloc + (size_t)blockIdx.x * P.lcap;
+
+  const size_t sl = (size_t)P.nij1 * P.nlev;
+  unsigned long long c_points = 0, c_solved = 0, c_fail = 0, c_nobs = 0, c_over = 0, c_iters = 0;
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tph = clock64();
+  auto phase = [&](int i) {
+    const long long now = clock64();
+    ph[i] += now - tph;
+    tph = now;
+  };
+  double *xm = colsc, *xdet = colsc + kMaxNV, *varg = colsc + 2 * kMaxNV, *vara = colsc + 3 * kMaxNV;
+  double *ssum = colsc + 4 * kMaxNV, *sdsum = colsc + 5 * kMaxNV, *inflv = colsc + 6 * kMaxNV;
+  double *parmv = colsc + 7 * kMaxNV;
+  double *bvec = Xall + (size_t)(kMaxNV - 2) * LD, *bdvec = Xall + (size_t)(kMaxNV - 1) * LD;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_work = (long long)atomicAdd(&P.counters[0], 1ull);
+    __syncthreads();
+    const long long wp = s_work;
+    if (wp >= P.npoints_total) break;
+    phase(7);
+    const int il = (int)(wp / P.nij1), ij = (int)(wp - (long long)il * P.nij1);
+    ++c_points;
+    const int nvtot = P.nv3d + (il == 0 ? P.nv2d : 0);
+    const size_t pbase = (size_t)ij + (size_t)il * P.nij1;
+
+    // ---- relax_beta (letkf_tools.f90:1911-1948) -----------------------------------------------
+    const double ri = P.rig1[ij], rj = P.rjg1[ij], rz = P.hgt1[pbase];
+    double beta = 1.0;
+    if (P.radar_only && rz > P.zcut) {
+      beta = 0.0;
+    } else if (P.BOUNDARY_BUFFER_WIDTH > 0.0) {
+      const double dist_bdy =
+          fmin(fmin(ri - P.IHALO, P.nlon + P.IHALO + 1 - ri) * P.DX,
+               fmin(rj - P.JHALO, P.nlat + P.JHALO + 1 - rj) * P.DY) / P.BOUNDARY_BUFFER_WIDTH;
+      if (dist_bdy < 1.0) beta = fmax(dist_bdy, 0.0);
+    }
+
+    // ---- load members, form perturbations (letkf_tools.f90:209-230), destroy gues ----------
+    auto gaddr = [&](int vv, int m) -> size_t {   // m 0-based slot
+      return (vv < P.nv3d) ? pbase + ((size_t)m + (size_t)vv * nens) * sl
+                           : (size_t)ij + ((size_t)m + (size_t)(vv - P.nv3d) * nens) * P.nij1;
+    };
+    if (tid < nvtot) {
+      const double *src = (tid < P.nv3d) ? P.gues3d : P.gues2d;
+      xm[tid] = src[gaddr(tid, k)];
+      xdet[tid] = P.det ? src[gaddr(tid, k + 1)] : 0.0;
+      double infl = P.INFL_MUL;
+      if (P.infl_from_field && tid < P.nv3d) infl = P.infl3d[pbase + (size_t)tid * sl];
+      if (P.INFL_MUL_MIN > 0.0) infl = fmax(infl, P.INFL_MUL_MIN);
+      inflv[tid] = infl;
+      parmv[tid] = P.RELAX_TO_INFLATED_PRIOR ? infl : 1.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kMaxNV * LD; idx += blockDim.x) {
+      const int vv = idx / LD, m = idx - vv * LD;
+      double pert = 0.0;
+      if (vv < nvtot && m < k) {
+        double *src = (vv < P.nv3d) ? P.gues3d : P.gues2d;
+        const size_t ad = gaddr(vv, m);
+        pert = src[ad] - xm[vv];
+        src[ad] = pert;
+      }
+      Xall[idx] = pert;
+    }
+    __syncthreads();
+    phase(0);
+    auto store_anal = [&](int vv, int m, double v) {
+      double *dst = (vv < P.nv3d) ? P.anal3d : P.anal2d;
+      dst[gaddr(vv, m)] = v;
+    };
+
+    if (beta == 0.0) {   // (letkf_tools.f90:333-359)
+      for (int idx = tid; idx < nvtot * k; idx += blockDim.x) {
+        const int vv = idx / k, m = idx - vv * k;
+        store_anal(vv, m, xm[vv] + Xall[(size_t)vv * LD + m]);
+      }
+      if (P.det && tid < nvtot) store_anal(tid, k + 1, xdet[tid]);
+      continue;
+    }
+    const double pmean = xm[P.iv3d_p - 1];
+    Point pt;
+    pt.ri = ri;
+    pt.rj = rj;
+    pt.rz = rz;
+    pt.lp = P.logp ? P.logp[pbase] : log(pmean);
+    bool solved_any = false;
+
+    for (int vg = 0; vg < P.nvgroup; ++vg) {
+      int cols[kMaxNV];
+      int nc = 0;
+      for (int vv = 0; vv < nvtot; ++vv) {
+        if (P.vgroup[vv] != vg) continue;
+        const bool masked = (vv < P.nv3d) && pmean < P.Q_UPDATE_TOP && (vv + 1) >= P.iv3d_q &&
+                            (vv + 1) <= P.iv3d_qg;
+        if (masked) {   // (letkf_tools.f90:371-385)
+          for (int m = tid; m < k; m += blockDim.x) store_anal(vv, m, xm[vv] + Xall[(size_t)vv * LD + m]);
+          if (P.det && tid == 0) store_anal(vv, k + 1, xdet[vv]);
+          if (P.infl3d && tid == 0 && vv < P.nv3d) P.infl3d[pbase + (size_t)vv * sl] = inflv[vv];
+        } else {
+          cols[nc++] = vv;
+        }
+      }
+      if (nc == 0) continue;
+      const int vtrig = cols[0];
+      const double infl = inflv[vtrig];   // parm_infl handed to letkf_core (work3d(ij,ilev,n))
+
+      // ---- local observations ---------------------------------------------------------------
+      const int nobsl = search_point(*P.T, P.rec, P.bstart, P.vlfac + (size_t)vg * P.T->nctype, pt, L, S);
+      if (nobsl < 0) ++c_over;
+      const int p_use = nobsl < 0 ? 0 : nobsl;
+      phase(1);
+      if (P.nobsl_out && vg == 0 && tid == 0) P.nobsl_out[pbase] = p_use;
+      c_nobs += (unsigned long long)p_use;
+      bool fail = false;
+      double wscale = sqrt(infl);   // (W dx)_m = wscale * Ts[c][m];  p == 0: W = sqrt(infl) I
+      double pscale = infl / (double)(k - 1);   // x^T Pa y = pscale * (t_x . t_y)
+
+      if (p_use > 0) {
+        solved_any = true;
+        // ---- Gram A = Yr^T Y (common_letkf.f90:111-128) on the tensor cores, b = Yr^T dep ------
+        double acc[NB][2];
+        zero_rowblock<NB>(acc);
+        double bacc = 0.0, bdacc = 0.0, tracc = 0.0, p1acc = 0.0, p3acc = 0.0;
+        double *Ys = Zb;
+        for (int o0 = 0; o0 < p_use; o0 += KP) {
+          const int nrows = min(KP, p_use - o0);
+          const int nrows4 = (nrows + 3) & ~3;
+          if (tid < nrows4) {
+            double wv = 0.0, dv = 0.0, ddv = 0.0;
+            if (tid < nrows) {
+              const int o = o0 + tid;
+              const int iob = L.iob[o];
+              wv = sqrt(1.0 / L.rdiag[o]);
+              dv = wv * P.val[iob];
+              ddv = P.det ? wv * P.ensval[(size_t)iob * P.ldens + k] : 0.0;
+              if (P.INFL_MUL_ADAPTIVE) {
+                p1acc += dv * dv;
+                p3acc += L.rloc[o];
+              }
+            }
+            sw[tid] = wv;
+            sd[tid] = dv;
+            sdd[tid] = ddv;
+          }
+          __syncthreads();
+          for (int idx = tid; idx < nrows4 * KP; idx += blockDim.x) {
+            const int o = idx / KP, m = idx - o * KP;
+            double v = 0.0;
+            if (o < nrows && m < k) v = P.ensval[(size_t)L.iob[o0 + o] * P.ldens + m] * sw[o];
+            Ys[(size_t)o * LD + m] = v;
+          }
+          __syncthreads();
+          gram_rowblock<NB, LD>(acc, Ys, nrows4, w, lane);
+          if (tid < k) {
+            for (int o = 0; o < nrows; ++o) {
+              const double y = Ys[(size_t)o * LD + tid];
+              bacc = fma(y, sd[o], bacc);
+              bdacc = fma(y, sdd[o], bdacc);
+              if (P.INFL_MUL_ADAPTIVE) tracc = fma(y, y, tracc);
+            }
+          }
+          __syncthreads();
+        }
+        if (tid < k) {
+          bvec[tid] = bacc;
+          bdvec[tid] = bdacc;
+        }
+        const double cdiag = (double)(k - 1) / infl;   // (common_letkf.f90:140-143)
+        {
+          const int r = lane >> 2, q = lane & 3, row = w * 8 + r;
+          if (row < k && (row >> 3) == w) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              if (j == w) {
+                if (2 * q == r) acc[j][0] += cdiag;
+                if (2 * q + 1 == r) acc[j][1] += cdiag;
+              }
+          }
+        }
+        if (P.INFL_MUL_ADAPTIVE) {   // (common_letkf.f90:229-254)
+          const double parm1 = block_sum(p1acc, red);
+          const double parm2 = block_sum(tid < k ? tracc : 0.0, red) / (double)(k - 1);
+          const double parm3 = block_sum(p3acc, red);
+          const double parm4 = (parm1 - parm3) / parm2 - infl;
+          const double tq = (infl * parm2 + parm3) / parm2;
+          const double sigma_o = 2.0 / parm3 * (tq * tq);
+          const double gain = 0.04 * 0.04 / (sigma_o + 0.04 * 0.04);
+          __syncthreads();
+          if (tid == 0) inflv[vtrig] = infl + gain * parm4;
+        }
+        phase(2);
+        // ---- Z = sqrt(s) A^-1/2 ------------------------------------------------------------------
+        double s_norm;
+        const int its = newton_schulz_invsqrt<NB>(acc, Yb, Zb, k, cdiag, red, P.max_sweeps + 20, &s_norm);
+        if (its < 0) fail = true;
+        c_iters += (unsigned long long)(its < 0 ? -its : its);
+        // mtx_eigen zeroes eigenvalues below lambda_max*sqrt(eps) (common_mtx.f90:69) and letkf_core
+        // would then divide by zero; ||A||_1 <= k lambda_max bounds the same condition.
+        if (!(cdiag * (double)k >= s_norm * 1.4901161193847656e-08)) fail = true;
+        phase(4);
+        // ---- Ts = Z [dX | b | bd]  (k x 16 skinny product on the tensor cores) --------------------
+        {
+          double a2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+          const int r = lane >> 2, q = lane & 3;
+          const double *pa = Zb + (size_t)(w * 8 + r) * LD + q;
+          const double *pb = Xall + (size_t)r * LD + q;
+#pragma unroll 2
+          for (int kb = 0; kb < 2 * NB; ++kb) {
+            const double a = pa[kb * 4];
+            dmma884(a2[0][0], a2[0][1], a, pb[kb * 4]);
+            dmma884(a2[1][0], a2[1][1], a, pb[(size_t)8 * LD + kb * 4]);
+          }
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) Ts[(size_t)(nt * 8 + 2 * q + e) * LD + w * 8 + r] = a2[nt][e];
+        }
+        __syncthreads();
+        wscale = sqrt((double)(k - 1) / s_norm);
+        pscale = 1.0 / s_norm;
+      } else {
+        // nobsl == 0 (common_letkf.f90:89-107): W = sqrt(infl) I, wbar = 0, Pa = infl/(k-1) I
+        for (int idx = tid; idx < kMaxNV * LD; idx += blockDim.x) {
+          const int vv = idx / LD;
+          Ts[idx] = (vv < kMaxNV - 2) ? Xall[idx] : 0.0;
+        }
+        __syncthreads();
+      }
+      // ---- per-column scalars: var_g = x.x, var_a = x^T Pa x, s = x^T Pa b, sd = x^T Pa bd ----------
+      {
+        const int nw = blockDim.x >> 5;
+        const double *tb = Ts + (size_t)(kMaxNV - 2) * LD, *tbd = Ts + (size_t)(kMaxNV - 1) * LD;
+        for (int c = w; c < nc; c += nw) {
+          const int vv = cols[c];
+          const double *x = Xall + (size_t)vv * LD, *t = Ts + (size_t)vv * LD;
+          double vg_ = 0.0, va_ = 0.0, s_ = 0.0, sdv_ = 0.0;
+          for (int m = lane; m < k; m += 32) {
+            const double xv = x[m], tv = t[m];
+            vg_ = fma(xv, xv, vg_);
+            va_ = fma(tv, tv, va_);
+            s_ = fma(tv, tb[m], s_);
+            sdv_ = fma(tv, tbd[m], sdv_);
+          }
+          vg_ = warp_sum(vg_);
+          va_ = warp_sum(va_);
+          s_ = warp_sum(s_);
+          sdv_ = warp_sum(sdv_);
+          if (lane == 0) {
+            varg[c] = vg_;
+            vara[c] = va_ * pscale;
+            ssum[c] = s_ * pscale;
+            sdsum[c] = P.det ? sdv_ * pscale : 0.0;
+          }
+        }
+      }
+      __syncthreads();
+      if (fail) ++c_fail;
+      phase(5);
+
+      // ---- relaxation + update (letkf_tools.f90:457-513); result staged in Ts -------------------
+      for (int idx = tid; idx < nc * k; idx += blockDim.x) {
+        const int c = idx / k, m = idx - c * k;
+        const int vv = cols[c];
+        const double x = Xall[(size_t)vv * LD + m];
+        const double z = wscale * Ts[(size_t)vv * LD + m];   // (W dx)_m
+        const double parm = parmv[vv];
+        double wx;   // (W_rlx dx)_m
+        if (P.RELAX_ALPHA != 0.0) {
+          wx = (1.0 - P.RELAX_ALPHA) * z + P.RELAX_ALPHA * sqrt(parm) * x;
+        } else if (P.RELAX_ALPHA_SPREAD != 0.0) {
+          double f = 1.0;
+          if (varg[c] > 0.0 && vara[c] > 0.0)
+            f = P.RELAX_ALPHA_SPREAD * sqrt(varg[c] * parm / (vara[c] * (double)(k - 1))) -
+                P.RELAX_ALPHA_SPREAD + 1.0;
+          wx = f * z;
+        } else {
+          wx = z;
+        }
+        Ts[(size_t)vv * LD + m] = xm[vv] + (wx + ssum[c]) * beta + (1.0 - beta) * x;
+      }
+      __syncthreads();
+      if (P.Q_SPRD_MAX > 0.0) {   // (letkf_tools.f90:500-513)
+        for (int c = 0; c < nc; ++c) {
+          if (cols[c] != P.iv3d_q - 1) continue;
+          double *tq = Ts + (size_t)cols[c] * LD;
+          double part = 0.0;
+          for (int m = tid; m < k; m += blockDim.x) part += tq[m];
+          const double q_mean = block_sum(part, red) / (double)k;
+          part = 0.0;
+          for (int m = tid; m < k; m += blockDim.x) {
+            const double d = tq[m] - q_mean;
+            part = fma(d, d, part);
+          }
+          const double q_sprd = sqrt(block_sum(part, red) / (double)(k - 1)) / q_mean;
+          if (q_sprd > P.Q_SPRD_MAX) {
+            for (int m = tid; m < k; m += blockDim.x) {
+              const double d = tq[m] - q_mean;
+              tq[m] = q_mean + d * P.Q_SPRD_MAX / q_sprd;
+            }
+          }
+          __syncthreads();
+        }
+      }
+      for (int idx = tid; idx < nc * k; idx += blockDim.x) {
+        const int c = idx / k, m = idx - c * k;
+        store_anal(cols[c], m, Ts[(size_t)cols[c] * LD + m]);
+      }
+      if (tid < nc) {
+        const int vv = cols[tid];
+        if (P.det) store_anal(vv, k + 1, xdet[vv] + sdsum[tid] * beta);   // (:489-497)
+        if (P.rtps_out && vv < P.nv3d) {
+          double f = 1.0;
+          if (P.RELAX_ALPHA == 0.0 && P.RELAX_ALPHA_SPREAD != 0.0 && varg[tid] > 0.0 && vara[tid] > 0.0)
+            f = P.RELAX_ALPHA_SPREAD * sqrt(varg[tid] * parmv[vv] / (vara[tid] * (double)(k - 1))) -
+                P.RELAX_ALPHA_SPREAD + 1.0;
+          P.rtps_out[pbase + (size_t)vv * sl] = f;
+        }
+        if (P.infl3d && vv < P.nv3d) {
+          const double v = (vv == vtrig || P.INFL_MUL_ADAPTIVE) ? inflv[P.INFL_MUL_ADAPTIVE ? P.vfirst[vv] : vv]
+                                                                 : inflv[vv];
+          P.infl3d[pbase + (size_t)vv * sl] = v;
+        }
+      }
+      __syncthreads();
+      phase(6);
+    }
+    if (solved_any) ++c_solved;
+  }
+  if (tid == 0) {
+    atomicAdd(&P.counters[1], c_points);
+    atomicAdd(&P.counters[2], c_solved);
+    atomicAdd(&P.counters[3], c_fail);
+    atomicAdd(&P.counters[4], c_nobs);
+    atomicAdd(&P.counters[5], c_over);
+    atomicAdd(&P.counters[6], c_iters);
+    for (int i = 0; i < 8; ++i) atomicAdd(&P.counters[8 + i], (unsigned long long)ph[i]);
+  }
+}
+
+}  // namespace letkf

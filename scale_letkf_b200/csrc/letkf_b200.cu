@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -12,6 +13,7 @@
 #include "../../include/letkf_b200.h"
 #include "aux_kernels.cuh"
 #include "das_kernel.cuh"
+#include "das_ns_kernel.cuh"
 
 using namespace letkf;
 
@@ -99,7 +101,8 @@ struct letkf_b200_handle {
   DevBuf<int> cb_i;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // stats of the last das call
-  long long st_points = 0, st_solved = 0, st_fail = 0, st_nobs = 0;
+  long long st_points = 0, st_solved = 0, st_fail = 0, st_nobs = 0, st_sweeps = 0;
+  long long st_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float last_ms = 0.f;
   int last_launches = 0;
 };
@@ -172,6 +175,30 @@ int launch_das(letkf_b200_handle *h, DasParams &P) {
   P.l_rloc = h->l_rloc.p;
   CK(cudaEventRecord(h->ev0, h->stream));
   das_kernel<KC><<<(unsigned)grid, SC::NT, smem, h->stream>>>(P);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->last_launches = 1;
+  return LETKF_B200_OK;
+}
+
+template <int NB>
+int launch_das_ns(letkf_b200_handle *h, DasParams &P) {
+  using C = NsCfg<NB>;
+  const size_t smem = das_ns_smem_bytes<NB>();
+  CK(cudaFuncSetAttribute(das_ns_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, das_ns_kernel<NB>, C::NT, smem));
+  if (occ < 1) return fail(h, LETKF_B200_EINVAL, "das_ns_kernel does not fit on an SM");
+  long long grid = (long long)occ * h->num_sms;
+  grid = std::min<long long>(grid, std::max<long long>(P.npoints_total, 1));
+  CK(h->l_iob.ensure((size_t)grid * P.lcap));
+  CK(h->l_rdiag.ensure((size_t)grid * P.lcap));
+  CK(h->l_rloc.ensure((size_t)grid * P.lcap));
+  P.l_iob = h->l_iob.p;
+  P.l_rdiag = h->l_rdiag.p;
+  P.l_rloc = h->l_rloc.p;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  das_ns_kernel<NB><<<(unsigned)grid, C::NT, smem, h->stream>>>(P);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, h->stream));
   h->last_launches = 1;
@@ -283,7 +310,7 @@ int letkf_b200_create(const letkf_b200_config *cfg, int device, letkf_b200_handl
   h->num_sms = prop.multiProcessorCount;
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
-  if (h->counters.ensure(8) != cudaSuccess) {
+  if (h->counters.ensure(16) != cudaSuccess) {
     delete h;
     return LETKF_B200_ECUDA;
   }
@@ -580,7 +607,7 @@ int letkf_b200_obs_local(letkf_b200_handle *h, int npts, const double *ri, const
   CK(h->l_iob.ensure((size_t)grid * h->maxl));
   CK(h->l_rdiag.ensure((size_t)grid * h->maxl));
   CK(h->l_rloc.ensure((size_t)grid * h->maxl));
-  CK(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
   P.T = h->d_tables.p; P.rec = h->rec.p; P.bstart = h->bstart.p; P.vlfac = h->vlfac_one.p;
   P.npts = npts; P.max_out = max_out;
   P.l_iob = h->l_iob.p; P.l_rdiag = h->l_rdiag.p; P.l_rloc = h->l_rloc.p; P.lcap = h->maxl;
@@ -672,8 +699,19 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   P.counters = h->counters.p;
   P.npoints_total = (long long)sl;
   P.max_sweeps = 30;
-  CK(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
   int r;
+  // MEMBER <= 104: tensor-core Newton-Schulz solve (das_ns_kernel.cuh); larger ensembles (two k x k
+  // matrices no longer fit in shared memory) and LETKF_B200_SOLVER=jacobi: Cholesky + one-sided Jacobi.
+  const char *sv = std::getenv("LETKF_B200_SOLVER");
+  const bool jacobi = (sv && std::strcmp(sv, "jacobi") == 0) || k > 104;
+  if (!jacobi) {
+    if (k <= 24) r = launch_das_ns<3>(h, P);
+    else if (k <= 40) r = launch_das_ns<5>(h, P);
+    else if (k <= 56) r = launch_das_ns<7>(h, P);
+    else if (k <= 64) r = launch_das_ns<8>(h, P);
+    else r = launch_das_ns<13>(h, P);
+  } else
   if (k <= 20) r = launch_das<20>(h, P);
   else if (k <= 52) r = launch_das<52>(h, P);
   else if (k <= 64) r = launch_das<64>(h, P);
@@ -695,10 +733,12 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
     if (a->rtps_infl_out) CK(cudaMemcpyAsync(a->rtps_infl_out, P.rtps_out, sizeof(double) * nf, cudaMemcpyDeviceToHost, h->stream));
     if (a->nobsl_out) CK(cudaMemcpyAsync(a->nobsl_out, P.nobsl_out, sizeof(int) * sl, cudaMemcpyDeviceToHost, h->stream));
   }
-  unsigned long long cnt[8];
+  unsigned long long cnt[16];
   CK(cudaMemcpyAsync(cnt, h->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  h->st_sweeps = (long long)cnt[6];
+  for (int i = 0; i < 8; ++i) h->st_phase[i] = (long long)cnt[8 + i];
   h->st_points = (long long)cnt[1];
   h->st_solved = (long long)cnt[2];
   h->st_fail = (long long)cnt[3];
@@ -721,6 +761,14 @@ int letkf_b200_das_kernel_ms(const letkf_b200_handle *h, float *ms, int *launche
   if (!h) return LETKF_B200_EINVAL;
   if (ms) *ms = h->last_ms;
   if (launches) *launches = h->last_launches;
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_das_phase_clocks(const letkf_b200_handle *h, int64_t *clocks, int64_t *solver_iterations) {
+  if (!h) return LETKF_B200_EINVAL;
+  if (clocks)
+    for (int i = 0; i < 8; ++i) clocks[i] = h->st_phase[i];
+  if (solver_iterations) *solver_iterations = h->st_sweeps;
   return LETKF_B200_OK;
 }
 
@@ -766,7 +814,7 @@ int letkf_b200_core_batch(letkf_b200_handle *h, int ne, int nobs, int npts, cons
   P.rdiag_wloc = rdiag_wloc; P.infl_update = infl_update;
   P.counters = h->counters.p;
   P.max_sweeps = 30;
-  CK(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
   if (npts > 0) {
     int r;
     if (ne <= 20) r = launch_core<20>(h, P);
