@@ -68,7 +68,10 @@ __global__ void bucket_rank_kernel(int nobs, const int *__restrict__ key, const 
   sorted_to_orig[b0 + rank] = me;
 }
 
-__global__ void obs_gather_kernel(int nobs, int nensobs, int ldens, const int *__restrict__ s2o,
+// Sorted observation table: rec[s], sval[s] and the row sens[s][0..ldens) =
+//   [ ensval(1..k) | val (= y - mean H(x), "dep") | ensval(k+1) (= y - H(x_det), "depd", DET_RUN) | 0 .. ]
+// so that one contiguous row copy brings everything the Gram + right-hand sides need.
+__global__ void obs_gather_kernel(int nobs, int nensobs, int k, int ldens, const int *__restrict__ s2o,
                                   const double *__restrict__ ri, const double *__restrict__ rj,
                                   const double *__restrict__ vc, const double *__restrict__ err,
                                   const double *__restrict__ val, const double *__restrict__ ensval,
@@ -86,8 +89,13 @@ __global__ void obs_gather_kernel(int nobs, int nensobs, int ldens, const int *_
     rec[s] = r;
     sval[s] = val[n];
   }
-  for (int m = threadIdx.x; m < ldens; m += blockDim.x)
-    sens[(size_t)s * ldens + m] = m < nensobs ? ensval[(size_t)n * nensobs + m] : 0.0;
+  for (int m = threadIdx.x; m < ldens; m += blockDim.x) {
+    double v = 0.0;
+    if (m < k) v = ensval[(size_t)n * nensobs + m];
+    else if (m == k) v = val[n];
+    else if (m == k + 1 && nensobs > k) v = ensval[(size_t)n * nensobs + k];
+    sens[(size_t)s * ldens + m] = v;
+  }
 }
 
 __global__ void fill_kernel(double *__restrict__ p, size_t n, double v) {

@@ -84,7 +84,7 @@ __device__ __forceinline__ void stage_chunk(const DasParams &P, const LocalList 
     const double w = sqrt(1.0 / L.rdiag[o]);
     sw[threadIdx.x] = w;
     sd[threadIdx.x] = w * P.val[iob];
-    sdd[threadIdx.x] = P.det ? w * P.ensval[(size_t)iob * P.ldens + k] : 0.0;
+    sdd[threadIdx.x] = P.det ? w * P.ensval[(size_t)iob * P.ldens + k + 1] : 0.0;
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < nrows * ldk; idx += blockDim.x) {

@@ -1,10 +1,11 @@
 // das_ns_kernel.cuh -- fused per-grid-point LETKF analysis kernel on the FP64 tensor cores (twin of
-// the main loop of das_letkf, scale/letkf/letkf_tools.f90:313-686), for MEMBER <= 104.
+// the main loop of das_letkf, scale/letkf/letkf_tools.f90:313-686), for MEMBER <= 102.
 //
 // Persistent CTAs (NB warps, one per 8-row block of the k x k matrices) pull (ij, ilev) points from
 // a global counter:
 //   relax_beta -> load members, form perturbations -> [per variable-localisation group]
-//   local-obs search -> DMMA Gram A = Yr^T Y from L2-resident obs rows -> interval-scaled coupled
+//   local-obs search -> DMMA Gram [A | b | bd] = Yr^T [Y | dep | depd] from L2-resident obs rows
+//   (cp.async double-buffered; dep and depd ride in the padding columns) -> interval-scaled coupled
 //   Newton-Schulz Z = sqrt(s) A^-1/2 (ns_solver.cuh) -> one skinny DMMA product Z [dX | b | bd]
 //   -> RTPP/RTPS relaxation -> xa = xmean + dX T -> store.
 // With t_c = A^-1/2 x_c:   dX W = sqrt(k-1) t_c,   x^T Pa y = t_x . t_y,   dX wbar = t_x . t_b,
@@ -18,32 +19,43 @@ namespace letkf {
 template <int NB>
 __host__ __device__ inline size_t das_ns_smem_bytes() {
   using C = NsCfg<NB>;
-  size_t d = 2 * (size_t)C::KP * C::LD;   // Y, Z (Z doubles as the obs-chunk staging area)
+  size_t d = 3 * (size_t)C::PSZ;          // packed Y, Z, T (Z+T double as the two obs-chunk staging buffers)
   d += 2 * (size_t)kMaxNV * C::LD;        // Xall, Ts
-  d += 3 * (size_t)C::KP;                 // sw, sd, sdd
-  d += 8 * kMaxNV + 32 + 8;               // per-column scalars, reductions
+  d += 2 * (size_t)C::CR;                 // per-row weights of the two staged chunks
+  d += 8 * kMaxNV + 40;                   // per-column scalars, reductions
   return d * sizeof(double) + sizeof(SearchSmem) + 64;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
 template <int NB>
 __global__ void __launch_bounds__(NsCfg<NB>::NT, NsCfg<NB>::MINB)
 das_ns_kernel(const DasParams P) {
   using C = NsCfg<NB>;
-  constexpr int KP = C::KP, LD = C::LD;
+  constexpr int KP = C::KP, LD = C::LD, H = C::H, CR = C::CR, PSZ = C::PSZ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = P.k, nens = P.nens;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  double *Yb = reinterpret_cast<double *>(smem_raw);
-  double *Zb = Yb + (size_t)KP * LD;
-  double *Xall = Zb + (size_t)KP * LD;          // [kMaxNV][LD]: perturbations of variable vv; rows 14/15: b, bd
+  double *Yp = reinterpret_cast<double *>(smem_raw);
+  double *Zp = Yp + PSZ;
+  double *Tp = Zp + PSZ;
+  double *stage = Zp;                           // 2 x CR x LD doubles inside Zp..Tp
+  double *Xall = Tp + PSZ;                      // [kMaxNV][LD]: perturbations of variable vv; rows 14/15: b, bd
   double *Ts = Xall + (size_t)kMaxNV * LD;      // [kMaxNV][LD]: Z Xall
-  double *sw = Ts + (size_t)kMaxNV * LD;
-  double *sd = sw + KP;
-  double *sdd = sd + KP;
-  double *colsc = sdd + KP;                     // [8][kMaxNV]
+  double *wv = Ts + (size_t)kMaxNV * LD;        // [2][CR]
+  double *colsc = wv + 2 * CR;                  // [8][kMaxNV]
   double *red = colsc + 8 * kMaxNV;
   SearchSmem &S = *reinterpret_cast<SearchSmem *>((reinterpret_cast<uintptr_t>(red + 40) + 15) & ~(uintptr_t)15);
   __shared__ long long s_work;
+  const LaneOfs lo = lane_offsets(lane);
 
   LocalList L;
   L.cap = P.lcap;
@@ -171,81 +183,90 @@ das_ns_kernel(const DasParams P) {
 
       if (p_use > 0) {
         solved_any = true;
-        // ---- Gram A = Yr^T Y (common_letkf.f90:111-128) on the tensor cores, b = Yr^T dep ------
-        double acc[NB][2];
-        zero_rowblock<NB>(acc);
-        double bacc = 0.0, bdacc = 0.0, tracc = 0.0, p1acc = 0.0, p3acc = 0.0;
-        double *Ys = Zb;
-        for (int o0 = 0; o0 < p_use; o0 += KP) {
-          const int nrows = min(KP, p_use - o0);
-          const int nrows4 = (nrows + 3) & ~3;
-          if (tid < nrows4) {
-            double wv = 0.0, dv = 0.0, ddv = 0.0;
-            if (tid < nrows) {
-              const int o = o0 + tid;
-              const int iob = L.iob[o];
-              wv = sqrt(1.0 / L.rdiag[o]);
-              dv = wv * P.val[iob];
-              ddv = P.det ? wv * P.ensval[(size_t)iob * P.ldens + k] : 0.0;
-              if (P.INFL_MUL_ADAPTIVE) {
-                p1acc += dv * dv;
-                p3acc += L.rloc[o];
-              }
-            }
-            sw[tid] = wv;
-            sd[tid] = dv;
-            sdd[tid] = ddv;
-          }
-          __syncthreads();
-          for (int idx = tid; idx < nrows4 * KP; idx += blockDim.x) {
-            const int o = idx / KP, m = idx - o * KP;
-            double v = 0.0;
-            if (o < nrows && m < k) v = P.ensval[(size_t)L.iob[o0 + o] * P.ldens + m] * sw[o];
-            Ys[(size_t)o * LD + m] = v;
-          }
-          __syncthreads();
-          gram_rowblock<NB, LD>(acc, Ys, nrows4, w, lane);
-          if (tid < k) {
-            for (int o = 0; o < nrows; ++o) {
-              const double y = Ys[(size_t)o * LD + tid];
-              bacc = fma(y, sd[o], bacc);
-              bdacc = fma(y, sdd[o], bdacc);
-              if (P.INFL_MUL_ADAPTIVE) tracc = fma(y, y, tracc);
-            }
-          }
-          __syncthreads();
-        }
-        if (tid < k) {
-          bvec[tid] = bacc;
-          bdvec[tid] = bdacc;
-        }
-        const double cdiag = (double)(k - 1) / infl;   // (common_letkf.f90:140-143)
-        {
-          const int r = lane >> 2, q = lane & 3, row = w * 8 + r;
-          if (row < k && (row >> 3) == w) {
+        // ---- Gram [A | b | bd] = Yr^T [Y | dep | depd] (common_letkf.f90:111-128,182-195) on the
+        // tensor cores: raw obs rows [y_1..y_k, dep, depd, 0..] stream in with cp.async, the
+        // R^-1 weight is applied to the A operand.
+        double acc[H + 1][2];
 #pragma unroll
-            for (int j = 0; j < NB; ++j)
-              if (j == w) {
-                if (2 * q == r) acc[j][0] += cdiag;
-                if (2 * q + 1 == r) acc[j][1] += cdiag;
-              }
+        for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
+        double p3acc = 0.0;
+        const int nchunks = (p_use + CR - 1) / CR;
+        auto issue = [&](int c) {
+          double *dst = stage + (size_t)(c & 1) * CR * LD;
+          double *wdst = wv + (c & 1) * CR;
+          const int o0 = c * CR;
+          const int nrows = min(CR, p_use - o0), nrows4 = (nrows + 3) & ~3;
+          for (int idx = tid; idx < nrows * (KP / 2); idx += blockDim.x) {
+            const int o = idx / (KP / 2), pc = idx - o * (KP / 2);
+            cp_async16(dst + (size_t)o * LD + 2 * pc, P.ensval + (size_t)L.iob[o0 + o] * P.ldens + 2 * pc);
           }
+          for (int idx = tid; idx < (nrows4 - nrows) * KP; idx += blockDim.x)
+            dst[(size_t)(nrows + idx / KP) * LD + idx % KP] = 0.0;
+          if (tid < nrows4) {
+            double wt = 0.0;
+            if (tid < nrows) {
+              wt = 1.0 / L.rdiag[o0 + tid];
+              if (P.INFL_MUL_ADAPTIVE) p3acc += L.rloc[o0 + tid];
+            }
+            wdst[tid] = wt;
+          }
+          cp_async_commit();
+        };
+        issue(0);
+        for (int c = 0; c < nchunks; ++c) {
+          if (c + 1 < nchunks) {
+            issue(c + 1);
+            cp_async_wait<1>();
+          } else {
+            cp_async_wait<0>();
+          }
+          __syncthreads();
+          const int nrows = min(CR, p_use - c * CR);
+          gram_circ<NB, LD>(acc, stage + (size_t)(c & 1) * CR * LD, wv + (c & 1) * CR, (nrows + 3) & ~3, w, lane);
+          __syncthreads();
         }
+        store_circ<NB>(acc, Yp, w, lo);
+        __syncthreads();
+        const double cdiag = (double)(k - 1) / infl;   // (common_letkf.f90:140-143)
+        // ---- s = ||A||_1, b, bd (and the adaptive-inflation statistics) from the stored tiles -------
+        double rs = 0.0, dgv = 0.0;
+        if (tid < k) {
+          for (int col = 0; col < k; ++col) rs += fabs(Yp[paddr(tid, col)]);
+          rs += cdiag;
+          dgv = Yp[paddr(tid, tid)];
+          bvec[tid] = Yp[paddr(tid, k)];
+          bdvec[tid] = P.det ? Yp[paddr(tid, k + 1)] : 0.0;
+        }
+        const double s_norm = block_max(rs, red);
         if (P.INFL_MUL_ADAPTIVE) {   // (common_letkf.f90:229-254)
-          const double parm1 = block_sum(p1acc, red);
-          const double parm2 = block_sum(tid < k ? tracc : 0.0, red) / (double)(k - 1);
+          const double parm1 = Yp[paddr(k, k)];   // sum w dep^2
+          const double parm2 = block_sum(dgv, red) / (double)(k - 1);
           const double parm3 = block_sum(p3acc, red);
           const double parm4 = (parm1 - parm3) / parm2 - infl;
           const double tq = (infl * parm2 + parm3) / parm2;
           const double sigma_o = 2.0 / parm3 * (tq * tq);
           const double gain = 0.04 * 0.04 / (sigma_o + 0.04 * 0.04);
-          __syncthreads();
           if (tid == 0) inflv[vtrig] = infl + gain * parm4;
         }
+        __syncthreads();
+        // ---- Y0 = (A + c0 I) / s on the leading k x k block, identity on the padding ----------------
+        {
+          const double is = 1.0 / s_norm;
+          for (int idx = tid; idx < PSZ; idx += blockDim.x) {
+            int bi, bj;
+            tile_coords(idx >> 6, bi, bj);
+            const int e = idx & 63, r = e >> 3, c = (e & 7) ^ ((r & 2) << 1);
+            const int row = bi * 8 + r, col = bj * 8 + c;
+            double v = Yp[idx];
+            if (row < k && col < k) v = (v + (row == col ? cdiag : 0.0)) * is;
+            else v = (row == col) ? 1.0 : 0.0;
+            Yp[idx] = v;
+          }
+        }
+        __syncthreads();
         phase(2);
-        // ---- Z = sqrt(s) A^-1/2 ------------------------------------------------------------------
-        double s_norm;
-        const int its = newton_schulz_invsqrt<NB>(acc, Yb, Zb, k, cdiag, red, P.max_sweeps + 20, &s_norm);
+        // ---- Z = (A/s)^-1/2 --------------------------------------------------------------------------
+        const int its = newton_schulz_invsqrt<NB>(Yp, Zp, Tp, cdiag / s_norm, red, P.max_sweeps + 20);
         if (its < 0) fail = true;
         c_iters += (unsigned long long)(its < 0 ? -its : its);
         // mtx_eigen zeroes eigenvalues below lambda_max*sqrt(eps) (common_mtx.f90:69) and letkf_core
@@ -256,13 +277,16 @@ das_ns_kernel(const DasParams P) {
         {
           double a2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
           const int r = lane >> 2, q = lane & 3;
-          const double *pa = Zb + (size_t)(w * 8 + r) * LD + q;
           const double *pb = Xall + (size_t)r * LD + q;
-#pragma unroll 2
-          for (int kb = 0; kb < 2 * NB; ++kb) {
-            const double a = pa[kb * 4];
-            dmma884(a2[0][0], a2[0][1], a, pb[kb * 4]);
-            dmma884(a2[1][0], a2[1][1], a, pb[(size_t)8 * LD + kb * 4]);
+#pragma unroll 1
+          for (int l = 0; l < NB; ++l) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const double a = afrag(Zp, w, l, h, lo);
+              const int kk = l * 8 + h * 4;
+              dmma884(a2[0][0], a2[0][1], a, pb[kk]);
+              dmma884(a2[1][0], a2[1][1], a, pb[(size_t)8 * LD + kk]);
+            }
           }
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt)

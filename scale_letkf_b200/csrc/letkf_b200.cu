@@ -43,6 +43,23 @@ int uid_obs_varlocal(int elm) {   // common_obs_scale.f90:216-242
   }
 }
 
+// Size class of the tensor-core solver (das_ns_kernel<NB>): NB odd 8-row blocks with k + 2 <= 8 NB
+// (two padding columns carry dep / depd); 0 = ensemble too large, Cholesky + Jacobi path.
+int ns_class(int k) {
+  if (k + 2 <= 24) return 3;
+  if (k + 2 <= 40) return 5;
+  if (k + 2 <= 56) return 7;
+  if (k + 2 <= 72) return 9;
+  if (k + 2 <= 104) return 13;
+  return 0;
+}
+// doubles per row of the sorted obs table: the padded width of the solver class, so that a row is
+// copied to shared memory as is
+int ns_row_doubles(int k) {
+  const int nb = ns_class(k);
+  return nb ? 8 * nb : round_up(k + 2, 2);
+}
+
 template <class T>
 struct DevBuf {
   T *p = nullptr;
@@ -446,7 +463,7 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
   }
   // ---- device bucket sort ------------------------------------------------------------------------
   h->nensobs = obs->nensobs;
-  h->ldens = round_up(std::max(need, 1), 2);
+  h->ldens = ns_row_doubles(c.MEMBER);   // [ensval(1..k) | dep | depd | 0..]
   h->nobstotal = nobs;
   DevBuf<int> d_ic, d_key, d_count, d_fill, d_tmp;
   DevBuf<double> d_ri, d_rj, d_vc, d_err, d_val, d_ens;
@@ -478,7 +495,7 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
     exclusive_scan_kernel<<<1, 256, 0, h->stream>>>(d_count.p, h->bstart.p, boff);
     bucket_scatter_kernel<<<gb, tb, 0, h->stream>>>(nobs, d_key.p, h->bstart.p, d_fill.p, d_tmp.p);
     bucket_rank_kernel<<<gb, tb, 0, h->stream>>>(nobs, d_key.p, h->bstart.p, d_tmp.p, h->s2o.p);
-    obs_gather_kernel<<<nobs, 64, 0, h->stream>>>(nobs, obs->nensobs, h->ldens, h->s2o.p, d_ri.p, d_rj.p, d_vc.p,
+    obs_gather_kernel<<<nobs, 64, 0, h->stream>>>(nobs, obs->nensobs, c.MEMBER, h->ldens, h->s2o.p, d_ri.p, d_rj.p, d_vc.p,
                                                   d_err.p, d_val.p, d_ens.p, h->rec.p, h->sval.p, h->sens.p);
     CK(cudaGetLastError());
   } else {
@@ -701,15 +718,16 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   P.max_sweeps = 30;
   CK(cudaMemsetAsync(h->counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
   int r;
-  // MEMBER <= 104: tensor-core Newton-Schulz solve (das_ns_kernel.cuh); larger ensembles (two k x k
+  // MEMBER <= 102: tensor-core Newton-Schulz solve (das_ns_kernel.cuh); larger ensembles (two k x k
   // matrices no longer fit in shared memory) and LETKF_B200_SOLVER=jacobi: Cholesky + one-sided Jacobi.
   const char *sv = std::getenv("LETKF_B200_SOLVER");
-  const bool jacobi = (sv && std::strcmp(sv, "jacobi") == 0) || k > 104;
+  const int nsc = ns_class(k);
+  const bool jacobi = (sv && std::strcmp(sv, "jacobi") == 0) || nsc == 0;
   if (!jacobi) {
-    if (k <= 24) r = launch_das_ns<3>(h, P);
-    else if (k <= 40) r = launch_das_ns<5>(h, P);
-    else if (k <= 56) r = launch_das_ns<7>(h, P);
-    else if (k <= 64) r = launch_das_ns<8>(h, P);
+    if (nsc == 3) r = launch_das_ns<3>(h, P);
+    else if (nsc == 5) r = launch_das_ns<5>(h, P);
+    else if (nsc == 7) r = launch_das_ns<7>(h, P);
+    else if (nsc == 9) r = launch_das_ns<9>(h, P);
     else r = launch_das_ns<13>(h, P);
   } else
   if (k <= 20) r = launch_das<20>(h, P);

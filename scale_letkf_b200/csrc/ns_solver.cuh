@@ -10,14 +10,16 @@
 // with s = ||A||_1 >= lambda_max, the eigenvalues of M bracketed by [a, b] (a0 = c0/s with the known
 // lowest eigenvalue bound c0 = (k-1)/rho, b0 = 1) and c = 3 / (a + sqrt(ab) + b), the scaling that
 // maps both interval ends onto the same image.  Every iterate is a polynomial in A, so all
-// matrices commute and the iteration is numerically stable and quadratically convergent, even
-// with the (k-p)-fold degenerate eigenvalue c0 (p < k).  6-7 iterations for cond(A) <= 100.
+// matrices are symmetric and commute: the iteration is numerically stable and quadratically
+// convergent even with the (k-p)-fold degenerate eigenvalue c0 (p < k).  5-7 iterations for
+// cond(A) <= 100.
 //
-// All products are k x k x k GEMMs on the FP64 tensor cores: mma.sync.aligned.m8n8k4.f64 (DMMA;
-// tcgen05/TMEM has no FP64 kind).  Warp w owns the 8-row block w of every product; operands are
-// read from shared memory with leading dimension LD = KP + 4 (== 4 or 12 mod 16 doubles), which
-// makes both fragment patterns bank-conflict free; T stays in registers and is converted from the
-// accumulator layout to the A-operand layout with warp shuffles, so only Y and Z live in smem.
+// All products are GEMMs on the FP64 tensor cores: mma.sync.aligned.m8n8k4.f64 (DMMA; tcgen05/TMEM
+// has no FP64 kind).  Because every matrix is symmetric, only the lower triangle of 8x8 tiles is
+// stored (packed, XOR-swizzled so that both the direct and the transposed fragment patterns are
+// bank-conflict free) and only one tile of each symmetric pair is computed: with NB (odd) row
+// blocks, warp w computes the "circulant" tiles (w, (w+d) mod NB), d = 0..(NB-1)/2, which covers
+// every unordered pair exactly once with perfect load balance.
 #pragma once
 #include "common.cuh"
 
@@ -25,12 +27,17 @@ namespace letkf {
 
 template <int NB_>
 struct NsCfg {
-  static constexpr int NB = NB_;          // 8-row blocks
-  static constexpr int KP = 8 * NB_;      // padded ensemble size
-  static constexpr int LD = KP + 4;       // leading dimension of every smem matrix
-  static constexpr int NT = 32 * NB_;     // one warp per row block
-  // resident CTAs per SM the register allocation is sized for (shared memory allows as many)
-  static constexpr int MINB = NB_ <= 3 ? 6 : NB_ <= 5 ? 4 : NB_ <= 7 ? 3 : NB_ <= 8 ? 2 : 1;
+  static_assert(NB_ % 2 == 1, "the circulant tile assignment needs an odd number of row blocks");
+  static constexpr int NB = NB_;                   // 8-row blocks
+  static constexpr int H = (NB_ - 1) / 2;          // warp w owns tiles (w, w+d mod NB), d = 0..H
+  static constexpr int KP = 8 * NB_;               // padded ensemble size (>= k + 2)
+  static constexpr int LD = KP + 4;                // row stride of row-major staging / vector blocks
+  static constexpr int NT = 32 * NB_;              // one warp per row block
+  static constexpr int NTILE = NB_ * (NB_ + 1) / 2;
+  static constexpr int PSZ = NTILE * 64;           // doubles per packed symmetric matrix
+  static constexpr int CR = (PSZ / LD) & ~3;       // obs rows per staging chunk (two chunks fit in 2 PSZ)
+  // resident CTAs per SM the register allocation is sized for
+  static constexpr int MINB = NB_ <= 3 ? 8 : NB_ <= 5 ? 5 : NB_ <= 7 ? 3 : NB_ <= 9 ? 2 : 1;
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -39,147 +46,164 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
       : "d"(a), "d"(b));
 }
 
-// accumulator tile (lane holds C[r][2q], C[r][2q+1]; r = lane>>2, q = lane&3) -> A fragment of
-// its k-step h (columns 4h..4h+3): A[r][4h + q]
-__device__ __forceinline__ double acc_to_afrag(double c0, double c1, int h, int lane) {
-  const int src = (lane & ~3) | (2 * h + ((lane & 3) >> 1));
-  const double v0 = __shfl_sync(LETKF_FULL_MASK, c0, src);
-  const double v1 = __shfl_sync(LETKF_FULL_MASK, c1, src);
-  return (lane & 1) ? v1 : v0;
+// ---- packed symmetric tile storage ---------------------------------------------------------------
+// tile (bi, bj), bi >= bj, at ((bi (bi+1))/2 + bj) * 64; element (r, c) of a stored tile at
+// r*8 + (c ^ ((r & 2) << 1)).
+__host__ __device__ __forceinline__ int ptile(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * 64; }
+__host__ __device__ __forceinline__ int pelem(int r, int c) { return r * 8 + (c ^ ((r & 2) << 1)); }
+// address of logical element (row, col) of a packed symmetric matrix
+__host__ __device__ __forceinline__ int paddr(int row, int col) {
+  const int bi = row >> 3, bj = col >> 3;
+  return (bi >= bj) ? ptile(bi, bj) + pelem(row & 7, col & 7) : ptile(bj, bi) + pelem(col & 7, row & 7);
 }
 
-// acc[j] += sum over k-blocks kb in [0, nkb) of  Afrag(kb) * B[kb*4.., j*8..]
-// A from a row-major smem matrix (rows w*8..): A[m][kk] = Am[m*LD + kk]
-// B from a row-major smem matrix:              B[kk][n] = Bm[kk*LD + n]
-template <int NB, int LD>
-__device__ __forceinline__ void gemm_rowblock_ss(double (&acc)[NB][2], const double *Am, const double *Bm,
-                                                 int w, int nkb, int lane) {
+struct LaneOfs {   // per-lane offsets of the two fragment patterns, k-halves h = 0, 1
+  int p1[2];       // stored (r, 4h+q): direct A operand / transposed B operand
+  int p2[2];       // stored (4h+q, r): transposed A operand / direct B operand
+  int st_n;        // accumulator store, direct:     stored (r, 2q) [double2]
+  int st_t[2];     // accumulator store, transposed: stored (2q+e, r)
+};
+__device__ __forceinline__ LaneOfs lane_offsets(int lane) {
   const int r = lane >> 2, q = lane & 3;
-  const double *pa = Am + (size_t)(w * 8 + r) * LD + q;
-  const double *pb = Bm + (size_t)q * LD + r;
-#pragma unroll 2
-  for (int kb = 0; kb < nkb; ++kb) {
-    const double a = pa[kb * 4];
-    const double *pbk = pb + (size_t)kb * 4 * LD;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) dmma884(acc[j][0], acc[j][1], a, pbk[j * 8]);
+  LaneOfs o;
+  o.p1[0] = pelem(r, q);
+  o.p1[1] = pelem(r, 4 + q);
+  o.p2[0] = pelem(q, r);
+  o.p2[1] = pelem(4 + q, r);
+  o.st_n = pelem(r, 2 * q);
+  o.st_t[0] = pelem(2 * q, r);
+  o.st_t[1] = pelem(2 * q + 1, r);
+  return o;
+}
+// A operand: logical block (bi, bl) of packed M, k-half h
+__device__ __forceinline__ double afrag(const double *M, int bi, int bl, int h, const LaneOfs &o) {
+  return (bi >= bl) ? M[ptile(bi, bl) + o.p1[h]] : M[ptile(bl, bi) + o.p2[h]];
+}
+// B operand: logical block (bl, bj) of packed M, k-half h
+__device__ __forceinline__ double bfrag(const double *M, int bl, int bj, int h, const LaneOfs &o) {
+  return (bl >= bj) ? M[ptile(bl, bj) + o.p2[h]] : M[ptile(bj, bl) + o.p1[h]];
+}
+// store / load one accumulator tile of logical block (bi, bj)
+__device__ __forceinline__ void store_tile(double *M, int bi, int bj, double c0, double c1, const LaneOfs &o) {
+  if (bi >= bj) {
+    *reinterpret_cast<double2 *>(M + ptile(bi, bj) + o.st_n) = make_double2(c0, c1);
+  } else {
+    double *t = M + ptile(bj, bi);
+    t[o.st_t[0]] = c0;
+    t[o.st_t[1]] = c1;
+  }
+}
+__device__ __forceinline__ void load_tile(const double *M, int bi, int bj, double &c0, double &c1,
+                                          const LaneOfs &o) {
+  if (bi >= bj) {
+    const double2 v = *reinterpret_cast<const double2 *>(M + ptile(bi, bj) + o.st_n);
+    c0 = v.x;
+    c1 = v.y;
+  } else {
+    const double *t = M + ptile(bj, bi);
+    c0 = t[o.st_t[0]];
+    c1 = t[o.st_t[1]];
   }
 }
 
-// acc[j] += T(w, :) * B   with the row block of T held in registers (accumulator layout)
-template <int NB, int LD>
-__device__ __forceinline__ void gemm_rowblock_rs(double (&acc)[NB][2], const double (&T)[NB][2],
-                                                 const double *Bm, int lane) {
-  const int r = lane >> 2, q = lane & 3;
-  const double *pb = Bm + (size_t)q * LD + r;
-#pragma unroll
+// acc[d] (+)= sum_l X(w, l) W(l, jd)   for the warp's circulant tiles jd = (w + d) mod NB
+template <int NB>
+__device__ __forceinline__ void symm_gemm(double (&acc)[(NB + 1) / 2][2], const double *X, const double *W,
+                                          int w, const LaneOfs &o) {
+  constexpr int H = (NB - 1) / 2;
+#pragma unroll 1
   for (int l = 0; l < NB; ++l) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const double a = acc_to_afrag(T[l][0], T[l][1], h, lane);
-      const double *pbk = pb + (size_t)(l * 8 + h * 4) * LD;
+      const double a = afrag(X, w, l, h, o);
 #pragma unroll
-      for (int j = 0; j < NB; ++j) dmma884(acc[j][0], acc[j][1], a, pbk[j * 8]);
+      for (int d = 0; d <= H; ++d) {
+        int j = w + d;
+        if (j >= NB) j -= NB;
+        dmma884(acc[d][0], acc[d][1], a, bfrag(W, l, j, h, o));
+      }
     }
   }
 }
 
-// Gram of a staged chunk: rows o of Ys (row-major [o][m], leading dimension LD, `nrows4` rows, a
-// multiple of 4, zero padded) -> acc(w-block, :) += Ys^T Ys
+template <int NB>
+__device__ __forceinline__ void store_circ(const double (&acc)[(NB + 1) / 2][2], double *M, int w,
+                                           const LaneOfs &o) {
+#pragma unroll
+  for (int d = 0; d <= (NB - 1) / 2; ++d) {
+    int j = w + d;
+    if (j >= NB) j -= NB;
+    store_tile(M, w, j, acc[d][0], acc[d][1], o);
+  }
+}
+
+// Gram of a staged chunk: raw obs rows Ys[o][m] (row-major, leading dimension LD, nrows4 rows, a
+// multiple of 4) with per-row weights wv[o] (0 for padding rows):
+//   acc[d] += sum_o wv[o] Ys[o][w-block]^T Ys[o][jd-block]
 template <int NB, int LD>
-__device__ __forceinline__ void gram_rowblock(double (&acc)[NB][2], const double *Ys, int nrows4, int w,
-                                              int lane) {
+__device__ __forceinline__ void gram_circ(double (&acc)[(NB + 1) / 2][2], const double *Ys, const double *wv,
+                                          int nrows4, int w, int lane) {
+  constexpr int H = (NB - 1) / 2;
   const int r = lane >> 2, q = lane & 3;
   const double *pa = Ys + (size_t)q * LD + w * 8 + r;
   const double *pb = Ys + (size_t)q * LD + r;
+  int jo[H + 1];
+#pragma unroll
+  for (int d = 0; d <= H; ++d) {
+    int j = w + d;
+    if (j >= NB) j -= NB;
+    jo[d] = j * 8;
+  }
 #pragma unroll 2
   for (int o = 0; o < nrows4; o += 4) {
-    const double a = pa[(size_t)o * LD];
+    const double a = pa[(size_t)o * LD] * wv[o + q];
     const double *pbk = pb + (size_t)o * LD;
 #pragma unroll
-    for (int j = 0; j < NB; ++j) dmma884(acc[j][0], acc[j][1], a, pbk[j * 8]);
+    for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], a, pbk[jo[d]]);
   }
 }
 
-// store the row block held in accumulator layout: element (w*8 + r, j*8 + 2q + e) -> M[row*LD + col]
-template <int NB, int LD>
-__device__ __forceinline__ void store_rowblock(const double (&acc)[NB][2], double *M, int w, int lane) {
-  const int r = lane >> 2, q = lane & 3;
-  double *p = M + (size_t)(w * 8 + r) * LD + 2 * q;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) *reinterpret_cast<double2 *>(p + j * 8) = make_double2(acc[j][0], acc[j][1]);
-}
-
+// Coupled, interval-scaled Newton-Schulz on packed symmetric matrices.  On entry Yp holds
+// Y0 = A / s (leading k x k block; identity on the padding rows), c0s = c0 / s the lower eigenvalue
+// bound.  On exit Zp holds Z ~= (A/s)^-1/2.  Tp: scratch.  `red`: >= 32 doubles of shared scratch.
+// Returns the number of iterations, negative if the residual test was not met within max_iter.
+// All NT = 32 NB threads of the CTA must call.
 template <int NB>
-__device__ __forceinline__ void zero_rowblock(double (&acc)[NB][2]) {
-#pragma unroll
-  for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = 0.0;
-}
-
-// Coupled, interval-scaled Newton-Schulz.  On entry warp w holds the row block w of A (including
-// the (k-1)/rho diagonal; rows/cols >= k are zero) in `acc`.  On exit Zb holds Z ~= sqrt(s) A^-1/2
-// (row-major, LD) for the leading k x k block and *s_out = s.  Ybuf/Zbuf: KP x LD doubles each.
-// `red`: >= 32 doubles of shared scratch.  Returns the number of iterations, negative if the
-// iteration did not converge within max_iter.  All threads of the CTA (NT = 32 NB) must call.
-template <int NB>
-__device__ __forceinline__ int newton_schulz_invsqrt(double (&acc)[NB][2], double *Yb, double *Zb, int k,
-                                                     double c0, double *red, int max_iter, double *s_out) {
-  using C = NsCfg<NB>;
-  constexpr int LD = C::LD;
+__device__ __forceinline__ int newton_schulz_invsqrt(double *Yp, double *Zp, double *Tp, double c0s,
+                                                     double *red, int max_iter) {
+  constexpr int H = (NB - 1) / 2;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int r = lane >> 2, q = lane & 3;
-  // ---- s = ||A||_1 (max absolute row sum; A symmetric) -----------------------------------------
-  double rs = 0.0;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) rs += fabs(acc[j][0]) + fabs(acc[j][1]);
-  rs += __shfl_xor_sync(LETKF_FULL_MASK, rs, 1);
-  rs += __shfl_xor_sync(LETKF_FULL_MASK, rs, 2);
-  rs = fmax(rs, __shfl_xor_sync(LETKF_FULL_MASK, rs, 4));
-  rs = fmax(rs, __shfl_xor_sync(LETKF_FULL_MASK, rs, 8));
-  rs = fmax(rs, __shfl_xor_sync(LETKF_FULL_MASK, rs, 16));
-  __syncthreads();
-  if (lane == 0) red[w] = rs;
-  __syncthreads();
-  double s = red[0];
-#pragma unroll
-  for (int i = 1; i < NB; ++i) s = fmax(s, red[i]);
-  *s_out = s;
-  const double is = 1.0 / s;
-  // ---- Y0 = A / s (padding rows: identity), M = Z0 Y0 = Y0 ---------------------------------------
-  const int row = w * 8 + r;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = j * 8 + 2 * q + e;
-      double v = acc[j][e] * is;
-      if (row >= k || col >= k) v = (row == col) ? 1.0 : 0.0;
-      acc[j][e] = v;
-    }
-  }
-  store_rowblock<NB, LD>(acc, Yb, w, lane);
-  double a = c0 * is, b = 1.0;   // eigenvalue bracket of M
-  double T[NB][2];
+  const LaneOfs o = lane_offsets(lane);
+  double a = c0s, b = 1.0;   // eigenvalue bracket of M = Z Y
+  double acc[H + 1][2], az[H + 1][2];
   int it = 0;
   bool first = true, done = false;
   while (!done) {
     ++it;
-    if (!first) {   // M = Z Y
-      zero_rowblock<NB>(acc);
-      gemm_rowblock_ss<NB, LD>(acc, Zb, Yb, w, 2 * NB, lane);
+    if (first) {   // M = Z0 Y0 = Y0
+#pragma unroll
+      for (int d = 0; d <= H; ++d) {
+        int j = w + d;
+        if (j >= NB) j -= NB;
+        load_tile(Yp, w, j, acc[d][0], acc[d][1], o);
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
+      symm_gemm<NB>(acc, Zp, Yp, w, o);
     }
-    // residual ||I - M||_max and the scaled T = sqrt(c) (3 I - c M) / 2
+    // residual ||I - M||_max (the warp's diagonal tile is d = 0)
     double res = 0.0;
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
+    for (int d = 0; d <= H; ++d) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int col = j * 8 + 2 * q + e;
-        res = fmax(res, fabs(((row == col) ? 1.0 : 0.0) - acc[j][e]));
+        const double dg = (d == 0 && r == 2 * q + e) ? 1.0 : 0.0;
+        res = fmax(res, fabs(dg - acc[d][e]));
       }
     }
     res = warp_max(res);
-    __syncthreads();   // every warp is done reading Y, Z for M
     if (lane == 0) red[w] = res;
     __syncthreads();
     res = red[0];
@@ -189,43 +213,42 @@ __device__ __forceinline__ int newton_schulz_invsqrt(double (&acc)[NB][2], doubl
     double c = 1.0;
     if (!last && (b - a) > 1.0e-3) c = 3.0 / (a + sqrt(a * b) + b);
     const double sc = sqrt(c), h0 = 1.5 * sc, h1 = -0.5 * c * sc;
+    // T = sqrt(c) (3 I - c M) / 2
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
+    for (int d = 0; d <= H; ++d) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int col = j * 8 + 2 * q + e;
-        T[j][e] = fma(h1, acc[j][e], (row == col) ? h0 : 0.0);
-      }
+      for (int e = 0; e < 2; ++e) acc[d][e] = fma(h1, acc[d][e], (d == 0 && r == 2 * q + e) ? h0 : 0.0);
     }
     if (first) {
-      // Z1 = T, Y1 = T Y0
-      zero_rowblock<NB>(acc);
-      gemm_rowblock_rs<NB, LD>(acc, T, Yb, lane);
-      store_rowblock<NB, LD>(T, Zb, w, lane);
-      __syncthreads();   // all reads of Y0 done
-      store_rowblock<NB, LD>(acc, Yb, w, lane);
+      // Z1 = T ; Y1 = T Y0
+      store_circ<NB>(acc, Zp, w, o);
+      store_circ<NB>(acc, Tp, w, o);
+      __syncthreads();
+#pragma unroll
+      for (int d = 0; d <= H; ++d) az[d][0] = az[d][1] = 0.0;
+      symm_gemm<NB>(az, Tp, Yp, w, o);
+      __syncthreads();   // all reads of Y0 done (also protects red)
+      store_circ<NB>(az, Yp, w, o);
       __syncthreads();
     } else {
-      zero_rowblock<NB>(acc);
-      gemm_rowblock_rs<NB, LD>(acc, T, Zb, lane);   // Z' = T Z
-      __syncthreads();                               // all reads of Z done
-      store_rowblock<NB, LD>(acc, Zb, w, lane);
+      store_circ<NB>(acc, Tp, w, o);
+      __syncthreads();
+#pragma unroll
+      for (int d = 0; d <= H; ++d) az[d][0] = az[d][1] = 0.0;
+      symm_gemm<NB>(az, Tp, Zp, w, o);   // Z' = T Z
       if (!last) {
-        zero_rowblock<NB>(acc);
-        gemm_rowblock_rs<NB, LD>(acc, T, Yb, lane);   // Y' = T Y
-        __syncthreads();
-        store_rowblock<NB, LD>(acc, Yb, w, lane);
+#pragma unroll
+        for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
+        symm_gemm<NB>(acc, Tp, Yp, w, o);   // Y' = T Y
       }
+      __syncthreads();   // all reads of Z, Y, T done
+      store_circ<NB>(az, Zp, w, o);
+      if (!last) store_circ<NB>(acc, Yp, w, o);
       __syncthreads();
     }
-    if (c != 1.0) {
-      const double t = c * a;
-      a = t * (3.0 - t) * (3.0 - t) * 0.25;
-      b = 1.0;
-    } else {
-      // unscaled step: x -> x (3 - x)^2 / 4 keeps [a, 1]
-      a = a * (3.0 - a) * (3.0 - a) * 0.25;
-    }
+    const double t = c * a;   // image of the bracket under x -> c x (3 - c x)^2 / 4 is [g(c a), 1]
+    a = t * (3.0 - t) * (3.0 - t) * 0.25;
+    b = 1.0;
     first = false;
     done = last;
     if (last && !(res < 1.0e-7)) it = -it;
