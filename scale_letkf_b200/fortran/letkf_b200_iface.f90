@@ -1,0 +1,335 @@
+!===============================================================================
+! letkf_b200_iface.f90 -- ISO_C_BINDING view of include/letkf_b200.h and the
+! drop-in replacements of the two reference entry points of the analysis path:
+!
+!     letkf_core(ne,nobs,nobsl,hdxb,rdiag,rloc,dep,parm_infl,trans,transm,pao,
+!                rdiag_wloc,infl_update,depd,transmd)     common/common_letkf.f90:52
+!     das_letkf(gues3d,gues2d,anal3d,anal2d)              scale/letkf/letkf_tools.f90:50
+!
+! The argument lists are the reference's, so a caller switches by
+!     USE letkf_tools   ->  USE letkf_b200_iface, ONLY: das_letkf => das_letkf_b200
+!     USE common_letkf  ->  USE letkf_b200_iface, ONLY: letkf_core => letkf_core_b200
+! and links libletkf_b200.so.  Module state the reference's das_letkf reads through
+! USE association (namelist scalars, rig1/rjg1/hgt1, obs(:), obsda_sort) is handed
+! over once per cycle by letkf_b200_setup (after set_common_mpi_grid and the QC
+! half of set_letkf_obs; the bucket-sort half of set_letkf_obs is done on device).
+!
+! NOT COMPILED IN THE BUILD CONTAINER (no Fortran front-end there): the struct
+! layouts below are the same field-for-field tables as scale_letkf_b200/capi.py,
+! whose ctypes mirror is checked against sizeof/offsetof by tests/test_capi_cpu.py.
+! Compile with the reference: gfortran -cpp -c letkf_b200_iface.f90 (needs the
+! reference's common_nml / common_scale / common_mpi_scale / common_obs_scale .mod).
+!===============================================================================
+module letkf_b200_iface
+  use, intrinsic :: iso_c_binding
+  implicit none
+  private
+  public :: letkf_b200_config, letkf_b200_obs, letkf_b200_das_args
+  public :: letkf_b200_setup, letkf_b200_finalize
+  public :: das_letkf_b200, letkf_core_b200
+  public :: scatter_grd_b200_pack, gather_grd_b200_unpack
+
+  integer(c_int), parameter, public :: LETKF_B200_NOBTYPE = 24
+  integer(c_int), parameter, public :: LETKF_B200_NID_VARLOCAL = 9
+  integer(c_int), parameter, public :: LETKF_B200_MAX_NV = 16
+  integer(c_int), parameter, public :: LETKF_B200_MEM_HOST = 0, LETKF_B200_MEM_DEVICE = 1
+  integer(c_int), parameter, public :: LETKF_B200_OK = 0, LETKF_B200_EEIGEN = -4
+
+  ! struct letkf_b200_config (include/letkf_b200.h:60-92)
+  type, bind(C) :: letkf_b200_config
+    integer(c_int32_t) :: MEMBER, DET_RUN
+    integer(c_int32_t) :: nlon, nlat, nlev
+    integer(c_int32_t) :: nv3d, nv2d
+    integer(c_int32_t) :: IHALO, JHALO
+    real(c_double)     :: DX, DY
+    integer(c_int32_t) :: iv3d_p, iv3d_q, iv3d_qg
+    real(c_double)     :: INFL_MUL, INFL_MUL_MIN
+    integer(c_int32_t) :: INFL_MUL_ADAPTIVE, RELAX_TO_INFLATED_PRIOR
+    real(c_double)     :: RELAX_ALPHA, RELAX_ALPHA_SPREAD
+    real(c_double)     :: Q_UPDATE_TOP, Q_SPRD_MAX, BOUNDARY_BUFFER_WIDTH
+    real(c_double)     :: HORI_LOCAL(LETKF_B200_NOBTYPE), VERT_LOCAL(LETKF_B200_NOBTYPE)
+    real(c_double)     :: HORI_LOCAL_RADAR_OBSNOREF, HORI_LOCAL_RADAR_VR, VERT_LOCAL_RADAR_VR
+    real(c_double)     :: VERT_LOCAL_RAIN_BASE
+    integer(c_int32_t) :: MAX_NOBS_PER_GRID(LETKF_B200_NOBTYPE)
+    integer(c_int32_t) :: MAX_NOBS_PER_GRID_CRITERION
+    real(c_double)     :: OBS_MIN_SPACING(LETKF_B200_NOBTYPE), OBS_SORT_GRID_SPACING(LETKF_B200_NOBTYPE)
+    ! C: VAR_LOCAL[iv][n]  ==  Fortran VAR_LOCAL(n, iv)
+    real(c_double)     :: VAR_LOCAL(LETKF_B200_MAX_NV, LETKF_B200_NID_VARLOCAL)
+    real(c_double)     :: RADAR_ZMAX
+    real(c_double)     :: dist_zero_fac, dist_zero_fac_square
+    integer(c_int32_t) :: reserved(8)
+  end type
+
+  ! struct letkf_b200_obs (include/letkf_b200.h:109-114)
+  type, bind(C) :: letkf_b200_obs
+    integer(c_int32_t) :: nobs, nensobs
+    type(c_ptr) :: elm, typ
+    type(c_ptr) :: ri, rj, lev, dat, err, val
+    type(c_ptr) :: ensval
+  end type
+
+  ! struct letkf_b200_das_args (include/letkf_b200.h:165-178)
+  type, bind(C) :: letkf_b200_das_args
+    type(c_ptr) :: gues3d, gues2d, anal3d, anal2d
+    type(c_ptr) :: infl3d, rtps_infl_out, nobsl_out, logp
+    integer(c_int32_t) :: mem_space, reserved
+  end type
+
+  type(c_ptr), save :: handle = c_null_ptr
+
+  interface
+    subroutine c_config_defaults(cfg) bind(C, name='letkf_b200_config_defaults')
+      import :: letkf_b200_config
+      type(letkf_b200_config), intent(out) :: cfg
+    end subroutine
+    subroutine c_config_resolve(cfg) bind(C, name='letkf_b200_config_resolve')
+      import :: letkf_b200_config
+      type(letkf_b200_config), intent(inout) :: cfg
+    end subroutine
+    integer(c_int) function c_create(cfg, device, h) bind(C, name='letkf_b200_create')
+      import :: letkf_b200_config, c_int, c_ptr
+      type(letkf_b200_config), intent(in) :: cfg
+      integer(c_int), value :: device
+      type(c_ptr), intent(out) :: h
+    end function
+    integer(c_int) function c_destroy(h) bind(C, name='letkf_b200_destroy')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+    end function
+    function c_last_error(h) result(msg) bind(C, name='letkf_b200_last_error')
+      import :: c_ptr
+      type(c_ptr), value :: h
+      type(c_ptr) :: msg
+    end function
+    integer(c_int) function c_core_batch(h, ne, nobs, npts, nobsl, hdxb, rdiag, rloc, dep, parm_infl, &
+                                         trans, transm, pao, rdiag_wloc, infl_update, depd, transmd, &
+                                         mem_space) bind(C, name='letkf_b200_core_batch')
+      import :: c_int, c_ptr, c_int32_t, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: ne, nobs, npts, rdiag_wloc, infl_update, mem_space
+      integer(c_int32_t), intent(in) :: nobsl(*)
+      real(c_double), intent(in) :: hdxb(*), rdiag(*), rloc(*), dep(*)
+      real(c_double), intent(inout) :: parm_infl(*)
+      real(c_double), intent(out) :: trans(*)
+      type(c_ptr), value :: transm, pao, depd, transmd   ! OPTIONAL absent -> c_null_ptr
+    end function
+    integer(c_int) function c_set_grid(h, nij1, rig1, rjg1, hgt1, mem_space) bind(C, name='letkf_b200_set_grid')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: nij1, mem_space
+      real(c_double), intent(in) :: rig1(*), rjg1(*), hgt1(*)
+    end function
+    integer(c_int) function c_set_obs(h, obs) bind(C, name='letkf_b200_set_obs')
+      import :: c_int, c_ptr, letkf_b200_obs
+      type(c_ptr), value :: h
+      type(letkf_b200_obs), intent(in) :: obs
+    end function
+    integer(c_int) function c_das_letkf(h, args) bind(C, name='letkf_b200_das_letkf')
+      import :: c_int, c_ptr, letkf_b200_das_args
+      type(c_ptr), value :: h
+      type(letkf_b200_das_args), intent(in) :: args
+    end function
+    integer(c_int) function c_ensmean_grd(h, mem, nens, nij, v3d, v2d, mem_space) bind(C, name='letkf_b200_ensmean_grd')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: mem, nens, nij, mem_space
+      real(c_double), intent(inout) :: v3d(*), v2d(*)
+    end function
+    integer(c_int) function c_grd_to_buf(h, np, v3dg, v2dg, bufs) bind(C, name='letkf_b200_grd_to_buf')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, v3dg, v2dg, bufs      ! device pointers
+      integer(c_int), value :: np
+    end function
+    integer(c_int) function c_buf_to_ens(h, np, myrank_e, nens, mstart, mend, bufr, v3d, v2d) &
+        bind(C, name='letkf_b200_buf_to_ens')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, bufr, v3d, v2d
+      integer(c_int), value :: np, myrank_e, nens, mstart, mend
+    end function
+    integer(c_int) function c_ens_to_buf(h, np, myrank_e, nens, mstart, mend, v3d, v2d, bufs) &
+        bind(C, name='letkf_b200_ens_to_buf')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, v3d, v2d, bufs
+      integer(c_int), value :: np, myrank_e, nens, mstart, mend
+    end function
+    integer(c_int) function c_buf_to_grd(h, np, bufr, v3dg, v2dg) bind(C, name='letkf_b200_buf_to_grd')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, bufr, v3dg, v2dg
+      integer(c_int), value :: np
+    end function
+  end interface
+
+contains
+
+  !-----------------------------------------------------------------------------
+  ! Hand the module state das_letkf reads to the library.  Call once per cycle,
+  ! after set_common_mpi_grid (rig1, rjg1, hgt1: common_mpi_scale.f90:303-308)
+  ! and after the QC / departure half of set_letkf_obs (letkf_obs.f90:268-622):
+  ! the arguments are the QC-passed observations in arrival order; the ctype
+  ! table, sorting mesh, counting sort and extended prefix sums
+  ! (letkf_obs.f90:308-342, 660-976) are rebuilt on the device.
+  !-----------------------------------------------------------------------------
+  subroutine letkf_b200_setup(device, nobs, nensobs, elm, typ, ri, rj, lev, dat, err, val, ensval)
+    use common_nml          ! MEMBER, DET_RUN, INFL_MUL, ..., HORI_LOCAL(:), VAR_LOCAL_*(:)
+    use common_scale, only: nlon, nlat, nlev, nv3d, nv2d, iv3d_p, iv3d_q, iv3d_qg
+    use common_mpi_scale, only: nij1, rig1, rjg1, hgt1
+    use letkf_obs, only: dist_zero_fac, dist_zero_fac_square
+    use scale_grid, only: DX, DY
+    use scale_grid_index, only: IHALO, JHALO
+    integer, intent(in) :: device, nobs, nensobs
+    integer(c_int32_t), intent(in), target :: elm(nobs), typ(nobs)
+    real(c_double), intent(in), target :: ri(nobs), rj(nobs), lev(nobs), dat(nobs), err(nobs), val(nobs)
+    real(c_double), intent(in), target :: ensval(nensobs, nobs)
+    type(letkf_b200_config) :: cfg
+    type(letkf_b200_obs) :: o
+    integer :: n
+
+    call c_config_defaults(cfg)
+    cfg%MEMBER = MEMBER
+    cfg%DET_RUN = merge(1, 0, DET_RUN)
+    cfg%nlon = nlon;  cfg%nlat = nlat;  cfg%nlev = nlev      ! this rank's sorting mesh (PRC subdomain)
+    cfg%nv3d = nv3d;  cfg%nv2d = nv2d
+    cfg%IHALO = IHALO; cfg%JHALO = JHALO
+    cfg%DX = DX; cfg%DY = DY
+    cfg%iv3d_p = iv3d_p; cfg%iv3d_q = iv3d_q; cfg%iv3d_qg = iv3d_qg
+    cfg%INFL_MUL = INFL_MUL; cfg%INFL_MUL_MIN = INFL_MUL_MIN
+    cfg%INFL_MUL_ADAPTIVE = merge(1, 0, INFL_MUL_ADAPTIVE)
+    cfg%RELAX_TO_INFLATED_PRIOR = merge(1, 0, RELAX_TO_INFLATED_PRIOR)
+    cfg%RELAX_ALPHA = RELAX_ALPHA; cfg%RELAX_ALPHA_SPREAD = RELAX_ALPHA_SPREAD
+    cfg%Q_UPDATE_TOP = Q_UPDATE_TOP; cfg%Q_SPRD_MAX = Q_SPRD_MAX
+    cfg%BOUNDARY_BUFFER_WIDTH = BOUNDARY_BUFFER_WIDTH
+    cfg%HORI_LOCAL = HORI_LOCAL; cfg%VERT_LOCAL = VERT_LOCAL
+    cfg%HORI_LOCAL_RADAR_OBSNOREF = HORI_LOCAL_RADAR_OBSNOREF
+    cfg%HORI_LOCAL_RADAR_VR = HORI_LOCAL_RADAR_VR
+    cfg%VERT_LOCAL_RADAR_VR = VERT_LOCAL_RADAR_VR
+    cfg%VERT_LOCAL_RAIN_BASE = VERT_LOCAL_RAIN_BASE
+    cfg%MAX_NOBS_PER_GRID = MAX_NOBS_PER_GRID
+    cfg%MAX_NOBS_PER_GRID_CRITERION = MAX_NOBS_PER_GRID_CRITERION
+    cfg%OBS_MIN_SPACING = OBS_MIN_SPACING
+    cfg%OBS_SORT_GRID_SPACING = OBS_SORT_GRID_SPACING
+    do n = 1, nv3d + nv2d       ! var_local(n, iv), letkf_tools.f90:130-141
+      cfg%VAR_LOCAL(n, 1) = VAR_LOCAL_UV(n)
+      cfg%VAR_LOCAL(n, 2) = VAR_LOCAL_T(n)
+      cfg%VAR_LOCAL(n, 3) = VAR_LOCAL_Q(n)
+      cfg%VAR_LOCAL(n, 4) = VAR_LOCAL_PS(n)
+      cfg%VAR_LOCAL(n, 5) = VAR_LOCAL_RAIN(n)
+      cfg%VAR_LOCAL(n, 6) = VAR_LOCAL_TC(n)
+      cfg%VAR_LOCAL(n, 7) = VAR_LOCAL_RADAR_REF(n)
+      cfg%VAR_LOCAL(n, 8) = VAR_LOCAL_RADAR_VR(n)
+      cfg%VAR_LOCAL(n, 9) = VAR_LOCAL_H08(n)
+    end do
+    cfg%RADAR_ZMAX = RADAR_ZMAX
+    ! default-REAL literals widened to double by the compiler that built the host program:
+    ! carried as data so that the cut-off tests are bit-identical (letkf_obs.f90:27-28)
+    cfg%dist_zero_fac = dist_zero_fac
+    cfg%dist_zero_fac_square = dist_zero_fac_square
+    call c_config_resolve(cfg)
+
+    if (c_associated(handle)) call check(c_destroy(handle), 'destroy')
+    call check(c_create(cfg, int(device, c_int), handle), 'create')
+    call check(c_set_grid(handle, int(nij1, c_int), rig1, rjg1, hgt1, LETKF_B200_MEM_HOST), 'set_grid')
+    o%nobs = nobs; o%nensobs = nensobs
+    o%elm = c_loc(elm); o%typ = c_loc(typ)
+    o%ri = c_loc(ri); o%rj = c_loc(rj); o%lev = c_loc(lev); o%dat = c_loc(dat)
+    o%err = c_loc(err); o%val = c_loc(val); o%ensval = c_loc(ensval)
+    call check(c_set_obs(handle, o), 'set_obs')
+  end subroutine letkf_b200_setup
+
+  subroutine letkf_b200_finalize()
+    if (c_associated(handle)) call check(c_destroy(handle), 'destroy')
+    handle = c_null_ptr
+  end subroutine
+
+  !-----------------------------------------------------------------------------
+  ! Drop-in for das_letkf (letkf_tools.f90:50): same arguments, same INTENTs
+  ! (gues3d/gues2d are destroyed: perturbations in slots 1..MEMBER, mean in mmean).
+  !-----------------------------------------------------------------------------
+  subroutine das_letkf_b200(gues3d, gues2d, anal3d, anal2d)
+    use common_scale, only: nlev, nv3d, nv2d
+    use common_mpi_scale, only: nij1, nens
+    real(c_double), intent(inout), target :: gues3d(nij1, nlev, nens, nv3d)
+    real(c_double), intent(inout), target :: gues2d(nij1, nens, nv2d)
+    real(c_double), intent(out), target :: anal3d(nij1, nlev, nens, nv3d)
+    real(c_double), intent(out), target :: anal2d(nij1, nens, nv2d)
+    type(letkf_b200_das_args) :: a
+    a%gues3d = c_loc(gues3d); a%anal3d = c_loc(anal3d)
+    a%gues2d = c_null_ptr;    a%anal2d = c_null_ptr
+    if (nv2d > 0) then
+      a%gues2d = c_loc(gues2d); a%anal2d = c_loc(anal2d)
+    end if
+    a%infl3d = c_null_ptr; a%rtps_infl_out = c_null_ptr; a%nobsl_out = c_null_ptr; a%logp = c_null_ptr
+    a%mem_space = LETKF_B200_MEM_HOST
+    a%reserved = 0
+    call check(c_das_letkf(handle, a), 'das_letkf')   ! the reference STOPs on eigensolver failure
+  end subroutine das_letkf_b200
+
+  !-----------------------------------------------------------------------------
+  ! Drop-in for letkf_core (common_letkf.f90:52): one point per call (npts = 1).
+  ! Callers that can batch points should call letkf_b200_core_batch directly.
+  !-----------------------------------------------------------------------------
+  subroutine letkf_core_b200(ne, nobs, nobsl, hdxb, rdiag, rloc, dep, parm_infl, trans, transm, pao, &
+                             rdiag_wloc, infl_update, depd, transmd)
+    integer, intent(in) :: ne, nobs, nobsl
+    real(c_double), intent(in) :: hdxb(nobs, ne), rdiag(nobs), rloc(nobs), dep(nobs)
+    real(c_double), intent(inout) :: parm_infl
+    real(c_double), intent(out) :: trans(ne, ne)
+    real(c_double), intent(out), optional, target :: transm(ne), pao(ne, ne)
+    logical, intent(in), optional :: rdiag_wloc, infl_update
+    real(c_double), intent(in), optional, target :: depd(nobs)
+    real(c_double), intent(out), optional, target :: transmd(ne)
+    integer(c_int32_t) :: nl(1)
+    real(c_double) :: infl(1)
+    integer(c_int) :: wl, iu
+    type(c_ptr) :: p_transm, p_pao, p_depd, p_transmd
+    nl(1) = nobsl; infl(1) = parm_infl
+    wl = 0; iu = 0
+    if (present(rdiag_wloc)) wl = merge(1, 0, rdiag_wloc)
+    if (present(infl_update)) iu = merge(1, 0, infl_update)
+    p_transm = c_null_ptr; p_pao = c_null_ptr; p_depd = c_null_ptr; p_transmd = c_null_ptr
+    if (present(transm)) p_transm = c_loc(transm)
+    if (present(pao)) p_pao = c_loc(pao)
+    if (present(depd) .and. present(transmd)) then    ! common_letkf.f90:196
+      p_depd = c_loc(depd); p_transmd = c_loc(transmd)
+    end if
+    call check(c_core_batch(handle, int(ne, c_int), int(nobs, c_int), 1_c_int, nl, hdxb, rdiag, rloc, dep, &
+                            infl, trans, p_transm, p_pao, wl, iu, p_depd, p_transmd, LETKF_B200_MEM_HOST), &
+               'letkf_core')
+    parm_infl = infl(1)
+  end subroutine letkf_core_b200
+
+  !-----------------------------------------------------------------------------
+  ! Pack / unpack halves of scatter_grd_mpi_alltoall / gather_grd_mpi_alltoall
+  ! (common_mpi_scale.f90:1279-1396) on DEVICE buffers; the exchange between them
+  ! is the caller's all-to-all (NCCL send/recv group, or CUDA-aware MPI_ALLTOALLV on
+  ! the same device pointers with the counts of set_alltoall_counts).
+  !-----------------------------------------------------------------------------
+  subroutine scatter_grd_b200_pack(np, d_v3dg, d_v2dg, d_bufs)
+    integer, intent(in) :: np
+    type(c_ptr), intent(in) :: d_v3dg, d_v2dg, d_bufs
+    call check(c_grd_to_buf(handle, int(np, c_int), d_v3dg, d_v2dg, d_bufs), 'grd_to_buf')
+  end subroutine
+  subroutine gather_grd_b200_unpack(np, d_bufr, d_v3dg, d_v2dg)
+    integer, intent(in) :: np
+    type(c_ptr), intent(in) :: d_bufr, d_v3dg, d_v2dg
+    call check(c_buf_to_grd(handle, int(np, c_int), d_bufr, d_v3dg, d_v2dg), 'buf_to_grd')
+  end subroutine
+
+  subroutine check(status, what)
+    integer(c_int), intent(in) :: status
+    character(len=*), intent(in) :: what
+    character(kind=c_char), pointer :: msg(:)
+    integer :: i
+    if (status == LETKF_B200_OK) return
+    write (6, '(3A,I4)') '[Error] letkf_b200 ', what, ' failed, status ', status
+    if (c_associated(handle)) then
+      call c_f_pointer(c_last_error(handle), msg, [256])
+      do i = 1, 256
+        if (msg(i) == c_null_char) exit
+        write (6, '(A)', advance='no') msg(i)
+      end do
+      write (6, *)
+    end if
+    stop 2        ! the reference's convention (common_mtx.f90:61-64)
+  end subroutine check
+
+end module letkf_b200_iface
