@@ -213,6 +213,10 @@ int letkf_b200_buf_to_grd(letkf_b200_handle *h, int np, const double *bufr, doub
 int letkf_b200_nij1(const letkf_b200_handle *h, int np, int myrank_e, int32_t *nij1,
                     int32_t *nij1max);
 
+/* sizeof() of the four public structs, in declaration order (config, ctype_info, obs, das_args):
+ * lets a foreign-language binding (ctypes, ISO_C_BINDING) check its mirror of the layouts */
+void letkf_b200_abi_sizes(int32_t sizes[4]);
+
 /* library build info (arch string, e.g. "sm_100a") */
 const char *letkf_b200_build_info(void);
 

@@ -117,6 +117,7 @@ PROTOTYPES = {
     "letkf_b200_ens_to_buf": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "letkf_b200_buf_to_grd": (_i, [_vp, _i, _vp, _vp, _vp]),
     "letkf_b200_nij1": (_i, [_vp, _i, _i, _ip, _ip]),
+    "letkf_b200_abi_sizes": (None, [C.POINTER(C.c_int32 * 4)]),
     "letkf_b200_build_info": (C.c_char_p, []),
 }
 

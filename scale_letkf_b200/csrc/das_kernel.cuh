@@ -51,8 +51,11 @@ struct DasParams {
   int *l_iob;
   double *l_rdiag, *l_rloc;
   int lcap;
+  double *l_cnd;          // [grid][ccap] candidate buffers of the obs-number-limited search
+  unsigned *l_cpk;
+  int ccap;
   unsigned long long *counters;   // [0] work, [1] npoints, [2] nsolved, [3] nfail, [4] nobsl_sum, [5] overflow, [6] Jacobi sweeps, [8..15] phase clocks
-  long long npoints_total;
+  long long point_begin, point_end;   // (ij, ilev) points [begin, end) of this launch, ilev-major
   int max_sweeps;
 };
 
@@ -128,6 +131,9 @@ das_kernel(const DasParams P) {
   L.iob = P.l_iob + (size_t)blockIdx.x * P.lcap;
   L.rdiag = P.l_rdiag + (size_t)blockIdx.x * P.lcap;
   L.rloc = P.l_rloc + (size_t)blockIdx.x * P.lcap;
+  L.ccap = P.ccap;
+  L.cnd = P.l_cnd + (size_t)blockIdx.x * P.ccap;
+  L.cpk = P.l_cpk + (size_t)blockIdx.x * P.ccap;
 
   const size_t sl = (size_t)P.nij1 * P.nlev;
   const int ntiles = ((k + 3) / 4) * ((k + 3) / 4 + 1) / 2;
@@ -146,10 +152,10 @@ das_kernel(const DasParams P) {
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_work = (long long)atomicAdd(&P.counters[0], 1ull);
+    if (tid == 0) s_work = P.point_begin + (long long)atomicAdd(&P.counters[0], 1ull);
     __syncthreads();
     const long long wp = s_work;
-    if (wp >= P.npoints_total) break;
+    if (wp >= P.point_end) break;
     phase(7);
     const int il = (int)(wp / P.nij1), ij = (int)(wp - (long long)il * P.nij1);
     ++c_points;
@@ -505,6 +511,9 @@ struct SearchParams {
   int *l_iob;
   double *l_rdiag, *l_rloc;
   int lcap;
+  double *l_cnd;
+  unsigned *l_cpk;
+  int ccap;
   unsigned long long *counters;
 };
 
@@ -516,6 +525,9 @@ __global__ void __launch_bounds__(128) search_kernel(const SearchParams P) {
   L.iob = P.l_iob + (size_t)blockIdx.x * P.lcap;
   L.rdiag = P.l_rdiag + (size_t)blockIdx.x * P.lcap;
   L.rloc = P.l_rloc + (size_t)blockIdx.x * P.lcap;
+  L.ccap = P.ccap;
+  L.cnd = P.l_cnd + (size_t)blockIdx.x * P.ccap;
+  L.cpk = P.l_cpk + (size_t)blockIdx.x * P.ccap;
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) s_work = (int)atomicAdd(&P.counters[0], 1ull);

@@ -43,7 +43,8 @@ das_ns_kernel(const DasParams P) {
   constexpr int KP = C::KP, LD = C::LD, H = C::H, CR = C::CR, PSZ = C::PSZ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = P.k, nens = P.nens;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int w = __shfl_sync(LETKF_FULL_MASK, tid >> 5, 0);   // warp-uniform: tile addressing on the uniform datapath
   double *Yp = reinterpret_cast<double *>(smem_raw);
   double *Zp = Yp + PSZ;
   double *Tp = Zp + PSZ;
@@ -62,6 +63,9 @@ das_ns_kernel(const DasParams P) {
   L.iob = P.l_iob + (size_t)blockIdx.x * P.lcap;
   L.rdiag = P.l_rdiag + (size_t)blockIdx.x * P.lcap;
   L.rloc = P.l_rloc + (size_t)blockIdx.x * P.lcap;
+  L.ccap = P.ccap;
+  L.cnd = P.l_cnd + (size_t)blockIdx.x * P.ccap;
+  L.cpk = P.l_cpk + (size_t)blockIdx.x * P.ccap;
 
   const size_t sl = (size_t)P.nij1 * P.nlev;
   unsigned long long c_points = 0, c_solved = 0, c_fail = 0, c_nobs = 0, c_over = 0, c_iters = 0;
@@ -79,10 +83,10 @@ das_ns_kernel(const DasParams P) {
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_work = (long long)atomicAdd(&P.counters[0], 1ull);
+    if (tid == 0) s_work = P.point_begin + (long long)atomicAdd(&P.counters[0], 1ull);
     __syncthreads();
     const long long wp = s_work;
-    if (wp >= P.npoints_total) break;
+    if (wp >= P.point_end) break;
     phase(7);
     const int il = (int)(wp / P.nij1), ij = (int)(wp - (long long)il * P.nij1);
     ++c_points;

@@ -110,13 +110,19 @@ struct letkf_b200_handle {
   DevBuf<double> vlfac_groups, vlfac_one;
   // scratch
   DevBuf<int> l_iob;
-  DevBuf<double> l_rdiag, l_rloc;
+  DevBuf<double> l_rdiag, l_rloc, l_cnd;
+  DevBuf<unsigned> l_cpk;
+  int ccap = 1;   // candidate-buffer entries per CTA (obs-number-limited search)
   DevBuf<unsigned long long> counters;
   DevBuf<double> st_gues, st_anal, st_gues2, st_anal2, st_infl, st_rtps, st_logp;
   DevBuf<int> st_nobsl;
   DevBuf<double> cb[10];
   DevBuf<int> cb_i;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // host-buffer pipeline of das_letkf: level chunks flow H2D -> analysis -> D2H on three streams
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_k0, ev_k1;
+  std::vector<std::pair<void *, size_t>> pinned;   // caller buffers page-locked by ensure_pinned
   // stats of the last das call
   long long st_points = 0, st_solved = 0, st_fail = 0, st_nobs = 0, st_sweeps = 0;
   long long st_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -174,52 +180,87 @@ void setup_var_groups(letkf_b200_handle *h) {
   }
 }
 
-template <int KC>
-int launch_das(letkf_b200_handle *h, DasParams &P) {
-  using SC = SizeClass<KC>;
-  const size_t smem = das_smem_bytes(P.k, SC::NT);
-  CK(cudaFuncSetAttribute(das_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, das_kernel<KC>, SC::NT, smem));
-  if (occ < 1) return fail(h, LETKF_B200_EINVAL, "das_kernel does not fit on an SM");
-  long long grid = (long long)occ * h->num_sms;
-  grid = std::min<long long>(grid, std::max<long long>(P.npoints_total, 1));
-  CK(h->l_iob.ensure((size_t)grid * P.lcap));
-  CK(h->l_rdiag.ensure((size_t)grid * P.lcap));
-  CK(h->l_rloc.ensure((size_t)grid * P.lcap));
+// One analysis launch configuration: kernel, block size, dynamic shared memory, resident grid.
+struct DasLaunch {
+  void (*kern)(DasParams) = nullptr;
+  int nt = 0;
+  size_t smem = 0;
+  long long grid = 0;
+};
+
+int plan_common(letkf_b200_handle *h, DasParams &P, DasLaunch &L, int occ, const char *what) {
+  if (occ < 1) return fail(h, LETKF_B200_EINVAL, what);
+  L.grid = (long long)occ * h->num_sms;   // persistent CTAs: one resident set per SM
+  CK(h->l_iob.ensure((size_t)L.grid * P.lcap));
+  CK(h->l_rdiag.ensure((size_t)L.grid * P.lcap));
+  CK(h->l_rloc.ensure((size_t)L.grid * P.lcap));
+  CK(h->l_cnd.ensure((size_t)L.grid * h->ccap));
+  CK(h->l_cpk.ensure((size_t)L.grid * h->ccap));
   P.l_iob = h->l_iob.p;
   P.l_rdiag = h->l_rdiag.p;
   P.l_rloc = h->l_rloc.p;
-  CK(cudaEventRecord(h->ev0, h->stream));
-  das_kernel<KC><<<(unsigned)grid, SC::NT, smem, h->stream>>>(P);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(h->ev1, h->stream));
-  h->last_launches = 1;
+  P.l_cnd = h->l_cnd.p;
+  P.l_cpk = h->l_cpk.p;
+  P.ccap = h->ccap;
   return LETKF_B200_OK;
 }
 
-template <int NB>
-int launch_das_ns(letkf_b200_handle *h, DasParams &P) {
-  using C = NsCfg<NB>;
-  const size_t smem = das_ns_smem_bytes<NB>();
-  CK(cudaFuncSetAttribute(das_ns_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int KC>
+int plan_das(letkf_b200_handle *h, DasParams &P, DasLaunch &L) {
+  using SC = SizeClass<KC>;
+  L.kern = das_kernel<KC>;
+  L.nt = SC::NT;
+  L.smem = das_smem_bytes(P.k, SC::NT);
+  CK(cudaFuncSetAttribute(das_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, das_ns_kernel<NB>, C::NT, smem));
-  if (occ < 1) return fail(h, LETKF_B200_EINVAL, "das_ns_kernel does not fit on an SM");
-  long long grid = (long long)occ * h->num_sms;
-  grid = std::min<long long>(grid, std::max<long long>(P.npoints_total, 1));
-  CK(h->l_iob.ensure((size_t)grid * P.lcap));
-  CK(h->l_rdiag.ensure((size_t)grid * P.lcap));
-  CK(h->l_rloc.ensure((size_t)grid * P.lcap));
-  P.l_iob = h->l_iob.p;
-  P.l_rdiag = h->l_rdiag.p;
-  P.l_rloc = h->l_rloc.p;
-  CK(cudaEventRecord(h->ev0, h->stream));
-  das_ns_kernel<NB><<<(unsigned)grid, C::NT, smem, h->stream>>>(P);
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, das_kernel<KC>, SC::NT, L.smem));
+  return plan_common(h, P, L, occ, "das_kernel does not fit on an SM");
+}
+
+template <int NB>
+int plan_das_ns(letkf_b200_handle *h, DasParams &P, DasLaunch &L) {
+  using C = NsCfg<NB>;
+  L.kern = das_ns_kernel<NB>;
+  L.nt = C::NT;
+  L.smem = das_ns_smem_bytes<NB>();
+  CK(cudaFuncSetAttribute(das_ns_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, das_ns_kernel<NB>, C::NT, L.smem));
+  return plan_common(h, P, L, occ, "das_ns_kernel does not fit on an SM");
+}
+
+// analyse points [begin, end) on the handle's compute stream, bracketed by the two events
+int launch_range(letkf_b200_handle *h, const DasLaunch &L, DasParams P, long long begin, long long end,
+                 cudaEvent_t e0, cudaEvent_t e1) {
+  P.point_begin = begin;
+  P.point_end = end;
+  const long long grid = std::min<long long>(L.grid, std::max<long long>(end - begin, 1));
+  CK(cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long), h->stream));   // work counter
+  CK(cudaEventRecord(e0, h->stream));
+  L.kern<<<(unsigned)grid, L.nt, L.smem, h->stream>>>(P);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(h->ev1, h->stream));
-  h->last_launches = 1;
+  CK(cudaEventRecord(e1, h->stream));
   return LETKF_B200_OK;
+}
+
+// Page-lock a caller-owned host buffer once (cached per handle) so that the chunked copies of
+// das_letkf overlap with the analysis kernels.  LETKF_B200_PIN=0 leaves pageable memory alone.
+void ensure_pinned(letkf_b200_handle *h, void *p, size_t bytes) {
+  if (!p || bytes == 0) return;
+  const char *pin = std::getenv("LETKF_B200_PIN");
+  if (pin && pin[0] == '0') return;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return; }
+  if (at.type != cudaMemoryTypeUnregistered) return;
+  for (auto it = h->pinned.begin(); it != h->pinned.end();) {   // stale registration of a moved buffer
+    char *q = (char *)it->first;
+    if ((char *)p < q + it->second && q < (char *)p + bytes) {
+      cudaHostUnregister(it->first);
+      it = h->pinned.erase(it);
+    } else ++it;
+  }
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) h->pinned.emplace_back(p, bytes);
+  else cudaGetLastError();
 }
 
 template <int KC>
@@ -241,6 +282,13 @@ int launch_core(letkf_b200_handle *h, CoreParams &P) {
 extern "C" {
 
 const char *letkf_b200_build_info(void) { return "libletkf_b200 sm_100a fp64 (CUDA " __DATE__ ")"; }
+
+void letkf_b200_abi_sizes(int32_t sizes[4]) {
+  sizes[0] = (int32_t)sizeof(letkf_b200_config);
+  sizes[1] = (int32_t)sizeof(letkf_b200_ctype_info);
+  sizes[2] = (int32_t)sizeof(letkf_b200_obs);
+  sizes[3] = (int32_t)sizeof(letkf_b200_das_args);
+}
 
 void letkf_b200_config_defaults(letkf_b200_config *c) {
   // scale/common/common_nml.f90 defaults (:40-46, :109-142, :160-229, :264)
@@ -327,6 +375,8 @@ int letkf_b200_create(const letkf_b200_config *cfg, int device, letkf_b200_handl
   h->num_sms = prop.multiProcessorCount;
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
+  cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
   if (h->counters.ensure(16) != cudaSuccess) {
     delete h;
     return LETKF_B200_ECUDA;
@@ -342,13 +392,19 @@ int letkf_b200_destroy(letkf_b200_handle *h) {
   h->rig1.release(); h->rjg1.release(); h->hgt1.release();
   h->d_tables.release(); h->rec.release(); h->bstart.release(); h->s2o.release();
   h->sval.release(); h->sens.release(); h->vlfac_groups.release(); h->vlfac_one.release();
-  h->l_iob.release(); h->l_rdiag.release(); h->l_rloc.release(); h->counters.release();
+  h->l_iob.release(); h->l_rdiag.release(); h->l_rloc.release(); h->l_cnd.release(); h->l_cpk.release(); h->counters.release();
   h->st_gues.release(); h->st_anal.release(); h->st_gues2.release(); h->st_anal2.release();
   h->st_infl.release(); h->st_rtps.release(); h->st_logp.release(); h->st_nobsl.release();
   for (auto &b : h->cb) b.release();
   h->cb_i.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (auto *v : {&h->ev_in, &h->ev_k0, &h->ev_k1})
+    for (cudaEvent_t e : *v) cudaEventDestroy(e);
+  if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+  if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+  for (auto &pr : h->pinned) cudaHostUnregister(pr.first);
+  cudaGetLastError();
   delete h;
   return LETKF_B200_OK;
 }
@@ -384,6 +440,7 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
   const int nobs = obs->nobs;
   const int need = c.DET_RUN ? c.MEMBER + 1 : c.MEMBER;
   if (nobs > 0 && obs->nensobs < need) return fail(h, LETKF_B200_EINVAL, "nensobs < MEMBER (+1 with DET_RUN)");
+  if (nobs >= (1 << 28)) return fail(h, LETKF_B200_EINVAL, "more than 2^28 observations");
   h->obs_set = false;
   // ---- ctype table (letkf_obs.f90:300-342) --------------------------------------------------
   bool use[LETKF_B200_NID_OBS][LETKF_B200_NOBTYPE];
@@ -437,6 +494,13 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
       else if (elm == ID_RAIN) { d.vmode = 2; d.vconst = std::log(c.VERT_LOCAL_RAIN_BASE); }
       else if (ityp == 22) d.vmode = 3;
       else d.vmode = 1;
+      {
+        const double guard = 1.0 + 9.094947017729282e-13;   // 1 + 2^-40
+        d.vmax = c.dist_zero_fac * std::fabs(d.vert_loc) * guard;
+        d.hmax2 = (c.dist_zero_fac * d.hori_loc) * (c.dist_zero_fac * d.hori_loc) * guard;
+        d.ih2 = 1.0 / (d.hori_loc * d.hori_loc);
+        d.iv2 = (d.vmode == 0) ? 0.0 : 1.0 / (d.vert_loc * d.vert_loc);
+      }
       info.elm = elm; info.elm_u = ielm_u; info.typ = ityp;
       info.ngrd_i = d.ngrd_i; info.ngrd_j = d.ngrd_j; info.ngrdsch_i = d.ngrdsch_i; info.ngrdsch_j = d.ngrdsch_j;
       info.ngrdext_i = d.ngrdext_i; info.ngrdext_j = d.ngrdext_j;
@@ -541,6 +605,16 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
   }
   for (int ic = 0; ic < nct; ++ic) h->ctinfo[ic].n_merge = n_merge[ic];
   h->maxl = std::max(maxl, 1);
+  {   // Candidate buffer entries per CTA.  Slices are laid out by candidate position (search.cuh), so the
+      // buffer must span the candidates of one search rectangle although only the survivors are
+      // written: 32 K entries cover a radar rectangle of ~3 search increments; pages never touched cost
+      // nothing.  Without an obs-number limit the scan is windowed and 4 K entries are plenty.
+    int nmax = 0;
+    for (int g = 0; g < T.ngroup; ++g) nmax = std::max(nmax, T.grp[g].limit);
+    h->ccap = nmax > 0 ? 32768 : 4096;
+    const char *ce = std::getenv("LETKF_B200_CAND_CAP");   // test hook: force the re-scan fallback
+    T.cand_cap_limit = ce ? std::max(0, std::atoi(ce)) : h->ccap;
+  }
   h->radar_only = true;   // letkf_tools.f90:197-203
   for (int ic = 0; ic < nct; ++ic)
     if (T.ct[ic].typ != 22) h->radar_only = false;
@@ -624,6 +698,9 @@ int letkf_b200_obs_local(letkf_b200_handle *h, int npts, const double *ri, const
   CK(h->l_iob.ensure((size_t)grid * h->maxl));
   CK(h->l_rdiag.ensure((size_t)grid * h->maxl));
   CK(h->l_rloc.ensure((size_t)grid * h->maxl));
+  CK(h->l_cnd.ensure((size_t)grid * h->ccap));
+  CK(h->l_cpk.ensure((size_t)grid * h->ccap));
+  P.l_cnd = h->l_cnd.p; P.l_cpk = h->l_cpk.p; P.ccap = h->ccap;
   CK(cudaMemsetAsync(h->counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
   P.T = h->d_tables.p; P.rec = h->rec.p; P.bstart = h->bstart.p; P.vlfac = h->vlfac_one.p;
   P.npts = npts; P.max_out = max_out;
@@ -660,31 +737,33 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   const size_t sl = (size_t)h->nij1 * c.nlev;
   const size_t n3 = sl * nens * c.nv3d, n2 = (size_t)h->nij1 * nens * c.nv2d, nf = sl * c.nv3d;
   const bool host = a->mem_space != LETKF_B200_MEM_DEVICE;
+  const bool back = !(a->reserved & 1);   // hand the destroyed gues (perturbations, mean) back to the host
   DasParams P;
   std::memset(&P, 0, sizeof(P));
   if (host) {
     CK(h->st_gues.ensure(n3));
     CK(h->st_anal.ensure(n3));
-    CK(cudaMemcpyAsync(h->st_gues.p, a->gues3d, sizeof(double) * n3, cudaMemcpyHostToDevice, h->stream));
     P.gues3d = h->st_gues.p;
     P.anal3d = h->st_anal.p;
+    ensure_pinned(h, a->gues3d, sizeof(double) * n3);
+    ensure_pinned(h, a->anal3d, sizeof(double) * n3);
     if (c.nv2d > 0) {
       CK(h->st_gues2.ensure(n2));
       CK(h->st_anal2.ensure(n2));
-      CK(cudaMemcpyAsync(h->st_gues2.p, a->gues2d, sizeof(double) * n2, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(h->st_gues2.p, a->gues2d, sizeof(double) * n2, cudaMemcpyHostToDevice, h->s_h2d));
       P.gues2d = h->st_gues2.p;
       P.anal2d = h->st_anal2.p;
     }
     if (a->infl3d) {
       CK(h->st_infl.ensure(nf));
-      if (c.INFL_MUL <= 0.0) CK(cudaMemcpyAsync(h->st_infl.p, a->infl3d, sizeof(double) * nf, cudaMemcpyHostToDevice, h->stream));
+      if (c.INFL_MUL <= 0.0) CK(cudaMemcpyAsync(h->st_infl.p, a->infl3d, sizeof(double) * nf, cudaMemcpyHostToDevice, h->s_h2d));
       P.infl3d = h->st_infl.p;
     }
     if (a->rtps_infl_out) { CK(h->st_rtps.ensure(nf)); P.rtps_out = h->st_rtps.p; }
     if (a->nobsl_out) { CK(h->st_nobsl.ensure(sl)); P.nobsl_out = h->st_nobsl.p; }
     if (a->logp) {
       CK(h->st_logp.ensure(sl));
-      CK(cudaMemcpyAsync(h->st_logp.p, a->logp, sizeof(double) * sl, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(h->st_logp.p, a->logp, sizeof(double) * sl, cudaMemcpyHostToDevice, h->s_h2d));
       P.logp = h->st_logp.p;
     }
   } else {
@@ -714,47 +793,90 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   P.IHALO = c.IHALO; P.JHALO = c.JHALO; P.nlon = c.nlon; P.nlat = c.nlat;
   P.lcap = h->maxl;
   P.counters = h->counters.p;
-  P.npoints_total = (long long)sl;
   P.max_sweeps = 30;
   CK(cudaMemsetAsync(h->counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
   int r;
+  DasLaunch L;
   // MEMBER <= 102: tensor-core Newton-Schulz solve (das_ns_kernel.cuh); larger ensembles (two k x k
   // matrices no longer fit in shared memory) and LETKF_B200_SOLVER=jacobi: Cholesky + one-sided Jacobi.
   const char *sv = std::getenv("LETKF_B200_SOLVER");
   const int nsc = ns_class(k);
   const bool jacobi = (sv && std::strcmp(sv, "jacobi") == 0) || nsc == 0;
   if (!jacobi) {
-    if (nsc == 3) r = launch_das_ns<3>(h, P);
-    else if (nsc == 5) r = launch_das_ns<5>(h, P);
-    else if (nsc == 7) r = launch_das_ns<7>(h, P);
-    else if (nsc == 9) r = launch_das_ns<9>(h, P);
-    else r = launch_das_ns<13>(h, P);
+    if (nsc == 3) r = plan_das_ns<3>(h, P, L);
+    else if (nsc == 5) r = plan_das_ns<5>(h, P, L);
+    else if (nsc == 7) r = plan_das_ns<7>(h, P, L);
+    else if (nsc == 9) r = plan_das_ns<9>(h, P, L);
+    else r = plan_das_ns<13>(h, P, L);
   } else
-  if (k <= 20) r = launch_das<20>(h, P);
-  else if (k <= 52) r = launch_das<52>(h, P);
-  else if (k <= 64) r = launch_das<64>(h, P);
-  else if (k <= 100) r = launch_das<100>(h, P);
-  else r = launch_das<128>(h, P);
+  if (k <= 20) r = plan_das<20>(h, P, L);
+  else if (k <= 52) r = plan_das<52>(h, P, L);
+  else if (k <= 64) r = plan_das<64>(h, P, L);
+  else if (k <= 100) r = plan_das<100>(h, P, L);
+  else r = plan_das<128>(h, P, L);
   if (r != LETKF_B200_OK) return r;
+
+  // Level chunks.  Device-resident state: one launch.  Host state: ~10 chunks pipelined over three
+  // streams -- H2D of chunk c+1 and D2H of chunk c-1 overlap the analysis of chunk c (PCIe is full
+  // duplex), so the call costs max(copy, compute) instead of their sum.
+  int nchunk = 1;
   if (host) {
-    CK(cudaMemcpyAsync(a->anal3d, P.anal3d, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
-    // gues3d is INTENT(INOUT) "destroyed" in the reference; hand the perturbations back too so
-    // that callers relying on slots 1..k holding dX / slot k+1 the mean keep working.
-    if (!(a->reserved & 1))
-      CK(cudaMemcpyAsync(a->gues3d, P.gues3d, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
-    if (c.nv2d > 0) {
-      CK(cudaMemcpyAsync(a->anal2d, P.anal2d, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
-      if (!(a->reserved & 1))
-        CK(cudaMemcpyAsync(a->gues2d, P.gues2d, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
+    const char *ce = std::getenv("LETKF_B200_CHUNKS");
+    nchunk = ce ? std::atoi(ce) : 10;
+    nchunk = std::max(1, std::min(nchunk, c.nlev));
+  }
+  while ((int)h->ev_in.size() < nchunk) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_in.push_back(e);
+    CK(cudaEventCreate(&e)); h->ev_k0.push_back(e);
+    CK(cudaEventCreate(&e)); h->ev_k1.push_back(e);
+  }
+  const size_t pitch = sizeof(double) * sl;   // distance between (member, variable) planes
+  const size_t planes = (size_t)nens * c.nv3d;
+  auto lev0 = [&](int ch) { return (int)((long long)c.nlev * ch / nchunk); };
+  if (host) {
+    for (int ch = 0; ch < nchunk; ++ch) {
+      const int l0 = lev0(ch), l1 = lev0(ch + 1);
+      const size_t off = (size_t)l0 * h->nij1, w = sizeof(double) * (size_t)(l1 - l0) * h->nij1;
+      CK(cudaMemcpy2DAsync(P.gues3d + off, pitch, a->gues3d + off, pitch, w, planes, cudaMemcpyHostToDevice, h->s_h2d));
+      CK(cudaEventRecord(h->ev_in[ch], h->s_h2d));
     }
-    if (a->infl3d) CK(cudaMemcpyAsync(a->infl3d, P.infl3d, sizeof(double) * nf, cudaMemcpyDeviceToHost, h->stream));
-    if (a->rtps_infl_out) CK(cudaMemcpyAsync(a->rtps_infl_out, P.rtps_out, sizeof(double) * nf, cudaMemcpyDeviceToHost, h->stream));
-    if (a->nobsl_out) CK(cudaMemcpyAsync(a->nobsl_out, P.nobsl_out, sizeof(int) * sl, cudaMemcpyDeviceToHost, h->stream));
+  }
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const int l0 = lev0(ch), l1 = lev0(ch + 1);
+    if (host) CK(cudaStreamWaitEvent(h->stream, h->ev_in[ch], 0));
+    r = launch_range(h, L, P, (long long)l0 * h->nij1, (long long)l1 * h->nij1, h->ev_k0[ch], h->ev_k1[ch]);
+    if (r != LETKF_B200_OK) return r;
+    if (host) {
+      const size_t off = (size_t)l0 * h->nij1, w = sizeof(double) * (size_t)(l1 - l0) * h->nij1;
+      CK(cudaStreamWaitEvent(h->s_d2h, h->ev_k1[ch], 0));
+      CK(cudaMemcpy2DAsync(a->anal3d + off, pitch, P.anal3d + off, pitch, w, planes, cudaMemcpyDeviceToHost, h->s_d2h));
+      // gues3d is INTENT(INOUT) "destroyed" in the reference; hand the perturbations back too so
+      // that callers relying on slots 1..k holding dX / slot k+1 the mean keep working.
+      if (back)
+        CK(cudaMemcpy2DAsync(a->gues3d + off, pitch, P.gues3d + off, pitch, w, planes, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+  }
+  h->last_launches = nchunk;
+  if (host) {
+    if (c.nv2d > 0) {
+      CK(cudaMemcpyAsync(a->anal2d, P.anal2d, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->s_d2h));
+      if (back) CK(cudaMemcpyAsync(a->gues2d, P.gues2d, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    if (a->infl3d) CK(cudaMemcpyAsync(a->infl3d, P.infl3d, sizeof(double) * nf, cudaMemcpyDeviceToHost, h->s_d2h));
+    if (a->rtps_infl_out) CK(cudaMemcpyAsync(a->rtps_infl_out, P.rtps_out, sizeof(double) * nf, cudaMemcpyDeviceToHost, h->s_d2h));
+    if (a->nobsl_out) CK(cudaMemcpyAsync(a->nobsl_out, P.nobsl_out, sizeof(int) * sl, cudaMemcpyDeviceToHost, h->s_d2h));
   }
   unsigned long long cnt[16];
   CK(cudaMemcpyAsync(cnt, h->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  if (host) CK(cudaStreamSynchronize(h->s_d2h));
+  h->last_ms = 0.f;
+  for (int ch = 0; ch < nchunk; ++ch) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev_k0[ch], h->ev_k1[ch]));
+    h->last_ms += ms;
+  }
   h->st_sweeps = (long long)cnt[6];
   for (int i = 0; i < 8; ++i) h->st_phase[i] = (long long)cnt[8 + i];
   h->st_points = (long long)cnt[1];

@@ -38,6 +38,8 @@ struct NsCfg {
   static constexpr int CR = (PSZ / LD) & ~3;       // obs rows per staging chunk (two chunks fit in 2 PSZ)
   // resident CTAs per SM the register allocation is sized for
   static constexpr int MINB = NB_ <= 3 ? 8 : NB_ <= 5 ? 5 : NB_ <= 7 ? 3 : NB_ <= 9 ? 2 : 1;
+  // (registers: each of the 4 SM sub-partitions holds 16 K registers and ceil(NB MINB / 4) warps, which
+  // is what __launch_bounds__(NT, MINB) makes ptxas budget for -- 128 for NB = 13, 80 for NB = 7)
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -106,24 +108,73 @@ __device__ __forceinline__ void load_tile(const double *M, int bi, int bj, doubl
   }
 }
 
-// acc[d] (+)= sum_l X(w, l) W(l, jd)   for the warp's circulant tiles jd = (w + d) mod NB
+// Operand fragments of one l-step of the circulant half-GEMM: A = X(w, l) (both k-halves) and
+// B = W(l, jd) for the warp's H + 1 column blocks.
+template <int NB>
+struct SymmFrag {
+  double a[2];
+  double b[(NB + 1) / 2][2];
+};
+// Running tile offsets (in doubles) of the operands.  Packed tile (bi, bj), bi >= bj, sits at
+// (bi (bi + 1) / 2 + bj) * 64, so walking l = 0, 1, ... along block-row x of a symmetric matrix adds
+// 64 per step up to the diagonal (stored row x) and (l + 1) * 64 per step below it (stored column x):
+// one compare + select + add per operand and step instead of re-deriving the tile address.
+template <int NB>
+struct SymmWalk {
+  int ta, tb[(NB + 1) / 2], j[(NB + 1) / 2];
+};
+template <int NB>
+__device__ __forceinline__ void symm_load(SymmFrag<NB> &f, SymmWalk<NB> &K, const double *X, const double *W,
+                                          int w, int l, const LaneOfs &o) {
+  {
+    const bool col = l > w;   // below the diagonal of block-row w: stored column w, transposed pattern
+    const double *t = X + K.ta;
+    f.a[0] = t[col ? o.p2[0] : o.p1[0]];
+    f.a[1] = t[col ? o.p2[1] : o.p1[1]];
+    K.ta += (l < w) ? 64 : (l + 1) * 64;
+  }
+#pragma unroll
+  for (int d = 0; d <= (NB - 1) / 2; ++d) {
+    const bool col = l >= K.j[d];
+    const double *t = W + K.tb[d];
+    f.b[d][0] = t[col ? o.p2[0] : o.p1[0]];
+    f.b[d][1] = t[col ? o.p2[1] : o.p1[1]];
+    K.tb[d] += (l < K.j[d]) ? 64 : (l + 1) * 64;
+  }
+}
+template <int NB>
+__device__ __forceinline__ void symm_mma(double (&acc)[(NB + 1) / 2][2], const SymmFrag<NB> &f) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int d = 0; d <= (NB - 1) / 2; ++d) dmma884(acc[d][0], acc[d][1], f.a[h], f.b[d][h]);
+}
+
+// acc[d] (+)= sum_l X(w, l) W(l, jd)   for the warp's circulant tiles jd = (w + d) mod NB.
+// Register double buffering: the fragments of step l + 1 are in flight while the DMMAs of step l issue.
 template <int NB>
 __device__ __forceinline__ void symm_gemm(double (&acc)[(NB + 1) / 2][2], const double *X, const double *W,
                                           int w, const LaneOfs &o) {
   constexpr int H = (NB - 1) / 2;
-#pragma unroll 1
-  for (int l = 0; l < NB; ++l) {
+  SymmWalk<NB> K;
+  K.ta = (w * (w + 1) / 2) * 64;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const double a = afrag(X, w, l, h, o);
-#pragma unroll
-      for (int d = 0; d <= H; ++d) {
-        int j = w + d;
-        if (j >= NB) j -= NB;
-        dmma884(acc[d][0], acc[d][1], a, bfrag(W, l, j, h, o));
-      }
-    }
+  for (int d = 0; d <= H; ++d) {
+    int j = w + d;
+    if (j >= NB) j -= NB;
+    K.j[d] = j;
+    K.tb[d] = (j * (j + 1) / 2) * 64;
   }
+  SymmFrag<NB> f0, f1;
+  symm_load<NB>(f0, K, X, W, w, 0, o);
+#pragma unroll 1
+  for (int l = 0; l < NB - 1; l += 2) {   // NB is odd: pairs (l, l + 1), then the last step
+    symm_load<NB>(f1, K, X, W, w, l + 1, o);
+    symm_mma<NB>(acc, f0);
+    symm_load<NB>(f0, K, X, W, w, l + 2, o);
+    symm_mma<NB>(acc, f1);
+  }
+  symm_mma<NB>(acc, f0);
 }
 
 template <int NB>
@@ -172,7 +223,8 @@ template <int NB>
 __device__ __forceinline__ int newton_schulz_invsqrt(double *Yp, double *Zp, double *Tp, double c0s,
                                                      double *red, int max_iter) {
   constexpr int H = (NB - 1) / 2;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int w = __shfl_sync(LETKF_FULL_MASK, threadIdx.x >> 5, 0);
   const int r = lane >> 2, q = lane & 3;
   const LaneOfs o = lane_offsets(lane);
   double a = c0s, b = 1.0;   // eigenvalue bracket of M = Z Y

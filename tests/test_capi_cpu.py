@@ -27,6 +27,13 @@ def test_header_symbols_exported(lib):
     assert names == set(capi.PROTOTYPES), "capi.PROTOTYPES out of sync with the header"
 
 
+def test_struct_layouts_match_ctypes_mirror(lib):
+    sizes = (C.c_int32 * 4)()
+    lib.letkf_b200_abi_sizes(C.byref(sizes))
+    assert list(sizes) == [C.sizeof(capi.Config), C.sizeof(capi.CtypeInfo), C.sizeof(capi.Obs),
+                           C.sizeof(capi.DasArgs)]
+
+
 def test_defaults_match_python_mirror(lib):
     a = capi.Config()
     lib.letkf_b200_config_defaults(C.byref(a))

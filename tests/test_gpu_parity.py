@@ -128,6 +128,37 @@ def test_search_bitexact_limited(oracle, criterion):
     e.close()
 
 
+@pytest.mark.parametrize("criterion", [1, 3])
+def test_search_limited_rescan_fallback(oracle, criterion, monkeypatch):
+    """candidate buffer too small (forced): the storage-free re-scan select gives the same sets"""
+    monkeypatch.setenv("LETKF_B200_CAND_CAP", "8")
+    cfg, rig1, rjg1, hgt1, obs, gues = radar_case(max_nobs=30)
+    cfg.MAX_NOBS_PER_GRID_CRITERION = criterion
+    o, e = _engines(cfg, rig1, rjg1, hgt1, obs, oracle)
+    pts = sample_points(cfg, rig1, rjg1, hgt1, gues, stride=5)
+    n1, i1, d1, l1 = o.obs_local(*pts, 1, 4096)
+    n2, i2, d2, l2 = e.obs_local(*pts, 1, 4096)
+    assert np.array_equal(n1, n2)
+    for p in range(len(n1)):
+        assert np.array_equal(np.sort(i1[p, :n1[p]]), np.sort(i2[p, :n2[p]]))
+    e.close()
+
+
+def test_search_limited_ties_in_scan_order(oracle):
+    """duplicated observations (exactly equal keys): the N-th place is shared; ties go to scan order,
+    so the selected multiset of keys must still equal the oracle's N smallest"""
+    cfg, rig1, rjg1, hgt1, obs, gues = radar_case(max_nobs=30)
+    dup = {k: np.concatenate([v, v]) for k, v in obs.items()}
+    o, e = _engines(cfg, rig1, rjg1, hgt1, dup, oracle)
+    pts = sample_points(cfg, rig1, rjg1, hgt1, gues, stride=9)
+    n1, i1, d1, l1 = o.obs_local(*pts, 1, 4096)
+    n2, i2, d2, l2 = e.obs_local(*pts, 1, 4096)
+    assert np.array_equal(n1, n2)
+    for p in range(len(n1)):
+        assert np.allclose(np.sort(d1[p, :n1[p]]), np.sort(d2[p, :n2[p]]), rtol=1e-14, atol=0)
+    e.close()
+
+
 def _das_compare(cfg, rig1, rjg1, hgt1, obs, gues, oracle, infl3d=False, check_rtps=True):
     o, e = _engines(cfg, rig1, rjg1, hgt1, obs, oracle)
     k = cfg.MEMBER
