@@ -200,9 +200,19 @@ das_ns_kernel(const DasParams P) {
           double *wdst = wv + (c & 1) * CR;
           const int o0 = c * CR;
           const int nrows = min(CR, p_use - o0), nrows4 = (nrows + 3) & ~3;
-          for (int idx = tid; idx < nrows * (KP / 2); idx += blockDim.x) {
-            const int o = idx / (KP / 2), pc = idx - o * (KP / 2);
-            cp_async16(dst + (size_t)o * LD + 2 * pc, P.ensval + (size_t)L.iob[o0 + o] * P.ldens + 2 * pc);
+          // one warp per obs row (a row is KP/2 16-byte pieces, two rounds of lanes); the row indices
+          // of up to four rows are fetched first so that their latencies overlap
+          for (int ob = w; ob < nrows; ob += 4 * NB) {
+            int iobs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) iobs[u] = (ob + u * NB < nrows) ? L.iob[o0 + ob + u * NB] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (iobs[u] < 0) continue;
+              const double *src = P.ensval + (size_t)iobs[u] * P.ldens;
+              double *drow = dst + (size_t)(ob + u * NB) * LD;
+              for (int pc = lane; pc < KP / 2; pc += 32) cp_async16(drow + 2 * pc, src + 2 * pc);
+            }
           }
           for (int idx = tid; idx < (nrows4 - nrows) * KP; idx += blockDim.x)
             dst[(size_t)(nrows + idx / KP) * LD + idx % KP] = 0.0;

@@ -99,6 +99,9 @@ struct SearchSmem {
   unsigned char seg_slot[kSegMax];
   int wcnt[kMaxWarps];   // survivors per warp chunk (fill_window)
   int wsel[kMaxWarps];   // selected per warp chunk / ties per warp chunk
+  ScanList sl;           // the scan in progress (built by one thread per ctype, see build_scan_*)
+  Rect tr[kMaxScan];     // per-entry rectangle / validity before compaction into `sl`
+  int tv[kMaxScan];
 };
 
 __device__ __forceinline__ int obsgrd_index(double r, int halo, int ngrd, int nl, int nsch) {
@@ -310,13 +313,14 @@ __device__ __forceinline__ void fill_window(const SearchSmem &S, int nrows, int 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int beg = v0 + w * C, end = min(v1, beg + C);
   int cnt = 0;
+  int sg = (beg + lane < end) ? seg_find(S, nrows, beg + lane) : 0;
   for (int vb = beg; vb < end; vb += 32) {
     const int v = vb + lane;
     bool ok = false;
     double nd = 0.0;
     unsigned pk = 0u;
     if (v < end) {
-      const int sg = seg_find(S, nrows, v);
+      while (v >= S.seg_cum[sg + 1]) ++sg;   // v only grows: walk, do not search
       const int iob = S.seg_start[sg] + (v - S.seg_cum[sg]);
       const int slot = (int)S.seg_slot[sg];
       ok = eval(iob, slot, nd);
@@ -366,12 +370,14 @@ __device__ __forceinline__ bool cand_eval(const SearchTables &T, const CtypeDev 
   else if (c.vmode == 2) dv = fabs(__dsub_rn(c.vconst, p.lp));
   else if (c.vmode == 3) dv = fabs(__dsub_rn(ve.x, p.rz));
   if (dv > c.vmax) return false;
+  const double v2 = dv * dv * c.iv2;
+  if (v2 > lim2 * 1.0000000000009095) return false;   // vertical part alone outside the radius
   const double2 rr = *reinterpret_cast<const double2 *>(&rec[iob].ri);
   const double rdx = __dmul_rn(__dsub_rn(p.ri, rr.x), T.DX);
   const double rdy = __dmul_rn(__dsub_rn(p.rj, rr.y), T.DY);
   const double h2 = __dadd_rn(__dmul_rn(rdx, rdx), __dmul_rn(rdy, rdy));
   if (h2 > c.hmax2) return false;
-  if (h2 * c.ih2 + dv * dv * c.iv2 > lim2 * 1.0000000000009095) return false;   // 1 + 2^-40
+  if (h2 * c.ih2 + v2 > lim2 * 1.0000000000009095) return false;   // 1 + 2^-40
   // exact path (letkf_tools.f90:1852-1895): same operations, same order, no contraction
   const double nd_v = (c.vmode == 0) ? 0.0 : __ddiv_rn(dv, c.vert_loc);
   if (nd_v > T.dzf) return false;
@@ -540,22 +546,38 @@ __device__ __forceinline__ int search_point(const SearchTables &T, const ObsRec 
   while (g < T.ngroup) {
     if (T.grp[g].limit <= 0) {
       // ---- run of groups without obs-number limit (letkf_tools.f90:1438-1476): one fused scan --
-      ScanList SL;
-      SL.n = 0;
-      while (g < T.ngroup && T.grp[g].limit <= 0 && SL.n + T.grp[g].n <= kMaxScan) {
+      // Entry e of the run = e-th (group, merged ctype) pair; thread e evaluates its cut-off rectangle
+      // (double divisions -- not worth repeating in every thread), thread 0 compacts the valid ones.
+      int ne = 0, my_ic = -1;
+      while (g < T.ngroup && T.grp[g].limit <= 0 && ne + T.grp[g].n <= kMaxScan) {
         const GroupDev &G = T.grp[g];
         for (int icm = 0; icm < G.n; ++icm) {
-          const int ic = G.ic[icm];
-          const CtypeDev &c = T.ct[ic];
-          if (vlfac[ic] < tiny || c.tot == 0) continue;
-          const Rect r = cutoff_rect(T, c, p);
-          if (r.imin > r.imax || r.jmin > r.jmax) continue;
-          SL.ic[SL.n] = ic;
-          SL.r[SL.n] = r;
-          ++SL.n;
+          if (ne == (int)threadIdx.x) my_ic = G.ic[icm];
+          ++ne;
         }
         ++g;
       }
+      ScanList &SL = S.sl;
+      __syncthreads();   // previous scan finished with S.sl / S.tr
+      if (my_ic >= 0) {
+        const CtypeDev &c = T.ct[my_ic];
+        Rect r = cutoff_rect(T, c, p);
+        const bool ok = !(vlfac[my_ic] < tiny) && c.tot != 0 && r.imin <= r.imax && r.jmin <= r.jmax;
+        S.tr[threadIdx.x] = r;
+        S.tv[threadIdx.x] = ok ? my_ic : -1;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int n = 0;
+        for (int e = 0; e < ne; ++e)
+          if (S.tv[e] >= 0) {
+            SL.ic[n] = S.tv[e];
+            SL.r[n] = S.tr[e];
+            ++n;
+          }
+        SL.n = n;
+      }
+      __syncthreads();
       if (SL.n == 0) continue;
       const int rows = scan_rows_total(SL);
       for (int row0 = 0; row0 < rows; row0 += kSegMax) {
@@ -583,43 +605,53 @@ __device__ __forceinline__ int search_point(const SearchTables &T, const ObsRec 
     const CtypeDev &cm = T.ct[G.ic[0]];
     double search_incr0 = __ddiv_rn(__dmul_rn(cm.hori_loc, T.dzf), 8.0);
     search_incr0 = fmax(search_incr0, fmax(cm.grdspc_i, cm.grdspc_j));
-    Rect rq[kMaxMerge];
-    ScanList SL;
+    ScanList &SL = S.sl;
     bool reach_cutoff = true, buffered = false;
     double dcf2 = T.dzf2;
     int count = 0, C = 32;
     for (int q = (crit == 1 ? 1 : 1 << 20);; ++q) {
-      reach_cutoff = true;
-      for (int icm = 0; icm < G.n; ++icm) {
+      // thread icm: search rectangle of merged ctype icm at step q (S.tr) and whether it already
+      // covers the cut-off rectangle (S.tv); thread 0: the scan list of the valid ones
+      __syncthreads();   // previous pass finished with S.sl / S.tr
+      if ((int)threadIdx.x < G.n) {
+        const int icm = threadIdx.x;
         const CtypeDev &c = T.ct[G.ic[icm]];
         const Rect rc = cutoff_rect(T, c, p);
+        Rect rr = rc;
+        int reach = 1;
         if (crit == 1 && q < (1 << 20)) {
           const double incr = (icm == 0) ? search_incr0 : search_incr0 / cm.hori_loc * c.hori_loc;
           const Rect r = rect_of(T, c, p, incr / T.DX * q, incr / T.DY * q);
-          if (r.imin <= rc.imin && r.imax >= rc.imax && r.jmin <= rc.jmin && r.jmax >= rc.jmax) {
-            rq[icm] = rc;
-          } else {
-            rq[icm] = clamp_rect(r, c);
-            reach_cutoff = false;
+          if (!(r.imin <= rc.imin && r.imax >= rc.imax && r.jmin <= rc.jmin && r.jmax >= rc.jmax)) {
+            rr = clamp_rect(r, c);
+            reach = 0;
           }
-        } else {
-          rq[icm] = rc;
         }
+        S.tr[icm] = rr;
+        S.tv[icm] = reach;
       }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int n = 0, reach = 1;
+        for (int icm = 0; icm < G.n; ++icm) {
+          reach &= S.tv[icm];
+          const int ic = G.ic[icm];
+          const Rect &r = S.tr[icm];
+          if (vlfac[ic] < tiny || T.ct[ic].tot == 0 || r.imin > r.imax || r.jmin > r.jmax) continue;
+          SL.ic[n] = ic;
+          SL.r[n] = r;
+          ++n;
+        }
+        SL.n = n;
+        S.misc[4] = reach;
+      }
+      __syncthreads();
+      reach_cutoff = S.misc[4] != 0;
       if (!reach_cutoff) {
         const double f = search_incr0 * q / cm.hori_loc;
         dcf2 = f * f;
       } else {
         dcf2 = T.dzf2;
-      }
-      SL.n = 0;
-      for (int icm = 0; icm < G.n; ++icm) {
-        const int ic = G.ic[icm];
-        if (vlfac[ic] < tiny || T.ct[ic].tot == 0) continue;
-        if (rq[icm].imin > rq[icm].imax || rq[icm].jmin > rq[icm].jmax) continue;
-        SL.ic[SL.n] = ic;
-        SL.r[SL.n] = rq[icm];
-        ++SL.n;
       }
       // valid candidates inside the current radius: counted and -- when the rectangle fits one
       // window of the candidate buffer -- kept, so that the last pass of the loop is also the only
@@ -655,6 +687,8 @@ __device__ __forceinline__ int search_point(const SearchTables &T, const ObsRec 
       continue;
     }
     if (!buffered) {
+      Rect rq[kMaxMerge];
+      for (int icm = 0; icm < G.n; ++icm) rq[icm] = S.tr[icm];
       select_rescan(T, rec, bstart, vlfac, p, G, rq, reach_cutoff, dcf2, count, L, S, nobsl, overflow);
       continue;
     }
