@@ -330,11 +330,13 @@ def main():
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get(name)
+                tj = json.load(f).get(name)
+            # ncu --set full capture of one launch, per analysed point x the points of this launch
+            traffic = tj["bytes_per_point"] * npoints / world if tj else None
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "das_kernel", "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+        "kernel": "das_ns_kernel" if k <= 102 else "das_tiled", "bound": "tensor", "pipe": "fp64 DMMA (mma.sync m8n8k4.f64)", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
         "frac": ach_tf / fp64_peak, "traffic": traffic,
         "peak_source": fp64_src + "; MEASURED_PEAKS.json holds no FP64 figure",
         "kernel_ms_per_launch": kms, "algorithmic_flops_per_launch": flops / world,
