@@ -34,7 +34,7 @@ extern "C" {
 #define LETKF_B200_NID_OBS 16       /* nid_obs, scale/common/common_nml.f90:21 */
 #define LETKF_B200_NID_VARLOCAL 9   /* nid_obs_varlocal, common_obs_scale.f90:43 */
 #define LETKF_B200_MAX_NV 16        /* upper bound on nv3d+nv2d (11+0 in the reference) */
-#define LETKF_B200_MAX_MEMBER 128   /* k limit of the one-CTA-per-point solver */
+#define LETKF_B200_MAX_MEMBER 4096  /* k <= 102: one CTA per point; larger: tiled whole-GPU path */
 
 /* status codes */
 #define LETKF_B200_OK 0

@@ -14,6 +14,7 @@
 #include "aux_kernels.cuh"
 #include "das_kernel.cuh"
 #include "das_ns_kernel.cuh"
+#include "tiled.cuh"
 
 using namespace letkf;
 
@@ -57,7 +58,7 @@ int ns_class(int k) {
 // copied to shared memory as is
 int ns_row_doubles(int k) {
   const int nb = ns_class(k);
-  return nb ? 8 * nb : round_up(k + 2, 2);
+  return nb ? 8 * nb : round_up(k + 2, 8);   // tiled path: n8
 }
 
 template <class T>
@@ -79,6 +80,8 @@ struct DevBuf {
     n = 0;
   }
 };
+
+struct TiledBufs;   // scratch of the large-ensemble path (tiled_host.cuh), allocated on first use
 
 }  // namespace
 
@@ -128,6 +131,7 @@ struct letkf_b200_handle {
   long long st_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float last_ms = 0.f;
   int last_launches = 0;
+  TiledBufs *tiled = nullptr;
 };
 
 #define CK(call)                                                                         \
@@ -263,6 +267,10 @@ void ensure_pinned(letkf_b200_handle *h, void *p, size_t bytes) {
   else cudaGetLastError();
 }
 
+}  // namespace
+#include "tiled_host.cuh"
+namespace {
+
 template <int KC>
 int launch_core(letkf_b200_handle *h, CoreParams &P) {
   using SC = SizeClass<KC>;
@@ -354,7 +362,7 @@ int letkf_b200_create(const letkf_b200_config *cfg, int device, letkf_b200_handl
     delete h;
     return LETKF_B200_EINVAL;
   };
-  if (c.MEMBER < 2 || c.MEMBER > LETKF_B200_MAX_MEMBER) return bad("MEMBER must be in [2, 128] (tiled k>=1000 path not built yet)");
+  if (c.MEMBER < 2 || c.MEMBER > LETKF_B200_MAX_MEMBER) return bad("MEMBER must be in [2, LETKF_B200_MAX_MEMBER]");
   if (c.nv3d < 1 || c.nv3d + c.nv2d > kMaxNV - 2) return bad("nv3d + nv2d must be in [1, 14]");
   if (c.nlon < 1 || c.nlat < 1 || c.nlev < 1) return bad("nlon/nlat/nlev must be positive");
   if (c.MAX_NOBS_PER_GRID_CRITERION < 1 || c.MAX_NOBS_PER_GRID_CRITERION > 3) return bad("Unsupported MAX_NOBS_PER_GRID_CRITERION");
@@ -397,6 +405,7 @@ int letkf_b200_destroy(letkf_b200_handle *h) {
   h->st_infl.release(); h->st_rtps.release(); h->st_logp.release(); h->st_nobsl.release();
   for (auto &b : h->cb) b.release();
   h->cb_i.release();
+  if (h->tiled) { h->tiled->release(); delete h->tiled; h->tiled = nullptr; }
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto *v : {&h->ev_in, &h->ev_k0, &h->ev_k1})
@@ -795,14 +804,19 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   P.counters = h->counters.p;
   P.max_sweeps = 30;
   CK(cudaMemsetAsync(h->counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
-  int r;
+  int r, nlaunch = 0;
   DasLaunch L;
-  // MEMBER <= 102: tensor-core Newton-Schulz solve (das_ns_kernel.cuh); larger ensembles (two k x k
-  // matrices no longer fit in shared memory) and LETKF_B200_SOLVER=jacobi: Cholesky + one-sided Jacobi.
+  // MEMBER <= 102: tensor-core Newton-Schulz solve, one CTA per point (das_ns_kernel.cuh); larger
+  // ensembles (the k x k matrices no longer fit in shared memory): tiled whole-GPU path (tiled.cuh).
+  // LETKF_B200_SOLVER=jacobi (MEMBER <= 128): Cholesky + one-sided Jacobi; =tiled forces the tiled path.
   const char *sv = std::getenv("LETKF_B200_SOLVER");
   const int nsc = ns_class(k);
-  const bool jacobi = (sv && std::strcmp(sv, "jacobi") == 0) || nsc == 0;
-  if (!jacobi) {
+  const bool jacobi = sv && std::strcmp(sv, "jacobi") == 0 && k <= 128;
+  const bool tiled = !jacobi && (nsc == 0 || (sv && std::strcmp(sv, "tiled") == 0));
+  if (tiled) {
+    if (!h->tiled) h->tiled = new TiledBufs();
+    r = LETKF_B200_OK;
+  } else if (!jacobi) {
     if (nsc == 3) r = plan_das_ns<3>(h, P, L);
     else if (nsc == 5) r = plan_das_ns<5>(h, P, L);
     else if (nsc == 7) r = plan_das_ns<7>(h, P, L);
@@ -845,7 +859,8 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   for (int ch = 0; ch < nchunk; ++ch) {
     const int l0 = lev0(ch), l1 = lev0(ch + 1);
     if (host) CK(cudaStreamWaitEvent(h->stream, h->ev_in[ch], 0));
-    r = launch_range(h, L, P, (long long)l0 * h->nij1, (long long)l1 * h->nij1, h->ev_k0[ch], h->ev_k1[ch]);
+    if (tiled) r = launch_range_tiled(h, *h->tiled, P, (long long)l0 * h->nij1, (long long)l1 * h->nij1, h->ev_k0[ch], h->ev_k1[ch], &nlaunch);
+    else r = launch_range(h, L, P, (long long)l0 * h->nij1, (long long)l1 * h->nij1, h->ev_k0[ch], h->ev_k1[ch]);
     if (r != LETKF_B200_OK) return r;
     if (host) {
       const size_t off = (size_t)l0 * h->nij1, w = sizeof(double) * (size_t)(l1 - l0) * h->nij1;
@@ -857,7 +872,7 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
         CK(cudaMemcpy2DAsync(a->gues3d + off, pitch, P.gues3d + off, pitch, w, planes, cudaMemcpyDeviceToHost, h->s_d2h));
     }
   }
-  h->last_launches = nchunk;
+  h->last_launches = tiled ? nlaunch : nchunk;
   if (host) {
     if (c.nv2d > 0) {
       CK(cudaMemcpyAsync(a->anal2d, P.anal2d, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->s_d2h));

@@ -1,0 +1,273 @@
+// tiled_host.cuh -- host orchestration of the large-ensemble analysis path (tiled.cuh).  Included by
+// letkf_b200.cu after the handle definition; everything runs on the handle's stream.
+#pragma once
+
+namespace {
+
+struct TiledBufs {
+  DevBuf<double> X, Ts, colsc, beta, ri, rj, lp, rz, cdiag, infl, rdiag, rloc, snorm, brk, h0, h1, misc, E, dw, U;
+  DevBuf<double> bZ0, bZ1, bY0, bY1, mT, mS;
+  DevBuf<int> skip, ncols, cols, nobsl, idx, dims, kd, state, zsel, iters, fail, nactive, adims, solved_any;
+  DevBuf<unsigned long long> snorm_bits, res, scounters;
+  int *h_pinned = nullptr;   // [0] nactive, [1..] nobsl readback
+  size_t h_pinned_n = 0;
+  void release() {
+    for (DevBuf<double> *b : {&X, &Ts, &colsc, &beta, &ri, &rj, &lp, &rz, &cdiag, &infl, &rdiag, &rloc, &snorm, &brk, &h0,
+                              &h1, &misc, &E, &dw, &U, &bZ0, &bZ1, &bY0, &bY1, &mT, &mS})
+      b->release();
+    for (DevBuf<int> *b : {&skip, &ncols, &cols, &nobsl, &idx, &dims, &kd, &state, &zsel, &iters, &fail, &nactive, &adims,
+                           &solved_any})
+      b->release();
+    snorm_bits.release();
+    res.release();
+    scounters.release();
+    if (h_pinned) cudaFreeHost(h_pinned);
+    h_pinned = nullptr;
+    h_pinned_n = 0;
+  }
+};
+
+// One batched NT GEMM launch; the tile shape follows the matrix size.
+int tl_gemm(letkf_b200_handle *h, const GemmParams &P, int items) {
+  if (items <= 0) return LETKF_B200_OK;
+  const int mmax = P.M;
+  const bool big = mmax >= 384 && (P.sym || P.N >= 128);
+  if (big) {
+    constexpr int BM = 128, BN = 128, ST = 3;
+    const size_t smem = gemm_smem_bytes<BM, BN, ST>();
+    static bool attr = false;
+    if (!attr) {
+      CK(cudaFuncSetAttribute(tl_gemm_kernel<BM, BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    const int tm = (mmax + BM - 1) / BM, tn = P.sym ? tm : (P.N + BN - 1) / BN;
+    const int tiles = P.sym ? tm * (tm + 1) / 2 : tm * tn;
+    dim3 grid((unsigned)tiles, (unsigned)(items * P.njobs));
+    tl_gemm_kernel<BM, BN, ST><<<grid, (BM / 32) * (BN / 32) * 32, smem, h->stream>>>(P);
+  } else {
+    constexpr int BM = 64, BN = 64, ST = 3;
+    const size_t smem = gemm_smem_bytes<BM, BN, ST>();
+    static bool attr = false;
+    if (!attr) {
+      CK(cudaFuncSetAttribute(tl_gemm_kernel<BM, BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    const int tm = (mmax + BM - 1) / BM, tn = P.sym ? tm : (P.N + BN - 1) / BN;
+    const int tiles = P.sym ? tm * (tm + 1) / 2 : tm * tn;
+    dim3 grid((unsigned)tiles, (unsigned)(items * P.njobs));
+    tl_gemm_kernel<BM, BN, ST><<<grid, (BM / 32) * (BN / 32) * 32, smem, h->stream>>>(P);
+  }
+  CK(cudaGetLastError());
+  return LETKF_B200_OK;
+}
+
+// Coupled Newton-Schulz on the whole batch: on entry bY[0] holds Y0 and the per-point state is armed;
+// on exit bZ[zsel[g]] (and bY[zsel[g]] when keep_y) hold the result of point g.
+int tl_ns_solve(letkf_b200_handle *h, TiledBufs &T, const TiledParams &B, int nmax, bool keep_y, int *launches) {
+  const int G = B.G;
+  const long long sN = (long long)nmax * nmax;
+  const dim3 egrid((unsigned)((sN + 1023) / 1024), (unsigned)G);
+  for (int it = 1; it <= B.max_iter + 1; ++it) {
+    const int cur = it & 1, prev = cur ^ 1;
+    if (it == 1) {
+      tl_res_kernel<<<egrid, 256, 0, h->stream>>>(B, B.bY[0], nmax);
+    } else {   // M = Z Y -> bZ[cur] (free: it holds Z of two iterations ago)
+      GemmParams P;
+      std::memset(&P, 0, sizeof(P));
+      P.njobs = 1;
+      P.job[0] = GemmJob{B.bZ[prev], nullptr, B.bY[prev], B.bZ[cur], sN, sN, sN, nmax, nmax, nmax};
+      P.M = P.N = P.K = nmax;
+      P.mdims = B.dims;
+      P.kdims = B.dims;
+      P.state = B.state;
+      P.state_skip = 1;   // points whose last iteration has just been completed are done
+      P.sym = 1;
+      P.res = B.res;
+      int r = tl_gemm(h, P, G);
+      if (r != LETKF_B200_OK) return r;
+    }
+    tl_step_kernel<<<1, 256, 0, h->stream>>>(B, cur);
+    CK(cudaMemcpyAsync(T.h_pinned, B.nactive, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *launches += 3;
+    if (T.h_pinned[0] == 0) break;
+    tl_poly_kernel<<<egrid, 256, 0, h->stream>>>(B, it == 1 ? B.bY[0] : B.bZ[cur], B.mT, it == 1 ? B.bZ[1] : nullptr, nmax);
+    GemmParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.M = P.N = P.K = nmax;
+    P.mdims = B.dims;
+    P.kdims = B.dims;
+    P.state = B.state;
+    P.state_skip = 2;
+    P.sym = 1;
+    P.skip_last = keep_y ? 0 : 1;
+    if (it == 1) {   // Z1 = T (written by tl_poly), Y1 = T Y0
+      P.njobs = 1;
+      P.job[0] = GemmJob{B.mT, nullptr, B.bY[0], B.bY[1], sN, sN, sN, nmax, nmax, nmax};
+    } else {
+      P.njobs = 2;
+      P.job[0] = GemmJob{B.mT, nullptr, B.bZ[prev], B.bZ[cur], sN, sN, sN, nmax, nmax, nmax};
+      P.job[1] = GemmJob{B.mT, nullptr, B.bY[prev], B.bY[cur], sN, sN, sN, nmax, nmax, nmax};
+    }
+    int r = tl_gemm(h, P, G);
+    if (r != LETKF_B200_OK) return r;
+    *launches += 2;
+  }
+  return LETKF_B200_OK;
+}
+
+// Analyse points [begin, end) with the tiled path, bracketed by the two events.
+int launch_range_tiled(letkf_b200_handle *h, TiledBufs &T, DasParams P, long long begin, long long end, cudaEvent_t e0,
+                       cudaEvent_t e1, int *launches_out) {
+  const letkf_b200_config &c = h->cfg;
+  const int k = c.MEMBER, n8 = round_up(k + 2, 8), kK = round_up(k, 16), maxl = h->maxl;
+  const char *fe = std::getenv("LETKF_B200_TILED_FORM");
+  const int form = (fe && !std::strcmp(fe, "primal")) ? 0 : (fe && !std::strcmp(fe, "dual")) ? 1 : 2;   // 2: auto
+  const char *me = std::getenv("LETKF_B200_TILED_MB");
+  const double budget = (me ? std::atof(me) : 4096.0) * 1048576.0;
+  const double item_bytes = 5.0 * n8 * (double)n8 * 8.0 + (double)maxl * 20.0 + 64.0 * n8;
+  long long G = (long long)(budget / item_bytes);
+  G = std::max<long long>(8, std::min<long long>(G, 4096));
+  G = std::min<long long>(G, std::max<long long>(end - begin, 1));
+  const size_t Gs = (size_t)G;
+  int launches = 0;
+
+  CK(T.X.ensure(Gs * kMaxNV * n8)); CK(T.Ts.ensure(Gs * n8 * kMaxNV)); CK(T.colsc.ensure(Gs * 8 * kMaxNV));
+  CK(T.beta.ensure(Gs)); CK(T.ri.ensure(Gs)); CK(T.rj.ensure(Gs)); CK(T.lp.ensure(Gs)); CK(T.rz.ensure(Gs));
+  CK(T.cdiag.ensure(Gs)); CK(T.infl.ensure(Gs)); CK(T.rdiag.ensure(Gs * maxl)); CK(T.rloc.ensure(Gs * maxl));
+  CK(T.snorm.ensure(Gs)); CK(T.brk.ensure(Gs)); CK(T.h0.ensure(Gs)); CK(T.h1.ensure(Gs)); CK(T.misc.ensure(Gs * 4));
+  CK(T.skip.ensure(Gs)); CK(T.ncols.ensure(Gs)); CK(T.cols.ensure(Gs * kMaxNV)); CK(T.nobsl.ensure(Gs));
+  CK(T.idx.ensure(Gs * maxl)); CK(T.dims.ensure(Gs)); CK(T.kd.ensure(Gs)); CK(T.state.ensure(Gs)); CK(T.zsel.ensure(Gs));
+  CK(T.iters.ensure(Gs)); CK(T.fail.ensure(Gs)); CK(T.nactive.ensure(1)); CK(T.adims.ensure(Gs)); CK(T.solved_any.ensure(Gs));
+  CK(T.snorm_bits.ensure(Gs)); CK(T.res.ensure(Gs)); CK(T.scounters.ensure(16));
+  if (T.h_pinned_n < Gs + 1) {
+    if (T.h_pinned) cudaFreeHost(T.h_pinned);
+    CK(cudaMallocHost((void **)&T.h_pinned, sizeof(int) * (Gs + 1)));
+    T.h_pinned_n = Gs + 1;
+  }
+  // scratch of the search kernel (one list per resident CTA)
+  const int sgrid = (int)std::max<long long>(1, std::min<long long>(G, (long long)h->num_sms * 8));
+  CK(h->l_iob.ensure((size_t)sgrid * maxl)); CK(h->l_rdiag.ensure((size_t)sgrid * maxl)); CK(h->l_rloc.ensure((size_t)sgrid * maxl));
+  CK(h->l_cnd.ensure((size_t)sgrid * h->ccap)); CK(h->l_cpk.ensure((size_t)sgrid * h->ccap));
+
+  TiledParams B;
+  std::memset(&B, 0, sizeof(B));
+  B.n8 = n8; B.kK = kK; B.maxl = maxl; B.max_iter = P.max_sweeps + 20;
+  B.X = T.X.p; B.Ts = T.Ts.p; B.colsc = T.colsc.p; B.beta = T.beta.p; B.ri = T.ri.p; B.rj = T.rj.p; B.lp = T.lp.p; B.rz = T.rz.p;
+  B.skip = T.skip.p; B.ncols = T.ncols.p; B.cols = T.cols.p; B.cdiag = T.cdiag.p; B.infl = T.infl.p; B.nobsl = T.nobsl.p;
+  B.idx = T.idx.p; B.rdiag = T.rdiag.p; B.rloc = T.rloc.p; B.dims = T.dims.p; B.kd = T.kd.p; B.state = T.state.p;
+  B.zsel = T.zsel.p; B.iters = T.iters.p; B.fail = T.fail.p; B.snorm = T.snorm.p; B.snorm_bits = T.snorm_bits.p;
+  B.brk = T.brk.p; B.h0 = T.h0.p; B.h1 = T.h1.p; B.res = T.res.p; B.misc = T.misc.p; B.nactive = T.nactive.p;
+  B.adims = T.adims.p; B.solved_any = T.solved_any.p;
+
+  CK(cudaEventRecord(e0, h->stream));
+  for (long long wp0 = begin; wp0 < end; wp0 += G) {
+    const int Gb = (int)std::min<long long>(G, end - wp0);
+    B.G = Gb;
+    B.wp0 = wp0;
+    tl_load_kernel<<<Gb, 256, 0, h->stream>>>(P, B);
+    ++launches;
+    for (int vg = 0; vg < h->nvgroup; ++vg) {
+      B.vg = vg;
+      B.dual = 0;
+      tl_group_kernel<<<Gb, 128, 0, h->stream>>>(P, B);
+      {   // local observations of every point of the batch
+        SearchParams S;
+        std::memset(&S, 0, sizeof(S));
+        S.T = h->d_tables.p; S.rec = h->rec.p; S.bstart = h->bstart.p;
+        S.vlfac = h->vlfac_groups.p + (size_t)vg * h->nctype;
+        S.ri = B.ri; S.rj = B.rj; S.lp = B.lp; S.rz = B.rz;
+        S.npts = Gb; S.max_out = maxl; S.nobsl = B.nobsl; S.idx = B.idx; S.rdiag = B.rdiag; S.rloc = B.rloc;
+        S.l_iob = h->l_iob.p; S.l_rdiag = h->l_rdiag.p; S.l_rloc = h->l_rloc.p; S.lcap = maxl;
+        S.l_cnd = h->l_cnd.p; S.l_cpk = h->l_cpk.p; S.ccap = h->ccap;
+        S.counters = T.scounters.p;
+        CK(cudaMemsetAsync(T.scounters.p, 0, 16 * sizeof(unsigned long long), h->stream));
+        search_kernel<<<std::min(sgrid, Gb), 128, 0, h->stream>>>(S);
+      }
+      tl_plan_kernel<<<(Gb + 127) / 128, 128, 0, h->stream>>>(P, B);
+      CK(cudaMemcpyAsync(T.h_pinned + 1, B.nobsl, sizeof(int) * Gb, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      launches += 3;
+      int pmax = 0;
+      for (int g = 0; g < Gb; ++g) pmax = std::max(pmax, T.h_pinned[1 + g]);
+      if (pmax > 0) {
+        const int pK = round_up(pmax, 16);
+        const bool dual = form == 1 || (form == 2 && pK * 10 <= k * 6);
+        B.dual = dual ? 1 : 0;
+        B.pK = pK;
+        tl_dims_kernel<<<(Gb + 127) / 128, 128, 0, h->stream>>>(B);
+        const int nmax = dual ? pK : n8;
+        B.nmax = nmax;
+        const size_t sN = (size_t)nmax * nmax;
+        const size_t mcap = Gs * std::max((size_t)n8 * n8, sN);   // (a forced dual form may have pK > n8)
+        CK(T.bZ0.ensure(mcap)); CK(T.bZ1.ensure(mcap)); CK(T.bY0.ensure(mcap)); CK(T.bY1.ensure(mcap)); CK(T.mT.ensure(mcap));
+        B.bZ[0] = T.bZ0.p; B.bZ[1] = T.bZ1.p; B.bY[0] = T.bY0.p; B.bY[1] = T.bY1.p; B.mT = T.mT.p;
+        const dim3 egrid((unsigned)((sN + 1023) / 1024), (unsigned)Gb);
+        if (!dual) {
+          CK(T.E.ensure(Gs * (size_t)n8 * pK));
+          B.E = T.E.p;
+          tl_gather_primal_kernel<<<dim3((unsigned)((pK + 31) / 32), (unsigned)Gb), dim3(32, 8), 0, h->stream>>>(P, B);
+          GemmParams Q;   // [A | b | bd] = E E^T  -> bZ[1]
+          std::memset(&Q, 0, sizeof(Q));
+          Q.njobs = 1;
+          Q.job[0] = GemmJob{B.E, nullptr, B.E, B.bZ[1], (long long)n8 * pK, (long long)n8 * pK, (long long)sN, pK, pK, n8};
+          Q.M = Q.N = n8; Q.K = pK; Q.kdims = B.kd; Q.state = B.state; Q.state_skip = 2; Q.sym = 1;
+          int r = tl_gemm(h, Q, Gb);
+          if (r != LETKF_B200_OK) return r;
+          tl_rowsum_kernel<<<dim3((unsigned)(n8 / 8), (unsigned)Gb), 256, 0, h->stream>>>(P, B);
+          tl_scale_kernel<<<egrid, 256, 0, h->stream>>>(P, B, B.bZ[1], B.bY[0], nmax, 0);
+          launches += 5;
+          r = tl_ns_solve(h, T, B, nmax, false, &launches);
+          if (r != LETKF_B200_OK) return r;
+          GemmParams A;   // Ts = Z [dX | b | bd]
+          std::memset(&A, 0, sizeof(A));
+          A.njobs = 1;
+          A.job[0] = GemmJob{B.bZ[0], B.bZ[1], B.X, B.Ts, (long long)sN, (long long)kMaxNV * n8, (long long)n8 * kMaxNV,
+                             n8, n8, kMaxNV};
+          A.M = n8; A.N = kMaxNV; A.K = n8; A.mdims = B.adims; A.sel = B.zsel;
+          r = tl_gemm(h, A, Gb);
+          if (r != LETKF_B200_OK) return r;
+          ++launches;
+        } else {
+          CK(T.E.ensure(Gs * (size_t)pK * kK)); CK(T.dw.ensure(2 * Gs * pK)); CK(T.U.ensure(3 * Gs * pK * kMaxNV));
+          CK(T.mS.ensure(Gs * sN));
+          B.E = T.E.p; B.dw = T.dw.p; B.U = T.U.p; B.mS = T.mS.p;
+          tl_gather_dual_kernel<<<dim3((unsigned)(pK / 8), (unsigned)Gb), 256, 0, h->stream>>>(P, B);
+          GemmParams Q;   // S = Yt Yt^T -> mS
+          std::memset(&Q, 0, sizeof(Q));
+          Q.njobs = 1;
+          Q.job[0] = GemmJob{B.E, nullptr, B.E, B.mS, (long long)pK * kK, (long long)pK * kK, (long long)sN, kK, kK, nmax};
+          Q.M = Q.N = nmax; Q.K = kK; Q.mdims = B.dims; Q.state = B.state; Q.state_skip = 2; Q.sym = 1;
+          int r = tl_gemm(h, Q, Gb);
+          if (r != LETKF_B200_OK) return r;
+          const dim3 rgrid((unsigned)(pK / 8), (unsigned)Gb);
+          tl_rowsum_dual_kernel<<<rgrid, 256, 0, h->stream>>>(B, B.mS, nmax, 1);
+          tl_scale_kernel<<<egrid, 256, 0, h->stream>>>(P, B, B.mS, B.bY[0], nmax, 1);
+          launches += 5;
+          r = tl_ns_solve(h, T, B, nmax, true, &launches);   // Z1 = (B/s1)^-1/2, Yfin = (B/s1)^1/2
+          if (r != LETKF_B200_OK) return r;
+          tl_dual_d_kernel<<<egrid, 256, 0, h->stream>>>(B, B.mT, nmax);          // D -> mT
+          tl_dual_keep_kernel<<<egrid, 256, 0, h->stream>>>(B, nmax);             // mS <- Z1
+          tl_dual_restart_kernel<<<(Gb + 127) / 128, 128, 0, h->stream>>>(P, B);
+          tl_rowsum_dual_kernel<<<rgrid, 256, 0, h->stream>>>(B, B.mT, nmax, 2);
+          tl_scale_kernel<<<egrid, 256, 0, h->stream>>>(P, B, B.mT, B.bY[0], nmax, 2);
+          launches += 5;
+          r = tl_ns_solve(h, T, B, nmax, false, &launches);  // Z2 = (D/s2)^-1/2
+          if (r != LETKF_B200_OK) return r;
+          tl_dual_apply_kernel<<<Gb, 256, 0, h->stream>>>(P, B);
+          ++launches;
+        }
+      }
+      tl_update_kernel<<<Gb, 256, 0, h->stream>>>(P, B);
+      ++launches;
+    }
+    tl_count_kernel<<<(Gb + 127) / 128, 128, 0, h->stream>>>(P, B);
+    ++launches;
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e1, h->stream));
+  *launches_out += launches;
+  return LETKF_B200_OK;
+}
+
+}  // namespace

@@ -59,7 +59,7 @@ def test_create_fails_loudly_without_gpu(lib):
 
 
 def test_create_rejects_bad_config(lib):
-    cfg = config.default_config(MEMBER=1000, nlon=8, nlat=8, nlev=2)
+    cfg = config.default_config(MEMBER=5000, nlon=8, nlat=8, nlev=2)   # > LETKF_B200_MAX_MEMBER (4096)
     h = C.c_void_p()
     assert lib.letkf_b200_create(C.byref(cfg), 0, C.byref(h)) == capi.EINVAL
     assert b"sm_100a" in lib.letkf_b200_build_info()
