@@ -44,6 +44,12 @@ WORKLOADS = {
                desc="C3: 256x256x60 500 m mesh, 100 members, dense radar, MAX_NOBS_PER_GRID(22)=500"),
     "c3small": dict(kind="radar", nlon=96, nlat=96, nlev=20, member=100, max_nobs=500,
                     desc="C3 shape on a 96x96x20 grid"),
+    "c4": dict(kind="radar", nlon=128, nlat=128, nlev=40, member=1000, max_nobs=100,
+               desc="C4: 128x128x40, 1000 members, dense radar, MAX_NOBS_PER_GRID(22)=100 (tiled path)"),
+    "c4small": dict(kind="radar", nlon=48, nlat=48, nlev=10, member=1000, max_nobs=100,
+                    desc="C4 shape on a 48x48x10 grid (tiled path)"),
+    "c5": dict(kind="radar", nlon=400, nlat=400, nlev=60, member=100, max_nobs=100,
+               desc="C5: 400x400x60 500 m mesh, 100 members, phased-array radar, MAX_NOBS_PER_GRID(22)=100"),
 }
 
 
@@ -181,6 +187,8 @@ class CpuSample:
         return r["npoints"], dt, r["nsolved"]
 
     def calibrate(self, target_s, calib_points=1500):
+        # the eigensolve costs O(k^3): shrink the calibration sample for large ensembles
+        calib_points = max(self.w["nlev"], int(calib_points * min(1.0, (100.0 / self.w["member"]) ** 3)))
         self.prepare(self._deal_width(max(1, calib_points // self.w["nlev"])))
         npts, dt, _ = self.run()
         want_cols = max(1, int(npts / dt * target_s / self.w["nlev"]))

@@ -39,6 +39,7 @@ struct GemmJob {
   double *C;
   long long sA, sB, sC;      // batch strides in doubles
   int lda, ldb, ldc;
+  const double *B_alt;       // alternative B base chosen per item by `selB`
 };
 struct GemmParams {
   GemmJob job[2];
@@ -49,6 +50,7 @@ struct GemmParams {
   const int *state;          // optional per-item solver state: >= state_skip skips the item, == 1 skips job 1 if skip_last
   int state_skip, skip_last;
   const int *sel;            // optional per-item selector of job[].A_alt
+  const int *selB;           // optional per-item selector of job[].B_alt
   int sym;                   // 1: C symmetric (M == N): lower-triangular tiles only, mirrored on store
   unsigned long long *res;   // optional per-item max |delta_ij - C_ij| of job 0 (bits of a double >= 0)
 };
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) tl_gemm_kernel(con
   if (m0 >= M || n0 >= N) return;
   const GemmJob &J = P.job[jb];
   const double *A = ((P.sel && P.sel[item]) ? J.A_alt : J.A) + (size_t)item * J.sA;
-  const double *B = J.B + (size_t)item * J.sB;
+  const double *B = ((P.selB && P.selB[item]) ? J.B_alt : J.B) + (size_t)item * J.sB;
   double *C = J.C + (size_t)item * J.sC;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int wm = wid / NWN, wn = wid - wm * NWN;
@@ -237,7 +239,8 @@ struct TiledParams {
   double *E;             // [G][n8][pK] (primal) or [G][pK][kK] (dual Yt)
   double *bZ[2], *bY[2], *mT, *mS;   // [G][nmax][nmax]: ping-pong iterates, T, dual: S then the kept Z1
   double *dw;            // [G][pK] dual: sqrt(w) dep ; [G][pK] sqrt(w) depd follows at + G*pK
-  double *U;             // dual: [G][pK][kMaxNV] skinny work matrices (3 of them)
+  double *U;             // dual: [3][G][kMaxNV][pK] skinny work matrices U1T, U2T, U3T
+  double *E2;            // dual: [G][n8][pK] = Yt^T (primal gather layout)
 };
 
 __device__ __forceinline__ size_t tl_gaddr(const DasParams &P, int vv, int m, int ij, size_t pbase, size_t sl) {
@@ -828,111 +831,38 @@ __global__ void tl_dual_restart_kernel(const DasParams P, const TiledParams B) {
   B.res[g] = 0ull;
 }
 
-// Skinny products of the dual apply, one CTA per point (all tiny next to the p x p solves):
-//   U1 = Yt X^T                         (p x nc)     u_c = Yt x_c
-//   U2 = Z2 U1 ; U3 = Z1 U2             (p x nc)     v_c = C^-1 (sqrt(c0) I + C)^-1 u_c   (scaled below)
-//   t_c = (x_c - Yt^T v_c) / sqrt(c0)
-//   t_b = Yt^T B^-1/2 dw,  t_bd likewise
-// Result: Ts[m][c] member-major like the primal path, with s = 1 conventions.
-__global__ void __launch_bounds__(256) tl_dual_apply_kernel(const DasParams P, const TiledParams B) {
-  const int g = blockIdx.x;
-  if (B.state[g] != 2 || B.skip[g] || B.ncols[g] == 0 || B.nobsl[g] == 0) return;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
-  const int k = P.k, n8 = B.n8, p = B.nobsl[g], kK = B.kK, nmax = B.nmax;
-  const double *Yt = B.E + (size_t)g * B.pK * kK;
+// Dual apply as skinny GEMMs (tl_gemm) around two small kernels:
+//   U1T = X Yt^T                 (16 x p)   u_c = Yt x_c
+//   U2T = U1T Z2 ; rows 14, 15 <- dw, dwd   (tl_dual_setb)
+//   U3T = U2T Z1                 (16 x p)
+//   Ts  = E U3T^T                (n8 x 16)  with E = Yt^T (gathered in the primal layout)
+//   tl_dual_fin:  t_c = x_c / sqrt(c0) - fv Ts_c  (variables),  t_b = fb Ts_b   (b, bd)
+// Z1 = (B/s1)^-1/2 = sqrt(s1) C^-1,  Z2 = (D/s2)^-1/2 = sqrt(s2) (sqrt(c0) I + C)^-1.
+__global__ void __launch_bounds__(256) tl_dual_setb_kernel(const TiledParams B, double *U2T) {
+  const int g = blockIdx.y;
+  if (B.adims[g] == 0) return;
+  const int o = blockIdx.x * 256 + threadIdx.x;
+  if (o >= B.pK) return;
+  const int p = B.nobsl[g];
+  double *u = U2T + (size_t)g * kMaxNV * B.pK;
+  u[(size_t)(kMaxNV - 2) * B.pK + o] = o < p ? B.dw[(size_t)g * B.pK + o] : 0.0;
+  u[(size_t)(kMaxNV - 1) * B.pK + o] = o < p ? B.dw[(size_t)(B.G + g) * B.pK + o] : 0.0;
+}
+__global__ void __launch_bounds__(256) tl_dual_fin_kernel(const DasParams P, const TiledParams B) {
+  const int g = blockIdx.y;
+  if (B.adims[g] == 0) return;
+  const int n8 = B.n8, k = P.k;
+  const double c0 = B.cdiag[g], s1 = B.snorm[g], s2 = B.misc[(size_t)g * 4 + 2];
+  const double isc0 = 1.0 / sqrt(c0), fv = isc0 / (sqrt(s1) * sqrt(s2)), fb = 1.0 / sqrt(s1);
   const double *X = B.X + (size_t)g * kMaxNV * n8;
   double *Ts = B.Ts + (size_t)g * n8 * kMaxNV;
-  double *U1 = B.U + (size_t)g * B.pK * kMaxNV, *U2 = U1 + (size_t)B.G * B.pK * kMaxNV, *U3 = U2 + (size_t)B.G * B.pK * kMaxNV;
-  const double *Z1 = B.mS + (size_t)g * nmax * nmax;   // kept result of the first solve
-  const double *Z2 = B.bZ[B.zsel[g]] + (size_t)g * nmax * nmax;
-  const double c0 = B.cdiag[g], s1 = B.snorm[g], s2 = B.misc[(size_t)g * 4 + 2];
-  const double *dw = B.dw + (size_t)g * B.pK, *dwd = B.dw + (size_t)(B.G + g) * B.pK;
-  constexpr int NV = kMaxNV - 2;
-  // U1[o][c] = sum_m Yt[o][m] X[c][m]   (one warp per obs row); columns 14, 15 carry dw, dwd
-  for (int o = w; o < p; o += nw) {
-    double acc[NV];
-#pragma unroll
-    for (int c = 0; c < NV; ++c) acc[c] = 0.0;
-    const double *yr = Yt + (size_t)o * kK;
-    for (int m = lane; m < k; m += 32) {
-      const double y = yr[m];
-#pragma unroll
-      for (int c = 0; c < NV; ++c) acc[c] = fma(y, X[(size_t)c * n8 + m], acc[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < NV; ++c) {
-      const double v = warp_sum(acc[c]);
-      if (lane == c) U1[(size_t)o * kMaxNV + c] = v;
-    }
-    if (lane == 0) {
-      U1[(size_t)o * kMaxNV + NV] = dw[o];
-      U1[(size_t)o * kMaxNV + NV + 1] = dwd[o];
-    }
-  }
-  __syncthreads();
-  // U2 = Z2 U1 for the variable columns (one warp per row, lanes over columns of Z)
-  for (int o = w; o < p; o += nw) {
-    double acc[NV];
-#pragma unroll
-    for (int c = 0; c < NV; ++c) acc[c] = 0.0;
-    const double *zr = Z2 + (size_t)o * nmax;
-    for (int j = lane; j < p; j += 32) {
-      const double z = zr[j];
-#pragma unroll
-      for (int c = 0; c < NV; ++c) acc[c] = fma(z, U1[(size_t)j * kMaxNV + c], acc[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < NV; ++c) {
-      const double v = warp_sum(acc[c]);
-      if (lane == c) U2[(size_t)o * kMaxNV + c] = v;
-    }
-    if (lane == 0) {   // b columns skip the second factor
-      U2[(size_t)o * kMaxNV + NV] = U1[(size_t)o * kMaxNV + NV];
-      U2[(size_t)o * kMaxNV + NV + 1] = U1[(size_t)o * kMaxNV + NV + 1];
-    }
-  }
-  __syncthreads();
-  // U3 = Z1 U2 (all 16 columns)
-  for (int o = w; o < p; o += nw) {
-    double acc[kMaxNV];
-#pragma unroll
-    for (int c = 0; c < kMaxNV; ++c) acc[c] = 0.0;
-    const double *zr = Z1 + (size_t)o * nmax;
-    for (int j = lane; j < p; j += 32) {
-      const double z = zr[j];
-#pragma unroll
-      for (int c = 0; c < kMaxNV; ++c) acc[c] = fma(z, U2[(size_t)j * kMaxNV + c], acc[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < kMaxNV; ++c) {
-      const double v = warp_sum(acc[c]);
-      if (lane == c) U3[(size_t)o * kMaxNV + c] = v;
-    }
-  }
-  __syncthreads();
-  // Z1 = (B/s1)^-1/2 = sqrt(s1) B^-1/2 = sqrt(s1) C^-1;  Z2 = (D/s2)^-1/2 = sqrt(s2) (sqrt(c0) I + C)^-1
-  const double isc0 = 1.0 / sqrt(c0);
-  const double fv = isc0 / (sqrt(s1) * sqrt(s2));   // variable columns: t = x / sqrt(c0) - fv Yt^T U3
-  const double fb = 1.0 / sqrt(s1);                 // b columns:        t = fb Yt^T U3
-  // Ts[m][c] = sum_o Yt[o][m] U3[o][c]: thread per member m, loop over obs (coalesced along m)
-  for (int m = tid; m < n8; m += blockDim.x) {
-    double acc[kMaxNV];
-#pragma unroll
-    for (int c = 0; c < kMaxNV; ++c) acc[c] = 0.0;
-    if (m < k) {
-      for (int o = 0; o < p; ++o) {
-        const double y = Yt[(size_t)o * kK + m];
-#pragma unroll
-        for (int c = 0; c < kMaxNV; ++c) acc[c] = fma(y, U3[(size_t)o * kMaxNV + c], acc[c]);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < kMaxNV; ++c) {
-      double v;
-      if (c < NV) v = (m < k) ? X[(size_t)c * n8 + m] * isc0 - fv * acc[c] : 0.0;
-      else v = fb * acc[c];
-      Ts[(size_t)m * kMaxNV + c] = v;
-    }
+  for (int e = blockIdx.x * 1024 + threadIdx.x; e < min(n8 * kMaxNV, (int)(blockIdx.x + 1) * 1024); e += 256) {
+    const int m = e / kMaxNV, c = e - m * kMaxNV;
+    const double acc = Ts[e];
+    double v;
+    if (c < kMaxNV - 2) v = (m < k) ? X[(size_t)c * n8 + m] * isc0 - fv * acc : 0.0;
+    else v = (m < k) ? fb * acc : 0.0;
+    Ts[e] = v;
   }
 }
 

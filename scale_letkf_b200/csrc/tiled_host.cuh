@@ -6,14 +6,14 @@ namespace {
 
 struct TiledBufs {
   DevBuf<double> X, Ts, colsc, beta, ri, rj, lp, rz, cdiag, infl, rdiag, rloc, snorm, brk, h0, h1, misc, E, dw, U;
-  DevBuf<double> bZ0, bZ1, bY0, bY1, mT, mS;
+  DevBuf<double> bZ0, bZ1, bY0, bY1, mT, mS, E2;
   DevBuf<int> skip, ncols, cols, nobsl, idx, dims, kd, state, zsel, iters, fail, nactive, adims, solved_any;
   DevBuf<unsigned long long> snorm_bits, res, scounters;
   int *h_pinned = nullptr;   // [0] nactive, [1..] nobsl readback
   size_t h_pinned_n = 0;
   void release() {
     for (DevBuf<double> *b : {&X, &Ts, &colsc, &beta, &ri, &rj, &lp, &rz, &cdiag, &infl, &rdiag, &rloc, &snorm, &brk, &h0,
-                              &h1, &misc, &E, &dw, &U, &bZ0, &bZ1, &bY0, &bY1, &mT, &mS})
+                              &h1, &misc, &E, &dw, &U, &bZ0, &bZ1, &bY0, &bY1, &mT, &mS, &E2})
       b->release();
     for (DevBuf<int> *b : {&skip, &ncols, &cols, &nobsl, &idx, &dims, &kd, &state, &zsel, &iters, &fail, &nactive, &adims,
                            &solved_any})
@@ -125,7 +125,12 @@ int launch_range_tiled(letkf_b200_handle *h, TiledBufs &T, DasParams P, long lon
   const int form = (fe && !std::strcmp(fe, "primal")) ? 0 : (fe && !std::strcmp(fe, "dual")) ? 1 : 2;   // 2: auto
   const char *me = std::getenv("LETKF_B200_TILED_MB");
   const double budget = (me ? std::atof(me) : 4096.0) * 1048576.0;
-  const double item_bytes = 5.0 * n8 * (double)n8 * 8.0 + (double)maxl * 20.0 + 64.0 * n8;
+  // When even the longest possible local list keeps every batch in the dual form, the solver matrices
+  // are p x p and the batch can be much larger.
+  const int pKcap = round_up(maxl, 16);
+  const bool always_dual = form == 1 || (form == 2 && pKcap * 10 <= k * 6);
+  const double mat = always_dual ? 6.0 * pKcap * (double)pKcap + (double)pKcap * (kK + n8) : 5.0 * n8 * (double)n8;
+  const double item_bytes = mat * 8.0 + (double)maxl * 20.0 + 2.0 * kMaxNV * n8 * 8.0 + 1024.0;
   long long G = (long long)(budget / item_bytes);
   G = std::max<long long>(8, std::min<long long>(G, 4096));
   G = std::min<long long>(G, std::max<long long>(end - begin, 1));
@@ -230,8 +235,10 @@ int launch_range_tiled(letkf_b200_handle *h, TiledBufs &T, DasParams P, long lon
           ++launches;
         } else {
           CK(T.E.ensure(Gs * (size_t)pK * kK)); CK(T.dw.ensure(2 * Gs * pK)); CK(T.U.ensure(3 * Gs * pK * kMaxNV));
-          CK(T.mS.ensure(Gs * sN));
-          B.E = T.E.p; B.dw = T.dw.p; B.U = T.U.p; B.mS = T.mS.p;
+          CK(T.mS.ensure(Gs * sN)); CK(T.E2.ensure(Gs * (size_t)n8 * pK));
+          B.E = T.E2.p;   // Yt^T in the primal layout (the apply needs both orientations)
+          tl_gather_primal_kernel<<<dim3((unsigned)((pK + 31) / 32), (unsigned)Gb), dim3(32, 8), 0, h->stream>>>(P, B);
+          B.E2 = T.E2.p; B.E = T.E.p; B.dw = T.dw.p; B.U = T.U.p; B.mS = T.mS.p;
           tl_gather_dual_kernel<<<dim3((unsigned)(pK / 8), (unsigned)Gb), 256, 0, h->stream>>>(P, B);
           GemmParams Q;   // S = Yt Yt^T -> mS
           std::memset(&Q, 0, sizeof(Q));
@@ -254,8 +261,43 @@ int launch_range_tiled(letkf_b200_handle *h, TiledBufs &T, DasParams P, long lon
           launches += 5;
           r = tl_ns_solve(h, T, B, nmax, false, &launches);  // Z2 = (D/s2)^-1/2
           if (r != LETKF_B200_OK) return r;
-          tl_dual_apply_kernel<<<Gb, 256, 0, h->stream>>>(P, B);
-          ++launches;
+          {   // apply: skinny GEMMs (see tiled.cuh)
+            const long long sU = (long long)kMaxNV * pK, sYt = (long long)pK * kK;
+            double *U1T = B.U, *U2T = B.U + (size_t)Gs * sU, *U3T = B.U + 2 * (size_t)Gs * sU;
+            GemmParams A1;   // U1T = X Yt^T
+            std::memset(&A1, 0, sizeof(A1));
+            A1.njobs = 1;
+            A1.job[0] = GemmJob{B.X, nullptr, B.E, U1T, (long long)kMaxNV * n8, sYt, sU, n8, kK, pK};
+            A1.M = kMaxNV; A1.N = pK; A1.K = round_up(k, 8);
+            r = tl_gemm(h, A1, Gb);
+            if (r != LETKF_B200_OK) return r;
+            GemmParams A2;   // U2T = U1T Z2
+            std::memset(&A2, 0, sizeof(A2));
+            A2.njobs = 1;
+            A2.job[0] = GemmJob{U1T, nullptr, B.bZ[0], U2T, sU, (long long)sN, sU, pK, nmax, pK};
+            A2.job[0].B_alt = B.bZ[1];
+            A2.selB = B.zsel;
+            A2.M = kMaxNV; A2.N = pK; A2.K = pK; A2.kdims = B.dims;
+            r = tl_gemm(h, A2, Gb);
+            if (r != LETKF_B200_OK) return r;
+            tl_dual_setb_kernel<<<dim3((unsigned)((pK + 255) / 256), (unsigned)Gb), 256, 0, h->stream>>>(B, U2T);
+            GemmParams A3;   // U3T = U2T Z1
+            std::memset(&A3, 0, sizeof(A3));
+            A3.njobs = 1;
+            A3.job[0] = GemmJob{U2T, nullptr, B.mS, U3T, sU, (long long)sN, sU, pK, nmax, pK};
+            A3.M = kMaxNV; A3.N = pK; A3.K = pK; A3.kdims = B.dims;
+            r = tl_gemm(h, A3, Gb);
+            if (r != LETKF_B200_OK) return r;
+            GemmParams A4;   // Ts = E2 U3T^T
+            std::memset(&A4, 0, sizeof(A4));
+            A4.njobs = 1;
+            A4.job[0] = GemmJob{B.E2, nullptr, U3T, B.Ts, (long long)n8 * pK, sU, (long long)n8 * kMaxNV, pK, pK, kMaxNV};
+            A4.M = n8; A4.N = kMaxNV; A4.K = pK; A4.mdims = B.adims; A4.kdims = B.dims;
+            r = tl_gemm(h, A4, Gb);
+            if (r != LETKF_B200_OK) return r;
+            tl_dual_fin_kernel<<<dim3((unsigned)((n8 * kMaxNV + 1023) / 1024), (unsigned)Gb), 256, 0, h->stream>>>(P, B);
+            launches += 6;
+          }
         }
       }
       tl_update_kernel<<<Gb, 256, 0, h->stream>>>(P, B);
