@@ -57,6 +57,15 @@ struct DasParams {
   unsigned long long *counters;   // [0] work, [1] npoints, [2] nsolved, [3] nfail, [4] nobsl_sum, [5] overflow, [6] Jacobi sweeps, [8..15] phase clocks
   long long point_begin, point_end;   // (ij, ilev) points [begin, end) of this launch, ilev-major
   int max_sweeps;
+  // Local lists produced ahead of time by presearch_kernel (das_ns_kernel.cuh) for the points
+  // [pl_base, ...): entry (wp - pl_base) * nvgroup + vg holds the count (pl_n, -1 = list overflow) and
+  // the offset into the pools (pl_off, -1 = not pre-searched: the solver searches by itself).
+  const int *pl_n;
+  const long long *pl_off;
+  int *pl_iob;
+  double *pl_rdiag, *pl_rloc;
+  long long pl_base, pl_cap;
+  unsigned long long *pl_cursor;
 };
 
 __host__ __device__ inline size_t das_smem_bytes(int k, int nthreads) {

@@ -174,8 +174,20 @@ das_ns_kernel(const DasParams P) {
       const int vtrig = cols[0];
       const double infl = inflv[vtrig];   // parm_infl handed to letkf_core (work3d(ij,ilev,n))
 
-      // ---- local observations ---------------------------------------------------------------
-      const int nobsl = search_point(*P.T, P.rec, P.bstart, P.vlfac + (size_t)vg * P.T->nctype, pt, L, S);
+      // ---- local observations: pre-searched list (presearch_kernel) or in-kernel search ----------
+      int nobsl;
+      const int *liob = L.iob;
+      const double *lrdiag = L.rdiag, *lrloc = L.rloc;
+      long long pl_off = -1;
+      if (P.pl_n) pl_off = P.pl_off[(wp - P.pl_base) * P.nvgroup + vg];
+      if (pl_off >= 0) {
+        nobsl = P.pl_n[(wp - P.pl_base) * P.nvgroup + vg];
+        liob = P.pl_iob + pl_off;
+        lrdiag = P.pl_rdiag + pl_off;
+        lrloc = P.pl_rloc ? P.pl_rloc + pl_off : nullptr;
+      } else {
+        nobsl = search_point(*P.T, P.rec, P.bstart, P.vlfac + (size_t)vg * P.T->nctype, pt, L, S);
+      }
       if (nobsl < 0) ++c_over;
       const int p_use = nobsl < 0 ? 0 : nobsl;
       phase(1);
@@ -205,7 +217,7 @@ das_ns_kernel(const DasParams P) {
           for (int ob = w; ob < nrows; ob += 4 * NB) {
             int iobs[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) iobs[u] = (ob + u * NB < nrows) ? L.iob[o0 + ob + u * NB] : -1;
+            for (int u = 0; u < 4; ++u) iobs[u] = (ob + u * NB < nrows) ? liob[o0 + ob + u * NB] : -1;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (iobs[u] < 0) continue;
@@ -219,8 +231,8 @@ das_ns_kernel(const DasParams P) {
           if (tid < nrows4) {
             double wt = 0.0;
             if (tid < nrows) {
-              wt = 1.0 / L.rdiag[o0 + tid];
-              if (P.INFL_MUL_ADAPTIVE) p3acc += L.rloc[o0 + tid];
+              wt = 1.0 / lrdiag[o0 + tid];
+              if (P.INFL_MUL_ADAPTIVE) p3acc += lrloc[o0 + tid];
             }
             wdst[tid] = wt;
           }
@@ -426,6 +438,93 @@ das_ns_kernel(const DasParams P) {
     atomicAdd(&P.counters[5], c_over);
     atomicAdd(&P.counters[6], c_iters);
     for (int i = 0; i < 8; ++i) atomicAdd(&P.counters[8 + i], (unsigned long long)ph[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// presearch_kernel: the local-observation search of das_letkf for the points [point_begin, point_end),
+// run AHEAD of the solver on its own stream so that its latency-bound work overlaps the solver's
+// tensor-core work on the same SMs.  Lists go to a pool (atomic bump allocation); a point that does
+// not fit keeps pl_off = -1 and is searched by the solver itself.  Same point / group activity rules
+// as das_ns_kernel (relax_beta, Q_UPDATE_TOP mask), same Point inputs, hence bit-identical lists.
+__global__ void __launch_bounds__(128) presearch_kernel(const DasParams P, int *pl_n, long long *pl_off) {
+  __shared__ SearchSmem S;
+  __shared__ long long s_work;
+  __shared__ long long s_off;
+  const int tid = threadIdx.x, k = P.k;
+  LocalList L;
+  L.cap = P.lcap;
+  L.iob = P.l_iob + (size_t)blockIdx.x * P.lcap;
+  L.rdiag = P.l_rdiag + (size_t)blockIdx.x * P.lcap;
+  L.rloc = P.l_rloc + (size_t)blockIdx.x * P.lcap;
+  L.ccap = P.ccap;
+  L.cnd = P.l_cnd + (size_t)blockIdx.x * P.ccap;
+  L.cpk = P.l_cpk + (size_t)blockIdx.x * P.ccap;
+  const size_t sl = (size_t)P.nij1 * P.nlev;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_work = P.point_begin + (long long)atomicAdd(&P.counters[0], 1ull);
+    __syncthreads();
+    const long long wp = s_work;
+    if (wp >= P.point_end) break;
+    const int il = (int)(wp / P.nij1), ij = (int)(wp - (long long)il * P.nij1);
+    const int nvtot = P.nv3d + (il == 0 ? P.nv2d : 0);
+    const size_t pbase = (size_t)ij + (size_t)il * P.nij1;
+    const double ri = P.rig1[ij], rj = P.rjg1[ij], rz = P.hgt1[pbase];
+    double beta = 1.0;
+    if (P.radar_only && rz > P.zcut) {
+      beta = 0.0;
+    } else if (P.BOUNDARY_BUFFER_WIDTH > 0.0) {
+      const double dist_bdy =
+          fmin(fmin(ri - P.IHALO, P.nlon + P.IHALO + 1 - ri) * P.DX,
+               fmin(rj - P.JHALO, P.nlat + P.JHALO + 1 - rj) * P.DY) / P.BOUNDARY_BUFFER_WIDTH;
+      if (dist_bdy < 1.0) beta = fmax(dist_bdy, 0.0);
+    }
+    const double pmean = P.gues3d[pbase + ((size_t)k + (size_t)(P.iv3d_p - 1) * P.nens) * sl];   // mean slot
+    Point pt;
+    pt.ri = ri;
+    pt.rj = rj;
+    pt.rz = rz;
+    pt.lp = P.logp ? P.logp[pbase] : log(pmean);
+    for (int vg = 0; vg < P.nvgroup; ++vg) {
+      const long long e = (wp - P.pl_base) * P.nvgroup + vg;
+      bool any = false;
+      if (beta != 0.0) {
+        for (int vv = 0; vv < nvtot; ++vv) {
+          if (P.vgroup[vv] != vg) continue;
+          const bool masked = (vv < P.nv3d) && pmean < P.Q_UPDATE_TOP && (vv + 1) >= P.iv3d_q && (vv + 1) <= P.iv3d_qg;
+          if (!masked) any = true;
+        }
+      }
+      if (!any) {   // the solver never asks for this list
+        if (tid == 0) {
+          pl_n[e] = 0;
+          pl_off[e] = 0;
+        }
+        continue;
+      }
+      const int n = search_point(*P.T, P.rec, P.bstart, P.vlfac + (size_t)vg * P.T->nctype, pt, L, S);
+      if (tid == 0) {
+        long long off = 0;
+        if (n > 0) {
+          const int n4 = (n + 3) & ~3;   // keep every list 32-byte aligned for the solver's staging loads
+          off = (long long)atomicAdd(P.pl_cursor, (unsigned long long)n4);
+          if (off + n4 > P.pl_cap) off = -1;
+        }
+        s_off = off;
+        pl_n[e] = n;
+        pl_off[e] = off;
+      }
+      __syncthreads();
+      const long long off = s_off;
+      if (n > 0 && off >= 0) {
+        for (int i = tid; i < n; i += blockDim.x) {
+          P.pl_iob[off + i] = L.iob[i];
+          P.pl_rdiag[off + i] = L.rdiag[i];
+          if (P.pl_rloc) P.pl_rloc[off + i] = L.rloc[i];
+        }
+      }
+    }
   }
 }
 

@@ -132,6 +132,15 @@ struct letkf_b200_handle {
   float last_ms = 0.f;
   int last_launches = 0;
   TiledBufs *tiled = nullptr;
+  // pre-search pipeline (presearch_kernel): two pools, chunk parity
+  cudaStream_t s_search = nullptr;
+  std::vector<cudaEvent_t> ev_s;
+  DevBuf<int> pl_n[2], pl_iob[2], ps_l_iob;
+  DevBuf<long long> pl_off[2];
+  DevBuf<double> pl_rdiag[2], pl_rloc[2], ps_l_rdiag, ps_l_rloc, ps_l_cnd;
+  DevBuf<unsigned> ps_l_cpk;
+  DevBuf<unsigned long long> ps_counters;   // [0..15] work counter block, [16], [17] pool cursors
+  int ps_grid = 0;
 };
 
 #define CK(call)                                                                         \
@@ -385,7 +394,12 @@ int letkf_b200_create(const letkf_b200_config *cfg, int device, letkf_b200_handl
   cudaEventCreate(&h->ev1);
   cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
-  if (h->counters.ensure(16) != cudaSuccess) {
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&h->s_search, cudaStreamNonBlocking, hi);
+  }
+  if (h->counters.ensure(16) != cudaSuccess || h->ps_counters.ensure(18) != cudaSuccess) {
     delete h;
     return LETKF_B200_ECUDA;
   }
@@ -406,6 +420,13 @@ int letkf_b200_destroy(letkf_b200_handle *h) {
   for (auto &b : h->cb) b.release();
   h->cb_i.release();
   if (h->tiled) { h->tiled->release(); delete h->tiled; h->tiled = nullptr; }
+  for (int b = 0; b < 2; ++b) {
+    h->pl_n[b].release(); h->pl_iob[b].release(); h->pl_off[b].release(); h->pl_rdiag[b].release(); h->pl_rloc[b].release();
+  }
+  h->ps_l_iob.release(); h->ps_l_rdiag.release(); h->ps_l_rloc.release(); h->ps_l_cnd.release(); h->ps_l_cpk.release();
+  h->ps_counters.release();
+  for (cudaEvent_t e : h->ev_s) cudaEventDestroy(e);
+  if (h->s_search) cudaStreamDestroy(h->s_search);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto *v : {&h->ev_in, &h->ev_k0, &h->ev_k1})
@@ -833,10 +854,16 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   // Level chunks.  Device-resident state: one launch.  Host state: ~10 chunks pipelined over three
   // streams -- H2D of chunk c+1 and D2H of chunk c-1 overlap the analysis of chunk c (PCIe is full
   // duplex), so the call costs max(copy, compute) instead of their sum.
+  // Pre-search (one-CTA-per-point solver only): the local-observation search of chunk c+1 runs in its own
+  // kernel on a high-priority stream while the solver works on chunk c, so the latency-bound search fills
+  // the issue slots the tensor-core solver leaves idle.  LETKF_B200_PRESEARCH=0 searches inside the solver.
+  const char *pe = std::getenv("LETKF_B200_PRESEARCH");
+  const bool pre = !tiled && !jacobi && !(pe && pe[0] == '0');
   int nchunk = 1;
-  if (host) {
+  {
     const char *ce = std::getenv("LETKF_B200_CHUNKS");
-    nchunk = ce ? std::atoi(ce) : 10;
+    if (host) nchunk = ce ? std::atoi(ce) : 10;
+    else if (pre) nchunk = ce ? std::atoi(ce) : 12;
     nchunk = std::max(1, std::min(nchunk, c.nlev));
   }
   while ((int)h->ev_in.size() < nchunk) {
@@ -844,10 +871,57 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_in.push_back(e);
     CK(cudaEventCreate(&e)); h->ev_k0.push_back(e);
     CK(cudaEventCreate(&e)); h->ev_k1.push_back(e);
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_s.push_back(e);
   }
   const size_t pitch = sizeof(double) * sl;   // distance between (member, variable) planes
   const size_t planes = (size_t)nens * c.nv3d;
   auto lev0 = [&](int ch) { return (int)((long long)c.nlev * ch / nchunk); };
+  long long pl_cap = 0;
+  size_t pl_entries_max = 0;
+  if (pre) {
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, presearch_kernel, 128, 0));
+    h->ps_grid = std::max(1, std::min(occ, 8)) * h->num_sms;
+    CK(h->ps_l_iob.ensure((size_t)h->ps_grid * h->maxl)); CK(h->ps_l_rdiag.ensure((size_t)h->ps_grid * h->maxl));
+    CK(h->ps_l_rloc.ensure((size_t)h->ps_grid * h->maxl));
+    CK(h->ps_l_cnd.ensure((size_t)h->ps_grid * h->ccap)); CK(h->ps_l_cpk.ensure((size_t)h->ps_grid * h->ccap));
+    int maxlev = 0;
+    for (int ch = 0; ch < nchunk; ++ch) maxlev = std::max(maxlev, lev0(ch + 1) - lev0(ch));
+    pl_entries_max = (size_t)maxlev * h->nij1 * h->nvgroup;
+    const char *pm = std::getenv("LETKF_B200_POOL_MB");
+    const double budget = (pm ? std::atof(pm) : 2048.0) * 1048576.0;
+    const size_t per = c.INFL_MUL_ADAPTIVE ? 20 : 12;
+    pl_cap = (long long)std::min<double>((double)pl_entries_max * (double)round_up(h->maxl, 4), budget / per);
+    pl_cap = std::max<long long>(pl_cap, 4);
+    for (int b = 0; b < 2; ++b) {
+      CK(h->pl_n[b].ensure(pl_entries_max)); CK(h->pl_off[b].ensure(pl_entries_max));
+      CK(h->pl_iob[b].ensure((size_t)pl_cap)); CK(h->pl_rdiag[b].ensure((size_t)pl_cap));
+      if (c.INFL_MUL_ADAPTIVE) CK(h->pl_rloc[b].ensure((size_t)pl_cap));
+    }
+  }
+  auto launch_search = [&](int ch) -> int {
+    const int b = ch & 1, l0 = lev0(ch), l1 = lev0(ch + 1);
+    if (host) CK(cudaStreamWaitEvent(h->s_search, h->ev_in[ch], 0));
+    if (ch >= 2) CK(cudaStreamWaitEvent(h->s_search, h->ev_k1[ch - 2], 0));   // the pool of chunk ch-2 is free again
+    DasParams Q = P;
+    Q.point_begin = (long long)l0 * h->nij1;
+    Q.point_end = (long long)l1 * h->nij1;
+    Q.pl_base = Q.point_begin;
+    Q.pl_cap = pl_cap;
+    Q.pl_iob = h->pl_iob[b].p; Q.pl_rdiag = h->pl_rdiag[b].p; Q.pl_rloc = c.INFL_MUL_ADAPTIVE ? h->pl_rloc[b].p : nullptr;
+    Q.pl_cursor = h->ps_counters.p + 16 + b;
+    Q.counters = h->ps_counters.p;
+    Q.l_iob = h->ps_l_iob.p; Q.l_rdiag = h->ps_l_rdiag.p; Q.l_rloc = h->ps_l_rloc.p; Q.l_cnd = h->ps_l_cnd.p; Q.l_cpk = h->ps_l_cpk.p;
+    Q.ccap = h->ccap;
+    CK(cudaMemsetAsync(h->ps_counters.p, 0, sizeof(unsigned long long), h->s_search));
+    CK(cudaMemsetAsync(h->ps_counters.p + 16 + b, 0, sizeof(unsigned long long), h->s_search));
+    const long long npts = Q.point_end - Q.point_begin;
+    presearch_kernel<<<(unsigned)std::min<long long>(h->ps_grid, std::max<long long>(npts, 1)), 128, 0, h->s_search>>>(
+        Q, h->pl_n[b].p, h->pl_off[b].p);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_s[ch], h->s_search));
+    return LETKF_B200_OK;
+  };
   if (host) {
     for (int ch = 0; ch < nchunk; ++ch) {
       const int l0 = lev0(ch), l1 = lev0(ch + 1);
@@ -856,9 +930,28 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
       CK(cudaEventRecord(h->ev_in[ch], h->s_h2d));
     }
   }
+  if (pre) {
+    // the search stream must not start before the work already queued on the compute stream (state restore,
+    // obs tables) is done
+    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaStreamWaitEvent(h->s_search, h->ev0, 0));
+    r = launch_search(0);
+    if (r != LETKF_B200_OK) return r;
+  }
   for (int ch = 0; ch < nchunk; ++ch) {
     const int l0 = lev0(ch), l1 = lev0(ch + 1);
+    if (pre && ch + 1 < nchunk) {
+      r = launch_search(ch + 1);
+      if (r != LETKF_B200_OK) return r;
+    }
     if (host) CK(cudaStreamWaitEvent(h->stream, h->ev_in[ch], 0));
+    if (pre) {
+      CK(cudaStreamWaitEvent(h->stream, h->ev_s[ch], 0));
+      const int b = ch & 1;
+      P.pl_n = h->pl_n[b].p; P.pl_off = h->pl_off[b].p; P.pl_iob = h->pl_iob[b].p; P.pl_rdiag = h->pl_rdiag[b].p;
+      P.pl_rloc = c.INFL_MUL_ADAPTIVE ? h->pl_rloc[b].p : nullptr;
+      P.pl_base = (long long)l0 * h->nij1;
+    }
     if (tiled) r = launch_range_tiled(h, *h->tiled, P, (long long)l0 * h->nij1, (long long)l1 * h->nij1, h->ev_k0[ch], h->ev_k1[ch], &nlaunch);
     else r = launch_range(h, L, P, (long long)l0 * h->nij1, (long long)l1 * h->nij1, h->ev_k0[ch], h->ev_k1[ch]);
     if (r != LETKF_B200_OK) return r;
