@@ -245,6 +245,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
+    ap.add_argument("--cycle", action="store_true", help="also time the full cycle (transposes + bucketing + analysis)")
+    ap.add_argument("--cycle-steps", type=int, default=3)
     ap.add_argument("--subsample", type=int, default=1,
                     help="profiling aid: analyse only every S-th column of the plane (same per-point work)")
     args = ap.parse_args()
@@ -353,6 +355,57 @@ def main():
                 "frac": ach_gbs / peaks.get("hbm_gbs"), "peak_source": peaks_src + " MEASURED_PEAKS.json"},
     }
 
+    # ---- full analysis cycle (SURVEY.md section 8d metric ii): member-major grids -> transpose in
+    # (CUDA pack + NCCL all-to-all + unpack, read_ens_mpi twin) -> ensemble mean -> observation
+    # bucketing (set_letkf_obs twin, H2D of the obs tables included) -> das_letkf -> analysis mean ->
+    # transpose out (write_ens_mpi twin).  Device timed, max over ranks.
+    cycle = None
+    if args.cycle and args.subsample == 1:
+        try:
+            from scale_letkf_b200.transpose import EnsTranspose
+            nens = gues0.shape[1]
+            tr = EnsTranspose(eng, world, rank, nlev, nv, 0, group=None, device=dev)
+            gsz = nlev * w["nlon"] * w["nlat"] * nv
+            rounds = list(tr.rounds(k))
+            gin = [torch.empty(gsz, dtype=torch.float64, device=dev) if im is not None else None for _, im, _, _ in rounds]
+            gout = [torch.empty(gsz, dtype=torch.float64, device=dev) if im is not None else None for _, im, _, _ in rounds]
+            gues.copy_(gues0)
+            tr.write_ens(gues, None, gin, None, k, nens)      # untimed: the member-major input of the cycle
+            names = ["transpose_in", "ensmean", "set_obs", "das_letkf", "anal_mean", "transpose_out"]
+            recs = []
+            for i in range(2 + args.cycle_steps):
+                barrier()
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+                ev[0].record()
+                tr.read_ens(gin, None, gues, None, k, nens)
+                ev[1].record()
+                eng.ensmean_grd(gues)
+                ev[2].record()
+                eng.set_letkf_obs(obs)
+                ev[3].record()
+                eng.das_letkf(gues, anal3d=anal)
+                ev[4].record()
+                eng.ensmean_grd(anal)
+                ev[5].record()
+                tr.write_ens(anal, None, gout, None, k, nens)
+                ev[6].record()
+                barrier()
+                if i >= 2:
+                    recs.append([ev[j].elapsed_time(ev[j + 1]) for j in range(len(names))])
+            arr = torch.tensor(recs, dtype=torch.float64, device=dev)       # (steps, phases)
+            tot = arr.sum(dim=1)
+            if world > 1:
+                dist.all_reduce(arr, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+            cycle = {"ms_median": float(tot.median()), "ms_min": float(tot.min()), "steps": args.cycle_steps,
+                     "phases_ms_median": dict(zip(names, [round(float(x), 3) for x in arr.median(dim=0).values])),
+                     "bytes_all_to_all_per_rank": int(2 * tr.block * world * 8 * len(rounds)),
+                     "what": "transpose in + mean + obs bucketing + analysis + mean + transpose out, n_gpus ranks"}
+            del gin, gout, tr
+        except Exception as e:   # never lose the main measurement to the optional leg
+            cycle = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+
     # ---- end-to-end leg: host buffers through the C ABI -----------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -402,7 +455,7 @@ def main():
                        "decomposition": f"cyclic column deal over {world} rank(s), obs replicated, no collective",
                        "l2": "inputs (%.1f GB state per rank) far larger than the 126 MB L2" % (state_bytes / 1e9)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches / world) * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "cycle": cycle,
             "kernel_ms_per_step": kms, "phase_share_rank0": phases,
         }
         if args.subsample > 1:

@@ -66,6 +66,11 @@ struct DasParams {
   double *pl_rdiag, *pl_rloc;
   long long pl_base, pl_cap;
   unsigned long long *pl_cursor;
+  // points the PRE solver could not take (list not in the pool), and the redo pass over them
+  long long *redo_list;
+  unsigned long long *redo_count;
+  const long long *point_list;
+  const unsigned long long *point_count;
 };
 
 __host__ __device__ inline size_t das_smem_bytes(int k, int nthreads) {

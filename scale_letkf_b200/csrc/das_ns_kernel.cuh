@@ -16,14 +16,14 @@
 
 namespace letkf {
 
-template <int NB>
+template <int NB, bool PRE = false>
 __host__ __device__ inline size_t das_ns_smem_bytes() {
   using C = NsCfg<NB>;
   size_t d = 3 * (size_t)C::PSZ;          // packed Y, Z, T (Z+T double as the two obs-chunk staging buffers)
   d += 2 * (size_t)kMaxNV * C::LD;        // Xall, Ts
   d += 2 * (size_t)C::CR;                 // per-row weights of the two staged chunks
   d += 8 * kMaxNV + 40;                   // per-column scalars, reductions
-  return d * sizeof(double) + sizeof(SearchSmem) + 64;
+  return d * sizeof(double) + (PRE ? 0 : sizeof(SearchSmem)) + 64;
 }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -36,7 +36,10 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
-template <int NB>
+// PRE = true: every local list comes from presearch_kernel's pool; the kernel contains no search code at
+// all (fewer live registers, no SearchSmem).  A point whose list did not fit the pool is appended to
+// P.redo_list untouched and analysed afterwards by the PRE = false instantiation (P.point_list mode).
+template <int NB, bool PRE>
 __global__ void __launch_bounds__(NsCfg<NB>::NT, NsCfg<NB>::MINB)
 das_ns_kernel(const DasParams P) {
   using C = NsCfg<NB>;
@@ -83,10 +86,29 @@ das_ns_kernel(const DasParams P) {
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_work = P.point_begin + (long long)atomicAdd(&P.counters[0], 1ull);
+    if (tid == 0) {
+      long long v;
+      if (!PRE && P.point_list) {   // redo mode: explicit list of points, its length produced on the device
+        const long long i = (long long)atomicAdd(&P.counters[0], 1ull);
+        v = (i < (long long)*P.point_count) ? P.point_list[i] : -2;
+      } else {
+        v = P.point_begin + (long long)atomicAdd(&P.counters[0], 1ull);
+        if (v >= P.point_end) v = -2;
+        if (PRE && v >= 0) {   // all lists of the point must be in the pool
+          bool ok = true;
+          for (int vg = 0; vg < P.nvgroup; ++vg) ok = ok && P.pl_off[(v - P.pl_base) * P.nvgroup + vg] >= 0;
+          if (!ok) {
+            P.redo_list[atomicAdd(P.redo_count, 1ull)] = v;
+            v = -1;
+          }
+        }
+      }
+      s_work = v;
+    }
     __syncthreads();
     const long long wp = s_work;
-    if (wp >= P.point_end) break;
+    if (wp == -2) break;      // no more work
+    if (wp < 0) continue;     // handed to the redo pass
     phase(7);
     const int il = (int)(wp / P.nij1), ij = (int)(wp - (long long)il * P.nij1);
     ++c_points;
@@ -175,16 +197,14 @@ das_ns_kernel(const DasParams P) {
       const double infl = inflv[vtrig];   // parm_infl handed to letkf_core (work3d(ij,ilev,n))
 
       // ---- local observations: pre-searched list (presearch_kernel) or in-kernel search ----------
+      // (L's pointers are simply re-aimed: no extra live registers in the Gram loop)
       int nobsl;
-      const int *liob = L.iob;
-      const double *lrdiag = L.rdiag, *lrloc = L.rloc;
-      long long pl_off = -1;
-      if (P.pl_n) pl_off = P.pl_off[(wp - P.pl_base) * P.nvgroup + vg];
-      if (pl_off >= 0) {
+      if constexpr (PRE) {
+        const long long pl_off = P.pl_off[(wp - P.pl_base) * P.nvgroup + vg];
         nobsl = P.pl_n[(wp - P.pl_base) * P.nvgroup + vg];
-        liob = P.pl_iob + pl_off;
-        lrdiag = P.pl_rdiag + pl_off;
-        lrloc = P.pl_rloc ? P.pl_rloc + pl_off : nullptr;
+        L.iob = P.pl_iob + pl_off;
+        L.rdiag = P.pl_rdiag + pl_off;
+        L.rloc = P.pl_rloc + pl_off;   // only dereferenced when INFL_MUL_ADAPTIVE (then the pool exists)
       } else {
         nobsl = search_point(*P.T, P.rec, P.bstart, P.vlfac + (size_t)vg * P.T->nctype, pt, L, S);
       }
@@ -217,7 +237,7 @@ das_ns_kernel(const DasParams P) {
           for (int ob = w; ob < nrows; ob += 4 * NB) {
             int iobs[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) iobs[u] = (ob + u * NB < nrows) ? liob[o0 + ob + u * NB] : -1;
+            for (int u = 0; u < 4; ++u) iobs[u] = (ob + u * NB < nrows) ? L.iob[o0 + ob + u * NB] : -1;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (iobs[u] < 0) continue;
@@ -231,8 +251,8 @@ das_ns_kernel(const DasParams P) {
           if (tid < nrows4) {
             double wt = 0.0;
             if (tid < nrows) {
-              wt = 1.0 / lrdiag[o0 + tid];
-              if (P.INFL_MUL_ADAPTIVE) p3acc += lrloc[o0 + tid];
+              wt = 1.0 / L.rdiag[o0 + tid];
+              if (P.INFL_MUL_ADAPTIVE) p3acc += L.rloc[o0 + tid];
             }
             wdst[tid] = wt;
           }

@@ -141,6 +141,7 @@ struct letkf_b200_handle {
   DevBuf<unsigned> ps_l_cpk;
   DevBuf<unsigned long long> ps_counters;   // [0..15] work counter block, [16], [17] pool cursors
   int ps_grid = 0;
+  DevBuf<long long> redo_list;
 };
 
 #define CK(call)                                                                         \
@@ -230,16 +231,24 @@ int plan_das(letkf_b200_handle *h, DasParams &P, DasLaunch &L) {
   return plan_common(h, P, L, occ, "das_kernel does not fit on an SM");
 }
 
-template <int NB>
+template <int NB, bool PRE>
 int plan_das_ns(letkf_b200_handle *h, DasParams &P, DasLaunch &L) {
   using C = NsCfg<NB>;
-  L.kern = das_ns_kernel<NB>;
+  L.kern = das_ns_kernel<NB, PRE>;
   L.nt = C::NT;
-  L.smem = das_ns_smem_bytes<NB>();
-  CK(cudaFuncSetAttribute(das_ns_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  L.smem = das_ns_smem_bytes<NB, PRE>();
+  CK(cudaFuncSetAttribute(das_ns_kernel<NB, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, das_ns_kernel<NB>, C::NT, L.smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, das_ns_kernel<NB, PRE>, C::NT, L.smem));
   return plan_common(h, P, L, occ, "das_ns_kernel does not fit on an SM");
+}
+template <bool PRE>
+int plan_das_ns_class(letkf_b200_handle *h, int nsc, DasParams &P, DasLaunch &L) {
+  if (nsc == 3) return plan_das_ns<3, PRE>(h, P, L);
+  if (nsc == 5) return plan_das_ns<5, PRE>(h, P, L);
+  if (nsc == 7) return plan_das_ns<7, PRE>(h, P, L);
+  if (nsc == 9) return plan_das_ns<9, PRE>(h, P, L);
+  return plan_das_ns<13, PRE>(h, P, L);
 }
 
 // analyse points [begin, end) on the handle's compute stream, bracketed by the two events
@@ -399,7 +408,7 @@ int letkf_b200_create(const letkf_b200_config *cfg, int device, letkf_b200_handl
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     cudaStreamCreateWithPriority(&h->s_search, cudaStreamNonBlocking, hi);
   }
-  if (h->counters.ensure(16) != cudaSuccess || h->ps_counters.ensure(18) != cudaSuccess) {
+  if (h->counters.ensure(16) != cudaSuccess || h->ps_counters.ensure(20) != cudaSuccess) {
     delete h;
     return LETKF_B200_ECUDA;
   }
@@ -424,7 +433,7 @@ int letkf_b200_destroy(letkf_b200_handle *h) {
     h->pl_n[b].release(); h->pl_iob[b].release(); h->pl_off[b].release(); h->pl_rdiag[b].release(); h->pl_rloc[b].release();
   }
   h->ps_l_iob.release(); h->ps_l_rdiag.release(); h->ps_l_rloc.release(); h->ps_l_cnd.release(); h->ps_l_cpk.release();
-  h->ps_counters.release();
+  h->ps_counters.release(); h->redo_list.release();
   for (cudaEvent_t e : h->ev_s) cudaEventDestroy(e);
   if (h->s_search) cudaStreamDestroy(h->s_search);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -838,11 +847,7 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
     if (!h->tiled) h->tiled = new TiledBufs();
     r = LETKF_B200_OK;
   } else if (!jacobi) {
-    if (nsc == 3) r = plan_das_ns<3>(h, P, L);
-    else if (nsc == 5) r = plan_das_ns<5>(h, P, L);
-    else if (nsc == 7) r = plan_das_ns<7>(h, P, L);
-    else if (nsc == 9) r = plan_das_ns<9>(h, P, L);
-    else r = plan_das_ns<13>(h, P, L);
+    r = plan_das_ns_class<false>(h, nsc, P, L);
   } else
   if (k <= 20) r = plan_das<20>(h, P, L);
   else if (k <= 52) r = plan_das<52>(h, P, L);
@@ -859,6 +864,11 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   // the issue slots the tensor-core solver leaves idle.  LETKF_B200_PRESEARCH=0 searches inside the solver.
   const char *pe = std::getenv("LETKF_B200_PRESEARCH");
   const bool pre = !tiled && !jacobi && !(pe && pe[0] == '0');
+  DasLaunch Lpre;   // the search-free solver; L (with in-kernel search) then only runs the redo pass
+  if (pre) {
+    r = plan_das_ns_class<true>(h, nsc, P, Lpre);
+    if (r != LETKF_B200_OK) return r;
+  }
   int nchunk = 1;
   {
     const char *ce = std::getenv("LETKF_B200_CHUNKS");
@@ -893,6 +903,7 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
     const size_t per = c.INFL_MUL_ADAPTIVE ? 20 : 12;
     pl_cap = (long long)std::min<double>((double)pl_entries_max * (double)round_up(h->maxl, 4), budget / per);
     pl_cap = std::max<long long>(pl_cap, 4);
+    CK(h->redo_list.ensure((size_t)maxlev * h->nij1));
     for (int b = 0; b < 2; ++b) {
       CK(h->pl_n[b].ensure(pl_entries_max)); CK(h->pl_off[b].ensure(pl_entries_max));
       CK(h->pl_iob[b].ensure((size_t)pl_cap)); CK(h->pl_rdiag[b].ensure((size_t)pl_cap));
@@ -952,8 +963,39 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
       P.pl_rloc = c.INFL_MUL_ADAPTIVE ? h->pl_rloc[b].p : nullptr;
       P.pl_base = (long long)l0 * h->nij1;
     }
-    if (tiled) r = launch_range_tiled(h, *h->tiled, P, (long long)l0 * h->nij1, (long long)l1 * h->nij1, h->ev_k0[ch], h->ev_k1[ch], &nlaunch);
-    else r = launch_range(h, L, P, (long long)l0 * h->nij1, (long long)l1 * h->nij1, h->ev_k0[ch], h->ev_k1[ch]);
+    if (tiled) {
+      r = launch_range_tiled(h, *h->tiled, P, (long long)l0 * h->nij1, (long long)l1 * h->nij1, h->ev_k0[ch], h->ev_k1[ch], &nlaunch);
+    } else if (pre) {
+      // search-free solver over the chunk, then the redo pass (normally empty) with in-kernel search
+      const long long pb = (long long)l0 * h->nij1, pe2 = (long long)l1 * h->nij1;
+      P.redo_list = h->redo_list.p;
+      P.redo_count = h->ps_counters.p + 18;
+      P.point_list = nullptr;
+      P.point_count = nullptr;
+      CK(cudaMemsetAsync(h->ps_counters.p + 18, 0, sizeof(unsigned long long), h->stream));
+      CK(cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long), h->stream));
+      CK(cudaEventRecord(h->ev_k0[ch], h->stream));
+      {
+        DasParams Q = P;
+        Q.point_begin = pb;
+        Q.point_end = pe2;
+        Lpre.kern<<<(unsigned)std::min<long long>(Lpre.grid, std::max<long long>(pe2 - pb, 1)), Lpre.nt, Lpre.smem, h->stream>>>(Q);
+        CK(cudaGetLastError());
+        Q.pl_n = nullptr;            // redo pass: the solver searches by itself
+        Q.pl_off = nullptr;
+        Q.point_list = h->redo_list.p;
+        Q.point_count = h->ps_counters.p + 18;
+        Q.point_begin = 0;
+        Q.point_end = pe2 - pb;      // upper bound; the real length is *point_count
+        CK(cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long), h->stream));
+        L.kern<<<(unsigned)std::min<long long>(L.grid, std::max<long long>(pe2 - pb, 1)), L.nt, L.smem, h->stream>>>(Q);
+        CK(cudaGetLastError());
+      }
+      CK(cudaEventRecord(h->ev_k1[ch], h->stream));
+      r = LETKF_B200_OK;
+    } else {
+      r = launch_range(h, L, P, (long long)l0 * h->nij1, (long long)l1 * h->nij1, h->ev_k0[ch], h->ev_k1[ch]);
+    }
     if (r != LETKF_B200_OK) return r;
     if (host) {
       const size_t off = (size_t)l0 * h->nij1, w = sizeof(double) * (size_t)(l1 - l0) * h->nij1;

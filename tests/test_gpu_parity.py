@@ -291,3 +291,29 @@ def test_ensmean_and_transposes(oracle):
         got = d_bufs.cpu().numpy().reshape(bufr.shape, order="F")
         assert np.array_equal(got[:nij1], bufr[:nij1])
     e.close()
+
+
+@pytest.mark.parametrize("pool_mb", ["0.0005", "0.02"])
+def test_das_presearch_pool_overflow_redo(oracle, monkeypatch, pool_mb):
+    """A pre-search pool that is far too small: the search-free solver hands the points whose lists did
+    not fit to the redo pass (in-kernel search); results must not change."""
+    monkeypatch.setenv("LETKF_B200_POOL_MB", pool_mb)
+    cfg, rig1, rjg1, hgt1, obs, gues = sonde_case(member=20, nsonde=30, nsfc=100)
+    cfg.BOUNDARY_BUFFER_WIDTH = 45.0e3
+    out, ref = _das_compare(cfg, rig1, rjg1, hgt1, obs, gues, oracle)
+    assert out["nsolved"] > 0
+
+
+def test_das_presearch_off_matches_on(oracle, monkeypatch):
+    cfg, rig1, rjg1, hgt1, obs, gues = radar_case(member=16, max_nobs=30, nlon=32, nlat=32, nlev=6, det=True)
+    e = sl.LETKF(cfg, device=0)
+    e.set_letkf_obs(obs)
+    e.set_common_mpi_grid(rig1, rjg1, hgt1)
+    lp = host_logp(cfg, gues)
+    on = e.das_letkf(gues.copy(order="F"), want_nobsl=True, logp=lp)
+    monkeypatch.setenv("LETKF_B200_PRESEARCH", "0")
+    off = e.das_letkf(gues.copy(order="F"), want_nobsl=True, logp=lp)
+    assert np.array_equal(on["nobsl"], off["nobsl"])
+    k = cfg.MEMBER
+    assert relerr(on["anal3d"][:, :, :k, :], off["anal3d"][:, :, :k, :], axis=(0, 1, 2)) <= 1e-12
+    e.close()
