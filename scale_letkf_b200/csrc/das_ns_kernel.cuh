@@ -20,7 +20,8 @@ template <int NB, bool PRE = false>
 __host__ __device__ inline size_t das_ns_smem_bytes() {
   using C = NsCfg<NB>;
   size_t d = 3 * (size_t)C::PSZ;          // packed Y, Z, T (Z+T double as the two obs-chunk staging buffers)
-  d += 2 * (size_t)kMaxNV * C::LD;        // Xall, Ts
+  d += (size_t)kMaxNV * C::LD;            // Xall
+  if (kMaxNV * C::LD > C::PSZ) d += (size_t)kMaxNV * C::LD;   // Ts (else it aliases T: the Newton-Schulz scratch is free by then)
   d += 2 * (size_t)C::CR;                 // per-row weights of the two staged chunks
   d += 8 * kMaxNV + 40;                   // per-column scalars, reductions
   return d * sizeof(double) + (PRE ? 0 : sizeof(SearchSmem)) + 64;
@@ -53,8 +54,9 @@ das_ns_kernel(const DasParams P) {
   double *Tp = Zp + PSZ;
   double *stage = Zp;                           // 2 x CR x LD doubles inside Zp..Tp
   double *Xall = Tp + PSZ;                      // [kMaxNV][LD]: perturbations of variable vv; rows 14/15: b, bd
-  double *Ts = Xall + (size_t)kMaxNV * LD;      // [kMaxNV][LD]: Z Xall
-  double *wv = Ts + (size_t)kMaxNV * LD;        // [2][CR]
+  constexpr bool TS_ALIAS = kMaxNV * LD <= PSZ;   // [kMaxNV][LD]: Z Xall -- lives in T's storage when it fits
+  double *Ts = TS_ALIAS ? Tp : Xall + (size_t)kMaxNV * LD;
+  double *wv = Xall + (size_t)(TS_ALIAS ? 1 : 2) * kMaxNV * LD;      // [2][CR]
   double *colsc = wv + 2 * CR;                  // [8][kMaxNV]
   double *red = colsc + 8 * kMaxNV;
   SearchSmem &S = *reinterpret_cast<SearchSmem *>((reinterpret_cast<uintptr_t>(red + 40) + 15) & ~(uintptr_t)15);

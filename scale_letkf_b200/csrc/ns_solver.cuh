@@ -37,7 +37,7 @@ struct NsCfg {
   static constexpr int PSZ = NTILE * 64;           // doubles per packed symmetric matrix
   static constexpr int CR = (PSZ / LD) & ~3;       // obs rows per staging chunk (two chunks fit in 2 PSZ)
   // resident CTAs per SM the register allocation is sized for
-  static constexpr int MINB = NB_ <= 3 ? 8 : NB_ <= 5 ? 5 : NB_ <= 7 ? 3 : NB_ <= 9 ? 2 : 1;
+  static constexpr int MINB = NB_ <= 3 ? 8 : NB_ <= 5 ? 5 : NB_ <= 7 ? 4 : NB_ <= 9 ? 2 : 1;
   // (registers: each of the 4 SM sub-partitions holds 16 K registers and ceil(NB MINB / 4) warps, which
   // is what __launch_bounds__(NT, MINB) makes ptxas budget for -- 128 for NB = 13, 80 for NB = 7)
 };
