@@ -245,7 +245,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
-    ap.add_argument("--cycle", action="store_true", help="also time the full cycle (transposes + bucketing + analysis)")
+    ap.add_argument("--no-cycle", dest="cycle", action="store_false",
+                    help="skip the full-cycle leg (transposes + bucketing + analysis)")
+    ap.set_defaults(cycle=True)
     ap.add_argument("--cycle-steps", type=int, default=3)
     ap.add_argument("--subsample", type=int, default=1,
                     help="profiling aid: analyse only every S-th column of the plane (same per-point work)")

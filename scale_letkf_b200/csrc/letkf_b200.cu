@@ -1007,7 +1007,7 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
         CK(cudaMemcpy2DAsync(a->gues3d + off, pitch, P.gues3d + off, pitch, w, planes, cudaMemcpyDeviceToHost, h->s_d2h));
     }
   }
-  h->last_launches = tiled ? nlaunch : nchunk;
+  h->last_launches = tiled ? nlaunch : (pre ? 3 * nchunk : nchunk);   // pre: presearch + solver + redo pass per chunk
   if (host) {
     if (c.nv2d > 0) {
       CK(cudaMemcpyAsync(a->anal2d, P.anal2d, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->s_d2h));
