@@ -1105,7 +1105,17 @@ int letkf_b200_core_batch(letkf_b200_handle *h, int ne, int nobs, int npts, cons
   P.counters = h->counters.p;
   P.max_sweeps = 30;
   CK(cudaMemsetAsync(h->counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
-  if (npts > 0) {
+  if (npts > 0 && ne > 128) {   // large ensembles: tiled whole-GPU solve (tiled.cuh)
+    if (!h->tiled) h->tiled = new TiledBufs();
+    CoreTiledParams C;
+    std::memset(&C, 0, sizeof(C));
+    C.ne = ne; C.nobs = nobs; C.npts = npts; C.rdiag_wloc = rdiag_wloc; C.infl_update = infl_update;
+    C.nobsl = P.nobsl; C.hdxb = P.hdxb; C.rdiag = P.rdiag; C.rloc = P.rloc; C.dep = P.dep; C.depd = P.depd;
+    C.parm_infl = P.parm_infl; C.trans = P.trans; C.transm = P.transm; C.pao = P.pao; C.transmd = P.transmd;
+    C.counters = h->counters.p;
+    const int r = core_batch_tiled(h, *h->tiled, C);
+    if (r != LETKF_B200_OK) return r;
+  } else if (npts > 0) {
     int r;
     if (ne <= 20) r = launch_core<20>(h, P);
     else if (ne <= 52) r = launch_core<52>(h, P);

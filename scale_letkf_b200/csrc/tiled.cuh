@@ -866,4 +866,148 @@ __global__ void __launch_bounds__(256) tl_dual_fin_kernel(const DasParams P, con
   }
 }
 
+// ================================================================================================
+// letkf_core twin for large ensembles (common/common_letkf.f90:52-257, ne > 128): explicit trans / transm /
+// pao from the same tiled machinery (primal form).
+// ================================================================================================
+struct CoreTiledParams {
+  int ne, nobs, npts, rdiag_wloc, infl_update;
+  int pt0;               // first point of the batch
+  const int *nobsl;
+  const double *hdxb, *rdiag, *rloc, *dep, *depd;
+  double *parm_infl, *trans, *transm, *pao, *transmd;
+  double *sw;            // [G][pK] sqrt(R^-1 weight)
+  unsigned long long *counters;
+};
+
+// per-point solver state + weights; grid (ceil(pK / 256), G)
+__global__ void __launch_bounds__(256) tlc_init_kernel(const CoreTiledParams C, const TiledParams B) {
+  const int g = blockIdx.y, pt = C.pt0 + g, o = blockIdx.x * 256 + threadIdx.x;
+  const int p = C.nobsl[pt];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double infl = C.parm_infl[pt];
+    B.nobsl[g] = p;
+    B.kd[g] = round_up(p, 16);
+    B.dims[g] = B.n8;
+    B.state[g] = p > 0 ? 0 : 2;
+    B.adims[g] = p > 0 ? B.n8 : 0;
+    B.skip[g] = 0;
+    B.infl[g] = infl;
+    B.cdiag[g] = (double)(C.ne - 1) / infl;
+    B.zsel[g] = 0;
+    B.iters[g] = 0;
+    B.fail[g] = 0;
+    B.snorm_bits[g] = 0ull;
+    B.res[g] = 0ull;
+    for (int i = 0; i < 3; ++i) B.misc[(size_t)g * 4 + i] = 0.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 32) B.misc[(size_t)g * 4 + 3] = 0.0;
+  if (o >= B.pK) return;
+  double w = 0.0;
+  if (o < p) {
+    const size_t a = (size_t)pt * C.nobs + o;
+    const double winv = C.rdiag_wloc ? 1.0 / C.rdiag[a] : C.rloc[a] / C.rdiag[a];   // (:111-123)
+    w = sqrt(winv);
+  }
+  C.sw[(size_t)g * B.pK + o] = w;
+}
+// sum of rloc (adaptive inflation, :229-254); grid G, block 256 -- after tlc_init
+__global__ void __launch_bounds__(256) tlc_rlocsum_kernel(const CoreTiledParams C, const TiledParams B) {
+  __shared__ double red[kMaxWarps];
+  const int g = blockIdx.x, pt = C.pt0 + g, p = C.nobsl[pt];
+  double s = 0.0;
+  for (int o = threadIdx.x; o < p; o += blockDim.x) s += C.rloc[(size_t)pt * C.nobs + o];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) B.misc[(size_t)g * 4 + 3] = s;
+}
+// E[m][o] = hdxb(o, m) sqrt(w_o); rows ne, ne+1: dep, depd; grid (n8 / 8, G), block 256 (one warp per row)
+__global__ void __launch_bounds__(256) tlc_gather_kernel(const CoreTiledParams C, const TiledParams B) {
+  const int g = blockIdx.y, pt = C.pt0 + g;
+  if (B.state[g] >= 2) return;
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= B.n8) return;
+  const int kd = B.kd[g];
+  const double *sw = C.sw + (size_t)g * B.pK;
+  double *row = B.E + ((size_t)g * B.n8 + m) * B.pK;
+  const double *src = nullptr;
+  if (m < C.ne) src = C.hdxb + ((size_t)pt * C.ne + m) * C.nobs;   // hdxb(nobs, ne) column-major: row m contiguous
+  else if (m == C.ne) src = C.dep + (size_t)pt * C.nobs;
+  else if (m == C.ne + 1 && C.depd) src = C.depd + (size_t)pt * C.nobs;
+  for (int o = lane; o < kd; o += 32) {
+    const double w = sw[o];
+    row[o] = (src && w != 0.0) ? src[o] * w : 0.0;
+  }
+}
+// transm = Pa b, transmd = Pa bd with Pa = Z Z / s in mT (unscaled Z Z); grid G, block 256
+__global__ void __launch_bounds__(256) tlc_transm_kernel(const CoreTiledParams C, const TiledParams B) {
+  const int g = blockIdx.x, pt = C.pt0 + g, ne = C.ne, n8 = B.n8;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double *wm = B.Ts + (size_t)g * n8 * kMaxNV;          // scratch: [0..n8) transm, [n8..2 n8) transmd
+  if (B.nobsl[g] == 0) {
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+      wm[i] = 0.0;
+      wm[n8 + i] = 0.0;
+      if (C.transm) C.transm[(size_t)pt * ne + i] = 0.0;
+      if (C.transmd) C.transmd[(size_t)pt * ne + i] = 0.0;
+    }
+    return;
+  }
+  const double is = 1.0 / B.snorm[g];
+  const double *ZZ = B.mT + (size_t)g * n8 * n8;
+  const double *b = B.X + (size_t)g * kMaxNV * n8 + (size_t)(kMaxNV - 2) * n8, *bd = b + n8;
+  for (int i = w; i < ne; i += nw) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = lane; j < ne; j += 32) {
+      const double z = ZZ[(size_t)i * n8 + j];
+      s1 = fma(z, b[j], s1);
+      s2 = fma(z, bd[j], s2);
+    }
+    s1 = warp_sum(s1) * is;
+    s2 = warp_sum(s2) * is;
+    if (lane == 0) {
+      wm[i] = s1;
+      wm[n8 + i] = s2;
+      if (C.transm) C.transm[(size_t)pt * ne + i] = s1;
+      if (C.transmd && C.depd) C.transmd[(size_t)pt * ne + i] = s2;
+    }
+  }
+  if (C.infl_update && threadIdx.x == 0) {   // (:229-254)
+    const double infl = B.infl[g];
+    const double parm1 = B.misc[(size_t)g * 4 + 0], parm2 = B.misc[(size_t)g * 4 + 1] / (double)(ne - 1);
+    const double parm3 = B.misc[(size_t)g * 4 + 3];
+    const double parm4 = (parm1 - parm3) / parm2 - infl;
+    const double tq = (infl * parm2 + parm3) / parm2;
+    const double sigma_o = 2.0 / parm3 * (tq * tq);
+    const double gain = 0.04 * 0.04 / (sigma_o + 0.04 * 0.04);
+    C.parm_infl[pt] = infl + gain * parm4;
+  }
+  if (threadIdx.x == 0 && B.fail[g]) atomicAdd(&C.counters[3], 1ull);
+}
+// trans = sqrt((ne-1)/s) Z (+ transm on every column when transm is absent, :218-226), pao = Z Z / s;
+// grid (ceil(ne^2 / 1024), G), block 256; outputs column-major (ne, ne)
+__global__ void __launch_bounds__(256) tlc_out_kernel(const CoreTiledParams C, const TiledParams B) {
+  const int g = blockIdx.y, pt = C.pt0 + g, ne = C.ne, n8 = B.n8;
+  const size_t k2 = (size_t)ne * ne;
+  const int p = B.nobsl[g];
+  const double infl = B.infl[g];
+  const double *Z = B.bZ[B.zsel[g]] + (size_t)g * n8 * n8, *ZZ = B.mT + (size_t)g * n8 * n8;
+  const double *wm = B.Ts + (size_t)g * n8 * kMaxNV;
+  const double s = p > 0 ? B.snorm[g] : 1.0;
+  const double ft = sqrt((double)(ne - 1) / s), is = 1.0 / s;
+  for (int e = blockIdx.x * 1024 + threadIdx.x; e < min((int)k2, (int)(blockIdx.x + 1) * 1024); e += 256) {
+    const int j = e / ne, i = e - j * ne;   // column j, row i
+    double t, pa;
+    if (p == 0) {   // (:89-107)
+      t = i == j ? sqrt(infl) : 0.0;
+      pa = i == j ? infl / (double)(ne - 1) : 0.0;
+    } else {
+      t = ft * Z[(size_t)i * n8 + j];
+      pa = ZZ[(size_t)i * n8 + j] * is;
+      if (!C.transm) t += wm[i];
+    }
+    C.trans[(size_t)pt * k2 + e] = t;
+    if (C.pao) C.pao[(size_t)pt * k2 + e] = pa;
+  }
+}
+
 }  // namespace letkf

@@ -312,4 +312,75 @@ int launch_range_tiled(letkf_b200_handle *h, TiledBufs &T, DasParams P, long lon
   return LETKF_B200_OK;
 }
 
+// letkf_core for ne > 128: device pointers; batches of G points through the primal tiled solve.
+int core_batch_tiled(letkf_b200_handle *h, TiledBufs &T, CoreTiledParams C) {
+  const int ne = C.ne, n8 = round_up(ne + 2, 8), pK = std::max(16, round_up(C.nobs, 16));
+  const char *me = std::getenv("LETKF_B200_TILED_MB");
+  const double budget = (me ? std::atof(me) : 4096.0) * 1048576.0;
+  const double item_bytes = (5.0 * n8 * (double)n8 + (double)n8 * pK + pK + 4.0 * kMaxNV * n8) * 8.0 + 1024.0;
+  long long G = (long long)(budget / item_bytes);
+  G = std::max<long long>(4, std::min<long long>(G, 4096));
+  G = std::min<long long>(G, std::max(C.npts, 1));
+  const size_t Gs = (size_t)G, sN = (size_t)n8 * n8;
+  CK(T.X.ensure(Gs * kMaxNV * n8)); CK(T.Ts.ensure(Gs * n8 * kMaxNV)); CK(T.cdiag.ensure(Gs)); CK(T.infl.ensure(Gs));
+  CK(T.snorm.ensure(Gs)); CK(T.brk.ensure(Gs)); CK(T.h0.ensure(Gs)); CK(T.h1.ensure(Gs)); CK(T.misc.ensure(Gs * 4));
+  CK(T.skip.ensure(Gs)); CK(T.nobsl.ensure(Gs)); CK(T.dims.ensure(Gs)); CK(T.kd.ensure(Gs)); CK(T.state.ensure(Gs));
+  CK(T.zsel.ensure(Gs)); CK(T.iters.ensure(Gs)); CK(T.fail.ensure(Gs)); CK(T.nactive.ensure(1)); CK(T.adims.ensure(Gs));
+  CK(T.snorm_bits.ensure(Gs)); CK(T.res.ensure(Gs)); CK(T.E.ensure(Gs * (size_t)n8 * pK)); CK(T.dw.ensure(Gs * pK));
+  CK(T.bZ0.ensure(Gs * sN)); CK(T.bZ1.ensure(Gs * sN)); CK(T.bY0.ensure(Gs * sN)); CK(T.bY1.ensure(Gs * sN)); CK(T.mT.ensure(Gs * sN));
+  if (T.h_pinned_n < Gs + 1) {
+    if (T.h_pinned) cudaFreeHost(T.h_pinned);
+    CK(cudaMallocHost((void **)&T.h_pinned, sizeof(int) * (Gs + 1)));
+    T.h_pinned_n = Gs + 1;
+  }
+  TiledParams B;
+  std::memset(&B, 0, sizeof(B));
+  B.n8 = n8; B.nmax = n8; B.pK = pK; B.maxl = 0; B.max_iter = 50; B.dual = 0;
+  B.X = T.X.p; B.Ts = T.Ts.p; B.cdiag = T.cdiag.p; B.infl = T.infl.p; B.snorm = T.snorm.p; B.brk = T.brk.p; B.h0 = T.h0.p;
+  B.h1 = T.h1.p; B.misc = T.misc.p; B.skip = T.skip.p; B.nobsl = T.nobsl.p; B.dims = T.dims.p; B.kd = T.kd.p;
+  B.state = T.state.p; B.zsel = T.zsel.p; B.iters = T.iters.p; B.fail = T.fail.p; B.nactive = T.nactive.p;
+  B.adims = T.adims.p; B.snorm_bits = T.snorm_bits.p; B.res = T.res.p; B.E = T.E.p;
+  B.bZ[0] = T.bZ0.p; B.bZ[1] = T.bZ1.p; B.bY[0] = T.bY0.p; B.bY[1] = T.bY1.p; B.mT = T.mT.p;
+  C.sw = T.dw.p;
+  DasParams P;   // only k and det are read by the shared kernels
+  std::memset(&P, 0, sizeof(P));
+  P.k = ne;
+  P.det = C.depd ? 1 : 0;
+  int launches = 0;
+  const dim3 egrid((unsigned)((sN + 1023) / 1024), 1);
+  for (long long p0 = 0; p0 < C.npts; p0 += G) {
+    const int Gb = (int)std::min<long long>(G, C.npts - p0);
+    B.G = Gb;
+    C.pt0 = (int)p0;
+    const dim3 eg(egrid.x, (unsigned)Gb);
+    tlc_init_kernel<<<dim3((unsigned)((pK + 255) / 256), (unsigned)Gb), 256, 0, h->stream>>>(C, B);
+    if (C.infl_update) tlc_rlocsum_kernel<<<Gb, 256, 0, h->stream>>>(C, B);
+    tlc_gather_kernel<<<dim3((unsigned)(n8 / 8), (unsigned)Gb), 256, 0, h->stream>>>(C, B);
+    GemmParams Q;   // [A | b | bd] = E E^T -> bZ[1]
+    std::memset(&Q, 0, sizeof(Q));
+    Q.njobs = 1;
+    Q.job[0] = GemmJob{B.E, nullptr, B.E, B.bZ[1], (long long)n8 * pK, (long long)n8 * pK, (long long)sN, pK, pK, n8};
+    Q.M = Q.N = n8; Q.K = pK; Q.kdims = B.kd; Q.state = B.state; Q.state_skip = 2; Q.sym = 1;
+    int r = tl_gemm(h, Q, Gb);
+    if (r != LETKF_B200_OK) return r;
+    tl_rowsum_kernel<<<dim3((unsigned)(n8 / 8), (unsigned)Gb), 256, 0, h->stream>>>(P, B);
+    tl_scale_kernel<<<eg, 256, 0, h->stream>>>(P, B, B.bZ[1], B.bY[0], n8, 0);
+    r = tl_ns_solve(h, T, B, n8, false, &launches);
+    if (r != LETKF_B200_OK) return r;
+    GemmParams Z2;   // Z Z -> mT   (Pa = Z Z / s)
+    std::memset(&Z2, 0, sizeof(Z2));
+    Z2.njobs = 1;
+    Z2.job[0] = GemmJob{B.bZ[0], B.bZ[1], B.bZ[0], B.mT, (long long)sN, (long long)sN, (long long)sN, n8, n8, n8};
+    Z2.job[0].B_alt = B.bZ[1];
+    Z2.sel = B.zsel; Z2.selB = B.zsel;
+    Z2.M = Z2.N = Z2.K = n8; Z2.mdims = B.adims; Z2.sym = 1;
+    r = tl_gemm(h, Z2, Gb);
+    if (r != LETKF_B200_OK) return r;
+    tlc_transm_kernel<<<Gb, 256, 0, h->stream>>>(C, B);
+    tlc_out_kernel<<<dim3((unsigned)(((size_t)ne * ne + 1023) / 1024), (unsigned)Gb), 256, 0, h->stream>>>(C, B);
+  }
+  CK(cudaGetLastError());
+  return LETKF_B200_OK;
+}
+
 }  // namespace

@@ -100,3 +100,48 @@ def test_tiled_k1000_primal(oracle, monkeypatch):
     cfg, rig1, rjg1, hgt1, obs, gues = radar_case(member=1000, max_nobs=100, nlon=4, nlat=4, nlev=2, radius=1.5e3)
     out, ref = _das_compare(cfg, rig1, rjg1, hgt1, obs, gues, oracle)
     assert out["nsolved"] > 0
+
+
+# ---- letkf_core twin for ne > 128 (tiled) ------------------------------------------------------------
+import numpy as np
+import scale_letkf_b200 as sl
+from scale_letkf_b200 import synth
+from helpers import TOL, relerr
+
+
+@pytest.fixture(scope="module")
+def core_engine():
+    cfg = sl.default_config(MEMBER=20, nlon=8, nlat=8, nlev=2)
+    e = sl.LETKF(sl.resolve_config(cfg), device=0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("ne,nobs,npts", [(136, 200, 12), (200, 60, 8), (1000, 120, 3)])
+def test_core_batch_tiled_sizes(core_engine, oracle, ne, nobs, npts):
+    """letkf_core (common/common_letkf.f90:52-257) with more than 128 members: trans, transm, pao, transmd."""
+    c = synth.make_core_batch(ne=ne, npts=npts, nobs=nobs, seed_no=300 + ne, det=True, infl=1.07)
+    args = (c["ne"], c["nobs"], c["nobsl"], c["hdxb"], c["rdiag"], c["rloc"], c["dep"], c["parm_infl"])
+    ref = oracle.core_batch(*args, depd=c["depd"])
+    r = core_engine.letkf_core(*args, depd=c["depd"])
+    for key in ("trans", "transm", "pao", "transmd"):
+        assert relerr(r[key], ref[key]) <= TOL, key
+    if (c["nobsl"] == 0).any():
+        i = int(np.argmax(c["nobsl"] == 0))
+        assert np.array_equal(r["trans"][i], np.sqrt(1.07) * np.eye(ne))
+
+
+def test_core_batch_tiled_options(core_engine, oracle):
+    c = synth.make_core_batch(ne=150, npts=10, nobs=50, seed_no=33, infl=1.1)
+    base = (c["ne"], c["nobs"], c["nobsl"], c["hdxb"])
+    err2 = c["rdiag"] * c["rloc"]
+    ref = oracle.core_batch(*base, err2, c["rloc"], c["dep"], c["parm_infl"], rdiag_wloc=False, infl_update=True)
+    r = core_engine.letkf_core(*base, err2, c["rloc"], c["dep"], c["parm_infl"], rdiag_wloc=False, infl_update=True)
+    for key in ("trans", "transm", "pao"):
+        assert relerr(r[key], ref[key]) <= TOL, key
+    sel = c["nobsl"] > 0
+    assert relerr(r["parm_infl"][sel], ref["parm_infl"][sel]) <= TOL
+    assert np.array_equal(r["parm_infl"][~sel], ref["parm_infl"][~sel])
+    ref = oracle.core_batch(*base, c["rdiag"], c["rloc"], c["dep"], c["parm_infl"], want_transm=False, want_pao=False)
+    r = core_engine.letkf_core(*base, c["rdiag"], c["rloc"], c["dep"], c["parm_infl"], want_transm=False, want_pao=False)
+    assert relerr(r["trans"], ref["trans"]) <= TOL
