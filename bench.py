@@ -201,6 +201,59 @@ class CpuSample:
                 f"{dt:.1f} s per pass")
 
 
+def run_c1(args):
+    """BASELINE config 1 (the reference's own CPU-runnable case): letkf_core batch, 20 members, 10^4 grid points,
+    <= 100 local obs each, fp64 -- through letkf_b200_core_batch with HOST buffers (this call has no
+    device-resident form in the reference's interface), next to the oracle on all host threads."""
+    import torch
+    import scale_letkf_b200 as sl
+    from scale_letkf_b200 import synth
+    c = synth.make_core_batch(ne=20, npts=10000, nobs=100, seed_no=1)
+    a = (c["ne"], c["nobs"], c["nobsl"], c["hdxb"], c["rdiag"], c["rloc"], c["dep"], c["parm_infl"])
+    if args.impl == "reference":
+        from oracle import oracle_py
+        oracle_py.build()
+        run = lambda: oracle_py.core_batch(*a)
+        cores = oracle_py.max_threads()
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference)")
+        eng = sl.LETKF(sl.resolve_config(sl.default_config(MEMBER=20, nlon=8, nlat=8, nlev=2)), device=0)
+        run = lambda: eng.letkf_core(*a)
+        cores = 0
+    ts = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        run()
+        if args.impl != "reference":
+            torch.cuda.synchronize()
+        if i >= args.warmup:
+            ts.append(time.perf_counter() - t0)
+    dt = float(np.mean(ts))
+    k, p = 20, float(c["nobsl"].mean())
+    flops = c["npts"] * (2.0 * p * k * k + 13.0 * k ** 3 + 2.0 * p * k + 2.0 * k * k)
+    nbytes = c["hdxb"].nbytes + 3 * c["rdiag"].nbytes + 2 * c["npts"] * k * k * 8 + c["npts"] * k * 8
+    line = {"metric": METRIC, "value": c["npts"] / dt, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "C1: letkf_core batch, 20 members, 10^4 grid points, <= 100 local obs each",
+                       "k": k, "points": c["npts"], "mean_local_obs": p,
+                       "note": "host buffers in and out (trans, transm, pao): H2D/D2H inside the timed call"},
+            "e2e": {"value": c["npts"] / dt, "unit": UNIT, "h2d_bytes_per_step": int(c["hdxb"].nbytes + 3 * c["rdiag"].nbytes),
+                    "d2h_bytes_per_step": int(2 * c["npts"] * k * k * 8 + c["npts"] * k * 8)},
+            "gpu_launches": 0 if args.impl == "reference" else args.steps,
+            "roofline": {"kernel": "core_kernel<20>", "bound": "hbm", "achieved": nbytes / dt * 1e-9, "peak": None,
+                         "unit": "GB/s", "frac": None, "traffic": None,
+                         "note": "PCIe-bound through host buffers; algorithmic %.2f GFLOP per call" % (flops * 1e-9)}}
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["cpu_baseline"] = {"value": line["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "oracle letkf_core on all 10^4 points"}
+        line["e2e"] = {"value": line["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    print(json.dumps(line))
+    return 0
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (C++ restatement under oracle/ -- the Fortran
     original cannot be built here: no Fortran compiler, no MPI, SCALE-RM/NetCDF not vendored)."""
@@ -240,7 +293,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c1"])
     ap.add_argument("--cpu-seconds", type=float, default=16.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
@@ -252,6 +305,8 @@ def main():
     ap.add_argument("--subsample", type=int, default=1,
                     help="profiling aid: analyse only every S-th column of the plane (same per-point work)")
     args = ap.parse_args()
+    if args.workload == "c1":
+        return run_c1(args) if int(os.environ.get("RANK", "0")) == 0 else 0
     if args.impl == "reference":
         return run_reference(args)
 
