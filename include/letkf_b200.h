@@ -151,6 +151,28 @@ int letkf_b200_get_ac_ext(const letkf_b200_handle *h, int ic, int32_t *ac_ext);
 /* sorted position -> original obs index (0-based): the order of obsda_sort */
 int letkf_b200_get_sorted_index(const letkf_b200_handle *h, int32_t *sorted_to_orig);
 
+/* ---- departure + QC half of set_letkf_obs (scale/letkf/letkf_obs.f90:355-560) -----------------
+ * Per observation n with qc[n] == 0 on entry:  radar acceptance rules (USE_RADAR_REF / USE_RADAR_VR,
+ * undef data, number of members above RADAR_REF_THRES_DBZ, :370-421), ensemble mean of H(x) (sequential
+ * sum m = 1..MEMBER then divide, :474-478), perturbations ensval(m,n) -= mean (:486-488), departure
+ * val[n] = dat - mean (:489), deterministic departure ensval(MEMBER+1,n) = dat - ensval(MEMBER+1,n) (:490-492),
+ * gross-error check |val| > GROSS_ERROR_x * err (:503-549).  qc is rewritten with the reference's codes
+ * (iqc_good 0, iqc_gross_err 5, iqc_ref_mem 12, iqc_obs_bad 50, iqc_otype 90, common_obs_scale.f90:139-151).
+ * Observations that fail a check before the departure step keep their ensval/val untouched, as in the
+ * reference (`cycle`).  The Himawari-8 branch (#ifdef H08) is not built.  ensval is (nensobs, nobs),
+ * member fastest.  The QC-passed observations (qc == 0) are what letkf_b200_set_obs takes. */
+typedef struct letkf_b200_qc_config {
+  double GROSS_ERROR, GROSS_ERROR_RAIN, GROSS_ERROR_RADAR_REF, GROSS_ERROR_RADAR_VR, GROSS_ERROR_RADAR_PRH;
+  double GROSS_ERROR_TCX, GROSS_ERROR_TCY, GROSS_ERROR_TCP;      /* common_nml.f90:129-137; < 0: GROSS_ERROR */
+  double RADAR_REF_THRES_DBZ;                                     /* common_nml.f90:257 */
+  int32_t USE_RADAR_REF, USE_RADAR_VR;                            /* common_nml.f90:248-249 */
+  int32_t MIN_RADAR_REF_MEMBER, MIN_RADAR_REF_MEMBER_OBSREF;      /* common_nml.f90:258-259 */
+} letkf_b200_qc_config;
+void letkf_b200_qc_config_defaults(letkf_b200_qc_config *q);
+int letkf_b200_obs_departure_qc(letkf_b200_handle *h, const letkf_b200_qc_config *q, int nobs, int nensobs,
+                                const int32_t *elm, const double *dat, const double *err, int32_t *qc,
+                                double *ensval, double *val, int mem_space);
+
 /* ---- obs_local twin (letkf_tools.f90:1325) ---------------------------------
  * For npts points (ri,rj,rlev=mean pressure,rz=height) and model variable nvar
  * (1-based, 0 = no variable localisation): writes nobsl[i] and, when not NULL, the
@@ -213,9 +235,11 @@ int letkf_b200_buf_to_grd(letkf_b200_handle *h, int np, const double *bufr, doub
 int letkf_b200_nij1(const letkf_b200_handle *h, int np, int myrank_e, int32_t *nij1,
                     int32_t *nij1max);
 
-/* sizeof() of the four public structs, in declaration order (config, ctype_info, obs, das_args):
+/* sizeof() of the four public structs, in declaration order (config, ctype_info, obs, das_args;
+ * letkf_b200_abi_size_qc() returns sizeof(letkf_b200_qc_config)):
  * lets a foreign-language binding (ctypes, ISO_C_BINDING) check its mirror of the layouts */
 void letkf_b200_abi_sizes(int32_t sizes[4]);
+int letkf_b200_abi_size_qc(void);
 
 /* library build info (arch string, e.g. "sm_100a") */
 const char *letkf_b200_build_info(void);

@@ -87,6 +87,10 @@ void oracle_ens_to_buf(int nlon, int nlat, int nlev, int nv3d, int nv2d, int np,
                        double *bufs);
 void oracle_buf_to_grd(int nlon, int nlat, int nlev, int nv3d, int nv2d, int np,
                        const double *bufr, double *v3dg, double *v2dg);
+/* scale/letkf/letkf_obs.f90:355-560: departure + QC half of set_letkf_obs (H08 branch not built) */
+void oracle_obs_departure_qc(const letkf_b200_qc_config *q, int member, int det, int nobs, int nensobs,
+                             const int32_t *elm, const double *dat, const double *err, int32_t *qc,
+                             double *ensval, double *val);
 int oracle_max_threads(void);
 
 #ifdef __cplusplus

@@ -900,6 +900,51 @@ void oracle_ensmean_grd(int mem, int nens, int nij, int nlev, int nv3d, int nv2d
     }
 }
 
+// set_letkf_obs, letkf_obs.f90:355-560: radar acceptance, ensemble mean / perturbation of H(x),
+// departures, gross-error QC.  qc codes: common_obs_scale.f90:139-151.
+void oracle_obs_departure_qc(const letkf_b200_qc_config *q, int member, int det, int nobs, int nensobs,
+                             const int32_t *elm, const double *dat, const double *err, int32_t *qc,
+                             double *ensval, double *val) {
+  const int iqc_gross_err = 5, iqc_ref_mem = 12, iqc_obs_bad = 50, iqc_otype = 90;
+  const double undef = -9.99e33;   // common/common.f90:38
+  auto ge = [&](double v) { return v < 0.0 ? q->GROSS_ERROR : v; };   // common_nml.f90:619-642
+  for (int n = 0; n < nobs; ++n) {
+    if (qc[n] > 0) continue;   // :362
+    double *ev = ensval + (size_t)n * nensobs;
+    if (elm[n] == ID_REF || elm[n] == ID_RE0) {   // :370-414
+      if (!q->USE_RADAR_REF) { qc[n] = iqc_otype; continue; }
+      if (dat[n] == undef) { qc[n] = iqc_obs_bad; continue; }
+      int mem_ref = 0;
+      for (int i = 0; i < member; ++i)
+        if (ev[i] > q->RADAR_REF_THRES_DBZ + 1.0e-6) ++mem_ref;
+      if (dat[n] > q->RADAR_REF_THRES_DBZ + 1.0e-6) {
+        if (mem_ref < q->MIN_RADAR_REF_MEMBER_OBSREF) { qc[n] = iqc_ref_mem; continue; }
+      } else {
+        if (mem_ref < q->MIN_RADAR_REF_MEMBER) { qc[n] = iqc_ref_mem; continue; }
+      }
+    }
+    if (elm[n] == ID_VR && !q->USE_RADAR_VR) { qc[n] = iqc_otype; continue; }   // :416-421
+    double v = ev[0];   // :474-478
+    for (int i = 1; i < member; ++i) v = v + ev[i];
+    v = v / (double)member;
+    for (int i = 0; i < member; ++i) ev[i] = ev[i] - v;   // :486-488
+    val[n] = dat[n] - v;                                  // :489
+    if (det) ev[member] = dat[n] - ev[member];            // :490-492
+    double g;
+    switch (elm[n]) {   // :503-549
+      case ID_RAIN: g = ge(q->GROSS_ERROR_RAIN); break;
+      case ID_REF: case ID_RE0: g = ge(q->GROSS_ERROR_RADAR_REF); break;
+      case ID_VR: g = ge(q->GROSS_ERROR_RADAR_VR); break;
+      case 4003: g = ge(q->GROSS_ERROR_RADAR_PRH); break;
+      case 99991: g = ge(q->GROSS_ERROR_TCX); break;
+      case 99992: g = ge(q->GROSS_ERROR_TCY); break;
+      case 99993: g = ge(q->GROSS_ERROR_TCP); break;
+      default: g = q->GROSS_ERROR; break;
+    }
+    if (std::fabs(val[n]) > g * err[n]) qc[n] = iqc_gross_err;
+  }
+}
+
 // set_common_mpi_grid, common_mpi_scale.f90:264-283
 void oracle_nij1(int nlon, int nlat, int np, int myrank_e, int32_t *nij1, int32_t *nij1max) {
   const int i = (nlon * nlat) % np;

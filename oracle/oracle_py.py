@@ -71,6 +71,8 @@ def lib():
         for name in ("oracle_buf_to_ens", "oracle_ens_to_buf"):
             getattr(L, name).restype = None
             getattr(L, name).argtypes = [i, i, i, i, i, i, i, i, i, i, vp, vp, vp]
+        L.oracle_obs_departure_qc.restype = None
+        L.oracle_obs_departure_qc.argtypes = [C.POINTER(capi.QcConfig), i, i, i, i, vp, vp, vp, vp, vp, vp]
         L.oracle_max_threads.restype = i
         _lib = L
     return _lib
@@ -260,3 +262,14 @@ def nij1(nlon, nlat, np_, rank):
 
 def max_threads():
     return lib().oracle_max_threads()
+
+
+def obs_departure_qc(qcfg, member, det, elm, dat, err, qc, ensval):
+    """scale/letkf/letkf_obs.f90:355-560; returns (qc, val, ensval) as new arrays."""
+    elm = np.ascontiguousarray(elm, dtype=np.int32)
+    qc = np.array(qc, dtype=np.int32, order="C")
+    ens = np.array(ensval, dtype=np.float64, order="C")
+    val = np.zeros(len(elm))
+    lib().oracle_obs_departure_qc(C.byref(qcfg), member, int(det), len(elm), ens.shape[1], _p(elm), _p(_f64(dat)),
+                                  _p(_f64(err)), _p(qc), _p(ens), _p(val))
+    return qc, val, ens

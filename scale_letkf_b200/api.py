@@ -122,6 +122,23 @@ class LETKF:
             setattr(o, kf, arr.ctypes.data)
         self._ck(self.lib.letkf_b200_set_obs(self.h, C.byref(o)))
 
+    def obs_departure_qc(self, elm, dat, err, qc, ensval, qcfg=None):
+        """Departure + QC half of set_letkf_obs (scale/letkf/letkf_obs.f90:355-560) on the device.
+        ensval (nobs, nensobs): H(x_m) per member on entry -> perturbations on exit; returns (qc, val,
+        ensval) as new arrays.  Observations with qc == 0 afterwards go to set_letkf_obs."""
+        if qcfg is None:
+            qcfg = capi.QcConfig()
+            self.lib.letkf_b200_qc_config_defaults(C.byref(qcfg))
+        elm = np.ascontiguousarray(elm, dtype=np.int32)
+        dat = np.ascontiguousarray(dat, dtype=np.float64)
+        err = np.ascontiguousarray(err, dtype=np.float64)
+        qc = np.array(qc, dtype=np.int32, order="C")
+        ens = np.array(ensval, dtype=np.float64, order="C")
+        val = np.zeros(len(elm))
+        self._ck(self.lib.letkf_b200_obs_departure_qc(self.h, C.byref(qcfg), len(elm), ens.shape[1], _ptr(elm), _ptr(dat),
+                                                      _ptr(err), _ptr(qc), _ptr(ens), _ptr(val), capi.MEM_HOST))
+        return qc, val, ens
+
     def obs_info(self):
         a, b = C.c_int32(), C.c_int32()
         self._ck(self.lib.letkf_b200_obs_info(self.h, C.byref(a), C.byref(b)))

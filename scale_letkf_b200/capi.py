@@ -14,7 +14,7 @@ NOBTYPE = 24
 NID_OBS = 16
 NID_VARLOCAL = 9
 MAX_NV = 16
-MAX_MEMBER = 128
+MAX_MEMBER = 4096
 
 OK, EINVAL, ECUDA, ESTATE, EEIGEN, ENOMEM = 0, -1, -2, -3, -4, -5
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -74,6 +74,24 @@ class Obs(C.Structure):
     ]
 
 
+class QcConfig(C.Structure):
+    """letkf_b200_qc_config: PARAM_LETKF gross-error factors and PARAM_LETKF_RADAR switches
+    (scale/common/common_nml.f90:129-137, 248-259)."""
+    _fields_ = [
+        ("GROSS_ERROR", C.c_double), ("GROSS_ERROR_RAIN", C.c_double), ("GROSS_ERROR_RADAR_REF", C.c_double),
+        ("GROSS_ERROR_RADAR_VR", C.c_double), ("GROSS_ERROR_RADAR_PRH", C.c_double),
+        ("GROSS_ERROR_TCX", C.c_double), ("GROSS_ERROR_TCY", C.c_double), ("GROSS_ERROR_TCP", C.c_double),
+        ("RADAR_REF_THRES_DBZ", C.c_double),
+        ("USE_RADAR_REF", C.c_int32), ("USE_RADAR_VR", C.c_int32),
+        ("MIN_RADAR_REF_MEMBER", C.c_int32), ("MIN_RADAR_REF_MEMBER_OBSREF", C.c_int32),
+    ]
+
+
+# QC codes (scale/common/common_obs_scale.f90:139-151)
+IQC_GOOD, IQC_GROSS_ERR, IQC_REF_MEM, IQC_OBS_BAD, IQC_OTYPE = 0, 5, 12, 50, 90
+UNDEF = -9.99e33   # common/common.f90:38
+
+
 class DasArgs(C.Structure):
     _fields_ = [
         ("gues3d", C.c_void_p), ("gues2d", C.c_void_p),
@@ -105,6 +123,9 @@ PROTOTYPES = {
     "letkf_b200_get_ctype": (_i, [_vp, _i, C.POINTER(CtypeInfo)]),
     "letkf_b200_get_ac_ext": (_i, [_vp, _i, _vp]),
     "letkf_b200_get_sorted_index": (_i, [_vp, _vp]),
+    "letkf_b200_qc_config_defaults": (None, [C.POINTER(QcConfig)]),
+    "letkf_b200_obs_departure_qc": (_i, [_vp, C.POINTER(QcConfig), _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "letkf_b200_abi_size_qc": (_i, []),
     "letkf_b200_obs_local": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i]),
     "letkf_b200_das_letkf": (_i, [_vp, C.POINTER(DasArgs)]),
     "letkf_b200_das_stats": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64),

@@ -190,4 +190,70 @@ __global__ void buf_to_ens_kernel(TransposeDims d, int nij1, int nens, int mstar
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Departure + QC half of set_letkf_obs (scale/letkf/letkf_obs.f90:355-560), one warp per observation.
+// Members are read 32 at a time (coalesced) and summed by lane 0 in member order, so the mean has the
+// reference's sequential rounding.
+struct QcParams {
+  double ge, ge_rain, ge_ref, ge_vr, ge_prh, ge_tcx, ge_tcy, ge_tcp, ref_thres;
+  int use_ref, use_vr, min_mem, min_mem_obsref;
+  int nobs, nensobs, member, det;
+  const int *elm;
+  const double *dat, *err;
+  int *qc;
+  double *ensval, *val;
+};
+__global__ void __launch_bounds__(256) obs_departure_qc_kernel(const QcParams P) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= P.nobs) return;
+  if (P.qc[n] > 0) return;
+  const int elm = P.elm[n], k = P.member;
+  const double dat = P.dat[n];
+  double *ev = P.ensval + (size_t)n * P.nensobs;
+  if (elm == 4001 || elm == 4004) {   // id_radar_ref_obs, id_radar_ref_zero_obs (:370-414)
+    if (!P.use_ref) { if (lane == 0) P.qc[n] = 90; return; }
+    if (dat == -9.99e33) { if (lane == 0) P.qc[n] = 50; return; }
+    int mem_ref = 0;
+    for (int i0 = 0; i0 < k; i0 += 32) {
+      const int i = i0 + lane;
+      const bool hit = i < k && ev[i] > P.ref_thres + 1.0e-6;
+      mem_ref += __popc(__ballot_sync(LETKF_FULL_MASK, hit));
+    }
+    const int need = (dat > P.ref_thres + 1.0e-6) ? P.min_mem_obsref : P.min_mem;
+    if (mem_ref < need) { if (lane == 0) P.qc[n] = 12; return; }
+  }
+  if (elm == 4002 && !P.use_vr) { if (lane == 0) P.qc[n] = 90; return; }   // id_radar_vr_obs (:416-421)
+  // mean of H(x): val = ensval(1); val += ensval(i), i = 2..MEMBER; val /= MEMBER   (:474-478)
+  double acc = 0.0;
+  for (int i0 = 0; i0 < k; i0 += 32) {
+    const int i = i0 + lane;
+    const double v = i < k ? ev[i] : 0.0;
+    const int cnt = min(32, k - i0);
+    for (int j = 0; j < cnt; ++j) {
+      const double vj = __shfl_sync(LETKF_FULL_MASK, v, j);
+      acc = (i0 + j == 0) ? vj : __dadd_rn(acc, vj);
+    }
+  }
+  const double mean = __ddiv_rn(acc, (double)k);
+  for (int i = lane; i < k; i += 32) ev[i] = __dsub_rn(ev[i], mean);   // Hdx (:486-488)
+  const double dep = __dsub_rn(dat, mean);                              // y - Hx (:489)
+  if (lane == 0) {
+    P.val[n] = dep;
+    if (P.det) ev[k] = __dsub_rn(dat, ev[k]);                           // (:490-492)
+    double ge;
+    switch (elm) {   // gross error (:503-549)
+      case 19999: ge = P.ge_rain; break;
+      case 4001: case 4004: ge = P.ge_ref; break;
+      case 4002: ge = P.ge_vr; break;
+      case 4003: ge = P.ge_prh; break;
+      case 99991: ge = P.ge_tcx; break;
+      case 99992: ge = P.ge_tcy; break;
+      case 99993: ge = P.ge_tcp; break;
+      default: ge = P.ge; break;
+    }
+    if (fabs(dep) > __dmul_rn(ge, P.err[n])) P.qc[n] = 5;
+  }
+}
+
 }  // namespace letkf

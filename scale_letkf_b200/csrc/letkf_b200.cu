@@ -673,6 +673,66 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
   return LETKF_B200_OK;
 }
 
+int letkf_b200_abi_size_qc(void) { return (int)sizeof(letkf_b200_qc_config); }
+
+void letkf_b200_qc_config_defaults(letkf_b200_qc_config *q) {   // common_nml.f90:129-137, 248-259
+  std::memset(q, 0, sizeof(*q));
+  q->GROSS_ERROR = 5.0;
+  q->GROSS_ERROR_RAIN = q->GROSS_ERROR_RADAR_REF = q->GROSS_ERROR_RADAR_VR = q->GROSS_ERROR_RADAR_PRH = -1.0;
+  q->GROSS_ERROR_TCX = q->GROSS_ERROR_TCY = q->GROSS_ERROR_TCP = -1.0;
+  q->RADAR_REF_THRES_DBZ = 15.0;
+  q->USE_RADAR_REF = 1;
+  q->USE_RADAR_VR = 1;
+  q->MIN_RADAR_REF_MEMBER = 1;
+  q->MIN_RADAR_REF_MEMBER_OBSREF = 1;
+}
+
+int letkf_b200_obs_departure_qc(letkf_b200_handle *h, const letkf_b200_qc_config *q, int nobs, int nensobs,
+                                const int32_t *elm, const double *dat, const double *err, int32_t *qc, double *ensval,
+                                double *val, int mem_space) {
+  if (!h || !q || nobs < 0) return LETKF_B200_EINVAL;
+  if (nobs == 0) return LETKF_B200_OK;
+  if (!elm || !dat || !err || !qc || !ensval || !val) return LETKF_B200_EINVAL;
+  const letkf_b200_config &c = h->cfg;
+  if (nensobs < (c.DET_RUN ? c.MEMBER + 1 : c.MEMBER)) return fail(h, LETKF_B200_EINVAL, "nensobs < MEMBER (+1 with DET_RUN)");
+  CK(cudaSetDevice(h->device));
+  const bool host = mem_space != LETKF_B200_MEM_DEVICE;
+  auto ge = [&](double v) { return v < 0.0 ? q->GROSS_ERROR : v; };   // (common_nml.f90:619-642)
+  QcParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.ge = q->GROSS_ERROR; P.ge_rain = ge(q->GROSS_ERROR_RAIN); P.ge_ref = ge(q->GROSS_ERROR_RADAR_REF);
+  P.ge_vr = ge(q->GROSS_ERROR_RADAR_VR); P.ge_prh = ge(q->GROSS_ERROR_RADAR_PRH); P.ge_tcx = ge(q->GROSS_ERROR_TCX);
+  P.ge_tcy = ge(q->GROSS_ERROR_TCY); P.ge_tcp = ge(q->GROSS_ERROR_TCP); P.ref_thres = q->RADAR_REF_THRES_DBZ;
+  P.use_ref = q->USE_RADAR_REF; P.use_vr = q->USE_RADAR_VR; P.min_mem = q->MIN_RADAR_REF_MEMBER;
+  P.min_mem_obsref = q->MIN_RADAR_REF_MEMBER_OBSREF;
+  P.nobs = nobs; P.nensobs = nensobs; P.member = c.MEMBER; P.det = c.DET_RUN ? 1 : 0;
+  const size_t ne = (size_t)nobs * nensobs;
+  DevBuf<int> d_elm, d_qc;
+  DevBuf<double> d_dat, d_err, d_ens, d_val;
+  if (host) {
+    CK(d_elm.ensure(nobs)); CK(d_qc.ensure(nobs)); CK(d_dat.ensure(nobs)); CK(d_err.ensure(nobs)); CK(d_ens.ensure(ne)); CK(d_val.ensure(nobs));
+    CK(cudaMemcpyAsync(d_elm.p, elm, sizeof(int) * nobs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_qc.p, qc, sizeof(int) * nobs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_dat.p, dat, sizeof(double) * nobs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_err.p, err, sizeof(double) * nobs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_ens.p, ensval, sizeof(double) * ne, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_val.p, val, sizeof(double) * nobs, cudaMemcpyHostToDevice, h->stream));
+    P.elm = d_elm.p; P.qc = d_qc.p; P.dat = d_dat.p; P.err = d_err.p; P.ensval = d_ens.p; P.val = d_val.p;
+  } else {
+    P.elm = elm; P.qc = qc; P.dat = dat; P.err = err; P.ensval = ensval; P.val = val;
+  }
+  obs_departure_qc_kernel<<<(unsigned)((nobs + 7) / 8), 256, 0, h->stream>>>(P);
+  CK(cudaGetLastError());
+  if (host) {
+    CK(cudaMemcpyAsync(qc, d_qc.p, sizeof(int) * nobs, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(ensval, d_ens.p, sizeof(double) * ne, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(val, d_val.p, sizeof(double) * nobs, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  d_elm.release(); d_qc.release(); d_dat.release(); d_err.release(); d_ens.release(); d_val.release();
+  return LETKF_B200_OK;
+}
+
 int letkf_b200_obs_info(const letkf_b200_handle *h, int32_t *nobstotal, int32_t *nctype) {
   if (!h || !h->obs_set) return LETKF_B200_ESTATE;
   if (nobstotal) *nobstotal = h->nobstotal;

@@ -75,6 +75,15 @@ module letkf_b200_iface
     integer(c_int32_t) :: mem_space, reserved
   end type
 
+  ! struct letkf_b200_qc_config (include/letkf_b200.h): gross-error factors and radar switches
+  type, bind(C), public :: letkf_b200_qc_config
+    real(c_double)     :: GROSS_ERROR, GROSS_ERROR_RAIN, GROSS_ERROR_RADAR_REF, GROSS_ERROR_RADAR_VR, GROSS_ERROR_RADAR_PRH
+    real(c_double)     :: GROSS_ERROR_TCX, GROSS_ERROR_TCY, GROSS_ERROR_TCP
+    real(c_double)     :: RADAR_REF_THRES_DBZ
+    integer(c_int32_t) :: USE_RADAR_REF, USE_RADAR_VR
+    integer(c_int32_t) :: MIN_RADAR_REF_MEMBER, MIN_RADAR_REF_MEMBER_OBSREF
+  end type
+
   type(c_ptr), save :: handle = c_null_ptr
 
   interface
@@ -112,6 +121,19 @@ module letkf_b200_iface
       real(c_double), intent(inout) :: parm_infl(*)
       real(c_double), intent(out) :: trans(*)
       type(c_ptr), value :: transm, pao, depd, transmd   ! OPTIONAL absent -> c_null_ptr
+    end function
+    ! departure + QC half of set_letkf_obs (scale/letkf/letkf_obs.f90:355-560): call with obsda%qc, obsda%ensval,
+    ! obsda%val and the obs(set)%{elm,dat,err}(idx) gathered per obsda entry, before the bucket sort
+    integer(c_int) function c_obs_departure_qc(h, q, nobs, nensobs, elm, dat, err, qc, ensval, val, mem_space) &
+        bind(C, name='letkf_b200_obs_departure_qc')
+      import :: c_int, c_ptr, c_int32_t, c_double, letkf_b200_qc_config
+      type(c_ptr), value :: h
+      type(letkf_b200_qc_config), intent(in) :: q
+      integer(c_int), value :: nobs, nensobs, mem_space
+      integer(c_int32_t), intent(in) :: elm(*)
+      real(c_double), intent(in) :: dat(*), err(*)
+      integer(c_int32_t), intent(inout) :: qc(*)
+      real(c_double), intent(inout) :: ensval(*), val(*)
     end function
     integer(c_int) function c_set_grid(h, nij1, rig1, rjg1, hgt1, mem_space) bind(C, name='letkf_b200_set_grid')
       import :: c_int, c_ptr, c_double

@@ -42,6 +42,29 @@ def make_core_batch(ne=20, npts=10000, nobs=100, seed_no=1, det=False, infl=1.0)
                 dep=dep, depd=depd, parm_infl=parm_infl)
 
 
+def make_raw_obs(member=12, nobs=600, det=False, seed_no=7):
+    """Raw observation-space ensemble for the departure/QC step (scale/letkf/letkf_obs.f90:355-560):
+    every element family of the gross-error `select case`, radar reflectivities scattered around
+    RADAR_REF_THRES_DBZ (so that the member-count rules fire), undef radar data, pre-rejected
+    observations (qc > 0) and gross outliers.  ensval (nobs, nensobs) holds H(x_m), not perturbations."""
+    g = rng(seed_no, 9)
+    elms = np.array([capi.ID_U, capi.ID_V, capi.ID_T, capi.ID_Q, capi.ID_PS, capi.ID_RAIN, capi.ID_RADAR_REF,
+                     capi.ID_RADAR_REF_ZERO, capi.ID_RADAR_VR, capi.ID_RADAR_PRH, 99991, 99992, 99993], dtype=np.int32)
+    elm = elms[g.integers(0, len(elms), size=nobs)]
+    nens = member + (1 if det else 0)
+    err = g.uniform(0.5, 3.0, size=nobs)
+    radar = (elm == capi.ID_RADAR_REF) | (elm == capi.ID_RADAR_REF_ZERO)
+    base = np.where(radar, g.uniform(5.0, 30.0, size=nobs), g.normal(0.0, 10.0, size=nobs))
+    spread = np.where(radar, 8.0, 1.5)
+    ens = base[:, None] + spread[:, None] * g.standard_normal((nobs, nens))
+    dat = base + err * g.standard_normal(nobs) * 2.0
+    out = g.uniform(size=nobs) < 0.08
+    dat = np.where(out, dat + 12.0 * err * np.sign(g.standard_normal(nobs)), dat)   # gross errors
+    dat = np.where(radar & (g.uniform(size=nobs) < 0.05), capi.UNDEF, dat)
+    qc = np.where(g.uniform(size=nobs) < 0.1, g.choice([10, 20, 98], size=nobs), 0).astype(np.int32)
+    return dict(elm=elm, dat=dat, err=err, qc=qc, ensval=np.ascontiguousarray(ens))
+
+
 # ----------------------------------------------------------------------------- grids
 def z_levels(nlev, zbot=100.0, ztop=28000.0):
     """stretched model-level heights (m)"""

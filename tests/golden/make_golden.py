@@ -22,6 +22,10 @@ restatements of the reference's algorithm:
   das_small.npz     das_letkf (letkf_tools.f90:50-932) analysis of a small sonde case, from the
                     C++ oracle (regression pin for the oracle and target for the CUDA path).
 
+  obsqc.npz         departure + QC half of set_letkf_obs (scale/letkf/letkf_obs.f90:355-560): qc codes,
+                    departures and H(x) perturbations of a 600-observation mixed-type case, from the
+                    vectorised numpy restatement in tests/test_obs_qc.py (independent of oracle/).
+
 Inputs are regenerated from seeds by scale_letkf_b200.synth in the tests; only outputs are stored.
 """
 import os
@@ -142,3 +146,15 @@ if __name__ == "__main__":
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+
+
+def make_obsqc():
+    from test_obs_qc import numpy_departure_qc, qc_defaults, CASE, GOLD
+    o = synth.make_raw_obs(**CASE)
+    qc, val, ens = numpy_departure_qc(qc_defaults(), CASE["member"], CASE["det"], o["elm"], o["dat"], o["err"],
+                                      o["qc"], o["ensval"])
+    np.savez_compressed(GOLD, qc=qc, val=val, ensval=ens)
+
+
+if __name__ == "__main__" and "--obsqc" in sys.argv:
+    make_obsqc()

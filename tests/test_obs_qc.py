@@ -1,0 +1,134 @@
+"""Departure + QC half of set_letkf_obs (scale/letkf/letkf_obs.f90:355-560).
+
+PARITY UNPINNED BY THE REFERENCE (no fixtures in gylien/scale-letkf, Fortran not buildable here): the
+C++ oracle is pinned against an INDEPENDENT numpy restatement written from the reference's text (and the
+fixture tests/golden/obsqc.npz frozen from it); the CUDA path must match the oracle bit for bit
+(integer QC codes, IEEE add / divide / subtract in the reference's order)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import scale_letkf_b200 as sl
+from scale_letkf_b200 import capi, synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "obsqc.npz")
+CASE = dict(member=12, nobs=600, det=True, seed_no=7)
+
+
+def qc_defaults(**kw):
+    q = capi.QcConfig()
+    q.GROSS_ERROR = 5.0
+    for f in ("GROSS_ERROR_RAIN", "GROSS_ERROR_RADAR_REF", "GROSS_ERROR_RADAR_VR", "GROSS_ERROR_RADAR_PRH",
+              "GROSS_ERROR_TCX", "GROSS_ERROR_TCY", "GROSS_ERROR_TCP"):
+        setattr(q, f, -1.0)
+    q.RADAR_REF_THRES_DBZ = 15.0
+    q.USE_RADAR_REF = q.USE_RADAR_VR = 1
+    q.MIN_RADAR_REF_MEMBER = q.MIN_RADAR_REF_MEMBER_OBSREF = 1
+    for k, v in kw.items():
+        setattr(q, k, v)
+    return q
+
+
+def numpy_departure_qc(q, member, det, elm, dat, err, qc, ensval):
+    """Vectorised restatement of letkf_obs.f90:362-549 (independent of oracle/)."""
+    qc, ens, val = qc.copy(), ensval.copy(), np.zeros(len(elm))
+    act = qc <= 0
+    ref = (elm == 4001) | (elm == 4004)
+    thr = q.RADAR_REF_THRES_DBZ + 1.0e-6
+    if not q.USE_RADAR_REF:
+        qc[act & ref] = 90
+    act = qc <= 0
+    bad = act & ref & (dat == -9.99e33)
+    qc[bad] = 50
+    act = qc <= 0
+    mem_ref = (ens[:, :member] > thr).sum(axis=1)
+    need = np.where(dat > thr, q.MIN_RADAR_REF_MEMBER_OBSREF, q.MIN_RADAR_REF_MEMBER)
+    qc[act & ref & (mem_ref < need)] = 12
+    act = qc <= 0
+    if not q.USE_RADAR_VR:
+        qc[act & (elm == 4002)] = 90
+    act = qc <= 0
+    s = ens[:, 0].copy()
+    for i in range(1, member):          # sequential member order, like the reference
+        s = s + ens[:, i]
+    mean = s / float(member)
+    ens[act, :member] = ens[act, :member] - mean[act, None]
+    val[act] = dat[act] - mean[act]
+    if det:
+        ens[act, member] = dat[act] - ens[act, member]
+    ge = lambda v: q.GROSS_ERROR if v < 0 else v
+    fac = np.full(len(elm), q.GROSS_ERROR)
+    fac[elm == 19999] = ge(q.GROSS_ERROR_RAIN)
+    fac[ref] = ge(q.GROSS_ERROR_RADAR_REF)
+    fac[elm == 4002] = ge(q.GROSS_ERROR_RADAR_VR)
+    fac[elm == 4003] = ge(q.GROSS_ERROR_RADAR_PRH)
+    fac[elm == 99991] = ge(q.GROSS_ERROR_TCX)
+    fac[elm == 99992] = ge(q.GROSS_ERROR_TCY)
+    fac[elm == 99993] = ge(q.GROSS_ERROR_TCP)
+    qc[act & (np.abs(val) > fac * err)] = 5
+    return qc, val, ens
+
+
+VARIANTS = [dict(), dict(USE_RADAR_REF=0), dict(USE_RADAR_VR=0), dict(MIN_RADAR_REF_MEMBER=5, MIN_RADAR_REF_MEMBER_OBSREF=9),
+            dict(GROSS_ERROR=3.0, GROSS_ERROR_RADAR_REF=1.5, GROSS_ERROR_RAIN=8.0, GROSS_ERROR_TCP=0.5)]
+
+
+@pytest.mark.parametrize("kw", VARIANTS)
+def test_oracle_matches_independent_numpy(oracle, kw):
+    o = synth.make_raw_obs(**CASE)
+    q = qc_defaults(**kw)
+    a = oracle.obs_departure_qc(q, CASE["member"], CASE["det"], o["elm"], o["dat"], o["err"], o["qc"], o["ensval"])
+    b = numpy_departure_qc(q, CASE["member"], CASE["det"], o["elm"], o["dat"], o["err"], o["qc"], o["ensval"])
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    if not kw:
+        assert set(np.unique(a[0])) >= {0, 5, 12, 50}   # every rule of the default configuration fires
+        assert np.abs(a[2][a[0] == 0, :CASE["member"]].sum(axis=1)).max() < 1e-9   # perturbations are zero-mean
+
+
+def test_oracle_matches_golden(oracle):
+    g = np.load(GOLD)
+    o = synth.make_raw_obs(**CASE)
+    qc, val, ens = oracle.obs_departure_qc(qc_defaults(), CASE["member"], CASE["det"], o["elm"], o["dat"], o["err"],
+                                           o["qc"], o["ensval"])
+    assert np.array_equal(qc, g["qc"]) and np.array_equal(val, g["val"]) and np.array_equal(ens, g["ensval"])
+
+
+def test_qc_config_abi(oracle):
+    lib = capi.load_library()
+    assert lib.letkf_b200_abi_size_qc() == C.sizeof(capi.QcConfig)
+    q = capi.QcConfig()
+    lib.letkf_b200_qc_config_defaults(C.byref(q))
+    d = qc_defaults()
+    for f, _ in capi.QcConfig._fields_:
+        assert getattr(q, f) == getattr(d, f), f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", VARIANTS)
+@pytest.mark.parametrize("member,det,nobs", [(12, True, 600), (50, False, 5000), (100, True, 3000), (1000, False, 400)])
+def test_cuda_departure_qc_bitexact(oracle, kw, member, det, nobs):
+    o = synth.make_raw_obs(member=member, nobs=nobs, det=det, seed_no=70 + member)
+    cfg = sl.default_config(MEMBER=member, nlon=8, nlat=8, nlev=2)
+    cfg.DET_RUN = 1 if det else 0
+    e = sl.LETKF(sl.resolve_config(cfg), device=0)
+    q = qc_defaults(**kw)
+    got = e.obs_departure_qc(o["elm"], o["dat"], o["err"], o["qc"], o["ensval"], q)
+    ref = oracle.obs_departure_qc(q, member, det, o["elm"], o["dat"], o["err"], o["qc"], o["ensval"])
+    for x, y in zip(got, ref):
+        assert np.array_equal(x, y)
+    e.close()
+
+
+@pytest.mark.gpu
+def test_cuda_departure_qc_golden():
+    g = np.load(GOLD)
+    o = synth.make_raw_obs(**CASE)
+    cfg = sl.default_config(MEMBER=CASE["member"], nlon=8, nlat=8, nlev=2)
+    cfg.DET_RUN = 1
+    e = sl.LETKF(sl.resolve_config(cfg), device=0)
+    qc, val, ens = e.obs_departure_qc(o["elm"], o["dat"], o["err"], o["qc"], o["ensval"])
+    assert np.array_equal(qc, g["qc"]) and np.array_equal(val, g["val"]) and np.array_equal(ens, g["ensval"])
+    e.close()
