@@ -412,7 +412,7 @@ def main():
                 "frac": ach_gbs / peaks.get("hbm_gbs"), "peak_source": peaks_src + " MEASURED_PEAKS.json"},
     }
 
-    # ---- full analysis cycle (SURVEY.md section 8d metric ii): member-major grids -> transpose in
+    # ---- full analysis cycle (SURVEY.md section 8d metric ii): member-major restart grids -> state_trans -> transpose in
     # (CUDA pack + NCCL all-to-all + unpack, read_ens_mpi twin) -> ensemble mean -> observation
     # bucketing (set_letkf_obs twin, H2D of the obs tables included) -> das_letkf -> analysis mean ->
     # transpose out (write_ens_mpi twin).  Device timed, max over ranks.
@@ -427,25 +427,38 @@ def main():
             gin = [torch.empty(gsz, dtype=torch.float64, device=dev) if im is not None else None for _, im, _, _ in rounds]
             gout = [torch.empty(gsz, dtype=torch.float64, device=dev) if im is not None else None for _, im, _, _ in rounds]
             gues.copy_(gues0)
-            tr.write_ens(gues, None, gin, None, k, nens)      # untimed: the member-major input of the cycle
-            names = ["transpose_in", "ensmean", "set_obs", "das_letkf", "anal_mean", "transpose_out"]
+            tr.write_ens(gues, None, gin, None, k, nens)      # untimed: the member-major input of the cycle ...
+            for gmem in gin:                                  # ... as SCALE restart variables (rho, rho u, .., rho theta)
+                if gmem is not None:
+                    eng.state_trans(gmem, inverse=True)
+            names = ["state_trans", "transpose_in", "ensmean", "set_obs", "das_letkf", "anal_mean", "transpose_out",
+                     "state_trans_inv"]
             recs = []
             for i in range(2 + args.cycle_steps):
                 barrier()
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
                 ev[0].record()
-                tr.read_ens(gin, None, gues, None, k, nens)
+                for j, gmem in enumerate(gin):                # restart variables -> u, v, w, T, p (work copy in gout)
+                    if gmem is not None:
+                        gout[j].copy_(gmem)
+                        eng.state_trans(gout[j])
                 ev[1].record()
-                eng.ensmean_grd(gues)
+                tr.read_ens(gout, None, gues, None, k, nens)
                 ev[2].record()
-                eng.set_letkf_obs(obs)
+                eng.ensmean_grd(gues)
                 ev[3].record()
-                eng.das_letkf(gues, anal3d=anal)
+                eng.set_letkf_obs(obs)
                 ev[4].record()
-                eng.ensmean_grd(anal)
+                eng.das_letkf(gues, anal3d=anal)
                 ev[5].record()
-                tr.write_ens(anal, None, gout, None, k, nens)
+                eng.ensmean_grd(anal)
                 ev[6].record()
+                tr.write_ens(anal, None, gout, None, k, nens)
+                ev[7].record()
+                for gmem in gout:
+                    if gmem is not None:
+                        eng.state_trans(gmem, inverse=True)
+                ev[8].record()
                 barrier()
                 if i >= 2:
                     recs.append([ev[j].elapsed_time(ev[j + 1]) for j in range(len(names))])
@@ -457,7 +470,7 @@ def main():
             cycle = {"ms_median": float(tot.median()), "ms_min": float(tot.min()), "steps": args.cycle_steps,
                      "phases_ms_median": dict(zip(names, [round(float(x), 3) for x in arr.median(dim=0).values])),
                      "bytes_all_to_all_per_rank": int(2 * tr.block * world * 8 * len(rounds)),
-                     "what": "transpose in + mean + obs bucketing + analysis + mean + transpose out, n_gpus ranks"}
+                     "what": "state_trans + transpose in + mean + obs bucketing + analysis + mean + transpose out + state_trans_inv, n_gpus ranks"}
             del gin, gout, tr
         except Exception as e:   # never lose the main measurement to the optional leg
             cycle = {"error": repr(e)[:300]}

@@ -215,6 +215,21 @@ int letkf_b200_das_phase_clocks(const letkf_b200_handle *h, int64_t *clocks, int
 int letkf_b200_ensmean_grd(letkf_b200_handle *h, int mem, int nens, int nij, double *v3d,
                            double *v2d, int mem_space);
 
+/* ---- state_trans / state_trans_inv twins (scale/common/common_scale.f90:1181-1280) -------------
+ * In place on ONE member-major grid v3dg(nlev,nlon,nlat,nv3d): SCALE restart variables
+ * (rho, rho u, rho v, rho w, rho theta, q...) <-> LETKF state variables (u, v, w, T, p, q...), including
+ * the POSITIVE_DEFINITE_Q / _QHYD clamps of the inverse (:1243-1250).  The thermodynamic constants come
+ * from the SCALE-RM library (scale_const, scale_tracer -- not vendored in the reference tree), so they
+ * are carried as data; letkf_b200_thermo_defaults() fills SCALE-RM's usual values. */
+typedef struct letkf_b200_thermo {
+  double Rdry, Rvap, CVdry, PRE00;
+  double TRACER_CV[LETKF_B200_MAX_NV];   /* CV of moisture variable iv3d_q + i (vapour, cloud, rain, ice, snow, graupel) */
+  int32_t POSITIVE_DEFINITE_Q, POSITIVE_DEFINITE_QHYD;   /* common_nml.f90 PARAM_LETKF */
+} letkf_b200_thermo;
+void letkf_b200_thermo_defaults(letkf_b200_thermo *t);
+int letkf_b200_state_trans(letkf_b200_handle *h, const letkf_b200_thermo *t, int inverse, double *v3dg,
+                           int mem_space);
+
 /* ---- member<->grid transposes (common_mpi_scale.f90:1279-1476) --------------
  * pack:   v3dg(nlev,nlon,nlat,nv3d), v2dg(nlon,nlat,nv2d) of ONE member ->
  *         bufs(nij1max,nlevall,np) with the cyclic column deal of grd_to_buf (:1428)

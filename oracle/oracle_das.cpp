@@ -945,6 +945,50 @@ void oracle_obs_departure_qc(const letkf_b200_qc_config *q, int member, int det,
   }
 }
 
+// state_trans (common_scale.f90:1181-1224) and state_trans_inv (:1229-1280), in place.
+void oracle_state_trans(const letkf_b200_thermo *t, int inverse, int nlev, int nlon, int nlat, int nv3d,
+                        int iv3d_q, double *v3dg) {
+  const size_t st = (size_t)nlev * nlon * nlat;
+  const int iq = iv3d_q - 1;
+  if (inverse) {   // :1243-1250
+    for (int n = 0; n < nv3d; ++n) {
+      const bool clamp = (n == iq) ? t->POSITIVE_DEFINITE_Q != 0 : (t->POSITIVE_DEFINITE_QHYD != 0 && n > iq && n <= iq + 5);
+      if (clamp)
+        for (size_t p = 0; p < st; ++p) v3dg[n * st + p] = std::max(v3dg[n * st + p], 0.0);
+    }
+  }
+  for (size_t p = 0; p < st; ++p) {
+    double *v = v3dg + p;
+    double qdry = 1.0, CVtot = 0.0;
+    for (int n = iq; n < nv3d; ++n) {
+      qdry = qdry - v[n * st];
+      CVtot = CVtot + v[n * st] * t->TRACER_CV[n - iq];
+    }
+    CVtot = t->CVdry * qdry + CVtot;
+    const double Rtot = t->Rdry * qdry + t->Rvap * v[iq * st];
+    if (!inverse) {
+      const double CPovCV = (CVtot + Rtot) / CVtot;
+      const double rho = v[0];
+      const double pres = t->PRE00 * std::pow(v[4 * st] * Rtot / t->PRE00, CPovCV);
+      const double temp = pres / (rho * Rtot);
+      v[0] = v[1 * st] / rho;
+      v[1 * st] = v[2 * st] / rho;
+      v[2 * st] = v[3 * st] / rho;
+      v[3 * st] = temp;
+      v[4 * st] = pres;
+    } else {
+      const double CVovCP = CVtot / (CVtot + Rtot);
+      const double rho = v[4 * st] / (Rtot * v[3 * st]);
+      const double rhot = t->PRE00 / Rtot * std::pow(v[4 * st] / t->PRE00, CVovCP);
+      v[4 * st] = rhot;
+      v[3 * st] = v[2 * st] * rho;
+      v[2 * st] = v[1 * st] * rho;
+      v[1 * st] = v[0] * rho;
+      v[0] = rho;
+    }
+  }
+}
+
 // set_common_mpi_grid, common_mpi_scale.f90:264-283
 void oracle_nij1(int nlon, int nlat, int np, int myrank_e, int32_t *nij1, int32_t *nij1max) {
   const int i = (nlon * nlat) % np;

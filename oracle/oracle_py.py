@@ -73,6 +73,8 @@ def lib():
             getattr(L, name).argtypes = [i, i, i, i, i, i, i, i, i, i, vp, vp, vp]
         L.oracle_obs_departure_qc.restype = None
         L.oracle_obs_departure_qc.argtypes = [C.POINTER(capi.QcConfig), i, i, i, i, vp, vp, vp, vp, vp, vp]
+        L.oracle_state_trans.restype = None
+        L.oracle_state_trans.argtypes = [C.POINTER(capi.Thermo), i, i, i, i, i, i, vp]
         L.oracle_max_threads.restype = i
         _lib = L
     return _lib
@@ -273,3 +275,11 @@ def obs_departure_qc(qcfg, member, det, elm, dat, err, qc, ensval):
     lib().oracle_obs_departure_qc(C.byref(qcfg), member, int(det), len(elm), ens.shape[1], _p(elm), _p(_f64(dat)),
                                   _p(_f64(err)), _p(qc), _p(ens), _p(val))
     return qc, val, ens
+
+
+def state_trans(thermo, v3dg, inverse=False, iv3d_q=6):
+    """In place on v3dg (nlev, nlon, nlat, nv3d) Fortran order (common_scale.f90:1181-1280)."""
+    assert v3dg.flags.f_contiguous
+    nlev, nlon, nlat, nv3d = v3dg.shape
+    lib().oracle_state_trans(C.byref(thermo), int(bool(inverse)), nlev, nlon, nlat, nv3d, iv3d_q, _p(v3dg))
+    return v3dg

@@ -229,6 +229,21 @@ class LETKF:
             space = capi.MEM_HOST
         self._ck(self.lib.letkf_b200_ensmean_grd(self.h, k, nens, nij, _ptr(v3d), _ptr(v2d), space))
 
+    def thermo_defaults(self):
+        t = capi.Thermo()
+        self.lib.letkf_b200_thermo_defaults(C.byref(t))
+        return t
+
+    def state_trans(self, v3dg, thermo=None, inverse=False):
+        """state_trans / state_trans_inv (scale/common/common_scale.f90:1181-1280), in place on one member-major
+        grid v3dg(nlev,nlon,nlat,nv3d): numpy F-order (host) or a torch CUDA tensor with the same memory."""
+        t = thermo if thermo is not None else self.thermo_defaults()
+        space = capi.MEM_DEVICE if _is_torch(v3dg) else capi.MEM_HOST
+        if space == capi.MEM_HOST:
+            assert v3dg.flags.f_contiguous and v3dg.dtype == np.float64
+        self._ck(self.lib.letkf_b200_state_trans(self.h, C.byref(t), int(bool(inverse)), _ptr(v3dg), space))
+        return v3dg
+
     # ---- transposes (device pointers; the all-to-all between them is the caller's NCCL call) --
     def nij1_of(self, nprocs_e, myrank_e):
         a, b = C.c_int32(), C.c_int32()

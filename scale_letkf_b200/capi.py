@@ -87,6 +87,15 @@ class QcConfig(C.Structure):
     ]
 
 
+class Thermo(C.Structure):
+    """letkf_b200_thermo: constants of state_trans / state_trans_inv (scale/common/common_scale.f90:1181-1280)."""
+    _fields_ = [
+        ("Rdry", C.c_double), ("Rvap", C.c_double), ("CVdry", C.c_double), ("PRE00", C.c_double),
+        ("TRACER_CV", C.c_double * MAX_NV),
+        ("POSITIVE_DEFINITE_Q", C.c_int32), ("POSITIVE_DEFINITE_QHYD", C.c_int32),
+    ]
+
+
 # QC codes (scale/common/common_obs_scale.f90:139-151)
 IQC_GOOD, IQC_GROSS_ERR, IQC_REF_MEM, IQC_OBS_BAD, IQC_OTYPE = 0, 5, 12, 50, 90
 UNDEF = -9.99e33   # common/common.f90:38
@@ -133,6 +142,8 @@ PROTOTYPES = {
     "letkf_b200_das_kernel_ms": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "letkf_b200_das_phase_clocks": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "letkf_b200_ensmean_grd": (_i, [_vp, _i, _i, _i, _vp, _vp, _i]),
+    "letkf_b200_thermo_defaults": (None, [C.POINTER(Thermo)]),
+    "letkf_b200_state_trans": (_i, [_vp, C.POINTER(Thermo), _i, _vp, _i]),
     "letkf_b200_grd_to_buf": (_i, [_vp, _i, _vp, _vp, _vp]),
     "letkf_b200_buf_to_ens": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "letkf_b200_ens_to_buf": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

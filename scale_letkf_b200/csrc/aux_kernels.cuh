@@ -256,4 +256,59 @@ __global__ void __launch_bounds__(256) obs_departure_qc_kernel(const QcParams P)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// state_trans / state_trans_inv (scale/common/common_scale.f90:1181-1280), one thread per grid point of a
+// member-major grid v3dg(nlev,nlon,nlat,nv3d): variable stride = npts, consecutive threads = consecutive
+// points (coalesced); HBM-bound, (nv3d + 5) * 8 bytes per point.
+struct StateTransParams {
+  double Rdry, Rvap, CVdry, PRE00;
+  double tracer_cv[16];
+  int pos_q, pos_qhyd;
+  int nv3d, iv3d_q;     // iv3d_q 1-based
+  long long npts;
+  double *v;
+};
+__global__ void __launch_bounds__(256) state_trans_kernel(const StateTransParams P, int inverse) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.npts) return;
+  double *v = P.v + p;
+  const long long st = P.npts;
+  const int iq = P.iv3d_q - 1;
+  if (inverse) {   // (:1243-1250) positive-definite clamps first
+    for (int n = iq; n < P.nv3d; ++n) {
+      const bool clamp = (n == iq) ? P.pos_q : (P.pos_qhyd && n <= iq + 5);
+      if (clamp) v[n * st] = fmax(v[n * st], 0.0);
+    }
+  }
+  double qdry = 1.0, cvtot = 0.0;
+  for (int n = iq; n < P.nv3d; ++n) {   // (:1199-1203 / :1257-1261) no FMA contraction: same rounding as the CPU
+    const double q = v[n * st];
+    qdry = __dsub_rn(qdry, q);
+    cvtot = __dadd_rn(cvtot, __dmul_rn(q, P.tracer_cv[n - iq]));
+  }
+  cvtot = __dadd_rn(__dmul_rn(P.CVdry, qdry), cvtot);
+  const double rtot = __dadd_rn(__dmul_rn(P.Rdry, qdry), __dmul_rn(P.Rvap, v[iq * st]));
+  if (!inverse) {
+    const double cpovcv = __ddiv_rn(__dadd_rn(cvtot, rtot), cvtot);
+    const double rho = v[0];
+    const double pres = __dmul_rn(P.PRE00, pow(__ddiv_rn(__dmul_rn(v[4 * st], rtot), P.PRE00), cpovcv));
+    const double temp = __ddiv_rn(pres, __dmul_rn(rho, rtot));
+    v[0] = __ddiv_rn(v[1 * st], rho);
+    v[1 * st] = __ddiv_rn(v[2 * st], rho);
+    v[2 * st] = __ddiv_rn(v[3 * st], rho);
+    v[3 * st] = temp;
+    v[4 * st] = pres;
+  } else {
+    const double cvovcp = __ddiv_rn(cvtot, __dadd_rn(cvtot, rtot));
+    const double pres = v[4 * st];
+    const double rho = __ddiv_rn(pres, __dmul_rn(rtot, v[3 * st]));
+    const double rhot = __dmul_rn(__ddiv_rn(P.PRE00, rtot), pow(__ddiv_rn(pres, P.PRE00), cvovcp));
+    v[4 * st] = rhot;
+    v[3 * st] = __dmul_rn(v[2 * st], rho);
+    v[2 * st] = __dmul_rn(v[1 * st], rho);
+    v[1 * st] = __dmul_rn(v[0], rho);
+    v[0] = rho;
+  }
+}
+
 }  // namespace letkf

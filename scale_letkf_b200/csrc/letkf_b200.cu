@@ -1231,6 +1231,49 @@ int letkf_b200_ensmean_grd(letkf_b200_handle *h, int mem, int nens, int nij, dou
   return LETKF_B200_OK;
 }
 
+void letkf_b200_thermo_defaults(letkf_b200_thermo *t) {   // SCALE-RM scale_const / scale_tracer values
+  std::memset(t, 0, sizeof(*t));
+  t->Rdry = 287.04;
+  t->Rvap = 461.46;
+  t->CVdry = 1004.64 - 287.04;
+  t->PRE00 = 1.0e5;
+  t->TRACER_CV[0] = 1845.60 - 461.46;   // vapour
+  t->TRACER_CV[1] = t->TRACER_CV[2] = 4218.0;                    // cloud water, rain
+  t->TRACER_CV[3] = t->TRACER_CV[4] = t->TRACER_CV[5] = 2006.0;  // ice, snow, graupel
+  t->POSITIVE_DEFINITE_Q = 0;
+  t->POSITIVE_DEFINITE_QHYD = 0;
+}
+
+int letkf_b200_state_trans(letkf_b200_handle *h, const letkf_b200_thermo *t, int inverse, double *v3dg, int mem_space) {
+  if (!h || !t || !v3dg) return LETKF_B200_EINVAL;
+  const letkf_b200_config &c = h->cfg;
+  if (c.nv3d < 6 || c.iv3d_q != 6 || c.iv3d_p != 5) return fail(h, LETKF_B200_EINVAL, "state_trans needs the u,v,w,T,p,q.. variable order");
+  CK(cudaSetDevice(h->device));
+  const long long npts = (long long)c.nlev * c.nlon * c.nlat;
+  const size_t n = (size_t)npts * c.nv3d;
+  const bool host = mem_space != LETKF_B200_MEM_DEVICE;
+  StateTransParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.Rdry = t->Rdry; P.Rvap = t->Rvap; P.CVdry = t->CVdry; P.PRE00 = t->PRE00;
+  for (int i = 0; i < 16; ++i) P.tracer_cv[i] = t->TRACER_CV[i];
+  P.pos_q = t->POSITIVE_DEFINITE_Q; P.pos_qhyd = t->POSITIVE_DEFINITE_QHYD;
+  P.nv3d = c.nv3d; P.iv3d_q = c.iv3d_q; P.npts = npts;
+  if (host) {
+    CK(h->cb[0].ensure(n));
+    CK(cudaMemcpyAsync(h->cb[0].p, v3dg, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    P.v = h->cb[0].p;
+  } else {
+    P.v = v3dg;
+  }
+  state_trans_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, h->stream>>>(P, inverse ? 1 : 0);
+  CK(cudaGetLastError());
+  if (host) {
+    CK(cudaMemcpyAsync(v3dg, P.v, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return LETKF_B200_OK;
+}
+
 int letkf_b200_nij1(const letkf_b200_handle *h, int np, int myrank_e, int32_t *nij1, int32_t *nij1max) {
   if (!h || np < 1 || myrank_e < 0 || myrank_e >= np) return LETKF_B200_EINVAL;
   const int tot = h->cfg.nlon * h->cfg.nlat;

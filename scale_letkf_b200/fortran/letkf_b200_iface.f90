@@ -84,6 +84,13 @@ module letkf_b200_iface
     integer(c_int32_t) :: MIN_RADAR_REF_MEMBER, MIN_RADAR_REF_MEMBER_OBSREF
   end type
 
+  ! struct letkf_b200_thermo (include/letkf_b200.h): constants of state_trans / state_trans_inv
+  type, bind(C), public :: letkf_b200_thermo
+    real(c_double)     :: Rdry, Rvap, CVdry, PRE00
+    real(c_double)     :: TRACER_CV(LETKF_B200_MAX_NV)
+    integer(c_int32_t) :: POSITIVE_DEFINITE_Q, POSITIVE_DEFINITE_QHYD
+  end type
+
   type(c_ptr), save :: handle = c_null_ptr
 
   interface
@@ -134,6 +141,15 @@ module letkf_b200_iface
       real(c_double), intent(in) :: dat(*), err(*)
       integer(c_int32_t), intent(inout) :: qc(*)
       real(c_double), intent(inout) :: ensval(*), val(*)
+    end function
+    ! state_trans (inverse = 0) / state_trans_inv (inverse = 1), scale/common/common_scale.f90:1181-1280:
+    ! fill letkf_b200_thermo from scale_const (Rdry, Rvap, CVdry, PRE00) and scale_tracer (TRACER_CV)
+    integer(c_int) function c_state_trans(h, t, inverse, v3dg, mem_space) bind(C, name='letkf_b200_state_trans')
+      import :: c_int, c_ptr, c_double, letkf_b200_thermo
+      type(c_ptr), value :: h
+      type(letkf_b200_thermo), intent(in) :: t
+      integer(c_int), value :: inverse, mem_space
+      real(c_double), intent(inout) :: v3dg(*)
     end function
     integer(c_int) function c_set_grid(h, nij1, rig1, rjg1, hgt1, mem_space) bind(C, name='letkf_b200_set_grid')
       import :: c_int, c_ptr, c_double
