@@ -317,3 +317,38 @@ def test_das_presearch_off_matches_on(oracle, monkeypatch):
     k = cfg.MEMBER
     assert relerr(on["anal3d"][:, :, :k, :], off["anal3d"][:, :, :k, :], axis=(0, 1, 2)) <= 1e-12
     e.close()
+
+
+def test_das_no_observations(oracle):
+    """nobstotal = 0: every point takes the nobsl == 0 branch (common_letkf.f90:89-107): W = sqrt(infl) I."""
+    cfg, rig1, rjg1, hgt1, obs, gues = sonde_case(member=8, nsonde=0, nsfc=0)
+    cfg.INFL_MUL = 1.1
+    out, ref = _das_compare(cfg, rig1, rjg1, hgt1, obs, gues, oracle)
+    assert out["nsolved"] == 0 and out["npoints"] == gues.shape[0] * gues.shape[1]
+
+
+@pytest.mark.parametrize("solver", ["ns", "tiled"])
+def test_das_with_2d_variables(oracle, monkeypatch, solver):
+    """nv2d > 0 (the reference carries nv2d = 0 today, common_nml.f90:20, but das_letkf analyses 2-D variables at
+    ilev = 1, letkf_tools.f90:300-312): gues2d / anal2d through both solver paths."""
+    if solver == "tiled":
+        monkeypatch.setenv("LETKF_B200_SOLVER", "tiled")
+    cfg, rig1, rjg1, hgt1, obs, gues = sonde_case(member=10, nsonde=30, nsfc=100, det=True)
+    cfg.nv2d = 2
+    k, nens, nij1 = cfg.MEMBER, gues.shape[2], gues.shape[0]
+    g = synth.rng(77)
+    gues2d = np.asfortranarray(g.standard_normal((nij1, nens, 2)) * 3.0 + 10.0)
+    m = gues2d[:, 0, :].copy()
+    for mm in range(1, k):
+        m += gues2d[:, mm, :]
+    gues2d[:, k, :] = m / k
+    o, e = _engines(cfg, rig1, rjg1, hgt1, obs, oracle)
+    g1, g2 = gues.copy(order="F"), gues.copy(order="F")
+    h1, h2 = gues2d.copy(order="F"), gues2d.copy(order="F")
+    ref = o.das_letkf(g1, gues2d=h1)
+    out = e.das_letkf(g2, gues2d=h2, logp=host_logp(cfg, gues))
+    slots = list(range(k)) + [k + 1]
+    assert relerr(out["anal3d"][:, :, slots, :], ref["anal3d"][:, :, slots, :], axis=(0, 1, 2)) <= TOL
+    assert relerr(out["anal2d"][:, slots, :], ref["anal2d"][:, slots, :], axis=(0, 1)) <= TOL
+    assert np.array_equal(h2[:, :k + 1, :], h1[:, :k + 1, :])
+    e.close()
