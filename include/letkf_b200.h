@@ -215,6 +215,12 @@ int letkf_b200_das_phase_clocks(const letkf_b200_handle *h, int64_t *clocks, int
 int letkf_b200_ensmean_grd(letkf_b200_handle *h, int mem, int nens, int nij, double *v3d,
                            double *v2d, int mem_space);
 
+/* ---- enssprd_grd twin (common_scale.f90:1557-1611): spread over members 1..mem around slot mem+1 (which
+ * must already hold the mean): v3ds(nij,nlev,nv3d), v2ds(nij,nv2d) = sqrt(sum_m (x_m - mean)^2 / (mem-1)),
+ * summed in member order. */
+int letkf_b200_enssprd_grd(letkf_b200_handle *h, int mem, int nens, int nij, const double *v3d,
+                           const double *v2d, double *v3ds, double *v2ds, int mem_space);
+
 /* ---- state_trans / state_trans_inv twins (scale/common/common_scale.f90:1181-1280) -------------
  * In place on ONE member-major grid v3dg(nlev,nlon,nlat,nv3d): SCALE restart variables
  * (rho, rho u, rho v, rho w, rho theta, q...) <-> LETKF state variables (u, v, w, T, p, q...), including

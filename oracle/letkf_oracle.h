@@ -91,6 +91,8 @@ void oracle_buf_to_grd(int nlon, int nlat, int nlev, int nv3d, int nv2d, int np,
 void oracle_obs_departure_qc(const letkf_b200_qc_config *q, int member, int det, int nobs, int nensobs,
                              const int32_t *elm, const double *dat, const double *err, int32_t *qc,
                              double *ensval, double *val);
+/* scale/common/common_scale.f90:1557-1611 (3-D part) */
+void oracle_enssprd_grd(int mem, int nens, int nij, int nlev, int nv3d, const double *v3d, double *v3ds);
 /* scale/common/common_scale.f90:1181-1280 */
 void oracle_state_trans(const letkf_b200_thermo *t, int inverse, int nlev, int nlon, int nlat, int nv3d,
                         int iv3d_q, double *v3dg);

@@ -945,6 +945,19 @@ void oracle_obs_departure_qc(const letkf_b200_qc_config *q, int member, int det,
   }
 }
 
+// enssprd_grd, common_scale.f90:1557-1611 (3-D part)
+void oracle_enssprd_grd(int mem, int nens, int nij, int nlev, int nv3d, const double *v3d, double *v3ds) {
+  const size_t sl = (size_t)nij * nlev;
+  for (int n = 0; n < nv3d; ++n)
+    for (size_t p = 0; p < sl; ++p) {
+      const double *b = v3d + p + (size_t)n * nens * sl;
+      const double mean = b[(size_t)mem * sl];
+      double a = (b[0] - mean) * (b[0] - mean);
+      for (int m = 1; m < mem; ++m) a = a + (b[(size_t)m * sl] - mean) * (b[(size_t)m * sl] - mean);
+      v3ds[p + (size_t)n * sl] = std::sqrt(a / (double)(mem - 1));
+    }
+}
+
 // state_trans (common_scale.f90:1181-1224) and state_trans_inv (:1229-1280), in place.
 void oracle_state_trans(const letkf_b200_thermo *t, int inverse, int nlev, int nlon, int nlat, int nv3d,
                         int iv3d_q, double *v3dg) {

@@ -73,6 +73,8 @@ def lib():
             getattr(L, name).argtypes = [i, i, i, i, i, i, i, i, i, i, vp, vp, vp]
         L.oracle_obs_departure_qc.restype = None
         L.oracle_obs_departure_qc.argtypes = [C.POINTER(capi.QcConfig), i, i, i, i, vp, vp, vp, vp, vp, vp]
+        L.oracle_enssprd_grd.restype = None
+        L.oracle_enssprd_grd.argtypes = [i, i, i, i, i, vp, vp]
         L.oracle_state_trans.restype = None
         L.oracle_state_trans.argtypes = [C.POINTER(capi.Thermo), i, i, i, i, i, i, vp]
         L.oracle_max_threads.restype = i
@@ -283,3 +285,10 @@ def state_trans(thermo, v3dg, inverse=False, iv3d_q=6):
     nlev, nlon, nlat, nv3d = v3dg.shape
     lib().oracle_state_trans(C.byref(thermo), int(bool(inverse)), nlev, nlon, nlat, nv3d, iv3d_q, _p(v3dg))
     return v3dg
+
+
+def enssprd_grd(mem, v3d):
+    nij, nlev, nens, nv3d = v3d.shape
+    out = np.zeros((nij, nlev, nv3d), order="F")
+    lib().oracle_enssprd_grd(mem, nens, nij, nlev, nv3d, _p(v3d), _p(out))
+    return out

@@ -229,6 +229,22 @@ class LETKF:
             space = capi.MEM_HOST
         self._ck(self.lib.letkf_b200_ensmean_grd(self.h, k, nens, nij, _ptr(v3d), _ptr(v2d), space))
 
+    def enssprd_grd(self, v3d):
+        """Ensemble spread around slot MEMBER+1 (common_scale.f90:1557-1611); v3d as in ensmean_grd."""
+        k = self.cfg.MEMBER
+        nens = k + 2 if self.cfg.DET_RUN else k + 1
+        if _is_torch(v3d):
+            import torch
+            nij = v3d.shape[-1]
+            out = torch.empty((self.cfg.nv3d, self.cfg.nlev, nij), dtype=torch.float64, device=v3d.device)
+            space = capi.MEM_DEVICE
+        else:
+            nij = v3d.shape[0]
+            out = np.zeros((nij, self.cfg.nlev, self.cfg.nv3d), order="F")
+            space = capi.MEM_HOST
+        self._ck(self.lib.letkf_b200_enssprd_grd(self.h, k, nens, nij, _ptr(v3d), None, _ptr(out), None, space))
+        return out
+
     def thermo_defaults(self):
         t = capi.Thermo()
         self.lib.letkf_b200_thermo_defaults(C.byref(t))

@@ -114,6 +114,24 @@ __global__ void ensmean_kernel(int mem, int nens, size_t sl, int nvar, double *_
   b[(size_t)mem * sl] = a / (double)mem;
 }
 
+// ---- enssprd_grd (common_scale.f90:1557-1611) -------------------------------------------------
+// sqrt(sum_m (x_m - mean)^2 / (mem - 1)), member order, no FMA contraction (bit-identical to the CPU).
+__global__ void enssprd_kernel(int mem, int nens, size_t sl, int nvar, const double *__restrict__ v,
+                               double *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sl * nvar) return;
+  const size_t n = i / sl, p = i - n * sl;
+  const double *b = v + p + n * (size_t)nens * sl;
+  const double mean = b[(size_t)mem * sl];
+  double d = __dsub_rn(b[0], mean);
+  double a = __dmul_rn(d, d);
+  for (int m = 1; m < mem; ++m) {
+    d = __dsub_rn(b[(size_t)m * sl], mean);
+    a = __dadd_rn(a, __dmul_rn(d, d));
+  }
+  out[i] = __dsqrt_rn(__ddiv_rn(a, (double)(mem - 1)));
+}
+
 // ---- transposes -----------------------------------------------------------------------------
 struct TransposeDims {
   int nlon, nlat, nlev, nv3d, nv2d, np, nij1max, nlevall;

@@ -592,6 +592,9 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
     CK(cudaMemcpyAsync(d_vc.p, vc.data(), nb, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_err.p, obs->err, nb, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_val.p, obs->val, nb, cudaMemcpyHostToDevice, h->stream));
+    // the observation-space ensemble is the one large table (C3: 1.2 GB): page-lock the caller's buffer once
+    // (cached per handle) so that the copy runs at PCIe speed instead of the pageable-memory staging rate
+    if (nb * obs->nensobs >= ((size_t)32 << 20)) ensure_pinned(h, const_cast<double *>(obs->ensval), nb * obs->nensobs);
     CK(cudaMemcpyAsync(d_ens.p, obs->ensval, nb * obs->nensobs, cudaMemcpyHostToDevice, h->stream));
     const int tb = 256, gb = (nobs + tb - 1) / tb;
     bucket_key_kernel<<<gb, tb, 0, h->stream>>>(h->d_tables.p, nobs, d_ic.p, d_ri.p, d_rj.p, d_key.p, d_count.p);
@@ -1226,6 +1229,37 @@ int letkf_b200_ensmean_grd(letkf_b200_handle *h, int mem, int nens, int nij, dou
   if (mem_space != LETKF_B200_MEM_DEVICE) {
     CK(cudaMemcpyAsync(v3d, d3, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
     if (c.nv2d > 0 && v2d) CK(cudaMemcpyAsync(v2d, d2, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_enssprd_grd(letkf_b200_handle *h, int mem, int nens, int nij, const double *v3d, const double *v2d,
+                           double *v3ds, double *v2ds, int mem_space) {
+  if (!h || mem < 2 || nens <= mem || nij < 1 || !v3d || !v3ds) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const letkf_b200_config &c = h->cfg;
+  const size_t sl = (size_t)nij * c.nlev, n3 = sl * nens * c.nv3d, n2 = (size_t)nij * nens * c.nv2d;
+  const size_t o3 = sl * c.nv3d, o2 = (size_t)nij * c.nv2d;
+  const bool host = mem_space != LETKF_B200_MEM_DEVICE, two = c.nv2d > 0 && v2d && v2ds;
+  const double *d3 = v3d, *d2 = v2d;
+  double *s3 = v3ds, *s2 = v2ds;
+  if (host) {
+    CK(h->st_gues.ensure(n3)); CK(h->st_rtps.ensure(o3));
+    CK(cudaMemcpyAsync(h->st_gues.p, v3d, sizeof(double) * n3, cudaMemcpyHostToDevice, h->stream));
+    d3 = h->st_gues.p; s3 = h->st_rtps.p;
+    if (two) {
+      CK(h->st_gues2.ensure(n2)); CK(h->st_anal2.ensure(o2));
+      CK(cudaMemcpyAsync(h->st_gues2.p, v2d, sizeof(double) * n2, cudaMemcpyHostToDevice, h->stream));
+      d2 = h->st_gues2.p; s2 = h->st_anal2.p;
+    }
+  }
+  enssprd_kernel<<<(unsigned)((o3 + 255) / 256), 256, 0, h->stream>>>(mem, nens, sl, c.nv3d, d3, s3);
+  if (two) enssprd_kernel<<<(unsigned)((o2 + 255) / 256), 256, 0, h->stream>>>(mem, nens, (size_t)nij, c.nv2d, d2, s2);
+  CK(cudaGetLastError());
+  if (host) {
+    CK(cudaMemcpyAsync(v3ds, s3, sizeof(double) * o3, cudaMemcpyDeviceToHost, h->stream));
+    if (two) CK(cudaMemcpyAsync(v2ds, s2, sizeof(double) * o2, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
   return LETKF_B200_OK;

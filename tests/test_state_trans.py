@@ -125,3 +125,23 @@ def test_cuda_state_trans(oracle, pos, shape):
     if pos == (0, 0):
         assert rel(got_b, x) <= 1e-12
     e.close()
+
+
+def test_oracle_enssprd_vs_numpy(oracle):
+    """enssprd_grd (common_scale.f90:1557-1611) against numpy's two-pass standard deviation."""
+    cfg = synth.config_c2(nlon=7, nlat=5, nlev=3, member=9)
+    rig1, rjg1, hgt1 = synth.make_grid(cfg)
+    g = synth.make_state(cfg, rig1, rjg1, hgt1, seed_no=8)
+    s = oracle.enssprd_grd(9, g)
+    ref = np.sqrt(((g[:, :, :9, :] - g[:, :, 9:10, :]) ** 2).sum(axis=2) / 8.0)
+    assert np.abs(s - ref).max() / np.abs(ref).max() < 1e-14
+
+
+@pytest.mark.gpu
+def test_cuda_enssprd_bitexact(oracle):
+    cfg = synth.config_c2(nlon=16, nlat=12, nlev=5, member=20)
+    rig1, rjg1, hgt1 = synth.make_grid(cfg)
+    g = synth.make_state(cfg, rig1, rjg1, hgt1, seed_no=9)
+    e = sl.LETKF(cfg, device=0)
+    assert np.array_equal(e.enssprd_grd(g), oracle.enssprd_grd(20, g))
+    e.close()
