@@ -277,15 +277,22 @@ das_ns_kernel(const DasParams P) {
         __syncthreads();
         const double cdiag = (double)(k - 1) / infl;   // (common_letkf.f90:140-143)
         // ---- s = ||A||_1, b, bd (and the adaptive-inflation statistics) from the stored tiles -------
-        double rs = 0.0, dgv = 0.0;
+        // lambda_max(A) = c0 + lambda_max(G) <= c0 + min(||G||_1, ||G||_F): the Frobenius norm is the tighter
+        // bound when the spectrum of G = Yr^T Y decays quickly, and a tighter s saves Newton-Schulz iterations
+        double rs = 0.0, dgv = 0.0, fs = 0.0;
         if (tid < k) {
-          for (int col = 0; col < k; ++col) rs += fabs(Yp[paddr(tid, col)]);
-          rs += cdiag;
+          for (int col = 0; col < k; ++col) {
+            const double g = Yp[paddr(tid, col)];
+            rs += fabs(g);
+            fs = fma(g, g, fs);
+          }
           dgv = Yp[paddr(tid, tid)];
           bvec[tid] = Yp[paddr(tid, k)];
           bdvec[tid] = P.det ? Yp[paddr(tid, k + 1)] : 0.0;
         }
-        const double s_norm = block_max(rs, red);
+        const double g1 = block_max(rs, red);
+        const double gf = sqrt(block_sum(fs, red)) * (1.0 + 1.0e-12);   // (rounding guard)
+        const double s_norm = cdiag + fmin(g1, gf);
         if (P.INFL_MUL_ADAPTIVE) {   // (common_letkf.f90:229-254)
           const double parm1 = Yp[paddr(k, k)];   // sum w dep^2
           const double parm2 = block_sum(dgv, red) / (double)(k - 1);

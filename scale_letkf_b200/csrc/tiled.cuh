@@ -459,12 +459,16 @@ __global__ void __launch_bounds__(256) tl_rowsum_kernel(const DasParams P, const
   const double *Mrow = B.bZ[1] + (size_t)g * n8 * n8 + (size_t)row * n8;
   double *X = B.X + (size_t)g * kMaxNV * n8;
   if (row < k) {
-    double rs = 0.0;
-    for (int c = lane; c < k; c += 32) rs += fabs(Mrow[c]);
+    double rs = 0.0, fs = 0.0;
+    for (int c = lane; c < k; c += 32) {
+      rs += fabs(Mrow[c]);
+      fs = fma(Mrow[c], Mrow[c], fs);
+    }
     rs = warp_sum(rs);
+    fs = warp_sum(fs);
     if (lane == 0) {
-      rs += B.cdiag[g];
-      atomicMax(&B.snorm_bits[g], (unsigned long long)__double_as_longlong(rs));
+      atomicMax(&B.snorm_bits[g], (unsigned long long)__double_as_longlong(rs));   // ||G||_1
+      atomicAdd(&B.misc[(size_t)g * 4 + 2], fs);                                   // ||G||_F^2
       X[(size_t)(kMaxNV - 2) * n8 + row] = Mrow[k];                    // b  = Yr^T dep
       X[(size_t)(kMaxNV - 1) * n8 + row] = P.det ? Mrow[k + 1] : 0.0;  // bd = Yr^T depd
       atomicAdd(&B.misc[(size_t)g * 4 + 1], Mrow[row]);                // trace(Yr^T Y)
@@ -488,7 +492,9 @@ __global__ void __launch_bounds__(256) tl_scale_kernel(const DasParams P, const 
   if (B.state[g] >= 2) return;
   const int n = B.dims[g];
   const int nact = mode == 0 ? P.k : B.nobsl[g];
-  const double s = __longlong_as_double((long long)B.snorm_bits[g]);
+  double s = __longlong_as_double((long long)B.snorm_bits[g]);
+  if (mode == 0)   // lambda_max(A) <= c0 + min(||G||_1, ||G||_F)  (tl_rowsum_kernel)
+    s = B.cdiag[g] + fmin(s, sqrt(B.misc[(size_t)g * 4 + 2]) * (1.0 + 1.0e-12));
   const double is = 1.0 / s, shift = mode == 2 ? 0.0 : B.cdiag[g];
   const size_t base = (size_t)g * nmax * nmax;
   for (int e = blockIdx.x * 1024 + threadIdx.x; e < min(n * n, (int)(blockIdx.x + 1) * 1024); e += 256) {
