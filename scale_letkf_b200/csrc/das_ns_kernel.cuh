@@ -22,7 +22,7 @@ __host__ __device__ inline size_t das_ns_smem_bytes() {
   size_t d = 3 * (size_t)C::PSZ;          // packed Y, Z, T (Z+T double as the two obs-chunk staging buffers)
   d += (size_t)kMaxNV * C::LD;            // Xall
   if (kMaxNV * C::LD > C::PSZ) d += (size_t)kMaxNV * C::LD;   // Ts (else it aliases T: the Newton-Schulz scratch is free by then)
-  d += 2 * (size_t)C::CR;                 // per-row weights of the two staged chunks
+  d += 3 * (size_t)C::CR;                 // per-row weights of the three staged chunks
   d += 8 * kMaxNV + 40;                   // per-column scalars, reductions
   return d * sizeof(double) + (PRE ? 0 : sizeof(SearchSmem)) + 64;
 }
@@ -52,12 +52,12 @@ das_ns_kernel(const DasParams P) {
   double *Yp = reinterpret_cast<double *>(smem_raw);
   double *Zp = Yp + PSZ;
   double *Tp = Zp + PSZ;
-  double *stage = Zp;                           // 2 x CR x LD doubles inside Zp..Tp
+  double *stage = Yp;                           // 3 x CR x LD doubles inside Yp..Tp
   double *Xall = Tp + PSZ;                      // [kMaxNV][LD]: perturbations of variable vv; rows 14/15: b, bd
   constexpr bool TS_ALIAS = kMaxNV * LD <= PSZ;   // [kMaxNV][LD]: Z Xall -- lives in T's storage when it fits
   double *Ts = TS_ALIAS ? Tp : Xall + (size_t)kMaxNV * LD;
   double *wv = Xall + (size_t)(TS_ALIAS ? 1 : 2) * kMaxNV * LD;      // [2][CR]
-  double *colsc = wv + 2 * CR;                  // [8][kMaxNV]
+  double *colsc = wv + 3 * CR;                  // [8][kMaxNV]
   double *red = colsc + 8 * kMaxNV;
   SearchSmem &S = *reinterpret_cast<SearchSmem *>((reinterpret_cast<uintptr_t>(red + 40) + 15) & ~(uintptr_t)15);
   __shared__ long long s_work;
@@ -134,6 +134,16 @@ das_ns_kernel(const DasParams P) {
       return (vv < P.nv3d) ? pbase + ((size_t)m + (size_t)vv * nens) * sl
                            : (size_t)ij + ((size_t)m + (size_t)(vv - P.nv3d) * nens) * P.nij1;
     };
+    // all member values of the point are requested before anything is consumed: one DRAM round trip instead of
+    // one per loop iteration (the write-back to gues3d would otherwise order the loads)
+    constexpr int NLD = (kMaxNV * LD + C::NT - 1) / C::NT;
+    double raw[NLD];
+#pragma unroll
+    for (int it = 0; it < NLD; ++it) {
+      const int idx = tid + it * C::NT, vv = idx / LD, m = idx - vv * LD;
+      raw[it] = 0.0;
+      if (idx < kMaxNV * LD && vv < nvtot && m < k) raw[it] = ((vv < P.nv3d) ? P.gues3d : P.gues2d)[gaddr(vv, m)];
+    }
     if (tid < nvtot) {
       const double *src = (tid < P.nv3d) ? P.gues3d : P.gues2d;
       xm[tid] = src[gaddr(tid, k)];
@@ -145,14 +155,14 @@ das_ns_kernel(const DasParams P) {
       parmv[tid] = P.RELAX_TO_INFLATED_PRIOR ? infl : 1.0;
     }
     __syncthreads();
-    for (int idx = tid; idx < kMaxNV * LD; idx += blockDim.x) {
-      const int vv = idx / LD, m = idx - vv * LD;
+#pragma unroll
+    for (int it = 0; it < NLD; ++it) {
+      const int idx = tid + it * C::NT, vv = idx / LD, m = idx - vv * LD;
+      if (idx >= kMaxNV * LD) break;
       double pert = 0.0;
       if (vv < nvtot && m < k) {
-        double *src = (vv < P.nv3d) ? P.gues3d : P.gues2d;
-        const size_t ad = gaddr(vv, m);
-        pert = src[ad] - xm[vv];
-        src[ad] = pert;
+        pert = raw[it] - xm[vv];
+        ((vv < P.nv3d) ? P.gues3d : P.gues2d)[gaddr(vv, m)] = pert;
       }
       Xall[idx] = pert;
     }
@@ -230,8 +240,8 @@ das_ns_kernel(const DasParams P) {
         double p3acc = 0.0;
         const int nchunks = (p_use + CR - 1) / CR;
         auto issue = [&](int c) {
-          double *dst = stage + (size_t)(c & 1) * CR * LD;
-          double *wdst = wv + (c & 1) * CR;
+          double *dst = stage + (size_t)(c % 3) * CR * LD;
+          double *wdst = wv + (c % 3) * CR;
           const int o0 = c * CR;
           const int nrows = min(CR, p_use - o0), nrows4 = (nrows + 3) & ~3;
           // one warp per obs row (a row is KP/2 16-byte pieces, two rounds of lanes); the row indices
@@ -260,35 +270,47 @@ das_ns_kernel(const DasParams P) {
           }
           cp_async_commit();
         };
+        // three staging buffers (Y, Z and T are all free while the Gram accumulates in registers): chunk c+2 is
+        // requested while chunk c is consumed, and ONE barrier per chunk both publishes chunk c and retires
+        // the buffer of chunk c-1 that the next request overwrites
         issue(0);
+        if (nchunks > 1) issue(1);
         for (int c = 0; c < nchunks; ++c) {
-          if (c + 1 < nchunks) {
-            issue(c + 1);
-            cp_async_wait<1>();
-          } else {
-            cp_async_wait<0>();
-          }
+          if (c + 1 < nchunks) cp_async_wait<1>();
+          else cp_async_wait<0>();
           __syncthreads();
+          if (c + 2 < nchunks) issue(c + 2);
           const int nrows = min(CR, p_use - c * CR);
-          gram_circ<NB, LD>(acc, stage + (size_t)(c & 1) * CR * LD, wv + (c & 1) * CR, (nrows + 3) & ~3, w, lane);
-          __syncthreads();
+          gram_circ<NB, LD>(acc, stage + (size_t)(c % 3) * CR * LD, wv + (c % 3) * CR, (nrows + 3) & ~3, w, lane);
         }
+        __syncthreads();   // the staging buffers (Y among them) are free again
         store_circ<NB>(acc, Yp, w, lo);
         __syncthreads();
         const double cdiag = (double)(k - 1) / infl;   // (common_letkf.f90:140-143)
         // ---- s = ||A||_1, b, bd (and the adaptive-inflation statistics) from the stored tiles -------
         // lambda_max(A) = c0 + lambda_max(G) <= c0 + min(||G||_1, ||G||_F): the Frobenius norm is the tighter
         // bound when the spectrum of G = Yr^T Y decays quickly, and a tighter s saves Newton-Schulz iterations
+        // four threads per row (NT = 4 KP): columns part, part + 4, ...; partial sums meet through two shuffles
         double rs = 0.0, dgv = 0.0, fs = 0.0;
-        if (tid < k) {
-          for (int col = 0; col < k; ++col) {
-            const double g = Yp[paddr(tid, col)];
-            rs += fabs(g);
-            fs = fma(g, g, fs);
+        {
+          const int row = tid >> 2, part = tid & 3;
+          if (row < k) {
+            for (int col = part; col < k; col += 4) {
+              const double g = Yp[paddr(row, col)];
+              rs += fabs(g);
+              fs = fma(g, g, fs);
+            }
           }
-          dgv = Yp[paddr(tid, tid)];
-          bvec[tid] = Yp[paddr(tid, k)];
-          bdvec[tid] = P.det ? Yp[paddr(tid, k + 1)] : 0.0;
+          rs += __shfl_xor_sync(LETKF_FULL_MASK, rs, 1);
+          rs += __shfl_xor_sync(LETKF_FULL_MASK, rs, 2);
+          fs += __shfl_xor_sync(LETKF_FULL_MASK, fs, 1);
+          fs += __shfl_xor_sync(LETKF_FULL_MASK, fs, 2);
+          if (part != 0) fs = 0.0;   // one contribution per row
+          if (row < k && part == 0) {
+            dgv = Yp[paddr(row, row)];
+            bvec[row] = Yp[paddr(row, k)];
+            bdvec[row] = P.det ? Yp[paddr(row, k + 1)] : 0.0;
+          }
         }
         const double g1 = block_max(rs, red);
         const double gf = sqrt(block_sum(fs, red)) * (1.0 + 1.0e-12);   // (rounding guard)
@@ -379,8 +401,13 @@ das_ns_kernel(const DasParams P) {
           s_ = warp_sum(s_);
           sdv_ = warp_sum(sdv_);
           if (lane == 0) {
+            // RTPS factor of the column (letkf_tools.f90:1971-2002), once per variable instead of per member
+            const double va = va_ * pscale;
+            double f = 1.0;
+            if (P.RELAX_ALPHA == 0.0 && P.RELAX_ALPHA_SPREAD != 0.0 && vg_ > 0.0 && va > 0.0)
+              f = P.RELAX_ALPHA_SPREAD * sqrt(vg_ * parmv[vv] / (va * (double)(k - 1))) - P.RELAX_ALPHA_SPREAD + 1.0;
             varg[c] = vg_;
-            vara[c] = va_ * pscale;
+            vara[c] = f;
             ssum[c] = s_ * pscale;
             sdsum[c] = P.det ? sdv_ * pscale : 0.0;
           }
@@ -401,11 +428,7 @@ das_ns_kernel(const DasParams P) {
         if (P.RELAX_ALPHA != 0.0) {
           wx = (1.0 - P.RELAX_ALPHA) * z + P.RELAX_ALPHA * sqrt(parm) * x;
         } else if (P.RELAX_ALPHA_SPREAD != 0.0) {
-          double f = 1.0;
-          if (varg[c] > 0.0 && vara[c] > 0.0)
-            f = P.RELAX_ALPHA_SPREAD * sqrt(varg[c] * parm / (vara[c] * (double)(k - 1))) -
-                P.RELAX_ALPHA_SPREAD + 1.0;
-          wx = f * z;
+          wx = vara[c] * z;
         } else {
           wx = z;
         }
@@ -442,11 +465,7 @@ das_ns_kernel(const DasParams P) {
         const int vv = cols[tid];
         if (P.det) store_anal(vv, k + 1, xdet[vv] + sdsum[tid] * beta);   // (:489-497)
         if (P.rtps_out && vv < P.nv3d) {
-          double f = 1.0;
-          if (P.RELAX_ALPHA == 0.0 && P.RELAX_ALPHA_SPREAD != 0.0 && varg[tid] > 0.0 && vara[tid] > 0.0)
-            f = P.RELAX_ALPHA_SPREAD * sqrt(varg[tid] * parmv[vv] / (vara[tid] * (double)(k - 1))) -
-                P.RELAX_ALPHA_SPREAD + 1.0;
-          P.rtps_out[pbase + (size_t)vv * sl] = f;
+          P.rtps_out[pbase + (size_t)vv * sl] = vara[tid];
         }
         if (P.infl3d && vv < P.nv3d) {
           const double v = (vv == vtrig || P.INFL_MUL_ADAPTIVE) ? inflv[P.INFL_MUL_ADAPTIVE ? P.vfirst[vv] : vv]
