@@ -239,22 +239,32 @@ das_ns_kernel(const DasParams P) {
         for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
         double p3acc = 0.0;
         const int nchunks = (p_use + CR - 1) / CR;
+        static_assert(CR <= 4 * NB, "a warp stages at most four rows of a chunk");
+        // One warp per obs row (a row is KP/2 16-byte pieces), rows w, w + NB, w + 2 NB, w + 3 NB of a chunk.
+        // Chunks are requested strictly in order, and the sorted-obs indices of the NEXT chunk are fetched
+        // while the current one is requested, so that a request only pays the row latency, not index + row.
+        int nxt[4];
+        auto fetch_idx = [&](int c) {
+          const int o0 = c * CR, nrows = min(CR, p_use - o0);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) nxt[u] = (w + u * NB < nrows) ? L.iob[o0 + w + u * NB] : -1;
+        };
+        fetch_idx(0);
         auto issue = [&](int c) {
           double *dst = stage + (size_t)(c % 3) * CR * LD;
           double *wdst = wv + (c % 3) * CR;
           const int o0 = c * CR;
           const int nrows = min(CR, p_use - o0), nrows4 = (nrows + 3) & ~3;
-          // one warp per obs row (a row is KP/2 16-byte pieces, two rounds of lanes); the row indices
-          // of up to four rows are fetched first so that their latencies overlap
-          for (int ob = w; ob < nrows; ob += 4 * NB) {
+          {
             int iobs[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) iobs[u] = (ob + u * NB < nrows) ? L.iob[o0 + ob + u * NB] : -1;
+            for (int u = 0; u < 4; ++u) iobs[u] = nxt[u];
+            fetch_idx(c + 1);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (iobs[u] < 0) continue;
               const double *src = P.ensval + (size_t)iobs[u] * P.ldens;
-              double *drow = dst + (size_t)(ob + u * NB) * LD;
+              double *drow = dst + (size_t)(w + u * NB) * LD;
               for (int pc = lane; pc < KP / 2; pc += 32) cp_async16(drow + 2 * pc, src + 2 * pc);
             }
           }
