@@ -47,8 +47,9 @@ struct GemmParams {
   int M, N, K;               // extents (upper bounds when mdims / kdims are given)
   const int *mdims;          // optional per-item M (= N when sym)
   const int *kdims;          // optional per-item K
-  const int *state;          // optional per-item solver state: >= state_skip skips the item, == 1 skips job 1 if skip_last
-  int state_skip, skip_last;
+  const int *state;          // optional per-item solver state (0 active, 1 last quadratic step in flight, 2 done,
+                             // 3 / 4 third- / fourth-order finishing step in flight)
+  unsigned mask[2];          // job j processes the items whose state bit is set in mask[j]
   const int *sel;            // optional per-item selector of job[].A_alt
   const int *selB;           // optional per-item selector of job[].B_alt
   int sym;                   // 1: C symmetric (M == N): lower-triangular tiles only, mirrored on store
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) tl_gemm_kernel(con
   const int item = blockIdx.y / P.njobs, jb = blockIdx.y - item * P.njobs;
   if (P.state) {
     const int st = P.state[item];
-    if (st >= P.state_skip || (st == 1 && jb == 1 && P.skip_last)) return;
+    if (!((P.mask[jb] >> st) & 1u)) return;
   }
   const int M = P.mdims ? P.mdims[item] : P.M;
   const int N = P.sym ? M : P.N;
@@ -533,21 +534,24 @@ __global__ void __launch_bounds__(256) tl_res_kernel(const TiledParams B, const 
 }
 
 // ---- tl_step: per-point iteration control (the scalar part of newton_schulz_invsqrt) -------------------
-// parity: index of the Z buffer the GEMMs of THIS iteration write.
-__global__ void tl_step_kernel(const TiledParams B, int parity) {
-  __shared__ int s_act;
-  if (threadIdx.x == 0) s_act = 0;
+// parity: index of the Z buffer the GEMMs of THIS iteration write.  allow_finish: once the residual is below
+// 2e-3 one third- / fourth-order step (states 3 / 4, see ns_solver.cuh) finishes the point.
+// nactive[0..2]: points still in flight, in state 3 or 4, in state 4.
+__global__ void tl_step_kernel(const TiledParams B, int parity, int allow_finish) {
+  __shared__ int s_act[3];
+  if (threadIdx.x < 3) s_act[threadIdx.x] = 0;
   __syncthreads();
   for (int g = threadIdx.x; g < B.G; g += blockDim.x) {
     int st = B.state[g];
-    if (st == 1) st = 2;   // the last iteration was completed by the previous GEMMs
+    if (st == 1 || st == 3 || st == 4) st = 2;   // the finishing GEMMs were issued by the previous iteration
     if (st == 0) {
       const double res = __longlong_as_double((long long)B.res[g]);
       const int it = B.iters[g] + 1;
       const bool conv = res < 1.0e-7;
       const bool last = conv || it >= B.max_iter;
+      const bool fin = allow_finish && !last && it > 1 && res < 2.0e-3;
       double a = B.brk[g], c = 1.0;
-      if (!last && (1.0 - a) > 1.0e-3) c = 3.0 / (a + sqrt(a) + 1.0);
+      if (!last && !fin && (1.0 - a) > 1.0e-3) c = 3.0 / (a + sqrt(a) + 1.0);
       const double sc = sqrt(c);
       B.h0[g] = 1.5 * sc;
       B.h1[g] = -0.5 * c * sc;
@@ -555,26 +559,29 @@ __global__ void tl_step_kernel(const TiledParams B, int parity) {
       B.brk[g] = t * (3.0 - t) * (3.0 - t) * 0.25;
       B.iters[g] = it;
       B.res[g] = 0ull;
-      if (last) {
-        st = 1;
+      if (last || fin) {
+        st = last ? 1 : (res < 2.0e-4 ? 3 : 4);
         B.zsel[g] = parity;
-        if (!conv) B.fail[g] = 1;
+        if (last && !conv) B.fail[g] = 1;
       }
     }
     B.state[g] = st;
-    if (st < 2) atomicAdd(&s_act, 1);
+    if (st != 2) atomicAdd(&s_act[0], 1);
+    if (st == 3 || st == 4) atomicAdd(&s_act[1], 1);
+    if (st == 4) atomicAdd(&s_act[2], 1);
   }
   __syncthreads();
-  if (threadIdx.x == 0) *B.nactive = s_act;
+  if (threadIdx.x < 3) B.nactive[threadIdx.x] = s_act[threadIdx.x];
 }
 
 // ---- tl_poly: T = h1 M + h0 I (and Z1 = T on the first iteration) --------------------------------------
 __global__ void __launch_bounds__(256) tl_poly_kernel(const TiledParams B, const double *Mat, double *T, double *Zfirst,
                                                        int nmax) {
   const int g = blockIdx.y;
-  if (B.state[g] >= 2) return;
+  if (B.state[g] == 2) return;
   const int n = B.dims[g];
-  const double h0 = B.h0[g], h1 = B.h1[g];
+  const bool fin = B.state[g] >= 3;              // finishing step: T holds E = I - M first
+  const double h0 = fin ? 1.0 : B.h0[g], h1 = fin ? -1.0 : B.h1[g];
   const size_t base = (size_t)g * nmax * nmax;
   for (int e = blockIdx.x * 1024 + threadIdx.x; e < min(n * n, (int)(blockIdx.x + 1) * 1024); e += 256) {
     const int row = e / n, col = e - row * n;
@@ -582,6 +589,23 @@ __global__ void __launch_bounds__(256) tl_poly_kernel(const TiledParams B, const
     const double v = fma(h1, Mat[ad], row == col ? h0 : 0.0);
     T[ad] = v;
     if (Zfirst) Zfirst[ad] = v;
+  }
+}
+
+// ---- tl_finish_poly: T = I + E/2 + 3 E^2/8 (+ 5 E^3/16) for the points in state 3 (4); E in T (in place) ----
+__global__ void __launch_bounds__(256) tl_finish_poly_kernel(const TiledParams B, double *T, const double *E2, const double *E3,
+                                                              int nmax) {
+  const int g = blockIdx.y;
+  const int st = B.state[g];
+  if (st != 3 && st != 4) return;
+  const int n = B.dims[g];
+  const size_t base = (size_t)g * nmax * nmax;
+  for (int e = blockIdx.x * 1024 + threadIdx.x; e < min(n * n, (int)(blockIdx.x + 1) * 1024); e += 256) {
+    const int row = e / n, col = e - row * n;
+    const size_t ad = base + (size_t)row * nmax + col;
+    double v = fma(0.375, E2[ad], fma(0.5, T[ad], row == col ? 1.0 : 0.0));
+    if (st == 4) v = fma(0.3125, E3[ad], v);
+    T[ad] = v;
   }
 }
 

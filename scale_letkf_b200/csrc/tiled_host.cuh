@@ -9,7 +9,7 @@ struct TiledBufs {
   DevBuf<double> bZ0, bZ1, bY0, bY1, mT, mS, E2;
   DevBuf<int> skip, ncols, cols, nobsl, idx, dims, kd, state, zsel, iters, fail, nactive, adims, solved_any;
   DevBuf<unsigned long long> snorm_bits, res, scounters;
-  int *h_pinned = nullptr;   // [0] nactive, [1..] nobsl readback
+  int *h_pinned = nullptr;   // [0..2] nactive counters of the solver loop; [1..] nobsl readback (before the solve)
   size_t h_pinned_n = 0;
   void release() {
     for (DevBuf<double> *b : {&X, &Ts, &colsc, &beta, &ri, &rj, &lp, &rz, &cdiag, &infl, &rdiag, &rloc, &snorm, &brk, &h0,
@@ -62,52 +62,72 @@ int tl_gemm(letkf_b200_handle *h, const GemmParams &P, int items) {
 }
 
 // Coupled Newton-Schulz on the whole batch: on entry bY[0] holds Y0 and the per-point state is armed;
-// on exit bZ[zsel[g]] (and bY[zsel[g]] when keep_y) hold the result of point g.
+// on exit bZ[zsel[g]] (and bY[zsel[g]] when keep_y) hold the result of point g.  Without keep_y a point whose
+// residual drops below 2e-3 is finished by one third- / fourth-order step (tl_step_kernel).
 int tl_ns_solve(letkf_b200_handle *h, TiledBufs &T, const TiledParams &B, int nmax, bool keep_y, int *launches) {
   const int G = B.G;
   const long long sN = (long long)nmax * nmax;
   const dim3 egrid((unsigned)((sN + 1023) / 1024), (unsigned)G);
+  auto base = [&](GemmParams &P) {
+    std::memset(&P, 0, sizeof(P));
+    P.M = P.N = P.K = nmax;
+    P.mdims = B.dims;
+    P.kdims = B.dims;
+    P.state = B.state;
+    P.sym = 1;
+  };
   for (int it = 1; it <= B.max_iter + 1; ++it) {
     const int cur = it & 1, prev = cur ^ 1;
     if (it == 1) {
       tl_res_kernel<<<egrid, 256, 0, h->stream>>>(B, B.bY[0], nmax);
     } else {   // M = Z Y -> bZ[cur] (free: it holds Z of two iterations ago)
       GemmParams P;
-      std::memset(&P, 0, sizeof(P));
+      base(P);
       P.njobs = 1;
       P.job[0] = GemmJob{B.bZ[prev], nullptr, B.bY[prev], B.bZ[cur], sN, sN, sN, nmax, nmax, nmax};
-      P.M = P.N = P.K = nmax;
-      P.mdims = B.dims;
-      P.kdims = B.dims;
-      P.state = B.state;
-      P.state_skip = 1;   // points whose last iteration has just been completed are done
-      P.sym = 1;
+      P.mask[0] = 1u << 0;   // points whose last step has just been completed are done
       P.res = B.res;
       int r = tl_gemm(h, P, G);
       if (r != LETKF_B200_OK) return r;
     }
-    tl_step_kernel<<<1, 256, 0, h->stream>>>(B, cur);
-    CK(cudaMemcpyAsync(T.h_pinned, B.nactive, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    tl_step_kernel<<<1, 256, 0, h->stream>>>(B, cur, keep_y ? 0 : 1);
+    CK(cudaMemcpyAsync(T.h_pinned, B.nactive, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *launches += 3;
     if (T.h_pinned[0] == 0) break;
     tl_poly_kernel<<<egrid, 256, 0, h->stream>>>(B, it == 1 ? B.bY[0] : B.bZ[cur], B.mT, it == 1 ? B.bZ[1] : nullptr, nmax);
+    if (T.h_pinned[1] > 0) {   // finishing steps: E^2 -> bY[cur], E^3 -> bY[prev] (Y of these points is dead), then T
+      GemmParams E2;
+      base(E2);
+      E2.njobs = 1;
+      E2.job[0] = GemmJob{B.mT, nullptr, B.mT, B.bY[cur], sN, sN, sN, nmax, nmax, nmax};
+      E2.mask[0] = (1u << 3) | (1u << 4);
+      int r = tl_gemm(h, E2, G);
+      if (r != LETKF_B200_OK) return r;
+      if (T.h_pinned[2] > 0) {
+        GemmParams E3;
+        base(E3);
+        E3.njobs = 1;
+        E3.job[0] = GemmJob{B.bY[cur], nullptr, B.mT, B.bY[prev], sN, sN, sN, nmax, nmax, nmax};
+        E3.mask[0] = 1u << 4;
+        r = tl_gemm(h, E3, G);
+        if (r != LETKF_B200_OK) return r;
+      }
+      tl_finish_poly_kernel<<<egrid, 256, 0, h->stream>>>(B, B.mT, B.bY[cur], B.bY[prev], nmax);
+      *launches += 3;
+    }
     GemmParams P;
-    std::memset(&P, 0, sizeof(P));
-    P.M = P.N = P.K = nmax;
-    P.mdims = B.dims;
-    P.kdims = B.dims;
-    P.state = B.state;
-    P.state_skip = 2;
-    P.sym = 1;
-    P.skip_last = keep_y ? 0 : 1;
+    base(P);
     if (it == 1) {   // Z1 = T (written by tl_poly), Y1 = T Y0
       P.njobs = 1;
       P.job[0] = GemmJob{B.mT, nullptr, B.bY[0], B.bY[1], sN, sN, sN, nmax, nmax, nmax};
+      P.mask[0] = (1u << 0) | (1u << 1);
     } else {
       P.njobs = 2;
       P.job[0] = GemmJob{B.mT, nullptr, B.bZ[prev], B.bZ[cur], sN, sN, sN, nmax, nmax, nmax};
       P.job[1] = GemmJob{B.mT, nullptr, B.bY[prev], B.bY[cur], sN, sN, sN, nmax, nmax, nmax};
+      P.mask[0] = (1u << 0) | (1u << 1) | (1u << 3) | (1u << 4);
+      P.mask[1] = keep_y ? ((1u << 0) | (1u << 1)) : (1u << 0);
     }
     int r = tl_gemm(h, P, G);
     if (r != LETKF_B200_OK) return r;
@@ -143,12 +163,12 @@ int launch_range_tiled(letkf_b200_handle *h, TiledBufs &T, DasParams P, long lon
   CK(T.snorm.ensure(Gs)); CK(T.brk.ensure(Gs)); CK(T.h0.ensure(Gs)); CK(T.h1.ensure(Gs)); CK(T.misc.ensure(Gs * 4));
   CK(T.skip.ensure(Gs)); CK(T.ncols.ensure(Gs)); CK(T.cols.ensure(Gs * kMaxNV)); CK(T.nobsl.ensure(Gs));
   CK(T.idx.ensure(Gs * maxl)); CK(T.dims.ensure(Gs)); CK(T.kd.ensure(Gs)); CK(T.state.ensure(Gs)); CK(T.zsel.ensure(Gs));
-  CK(T.iters.ensure(Gs)); CK(T.fail.ensure(Gs)); CK(T.nactive.ensure(1)); CK(T.adims.ensure(Gs)); CK(T.solved_any.ensure(Gs));
+  CK(T.iters.ensure(Gs)); CK(T.fail.ensure(Gs)); CK(T.nactive.ensure(4)); CK(T.adims.ensure(Gs)); CK(T.solved_any.ensure(Gs));
   CK(T.snorm_bits.ensure(Gs)); CK(T.res.ensure(Gs)); CK(T.scounters.ensure(16));
-  if (T.h_pinned_n < Gs + 1) {
+  if (T.h_pinned_n < Gs + 4) {
     if (T.h_pinned) cudaFreeHost(T.h_pinned);
-    CK(cudaMallocHost((void **)&T.h_pinned, sizeof(int) * (Gs + 1)));
-    T.h_pinned_n = Gs + 1;
+    CK(cudaMallocHost((void **)&T.h_pinned, sizeof(int) * (Gs + 4)));
+    T.h_pinned_n = Gs + 4;
   }
   // scratch of the search kernel (one list per resident CTA)
   const int sgrid = (int)std::max<long long>(1, std::min<long long>(G, (long long)h->num_sms * 8));
@@ -216,7 +236,7 @@ int launch_range_tiled(letkf_b200_handle *h, TiledBufs &T, DasParams P, long lon
           std::memset(&Q, 0, sizeof(Q));
           Q.njobs = 1;
           Q.job[0] = GemmJob{B.E, nullptr, B.E, B.bZ[1], (long long)n8 * pK, (long long)n8 * pK, (long long)sN, pK, pK, n8};
-          Q.M = Q.N = n8; Q.K = pK; Q.kdims = B.kd; Q.state = B.state; Q.state_skip = 2; Q.sym = 1;
+          Q.M = Q.N = n8; Q.K = pK; Q.kdims = B.kd; Q.state = B.state; Q.mask[0] = 3u; Q.sym = 1;
           int r = tl_gemm(h, Q, Gb);
           if (r != LETKF_B200_OK) return r;
           tl_rowsum_kernel<<<dim3((unsigned)(n8 / 8), (unsigned)Gb), 256, 0, h->stream>>>(P, B);
@@ -244,7 +264,7 @@ int launch_range_tiled(letkf_b200_handle *h, TiledBufs &T, DasParams P, long lon
           std::memset(&Q, 0, sizeof(Q));
           Q.njobs = 1;
           Q.job[0] = GemmJob{B.E, nullptr, B.E, B.mS, (long long)pK * kK, (long long)pK * kK, (long long)sN, kK, kK, nmax};
-          Q.M = Q.N = nmax; Q.K = kK; Q.mdims = B.dims; Q.state = B.state; Q.state_skip = 2; Q.sym = 1;
+          Q.M = Q.N = nmax; Q.K = kK; Q.mdims = B.dims; Q.state = B.state; Q.mask[0] = 3u; Q.sym = 1;
           int r = tl_gemm(h, Q, Gb);
           if (r != LETKF_B200_OK) return r;
           const dim3 rgrid((unsigned)(pK / 8), (unsigned)Gb);
@@ -325,13 +345,13 @@ int core_batch_tiled(letkf_b200_handle *h, TiledBufs &T, CoreTiledParams C) {
   CK(T.X.ensure(Gs * kMaxNV * n8)); CK(T.Ts.ensure(Gs * n8 * kMaxNV)); CK(T.cdiag.ensure(Gs)); CK(T.infl.ensure(Gs));
   CK(T.snorm.ensure(Gs)); CK(T.brk.ensure(Gs)); CK(T.h0.ensure(Gs)); CK(T.h1.ensure(Gs)); CK(T.misc.ensure(Gs * 4));
   CK(T.skip.ensure(Gs)); CK(T.nobsl.ensure(Gs)); CK(T.dims.ensure(Gs)); CK(T.kd.ensure(Gs)); CK(T.state.ensure(Gs));
-  CK(T.zsel.ensure(Gs)); CK(T.iters.ensure(Gs)); CK(T.fail.ensure(Gs)); CK(T.nactive.ensure(1)); CK(T.adims.ensure(Gs));
+  CK(T.zsel.ensure(Gs)); CK(T.iters.ensure(Gs)); CK(T.fail.ensure(Gs)); CK(T.nactive.ensure(4)); CK(T.adims.ensure(Gs));
   CK(T.snorm_bits.ensure(Gs)); CK(T.res.ensure(Gs)); CK(T.E.ensure(Gs * (size_t)n8 * pK)); CK(T.dw.ensure(Gs * pK));
   CK(T.bZ0.ensure(Gs * sN)); CK(T.bZ1.ensure(Gs * sN)); CK(T.bY0.ensure(Gs * sN)); CK(T.bY1.ensure(Gs * sN)); CK(T.mT.ensure(Gs * sN));
-  if (T.h_pinned_n < Gs + 1) {
+  if (T.h_pinned_n < Gs + 4) {
     if (T.h_pinned) cudaFreeHost(T.h_pinned);
-    CK(cudaMallocHost((void **)&T.h_pinned, sizeof(int) * (Gs + 1)));
-    T.h_pinned_n = Gs + 1;
+    CK(cudaMallocHost((void **)&T.h_pinned, sizeof(int) * (Gs + 4)));
+    T.h_pinned_n = Gs + 4;
   }
   TiledParams B;
   std::memset(&B, 0, sizeof(B));
@@ -360,7 +380,7 @@ int core_batch_tiled(letkf_b200_handle *h, TiledBufs &T, CoreTiledParams C) {
     std::memset(&Q, 0, sizeof(Q));
     Q.njobs = 1;
     Q.job[0] = GemmJob{B.E, nullptr, B.E, B.bZ[1], (long long)n8 * pK, (long long)n8 * pK, (long long)sN, pK, pK, n8};
-    Q.M = Q.N = n8; Q.K = pK; Q.kdims = B.kd; Q.state = B.state; Q.state_skip = 2; Q.sym = 1;
+    Q.M = Q.N = n8; Q.K = pK; Q.kdims = B.kd; Q.state = B.state; Q.mask[0] = 3u; Q.sym = 1;
     int r = tl_gemm(h, Q, Gb);
     if (r != LETKF_B200_OK) return r;
     tl_rowsum_kernel<<<dim3((unsigned)(n8 / 8), (unsigned)Gb), 256, 0, h->stream>>>(P, B);
