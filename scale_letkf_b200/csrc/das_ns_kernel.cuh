@@ -61,6 +61,8 @@ das_ns_kernel(const DasParams P) {
   double *red = colsc + 8 * kMaxNV;
   SearchSmem &S = *reinterpret_cast<SearchSmem *>((reinterpret_cast<uintptr_t>(red + 40) + 15) & ~(uintptr_t)15);
   __shared__ long long s_work;
+  __shared__ long long s_ploff[kMaxNV];
+  __shared__ int s_pln[kMaxNV];
   const LaneOfs lo = lane_offsets(lane);
 
   LocalList L;
@@ -98,7 +100,12 @@ das_ns_kernel(const DasParams P) {
         if (v >= P.point_end) v = -2;
         if (PRE && v >= 0) {   // all lists of the point must be in the pool
           bool ok = true;
-          for (int vg = 0; vg < P.nvgroup; ++vg) ok = ok && P.pl_off[(v - P.pl_base) * P.nvgroup + vg] >= 0;
+          for (int vg = 0; vg < P.nvgroup; ++vg) {   // (kept in shared memory: the group loop needs them again)
+            const long long e = (v - P.pl_base) * P.nvgroup + vg;
+            s_ploff[vg] = P.pl_off[e];
+            s_pln[vg] = P.pl_n[e];
+            ok = ok && s_ploff[vg] >= 0;
+          }
           if (!ok) {
             P.redo_list[atomicAdd(P.redo_count, 1ull)] = v;
             v = -1;
@@ -212,8 +219,8 @@ das_ns_kernel(const DasParams P) {
       // (L's pointers are simply re-aimed: no extra live registers in the Gram loop)
       int nobsl;
       if constexpr (PRE) {
-        const long long pl_off = P.pl_off[(wp - P.pl_base) * P.nvgroup + vg];
-        nobsl = P.pl_n[(wp - P.pl_base) * P.nvgroup + vg];
+        const long long pl_off = s_ploff[vg];
+        nobsl = s_pln[vg];
         L.iob = P.pl_iob + pl_off;
         L.rdiag = P.pl_rdiag + pl_off;
         L.rloc = P.pl_rloc + pl_off;   // only dereferenced when INFL_MUL_ADAPTIVE (then the pool exists)

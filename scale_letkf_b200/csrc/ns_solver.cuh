@@ -206,7 +206,7 @@ __device__ __forceinline__ void gram_circ(double (&acc)[(NB + 1) / 2][2], const 
     if (j >= NB) j -= NB;
     jo[d] = j * 8;
   }
-#pragma unroll 2
+#pragma unroll 4
   for (int o = 0; o < nrows4; o += 4) {
     const double a = pa[(size_t)o * LD] * wv[o + q];
     const double *pbk = pb + (size_t)o * LD;
