@@ -447,7 +447,9 @@ def main():
                 ev[2].record()
                 eng.ensmean_grd(gues)
                 ev[3].record()
+                th0 = time.perf_counter()
                 eng.set_letkf_obs(obs)
+                host_setobs_ms = (time.perf_counter() - th0) * 1e3
                 ev[4].record()
                 eng.das_letkf(gues, anal3d=anal)
                 ev[5].record()
@@ -470,6 +472,7 @@ def main():
             cycle = {"ms_median": float(tot.median()), "ms_min": float(tot.min()), "steps": args.cycle_steps,
                      "phases_ms_median": dict(zip(names, [round(float(x), 3) for x in arr.median(dim=0).values])),
                      "bytes_all_to_all_per_rank": int(2 * tr.block * world * 8 * len(rounds)),
+                     "set_obs_host_ms_last": round(host_setobs_ms, 3),
                      "what": "state_trans + transpose in + mean + obs bucketing + analysis + mean + transpose out + state_trans_inv, n_gpus ranks"}
             del gin, gout, tr
         except Exception as e:   # never lose the main measurement to the optional leg

@@ -142,6 +142,9 @@ struct letkf_b200_handle {
   DevBuf<unsigned long long> ps_counters;   // [0..15] work counter block, [16], [17] pool cursors
   int ps_grid = 0;
   DevBuf<long long> redo_list;
+  // scratch of set_obs
+  DevBuf<int> so_ic, so_key, so_count, so_fill, so_tmp;
+  DevBuf<double> so_ri, so_rj, so_vc, so_err, so_val, so_ens;
 };
 
 #define CK(call)                                                                         \
@@ -434,6 +437,8 @@ int letkf_b200_destroy(letkf_b200_handle *h) {
   }
   h->ps_l_iob.release(); h->ps_l_rdiag.release(); h->ps_l_rloc.release(); h->ps_l_cnd.release(); h->ps_l_cpk.release();
   h->ps_counters.release(); h->redo_list.release();
+  h->so_ic.release(); h->so_key.release(); h->so_count.release(); h->so_fill.release(); h->so_tmp.release();
+  h->so_ri.release(); h->so_rj.release(); h->so_vc.release(); h->so_err.release(); h->so_val.release(); h->so_ens.release();
   for (cudaEvent_t e : h->ev_s) cudaEventDestroy(e);
   if (h->s_search) cudaStreamDestroy(h->s_search);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -568,8 +573,10 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
   h->nensobs = obs->nensobs;
   h->ldens = ns_row_doubles(c.MEMBER);   // [ensval(1..k) | dep | depd | 0..]
   h->nobstotal = nobs;
-  DevBuf<int> d_ic, d_key, d_count, d_fill, d_tmp;
-  DevBuf<double> d_ri, d_rj, d_vc, d_err, d_val, d_ens;
+  // scratch of the sort: kept in the handle (grow-only) -- eleven cudaMalloc/cudaFree pairs per call cost
+  // 100-500 ms inside a process that holds ~100 GB of device memory (cudaFree synchronises the device)
+  DevBuf<int> &d_ic = h->so_ic, &d_key = h->so_key, &d_count = h->so_count, &d_fill = h->so_fill, &d_tmp = h->so_tmp;
+  DevBuf<double> &d_ri = h->so_ri, &d_rj = h->so_rj, &d_vc = h->so_vc, &d_err = h->so_err, &d_val = h->so_val, &d_ens = h->so_ens;
   CK(h->d_tables.ensure(1));
   CK(cudaMemcpyAsync(h->d_tables.p, &T, sizeof(T), cudaMemcpyHostToDevice, h->stream));
   CK(h->bstart.ensure((size_t)boff + 1));
@@ -613,8 +620,6 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
   CK(cudaMemcpyAsync(h->h_bstart.data(), h->bstart.p, sizeof(int) * ((size_t)boff + 1), cudaMemcpyDeviceToHost, h->stream));
   if (nobs > 0) CK(cudaMemcpyAsync(h->h_s2o.data(), h->s2o.p, sizeof(int) * nobs, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  d_ic.release(); d_key.release(); d_count.release(); d_fill.release(); d_tmp.release();
-  d_ri.release(); d_rj.release(); d_vc.release(); d_err.release(); d_val.release(); d_ens.release();
   for (int ic = 0; ic < nct; ++ic) {
     const CtypeDev &d = T.ct[ic];
     const int b0 = h->h_bstart[d.boff], b1 = h->h_bstart[d.boff + d.ngrdext_i * d.ngrdext_j];
