@@ -252,6 +252,12 @@ int letkf_b200_ens_to_buf(letkf_b200_handle *h, int np, int myrank_e, int nens, 
                           int mend, const double *v3d, const double *v2d, double *bufs);
 int letkf_b200_buf_to_grd(letkf_b200_handle *h, int np, const double *bufr, double *v3dg,
                           double *v2dg);
+/* pack with state_trans fused in front (restart variables -> LETKF variables while packing), unpack with
+ * state_trans_inv fused behind (common_scale.f90:1181-1280 inside common_mpi_scale.f90:1428-1476); t == NULL: plain */
+int letkf_b200_grd_to_buf_trans(letkf_b200_handle *h, int np, const letkf_b200_thermo *t, const double *v3dg,
+                                const double *v2dg, double *bufs);
+int letkf_b200_buf_to_grd_trans(letkf_b200_handle *h, int np, const letkf_b200_thermo *t, const double *bufr,
+                                double *v3dg, double *v2dg);
 /* nij1 / nij1max of rank myrank_e among np ranks (set_common_mpi_grid :264-283) */
 int letkf_b200_nij1(const letkf_b200_handle *h, int np, int myrank_e, int32_t *nij1,
                     int32_t *nij1max);

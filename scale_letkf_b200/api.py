@@ -266,11 +266,15 @@ class LETKF:
         self._ck(self.lib.letkf_b200_nij1(self.h, nprocs_e, myrank_e, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def grd_to_buf(self, nprocs_e, v3dg, v2dg, bufs):
-        self._ck(self.lib.letkf_b200_grd_to_buf(self.h, nprocs_e, _ptr(v3dg), _ptr(v2dg), _ptr(bufs)))
+    def grd_to_buf(self, nprocs_e, v3dg, v2dg, bufs, thermo=None):
+        """thermo given: state_trans is applied on the fly while packing (restart -> LETKF variables)."""
+        t = C.byref(thermo) if thermo is not None else None
+        self._ck(self.lib.letkf_b200_grd_to_buf_trans(self.h, nprocs_e, t, _ptr(v3dg), _ptr(v2dg), _ptr(bufs)))
 
-    def buf_to_grd(self, nprocs_e, bufr, v3dg, v2dg):
-        self._ck(self.lib.letkf_b200_buf_to_grd(self.h, nprocs_e, _ptr(bufr), _ptr(v3dg), _ptr(v2dg)))
+    def buf_to_grd(self, nprocs_e, bufr, v3dg, v2dg, thermo=None):
+        """thermo given: state_trans_inv is applied on the fly while unpacking."""
+        t = C.byref(thermo) if thermo is not None else None
+        self._ck(self.lib.letkf_b200_buf_to_grd_trans(self.h, nprocs_e, t, _ptr(bufr), _ptr(v3dg), _ptr(v2dg)))
 
     def buf_to_ens(self, nprocs_e, myrank_e, nens, mstart, mend, bufr, v3d, v2d):
         self._ck(self.lib.letkf_b200_buf_to_ens(self.h, nprocs_e, myrank_e, nens, mstart, mend, _ptr(bufr),

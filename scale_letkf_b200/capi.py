@@ -146,6 +146,8 @@ PROTOTYPES = {
     "letkf_b200_thermo_defaults": (None, [C.POINTER(Thermo)]),
     "letkf_b200_state_trans": (_i, [_vp, C.POINTER(Thermo), _i, _vp, _i]),
     "letkf_b200_grd_to_buf": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "letkf_b200_grd_to_buf_trans": (_i, [_vp, _i, C.POINTER(Thermo), _vp, _vp, _vp]),
+    "letkf_b200_buf_to_grd_trans": (_i, [_vp, _i, C.POINTER(Thermo), _vp, _vp, _vp]),
     "letkf_b200_buf_to_ens": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "letkf_b200_ens_to_buf": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "letkf_b200_buf_to_grd": (_i, [_vp, _i, _vp, _vp, _vp]),

@@ -329,4 +329,121 @@ __global__ void __launch_bounds__(256) state_trans_kernel(const StateTransParams
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared-memory tiled pack / unpack of one member-major grid with the state transform fused in
+// (SURVEY.md section 8f rank 2): grd_to_buf + state_trans, buf_to_grd + state_trans_inv.
+// A CTA owns a tile of 32 columns (of the cyclic deal of rank m) x 32 levels for ALL nv3d variables:
+// reads run along the level index (contiguous in v3dg), writes along the column index (contiguous in the
+// buffer), the transform works on the tile in shared memory.  grid (ceil(nij1max/32), ceil(nlev/32), np),
+// block (32, 8), dynamic shared memory nv3d * 32 * 33 doubles.
+__device__ __forceinline__ void state_trans_point(const StateTransParams &P, double *v, int st, int inverse) {
+  // v[n * st]: variable n of one grid point (st = stride between variables); same arithmetic as state_trans_kernel
+  const int iq = P.iv3d_q - 1;
+  if (inverse) {
+    for (int n = iq; n < P.nv3d; ++n) {
+      const bool clamp = (n == iq) ? P.pos_q : (P.pos_qhyd && n <= iq + 5);
+      if (clamp) v[n * st] = fmax(v[n * st], 0.0);
+    }
+  }
+  double qdry = 1.0, cvtot = 0.0;
+  for (int n = iq; n < P.nv3d; ++n) {
+    const double q = v[n * st];
+    qdry = __dsub_rn(qdry, q);
+    cvtot = __dadd_rn(cvtot, __dmul_rn(q, P.tracer_cv[n - iq]));
+  }
+  cvtot = __dadd_rn(__dmul_rn(P.CVdry, qdry), cvtot);
+  const double rtot = __dadd_rn(__dmul_rn(P.Rdry, qdry), __dmul_rn(P.Rvap, v[iq * st]));
+  if (!inverse) {
+    const double cpovcv = __ddiv_rn(__dadd_rn(cvtot, rtot), cvtot);
+    const double rho = v[0];
+    const double pres = __dmul_rn(P.PRE00, pow(__ddiv_rn(__dmul_rn(v[4 * st], rtot), P.PRE00), cpovcv));
+    const double temp = __ddiv_rn(pres, __dmul_rn(rho, rtot));
+    v[0] = __ddiv_rn(v[1 * st], rho);
+    v[1 * st] = __ddiv_rn(v[2 * st], rho);
+    v[2 * st] = __ddiv_rn(v[3 * st], rho);
+    v[3 * st] = temp;
+    v[4 * st] = pres;
+  } else {
+    const double cvovcp = __ddiv_rn(cvtot, __dadd_rn(cvtot, rtot));
+    const double pres = v[4 * st];
+    const double rho = __ddiv_rn(pres, __dmul_rn(rtot, v[3 * st]));
+    const double rhot = __dmul_rn(__ddiv_rn(P.PRE00, rtot), pow(__ddiv_rn(pres, P.PRE00), cvovcp));
+    v[4 * st] = rhot;
+    v[3 * st] = __dmul_rn(v[2 * st], rho);
+    v[2 * st] = __dmul_rn(v[1 * st], rho);
+    v[1 * st] = __dmul_rn(v[0], rho);
+    v[0] = rho;
+  }
+}
+
+// dir = 0: v3dg -> (state_trans when trans) -> bufs;  dir = 1: bufr -> (state_trans_inv when trans) -> v3dg
+__global__ void __launch_bounds__(256) grd_buf_tiled_kernel(TransposeDims d, StateTransParams T, int trans, int dir,
+                                                            double *__restrict__ v3dg, double *__restrict__ buf) {
+  extern __shared__ double tile[];   // [nv3d][32 columns][33]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32, m = blockIdx.z;
+  const int nij1 = nij1_of(d, m);
+  const size_t npts = (size_t)d.nlev * d.nlon * d.nlat;
+  constexpr int TS = 32 * 33;
+  auto gcol = [&](int i) -> size_t {   // first level of column i of rank m in a member-major field
+    const int j = m + d.np * i;
+    const int ilon = j % d.nlon, ilat = j / d.nlon;
+    return (size_t)d.nlev * (ilon + (size_t)d.nlon * ilat);
+  };
+  auto bidx = [&](int i, int k, int n) -> size_t {
+    return (size_t)i + (size_t)d.nij1max * ((size_t)k + (size_t)d.nlev * n + (size_t)d.nlevall * m);
+  };
+  if (dir == 0) {
+    for (int n = 0; n < d.nv3d; ++n)
+      for (int ii = ty; ii < 32; ii += 8) {
+        const int i = i0 + ii, k = k0 + tx;
+        tile[n * TS + ii * 33 + tx] = (i < nij1 && k < d.nlev) ? v3dg[gcol(i) + k + npts * n] : 0.0;
+      }
+  } else {
+    for (int n = 0; n < d.nv3d; ++n)
+      for (int kk = ty; kk < 32; kk += 8) {
+        const int i = i0 + tx, k = k0 + kk;
+        tile[n * TS + tx * 33 + kk] = (i < nij1 && k < d.nlev) ? buf[bidx(i, k, n)] : 0.0;
+      }
+  }
+  __syncthreads();
+  if (trans) {
+    for (int e = ty * 32 + tx; e < 1024; e += 256) {
+      const int ii = e >> 5, kk = e & 31;
+      if (i0 + ii < nij1 && k0 + kk < d.nlev) state_trans_point(T, tile + ii * 33 + kk, TS, dir);
+    }
+    __syncthreads();
+  }
+  if (dir == 0) {
+    for (int n = 0; n < d.nv3d; ++n)
+      for (int kk = ty; kk < 32; kk += 8) {
+        const int i = i0 + tx, k = k0 + kk;
+        if (i < d.nij1max && k < d.nlev) buf[bidx(i, k, n)] = (i < nij1) ? tile[n * TS + tx * 33 + kk] : -9.99e33;   // undef padding row
+      }
+  } else {
+    for (int n = 0; n < d.nv3d; ++n)
+      for (int ii = ty; ii < 32; ii += 8) {
+        const int i = i0 + ii, k = k0 + tx;
+        if (i < nij1 && k < d.nlev) v3dg[gcol(i) + k + npts * n] = tile[n * TS + ii * 33 + tx];
+      }
+  }
+}
+// 2-D variables of the pack / unpack (v2dg(nlon,nlat,nv2d) <-> rows nlev*nv3d.. of the buffer)
+__global__ void grd_buf_2d_kernel(TransposeDims d, int dir, double *__restrict__ v2dg, double *__restrict__ buf) {
+  const size_t total = (size_t)d.nij1max * d.nv2d * d.np;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % d.nij1max);
+    const size_t t = idx / d.nij1max;
+    const int n = (int)(t % d.nv2d), m = (int)(t / d.nv2d);
+    const size_t b = (size_t)i + (size_t)d.nij1max * ((size_t)d.nlev * d.nv3d + n + (size_t)d.nlevall * m);
+    if (i < nij1_of(d, m)) {
+      const int j = m + d.np * i;
+      const size_t g = (j % d.nlon) + (size_t)d.nlon * ((j / d.nlon) + (size_t)d.nlat * n);
+      if (dir == 0) buf[b] = v2dg[g]; else v2dg[g] = buf[b];
+    } else if (dir == 0) {
+      buf[b] = -9.99e33;
+    }
+  }
+}
+
 }  // namespace letkf

@@ -1333,21 +1333,52 @@ static TransposeDims make_dims(const letkf_b200_handle *h, int np) {
   return d;
 }
 
-int letkf_b200_grd_to_buf(letkf_b200_handle *h, int np, const double *v3dg, const double *v2dg, double *bufs) {
-  if (!h || np < 1 || !v3dg || !bufs) return LETKF_B200_EINVAL;
+// tiled pack (dir 0) / unpack (dir 1) with the optional fused state transform
+static int grd_buf_tiled(letkf_b200_handle *h, int np, const letkf_b200_thermo *t, int dir, double *v3dg, double *v2dg,
+                         double *buf) {
   CK(cudaSetDevice(h->device));
+  const letkf_b200_config &c = h->cfg;
+  if (t && (c.nv3d < 6 || c.iv3d_q != 6 || c.iv3d_p != 5))
+    return fail(h, LETKF_B200_EINVAL, "state_trans needs the u,v,w,T,p,q.. variable order");
   const TransposeDims d = make_dims(h, np);
-  grd_to_buf_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(d, v3dg, v2dg, bufs);
+  StateTransParams P;
+  std::memset(&P, 0, sizeof(P));
+  if (t) {
+    P.Rdry = t->Rdry; P.Rvap = t->Rvap; P.CVdry = t->CVdry; P.PRE00 = t->PRE00;
+    for (int i = 0; i < 16; ++i) P.tracer_cv[i] = t->TRACER_CV[i];
+    P.pos_q = t->POSITIVE_DEFINITE_Q; P.pos_qhyd = t->POSITIVE_DEFINITE_QHYD;
+  }
+  P.nv3d = c.nv3d; P.iv3d_q = c.iv3d_q;
+  const size_t smem = (size_t)c.nv3d * 32 * 33 * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(grd_buf_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 32 * 33 * (int)sizeof(double)));
+    attr = true;
+  }
+  const dim3 grid((unsigned)((d.nij1max + 31) / 32), (unsigned)((c.nlev + 31) / 32), (unsigned)np);
+  grd_buf_tiled_kernel<<<grid, dim3(32, 8), smem, h->stream>>>(d, P, t ? 1 : 0, dir, v3dg, buf);
+  if (c.nv2d > 0 && v2dg) grd_buf_2d_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(d, dir, v2dg, buf);
   CK(cudaGetLastError());
   return LETKF_B200_OK;
 }
+
+int letkf_b200_grd_to_buf(letkf_b200_handle *h, int np, const double *v3dg, const double *v2dg, double *bufs) {
+  if (!h || np < 1 || !v3dg || !bufs) return LETKF_B200_EINVAL;
+  return grd_buf_tiled(h, np, nullptr, 0, const_cast<double *>(v3dg), const_cast<double *>(v2dg), bufs);
+}
 int letkf_b200_buf_to_grd(letkf_b200_handle *h, int np, const double *bufr, double *v3dg, double *v2dg) {
   if (!h || np < 1 || !v3dg || !bufr) return LETKF_B200_EINVAL;
-  CK(cudaSetDevice(h->device));
-  const TransposeDims d = make_dims(h, np);
-  buf_to_grd_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(d, bufr, v3dg, v2dg);
-  CK(cudaGetLastError());
-  return LETKF_B200_OK;
+  return grd_buf_tiled(h, np, nullptr, 1, v3dg, v2dg, const_cast<double *>(bufr));
+}
+int letkf_b200_grd_to_buf_trans(letkf_b200_handle *h, int np, const letkf_b200_thermo *t, const double *v3dg,
+                                const double *v2dg, double *bufs) {
+  if (!h || np < 1 || !v3dg || !bufs) return LETKF_B200_EINVAL;
+  return grd_buf_tiled(h, np, t, 0, const_cast<double *>(v3dg), const_cast<double *>(v2dg), bufs);
+}
+int letkf_b200_buf_to_grd_trans(letkf_b200_handle *h, int np, const letkf_b200_thermo *t, const double *bufr, double *v3dg,
+                                double *v2dg) {
+  if (!h || np < 1 || !v3dg || !bufr) return LETKF_B200_EINVAL;
+  return grd_buf_tiled(h, np, t, 1, v3dg, v2dg, const_cast<double *>(bufr));
 }
 int letkf_b200_buf_to_ens(letkf_b200_handle *h, int np, int myrank_e, int nens, int mstart, int mend,
                           const double *bufr, double *v3d, double *v2d) {

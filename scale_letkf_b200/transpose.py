@@ -37,8 +37,12 @@ def set_alltoallv_counts(mcount, ngpblock, nprocs_e, myrank_e):
 
 
 class EnsTranspose:
-    def __init__(self, ops, nprocs_e, myrank_e, nlev, nv3d, nv2d, group=None, device=None, dtype=torch.float64):
+    def __init__(self, ops, nprocs_e, myrank_e, nlev, nv3d, nv2d, group=None, device=None, dtype=torch.float64,
+                 thermo=None):
+        """thermo (capi.Thermo): the member-major grids hold SCALE restart variables; state_trans is fused into the
+        pack of the scatter and state_trans_inv into the unpack of the gather (common_scale.f90:1181-1280)."""
         self.ops, self.np, self.rank, self.group = ops, int(nprocs_e), int(myrank_e), group
+        self.kw = {"thermo": thermo} if thermo is not None else {}
         self.nlevall = nlev * nv3d + nv2d
         self.nij1, self.nij1max = ops.nij1_of(self.np, self.rank)
         self.block = self.nij1max * self.nlevall
@@ -68,7 +72,7 @@ class EnsTranspose:
         mcount = mend - mstart + 1
         assert 0 < mcount <= self.np
         if self.rank < mcount:
-            self.ops.grd_to_buf(self.np, v3dg, v2dg, self.bufs)
+            self.ops.grd_to_buf(self.np, v3dg, v2dg, self.bufs, **self.kw)
         self._exchange(mcount, to_grid_side=True)
         self.ops.buf_to_ens(self.np, self.rank, nens, mstart, mend, self.bufr, v3d, v2d)
 
@@ -78,7 +82,7 @@ class EnsTranspose:
         self.ops.ens_to_buf(self.np, self.rank, nens, mstart, mend, v3d, v2d, self.bufs)
         self._exchange(mcount, to_grid_side=False)
         if self.rank < mcount:
-            self.ops.buf_to_grd(self.np, self.bufr, v3dg, v2dg)
+            self.ops.buf_to_grd(self.np, self.bufr, v3dg, v2dg, **self.kw)
 
     # ---- member loops of read_ens_mpi / write_ens_mpi (:1099-1274) -----------------------------
     def rounds(self, nmem):

@@ -145,3 +145,44 @@ def test_cuda_enssprd_bitexact(oracle):
     e = sl.LETKF(cfg, device=0)
     assert np.array_equal(e.enssprd_grd(g), oracle.enssprd_grd(20, g))
     e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("np_", [1, 4])
+def test_cuda_fused_pack_unpack(oracle, np_):
+    """grd_to_buf with state_trans fused == state_trans then grd_to_buf (bit for bit: same arithmetic), and the pack
+    itself equals the oracle's grd_to_buf (common_mpi_scale.f90:1428-1440); likewise buf_to_grd + state_trans_inv.
+    Ragged shapes: nlev, nij1max not multiples of the 32 x 32 tile, unequal column counts per rank."""
+    import ctypes as C
+    import torch
+    nlev, nlon, nlat = 37, 9, 7
+    cfg = sl.resolve_config(sl.default_config(MEMBER=4, nlon=nlon, nlat=nlat, nlev=nlev))
+    e = sl.LETKF(cfg, device=0)
+    t = thermo(1, 1)
+    x = restart_state(nlev, nlon, nlat, seed=91)
+    _, nmax = e.nij1_of(np_, 0)
+    nlevall = nlev * 11
+    flat = lambda a: torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).cuda()
+    # pack
+    d_x = flat(x)
+    fused = torch.zeros(nmax * nlevall * np_, dtype=torch.float64, device="cuda")
+    e.grd_to_buf(np_, d_x, None, fused, thermo=t)
+    d_y = flat(x)
+    e.state_trans(d_y, t, inverse=False)
+    plain = torch.zeros_like(fused)
+    e.grd_to_buf(np_, d_y, None, plain)
+    assert torch.equal(fused, plain)
+    ref = np.zeros((nmax, nlevall, np_), order="F")
+    y = d_y.cpu().numpy().reshape(x.shape, order="F").copy(order="F")
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    oracle.lib().oracle_grd_to_buf(nlon, nlat, nlev, 11, 0, np_, P(y), None, P(ref))
+    assert np.array_equal(plain.cpu().numpy(), ref.ravel(order="F"))
+    # unpack
+    back_f = torch.zeros_like(d_x)
+    e.buf_to_grd(np_, plain, back_f, None, thermo=t)
+    back_p = torch.zeros_like(d_x)
+    e.buf_to_grd(np_, plain, back_p, None)
+    assert torch.equal(back_p, d_y)
+    e.state_trans(back_p, t, inverse=True)
+    assert torch.equal(back_f, back_p)
+    e.close()
