@@ -3,11 +3,13 @@
 //
 // Persistent CTAs (NB warps, one per 8-row block of the k x k matrices) pull (ij, ilev) points from
 // a global counter:
-//   relax_beta -> load members, form perturbations -> [per variable-localisation group]
-//   local-obs search -> DMMA Gram [A | b | bd] = Yr^T [Y | dep | depd] from L2-resident obs rows
-//   (cp.async double-buffered; dep and depd ride in the padding columns) -> interval-scaled coupled
-//   Newton-Schulz Z = sqrt(s) A^-1/2 (ns_solver.cuh) -> one skinny DMMA product Z [dX | b | bd]
-//   -> RTPP/RTPS relaxation -> xa = xmean + dX T -> store.
+//   relax_beta -> load members (all loads of the point in flight together), form perturbations ->
+//   [per variable-localisation group] local observations (pooled list of presearch_kernel, PRE = true, or
+//   in-kernel search) -> DMMA Gram [A | b | bd] = Yr^T [Y | dep | depd] from L2-resident obs rows
+//   (cp.async, three staging buffers, one barrier per chunk; dep and depd ride in the padding columns)
+//   -> interval-scaled coupled Newton-Schulz Z = sqrt(s) A^-1/2 with a third/fourth-order finishing step
+//   (ns_solver.cuh) -> one skinny DMMA product Z [dX | b | bd] -> RTPP/RTPS relaxation ->
+//   xa = xmean + dX T -> store.
 // With t_c = A^-1/2 x_c:   dX W = sqrt(k-1) t_c,   x^T Pa y = t_x . t_y,   dX wbar = t_x . t_b,
 // so neither W nor Pa is formed and nothing k x k ever goes to HBM.
 #pragma once
@@ -19,7 +21,7 @@ namespace letkf {
 template <int NB, bool PRE = false>
 __host__ __device__ inline size_t das_ns_smem_bytes() {
   using C = NsCfg<NB>;
-  size_t d = 3 * (size_t)C::PSZ;          // packed Y, Z, T (Z+T double as the two obs-chunk staging buffers)
+  size_t d = 3 * (size_t)C::PSZ;          // packed Y, Z, T (together: the three obs-chunk staging buffers of the Gram)
   d += (size_t)kMaxNV * C::LD;            // Xall
   if (kMaxNV * C::LD > C::PSZ) d += (size_t)kMaxNV * C::LD;   // Ts (else it aliases T: the Newton-Schulz scratch is free by then)
   d += 3 * (size_t)C::CR;                 // per-row weights of the three staged chunks

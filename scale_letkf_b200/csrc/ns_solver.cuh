@@ -36,7 +36,7 @@ struct NsCfg {
   static constexpr int NT = 32 * NB_;              // one warp per row block
   static constexpr int NTILE = NB_ * (NB_ + 1) / 2;
   static constexpr int PSZ = NTILE * 64;           // doubles per packed symmetric matrix
-  static constexpr int CR = (PSZ / LD) & ~3;       // obs rows per staging chunk (two chunks fit in 2 PSZ)
+  static constexpr int CR = (PSZ / LD) & ~3;       // obs rows per staging chunk (three chunks fit in 3 PSZ); CR == 4 NB
   // resident CTAs per SM the register allocation is sized for
   static constexpr int MINB = NB_ <= 3 ? 8 : NB_ <= 5 ? 5 : NB_ <= 7 ? 4 : NB_ <= 9 ? 2 : 1;
   // (registers: each of the 4 SM sub-partitions holds 16 K registers and ceil(NB MINB / 4) warps, which

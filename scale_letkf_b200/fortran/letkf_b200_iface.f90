@@ -178,6 +178,17 @@ module letkf_b200_iface
       type(c_ptr), value :: h, v3dg, v2dg, bufs      ! device pointers
       integer(c_int), value :: np
     end function
+    ! pack / unpack with state_trans / state_trans_inv fused in (t = c_null_ptr: plain pack / unpack)
+    integer(c_int) function c_grd_to_buf_trans(h, np, t, v3dg, v2dg, bufs) bind(C, name='letkf_b200_grd_to_buf_trans')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, t, v3dg, v2dg, bufs
+      integer(c_int), value :: np
+    end function
+    integer(c_int) function c_buf_to_grd_trans(h, np, t, bufr, v3dg, v2dg) bind(C, name='letkf_b200_buf_to_grd_trans')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, t, bufr, v3dg, v2dg
+      integer(c_int), value :: np
+    end function
     integer(c_int) function c_buf_to_ens(h, np, myrank_e, nens, mstart, mend, bufr, v3d, v2d) &
         bind(C, name='letkf_b200_buf_to_ens')
       import :: c_int, c_ptr
