@@ -324,6 +324,11 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on file descriptor 1; stdout must carry the ONE JSON line only, so fd 1
+        # points at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -523,7 +528,10 @@ def main():
         }
         if args.subsample > 1:
             line["config"]["subsample"] = f"every {args.subsample}-th column only (profiling aid, not a bench value)"
-        print(json.dumps(line))
+        if world > 1:
+            sys.stdout.flush()
+            os.dup2(saved_stdout_fd, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     eng.close()
