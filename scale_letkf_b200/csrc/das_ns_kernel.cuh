@@ -252,11 +252,19 @@ das_ns_kernel(const DasParams P) {
         // One warp per obs row (a row is KP/2 16-byte pieces), rows w, w + NB, w + 2 NB, w + 3 NB of a chunk.
         // Chunks are requested strictly in order, and the sorted-obs indices of the NEXT chunk are fetched
         // while the current one is requested, so that a request only pays the row latency, not index + row.
+        // The same holds for the R^-1 weights: the thread that owns row `tid` of a chunk loads rdiag one chunk
+        // ahead, otherwise its warp would sit out an L2 round trip inside every request while the other
+        // warps wait for it at the chunk barrier.
         int nxt[4];
+        double rd_nxt = 0.0, rl_nxt = 0.0;
         auto fetch_idx = [&](int c) {
           const int o0 = c * CR, nrows = min(CR, p_use - o0);
 #pragma unroll
           for (int u = 0; u < 4; ++u) nxt[u] = (w + u * NB < nrows) ? L.iob[o0 + w + u * NB] : -1;
+          if (tid < nrows) {
+            rd_nxt = L.rdiag[o0 + tid];
+            if (P.INFL_MUL_ADAPTIVE) rl_nxt = L.rloc[o0 + tid];
+          }
         };
         fetch_idx(0);
         auto issue = [&](int c) {
@@ -264,6 +272,7 @@ das_ns_kernel(const DasParams P) {
           double *wdst = wv + (c % 3) * CR;
           const int o0 = c * CR;
           const int nrows = min(CR, p_use - o0), nrows4 = (nrows + 3) & ~3;
+          const double rd_cur = rd_nxt, rl_cur = rl_nxt;
           {
             int iobs[4];
 #pragma unroll
@@ -282,8 +291,8 @@ das_ns_kernel(const DasParams P) {
           if (tid < nrows4) {
             double wt = 0.0;
             if (tid < nrows) {
-              wt = 1.0 / L.rdiag[o0 + tid];
-              if (P.INFL_MUL_ADAPTIVE) p3acc += L.rloc[o0 + tid];
+              wt = 1.0 / rd_cur;
+              if (P.INFL_MUL_ADAPTIVE) p3acc += rl_cur;
             }
             wdst[tid] = wt;
           }
