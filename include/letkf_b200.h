@@ -173,6 +173,13 @@ int letkf_b200_obs_departure_qc(letkf_b200_handle *h, const letkf_b200_qc_config
                                 const int32_t *elm, const double *dat, const double *err, int32_t *qc,
                                 double *ensval, double *val, int mem_space);
 
+/* ---- monit_dep twin (scale/common/common_obs_scale.f90:1851-1895): departure statistics per observed
+ * element uid (1..16, Tv counted as T, RE0 as REF) over the observations with qc == 0: count, bias = mean(dep),
+ * rmse = sqrt(mean(dep^2)); undef (-9.99e33) where the count is zero.  The reference sums serially in
+ * observation order; here the sums are a fixed-shape tree (deterministic, rounding differs: tested at 1e-12). */
+int letkf_b200_monit_dep(letkf_b200_handle *h, int nobs, const int32_t *elm, const double *dep, const int32_t *qc,
+                         int32_t *nobs_out, double *bias, double *rmse, int mem_space);
+
 /* ---- obs_local twin (letkf_tools.f90:1325) ---------------------------------
  * For npts points (ri,rj,rlev=mean pressure,rz=height) and model variable nvar
  * (1-based, 0 = no variable localisation): writes nobsl[i] and, when not NULL, the

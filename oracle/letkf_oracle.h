@@ -96,6 +96,9 @@ void oracle_enssprd_grd(int mem, int nens, int nij, int nlev, int nv3d, const do
 /* scale/common/common_scale.f90:1181-1280 */
 void oracle_state_trans(const letkf_b200_thermo *t, int inverse, int nlev, int nlon, int nlat, int nv3d,
                         int iv3d_q, double *v3dg);
+/* scale/common/common_obs_scale.f90:1851-1895 (serial sums in observation order) */
+void oracle_monit_dep(int nn, const int32_t *elm, const double *dep, const int32_t *qc, int32_t *nobs,
+                      double *bias, double *rmse);
 int oracle_max_threads(void);
 
 #ifdef __cplusplus

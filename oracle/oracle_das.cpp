@@ -1002,6 +1002,27 @@ void oracle_state_trans(const letkf_b200_thermo *t, int inverse, int nlev, int n
   }
 }
 
+// monit_dep, common_obs_scale.f90:1851-1895
+void oracle_monit_dep(int nn, const int32_t *elm, const double *dep, const int32_t *qc, int32_t *nobs,
+                      double *bias, double *rmse) {
+  for (int i = 0; i < NID_OBS; ++i) { nobs[i] = 0; bias[i] = 0.0; rmse[i] = 0.0; }
+  for (int n = 0; n < nn; ++n) {
+    if (qc[n] != 0) continue;
+    int ielm = elm[n];
+    if (ielm == 3074) ielm = 3073;        // Tv as T
+    if (ielm == ID_RE0) ielm = ID_REF;    // RE0 as REF
+    const int i = uid_obs(ielm) - 1;
+    if (i < 0) continue;
+    nobs[i] += 1;
+    bias[i] = bias[i] + dep[n];
+    rmse[i] = rmse[i] + dep[n] * dep[n];
+  }
+  for (int i = 0; i < NID_OBS; ++i) {
+    if (nobs[i] == 0) { bias[i] = -9.99e33; rmse[i] = -9.99e33; }
+    else { bias[i] = bias[i] / (double)nobs[i]; rmse[i] = std::sqrt(rmse[i] / (double)nobs[i]); }
+  }
+}
+
 // set_common_mpi_grid, common_mpi_scale.f90:264-283
 void oracle_nij1(int nlon, int nlat, int np, int myrank_e, int32_t *nij1, int32_t *nij1max) {
   const int i = (nlon * nlat) % np;

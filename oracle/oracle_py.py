@@ -77,6 +77,8 @@ def lib():
         L.oracle_enssprd_grd.argtypes = [i, i, i, i, i, vp, vp]
         L.oracle_state_trans.restype = None
         L.oracle_state_trans.argtypes = [C.POINTER(capi.Thermo), i, i, i, i, i, i, vp]
+        L.oracle_monit_dep.restype = None
+        L.oracle_monit_dep.argtypes = [i, vp, vp, vp, vp, vp, vp]
         L.oracle_max_threads.restype = i
         _lib = L
     return _lib
@@ -292,3 +294,12 @@ def enssprd_grd(mem, v3d):
     out = np.zeros((nij, nlev, nv3d), order="F")
     lib().oracle_enssprd_grd(mem, nens, nij, nlev, nv3d, _p(v3d), _p(out))
     return out
+
+
+def monit_dep(elm, dep, qc):
+    """common_obs_scale.f90:1851-1895 -> (nobs[16], bias[16], rmse[16])."""
+    elm = np.ascontiguousarray(elm, dtype=np.int32)
+    qc = np.ascontiguousarray(qc, dtype=np.int32)
+    n, b, r = np.zeros(16, dtype=np.int32), np.zeros(16), np.zeros(16)
+    lib().oracle_monit_dep(len(elm), _p(elm), _p(_f64(dep)), _p(qc), _p(n), _p(b), _p(r))
+    return n, b, r

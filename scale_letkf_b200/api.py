@@ -139,6 +139,16 @@ class LETKF:
                                                       _ptr(err), _ptr(qc), _ptr(ens), _ptr(val), capi.MEM_HOST))
         return qc, val, ens
 
+    def monit_dep(self, elm, dep, qc):
+        """monit_dep (scale/common/common_obs_scale.f90:1851-1895): (nobs[16], bias[16], rmse[16]) per element uid."""
+        elm = np.ascontiguousarray(elm, dtype=np.int32)
+        dep = np.ascontiguousarray(dep, dtype=np.float64)
+        qc = np.ascontiguousarray(qc, dtype=np.int32)
+        n, b, r = np.zeros(16, dtype=np.int32), np.zeros(16), np.zeros(16)
+        self._ck(self.lib.letkf_b200_monit_dep(self.h, len(elm), _ptr(elm), _ptr(dep), _ptr(qc), _ptr(n), _ptr(b), _ptr(r),
+                                               capi.MEM_HOST))
+        return n, b, r
+
     def obs_info(self):
         a, b = C.c_int32(), C.c_int32()
         self._ck(self.lib.letkf_b200_obs_info(self.h, C.byref(a), C.byref(b)))

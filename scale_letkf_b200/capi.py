@@ -135,6 +135,7 @@ PROTOTYPES = {
     "letkf_b200_qc_config_defaults": (None, [C.POINTER(QcConfig)]),
     "letkf_b200_obs_departure_qc": (_i, [_vp, C.POINTER(QcConfig), _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "letkf_b200_abi_size_qc": (_i, []),
+    "letkf_b200_monit_dep": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "letkf_b200_obs_local": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i]),
     "letkf_b200_das_letkf": (_i, [_vp, C.POINTER(DasArgs)]),
     "letkf_b200_das_stats": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64),

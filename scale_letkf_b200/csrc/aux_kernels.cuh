@@ -446,4 +446,69 @@ __global__ void grd_buf_2d_kernel(TransposeDims d, int dir, double *__restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// monit_dep (scale/common/common_obs_scale.f90:1851-1895): per-element departure statistics.  Stage 1: every
+// CTA reduces its grid-stride slice into 16 (count, sum, sum of squares) bins with a fixed tree; stage 2: one
+// CTA adds the per-CTA partials in CTA order.  Deterministic.
+__device__ __forceinline__ int monit_uid(int elm) {   // uid_obs(elm) - 1 with Tv -> T, RE0 -> REF; -1: unknown
+  if (elm == 3074) elm = 3073;
+  if (elm == 4004) elm = 4001;
+  switch (elm) {
+    case 2819: return 0; case 2820: return 1; case 3073: return 2; case 3074: return 3; case 3330: return 4;
+    case 3331: return 5; case 14593: return 6; case 19999: return 7; case 4001: return 8; case 4004: return 9;
+    case 4002: return 10; case 4003: return 11; case 8800: return 12; case 99991: return 13; case 99992: return 14;
+    case 99993: return 15; default: return -1;
+  }
+}
+__global__ void __launch_bounds__(256) monit_partial_kernel(int nobs, const int *__restrict__ elm, const double *__restrict__ dep,
+                                                            const int *__restrict__ qc, double *__restrict__ part) {
+  __shared__ double sm[3][16][8];   // [quantity][bin][warp]
+  double cnt[16], sum[16], sq[16];
+#pragma unroll
+  for (int b = 0; b < 16; ++b) cnt[b] = sum[b] = sq[b] = 0.0;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < nobs; n += gridDim.x * blockDim.x) {
+    if (qc[n] != 0) continue;
+    const int u = monit_uid(elm[n]);
+    const double d = dep[n];
+#pragma unroll
+    for (int b = 0; b < 16; ++b)
+      if (b == u) {
+        cnt[b] += 1.0;
+        sum[b] += d;
+        sq[b] = fma(d, d, sq[b]);
+      }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int b = 0; b < 16; ++b) {
+    const double c = warp_sum(cnt[b]), s = warp_sum(sum[b]), q = warp_sum(sq[b]);
+    if (lane == 0) {
+      sm[0][b][w] = c;
+      sm[1][b][w] = s;
+      sm[2][b][w] = q;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 48) {
+    const int qn = threadIdx.x / 16, b = threadIdx.x % 16;
+    double a = 0.0;
+    for (int i = 0; i < 8; ++i) a += sm[qn][b][i];
+    part[(size_t)blockIdx.x * 48 + threadIdx.x] = a;
+  }
+}
+__global__ void monit_final_kernel(int nblocks, const double *__restrict__ part, int *__restrict__ nobs_out,
+                                   double *__restrict__ bias, double *__restrict__ rmse) {
+  const int b = threadIdx.x;
+  if (b >= 16) return;
+  double c = 0.0, s = 0.0, q = 0.0;
+  for (int i = 0; i < nblocks; ++i) {
+    c += part[(size_t)i * 48 + b];
+    s += part[(size_t)i * 48 + 16 + b];
+    q += part[(size_t)i * 48 + 32 + b];
+  }
+  nobs_out[b] = (int)c;
+  bias[b] = c > 0.0 ? s / c : -9.99e33;
+  rmse[b] = c > 0.0 ? sqrt(q / c) : -9.99e33;
+}
+
 }  // namespace letkf

@@ -741,6 +741,38 @@ int letkf_b200_obs_departure_qc(letkf_b200_handle *h, const letkf_b200_qc_config
   return LETKF_B200_OK;
 }
 
+int letkf_b200_monit_dep(letkf_b200_handle *h, int nobs, const int32_t *elm, const double *dep, const int32_t *qc,
+                         int32_t *nobs_out, double *bias, double *rmse, int mem_space) {
+  if (!h || nobs < 0 || !nobs_out || !bias || !rmse) return LETKF_B200_EINVAL;
+  if (nobs > 0 && (!elm || !dep || !qc)) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const bool host = mem_space != LETKF_B200_MEM_DEVICE;
+  const int nblocks = std::max(1, std::min((nobs + 255) / 256, h->num_sms * 4));
+  CK(h->cb[0].ensure((size_t)nblocks * 48 + 32));
+  CK(h->cb_i.ensure(16));
+  const int *d_elm = elm, *d_qc = qc;
+  const double *d_dep = dep;
+  if (host && nobs > 0) {
+    CK(h->so_ic.ensure(nobs)); CK(h->so_key.ensure(nobs)); CK(h->so_val.ensure(nobs));
+    CK(cudaMemcpyAsync(h->so_ic.p, elm, sizeof(int) * nobs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->so_key.p, qc, sizeof(int) * nobs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->so_val.p, dep, sizeof(double) * nobs, cudaMemcpyHostToDevice, h->stream));
+    d_elm = h->so_ic.p; d_qc = h->so_key.p; d_dep = h->so_val.p;
+  }
+  double *part = h->cb[0].p, *d_bias = part + (size_t)nblocks * 48, *d_rmse = d_bias + 16;
+  monit_partial_kernel<<<nblocks, 256, 0, h->stream>>>(nobs, d_elm, d_dep, d_qc, part);
+  monit_final_kernel<<<1, 32, 0, h->stream>>>(nblocks, part, host ? h->cb_i.p : nobs_out, host ? d_bias : bias,
+                                              host ? d_rmse : rmse);
+  CK(cudaGetLastError());
+  if (host) {
+    CK(cudaMemcpyAsync(nobs_out, h->cb_i.p, sizeof(int) * 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(bias, d_bias, sizeof(double) * 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(rmse, d_rmse, sizeof(double) * 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return LETKF_B200_OK;
+}
+
 int letkf_b200_obs_info(const letkf_b200_handle *h, int32_t *nobstotal, int32_t *nctype) {
   if (!h || !h->obs_set) return LETKF_B200_ESTATE;
   if (nobstotal) *nobstotal = h->nobstotal;

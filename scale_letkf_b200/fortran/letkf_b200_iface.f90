@@ -151,6 +151,16 @@ module letkf_b200_iface
       integer(c_int), value :: inverse, mem_space
       real(c_double), intent(inout) :: v3dg(*)
     end function
+    ! monit_dep (scale/common/common_obs_scale.f90:1851): nobs(nid_obs), bias(nid_obs), rmse(nid_obs)
+    integer(c_int) function c_monit_dep(h, nn, elm, dep, qc, nobs, bias, rmse, mem_space) bind(C, name='letkf_b200_monit_dep')
+      import :: c_int, c_ptr, c_int32_t, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: nn, mem_space
+      integer(c_int32_t), intent(in) :: elm(*), qc(*)     ! elm: NINT(obs%elm)
+      real(c_double), intent(in) :: dep(*)
+      integer(c_int32_t), intent(out) :: nobs(*)
+      real(c_double), intent(out) :: bias(*), rmse(*)
+    end function
     integer(c_int) function c_set_grid(h, nij1, rig1, rjg1, hgt1, mem_space) bind(C, name='letkf_b200_set_grid')
       import :: c_int, c_ptr, c_double
       type(c_ptr), value :: h

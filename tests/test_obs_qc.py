@@ -132,3 +132,54 @@ def test_cuda_departure_qc_golden():
     qc, val, ens = e.obs_departure_qc(o["elm"], o["dat"], o["err"], o["qc"], o["ensval"])
     assert np.array_equal(qc, g["qc"]) and np.array_equal(val, g["val"]) and np.array_equal(ens, g["ensval"])
     e.close()
+
+
+# ---- monit_dep (scale/common/common_obs_scale.f90:1851-1895) -----------------
+UIDS = [2819, 2820, 3073, 3074, 3330, 3331, 14593, 19999, 4001, 4004, 4002, 4003, 8800, 99991, 99992, 99993]
+
+
+def numpy_monit_dep(elm, dep, qc):
+    e = np.where(elm == 3074, 3073, elm)
+    e = np.where(e == 4004, 4001, e)
+    n, b, r = np.zeros(16, dtype=np.int32), np.full(16, -9.99e33), np.full(16, -9.99e33)
+    for i, u in enumerate(UIDS):
+        m = (e == u) & (qc == 0)
+        n[i] = m.sum()
+        if n[i]:
+            b[i] = dep[m].mean()
+            r[i] = np.sqrt((dep[m] ** 2).mean())
+    return n, b, r
+
+
+def _monit_case():
+    o = synth.make_raw_obs(member=12, nobs=20000, det=False, seed_no=17)
+    q = qc_defaults()
+    return o, q
+
+
+def test_oracle_monit_dep_vs_numpy(oracle):
+    o, q = _monit_case()
+    qc, val, _ = oracle.obs_departure_qc(q, 12, False, o["elm"], o["dat"], o["err"], o["qc"], o["ensval"])
+    n, b, r = oracle.monit_dep(o["elm"], val, qc)
+    n2, b2, r2 = numpy_monit_dep(o["elm"], val, qc)
+    assert np.array_equal(n, n2) and n[3] == 0 and n[9] == 0 and b[3] == -9.99e33   # Tv / RE0 folded into T / REF
+    ok = n > 0
+    assert np.abs(b[ok] - b2[ok]).max() <= 1e-12 * np.abs(b2[ok]).max() + 1e-13
+    assert np.abs(r[ok] - r2[ok]).max() <= 1e-12 * np.abs(r2[ok]).max()
+
+
+@pytest.mark.gpu
+def test_cuda_monit_dep(oracle):
+    o, q = _monit_case()
+    qc, val, _ = oracle.obs_departure_qc(q, 12, False, o["elm"], o["dat"], o["err"], o["qc"], o["ensval"])
+    e = sl.LETKF(sl.resolve_config(sl.default_config(MEMBER=12, nlon=8, nlat=8, nlev=2)), device=0)
+    n, b, r = e.monit_dep(o["elm"], val, qc)
+    n2, b2, r2 = oracle.monit_dep(o["elm"], val, qc)
+    assert np.array_equal(n, n2)
+    ok = n2 > 0
+    assert np.array_equal(b[~ok], b2[~ok]) and np.array_equal(r[~ok], r2[~ok])      # undef where empty
+    assert np.abs(b[ok] - b2[ok]).max() <= 1e-12 * np.abs(b2[ok]).max() + 1e-13     # tree vs serial summation
+    assert np.abs(r[ok] - r2[ok]).max() <= 1e-12 * np.abs(r2[ok]).max()
+    n3, b3, r3 = e.monit_dep(o["elm"], val, qc)
+    assert np.array_equal(b, b3) and np.array_equal(r, r3)                           # deterministic
+    e.close()
