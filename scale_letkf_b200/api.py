@@ -149,6 +149,23 @@ class LETKF:
                                                capi.MEM_HOST))
         return n, b, r
 
+    def set_letkf_obs_raw(self, raw, qcfg=None, qc_in=None):
+        """The whole of set_letkf_obs (scale/letkf/letkf_obs.f90:78) for observations still carrying H(x_m):
+        departure + QC on the device (:355-560), departure statistics of the accepted observations (monit_dep,
+        :577-586), then the bucket sort of the qc == 0 observations (:660-976).  `raw`: dict(elm, typ, ri, rj, lev,
+        dat, err, ensval (nobs, nensobs) = H(x_m)).  Returns dict(qc, val, nobs, bias, rmse, kept)."""
+        n = len(raw["elm"])
+        qc0 = np.zeros(n, dtype=np.int32) if qc_in is None else qc_in
+        qc, val, ens = self.obs_departure_qc(raw["elm"], raw["dat"], raw["err"], qc0, raw["ensval"], qcfg)
+        cnt, bias, rmse = self.monit_dep(raw["elm"], val, qc)
+        keep = qc == 0
+        obs = {kf: np.ascontiguousarray(np.asarray(raw[kf])[keep]) for kf in ("elm", "typ", "ri", "rj", "lev", "dat", "err")}
+        obs["val"] = np.ascontiguousarray(val[keep])
+        obs["ensval"] = np.ascontiguousarray(ens[keep])
+        self._obs_keepalive = obs   # (set_obs may page-lock the ensemble table)
+        self.set_letkf_obs(obs)
+        return dict(qc=qc, val=val, nobs=cnt, bias=bias, rmse=rmse, kept=int(keep.sum()))
+
     def obs_info(self):
         a, b = C.c_int32(), C.c_int32()
         self._ck(self.lib.letkf_b200_obs_info(self.h, C.byref(a), C.byref(b)))

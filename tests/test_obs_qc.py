@@ -183,3 +183,45 @@ def test_cuda_monit_dep(oracle):
     n3, b3, r3 = e.monit_dep(o["elm"], val, qc)
     assert np.array_equal(b, b3) and np.array_equal(r, r3)                           # deterministic
     e.close()
+
+
+@pytest.mark.gpu
+def test_set_letkf_obs_raw_pipeline(oracle):
+    """set_letkf_obs as a whole: H(x_m) of every member -> device QC / departures -> bucket sort -> das_letkf;
+    must equal the oracle fed with the oracle's own QC-passed departures."""
+    from helpers import sonde_case, host_logp, relerr, TOL
+    cfg, rig1, rjg1, hgt1, obs, gues = sonde_case(member=12, nsonde=30, nsfc=100, det=True)
+    k = cfg.MEMBER
+    g = synth.rng(123)
+    # raw H(x_m) = perturbation + (y - departure): the mean of H(x) reproduces the case's departures, the data keep
+    # their physical values (PS observations enter the vertical localisation through log(dat)); 5 % of the rows get
+    # an ensemble far from the data -> gross error
+    dat = obs["dat"].copy()
+    ens_raw = obs["ensval"].copy()
+    ens_raw[:, :k] += (dat - obs["val"])[:, None]
+    ens_raw[:, k] = dat - obs["ensval"][:, k]          # H(x_det) such that y - H(x_det) = the case's depd
+    out_mask = g.uniform(size=len(dat)) < 0.05
+    ens_raw[out_mask, :k] += (40.0 * obs["err"])[out_mask, None]
+    raw = dict(obs, dat=dat, ensval=ens_raw)
+    q = qc_defaults()
+    e = sl.LETKF(cfg, device=0)
+    info = e.set_letkf_obs_raw(raw, q)
+    e.set_common_mpi_grid(rig1, rjg1, hgt1)
+    # reference chain on the CPU
+    qc, val, ens = oracle.obs_departure_qc(q, k, True, raw["elm"], raw["dat"], raw["err"], np.zeros(len(dat), np.int32), ens_raw)
+    assert np.array_equal(info["qc"], qc) and np.array_equal(info["val"], val)
+    assert info["kept"] == int((qc == 0).sum()) and 0 < info["kept"] < len(dat)
+    keep = qc == 0
+    ref_obs = {kf: np.ascontiguousarray(np.asarray(raw[kf])[keep]) for kf in ("elm", "typ", "ri", "rj", "lev", "dat", "err")}
+    ref_obs["val"], ref_obs["ensval"] = np.ascontiguousarray(val[keep]), np.ascontiguousarray(ens[keep])
+    o = oracle.Oracle(cfg)
+    o.set_obs(ref_obs)
+    o.set_grid(rig1, rjg1, hgt1)
+    ref = o.das_letkf(gues.copy(order="F"), want_nobsl=True)
+    got = e.das_letkf(gues.copy(order="F"), want_nobsl=True, logp=host_logp(cfg, gues))
+    assert np.array_equal(got["nobsl"], ref["nobsl"])
+    slots = list(range(k)) + [k + 1]
+    assert relerr(got["anal3d"][:, :, slots, :], ref["anal3d"][:, :, slots, :], axis=(0, 1, 2)) <= TOL
+    n2, b2, r2 = oracle.monit_dep(raw["elm"], val, qc)
+    assert np.array_equal(info["nobs"], n2)
+    e.close()
