@@ -30,11 +30,20 @@ class HostOps:
     def nij1_of(self, np_, rank):
         return self.o.nij1(self.d[0], self.d[1], np_, rank)
 
-    def grd_to_buf(self, np_, v3dg, v2dg, bufs):
+    def _trans(self, v3dg, thermo, inverse):
+        nlon, nlat, nlev, nv3d, _ = self.d
+        self.L.oracle_state_trans(C.byref(thermo), int(inverse), nlev, nlon, nlat, nv3d, 6, self._p(v3dg))
+
+    def grd_to_buf(self, np_, v3dg, v2dg, bufs, thermo=None):
+        if thermo is not None:   # host stand-in of the fused pack: state_trans on a copy, then pack
+            v3dg = v3dg.clone()
+            self._trans(v3dg, thermo, False)
         self.L.oracle_grd_to_buf(*self.d, np_, self._p(v3dg), self._p(v2dg), self._p(bufs))
 
-    def buf_to_grd(self, np_, bufr, v3dg, v2dg):
+    def buf_to_grd(self, np_, bufr, v3dg, v2dg, thermo=None):
         self.L.oracle_buf_to_grd(*self.d, np_, self._p(bufr), self._p(v3dg), self._p(v2dg))
+        if thermo is not None:
+            self._trans(v3dg, thermo, True)
 
     def buf_to_ens(self, np_, rank, nens, mstart, mend, bufr, v3d, v2d):
         self.L.oracle_buf_to_ens(*self.d, np_, rank, nens, mstart, mend, self._p(bufr), self._p(v3d), self._p(v2d))
@@ -98,6 +107,50 @@ def run(rank, world, port, nmem, q):
         assert n_mem == ([10] * world if rank == 0 else [0] * world)
         q.put((rank, "ok"))
     except Exception as e:   # report instead of hanging the peer
+        import traceback
+        q.put((rank, "FAIL " + repr(e) + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def run_thermo(rank, world, port, q):
+    """world_size-2 gloo: EnsTranspose(thermo=...) -- state_trans fused into the scatter's pack, state_trans_inv into
+    the gather's unpack (host stand-ins): the dealt columns hold u, v, w, T, p and the way back restores the restart
+    variables (common_scale.f90:1181-1280 inside common_mpi_scale.f90:1099-1274)."""
+    import torch
+    import torch.distributed as dist
+    from scale_letkf_b200 import synth, capi
+    from scale_letkf_b200.transpose import EnsTranspose
+    from oracle import oracle_py
+    from test_state_trans import restart_state, thermo
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        nlon, nlat, nlev, nv3d, nmem = 7, 5, 3, 11, 3
+        nens = nmem + 1
+        t = thermo()
+        ops = HostOps(nlon, nlat, nlev, nv3d, 0)
+        tr = EnsTranspose(ops, world, rank, nlev, nv3d, 0, thermo=t)
+        F = lambda a: torch.from_numpy(np.ascontiguousarray(a.ravel(order="F")))
+        mine = []
+        for it, im, mstart, mend in tr.rounds(nmem):
+            mine.append(None if im is None else F(restart_state(nlev, nlon, nlat, seed=200 + im)))
+        v3d = torch.zeros(tr.nij1 * nlev * nens * nv3d, dtype=torch.float64)
+        tr.read_ens(mine, None, v3d, None, nmem, nens)
+        a3 = v3d.numpy().reshape((tr.nij1, nlev, nens, nv3d), order="F")
+        ilon, ilat = synth.column_deal(nlon, nlat, world, rank)
+        for m in range(1, nmem + 1):
+            ref = oracle_py.state_trans(t, restart_state(nlev, nlon, nlat, seed=200 + m), inverse=False)
+            assert np.array_equal(a3[:, :, m - 1, :], ref[:, ilon - 1, ilat - 1, :].transpose(1, 0, 2)), ("scatter+trans", m)
+        out = [None if x is None else torch.zeros_like(x) for x in mine]
+        tr.write_ens(v3d, None, out, None, nmem, nens)
+        for x, o in zip(mine, out):
+            if x is not None:
+                err = float((o - x).abs().max() / x.abs().max())
+                assert err <= 1e-12, ("gather+trans_inv", err)
+        q.put((rank, "ok"))
+    except Exception as e:
         import traceback
         q.put((rank, "FAIL " + repr(e) + traceback.format_exc()))
     finally:

@@ -33,6 +33,22 @@ def test_transposes_world2_gloo(nmem):
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
 
 
+def test_transposes_with_fused_state_trans_world2_gloo():
+    """EnsTranspose(thermo=...): restart variables in, LETKF variables on the dealt columns, restart variables back."""
+    import torch.multiprocessing as mp
+    import mr_worker
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=mr_worker.run_thermo, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_column_deal_partitions_the_plane(world):
     """every (ilon, ilat) column is analysed by exactly one rank; nij1 follows set_common_mpi_grid"""
