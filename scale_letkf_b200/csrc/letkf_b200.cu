@@ -565,6 +565,10 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
     const int ic = ctype_elmtyp[uid_obs(obs->elm[n]) - 1][obs->typ[n] - 1] - 1;
     ic_of[n] = ic;
     const CtypeDev &d = T.ct[ic];
+    if (d.vmode == 1) {   // localised in ln p: a non-positive pressure would put NaN into every distance test
+      const double pr = (obs->elm[n] == ID_PS) ? obs->dat[n] : obs->lev[n];
+      if (!(pr > 0.0)) return fail(h, LETKF_B200_EINVAL, "non-positive pressure in an observation localised in ln p");
+    }
     if (d.vmode == 3) vc[n] = obs->lev[n];
     else if (obs->elm[n] == ID_PS) vc[n] = std::log(obs->dat[n]);
     else vc[n] = std::log(obs->lev[n]);

@@ -352,3 +352,19 @@ def test_das_with_2d_variables(oracle, monkeypatch, solver):
     assert relerr(out["anal2d"][:, slots, :], ref["anal2d"][:, slots, :], axis=(0, 1)) <= TOL
     assert np.array_equal(h2[:, :k + 1, :], h1[:, :k + 1, :])
     e.close()
+
+
+def test_set_obs_rejects_non_positive_pressure():
+    """An observation localised in ln p with a non-positive pressure (PS: dat, others: lev) is refused instead of
+    silently spreading NaN through every distance test."""
+    cfg, rig1, rjg1, hgt1, obs, _ = sonde_case(nsonde=10, nsfc=20)
+    bad = dict(obs)
+    bad["lev"] = obs["lev"].copy()
+    i = int(np.argmax(obs["elm"] != 14593))
+    bad["lev"][i] = -5.0
+    e = sl.LETKF(cfg, device=0)
+    with pytest.raises(sl.api.LetkfError) as ei:
+        e.set_letkf_obs(bad)
+    assert ei.value.code == sl.capi.EINVAL
+    e.set_letkf_obs(obs)   # the handle stays usable
+    e.close()
