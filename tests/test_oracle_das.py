@@ -227,3 +227,75 @@ def test_transpose_roundtrip(oracle):
         o3 = np.zeros_like(v3dg[r]); o2 = np.zeros_like(v2dg[r])
         L.oracle_buf_to_grd(nlon, nlat, nlev, nv3d, nv2d, np_, P(br), P(o3), P(o2))
         assert np.array_equal(o3, v3dg[r]) and np.array_equal(o2, v2dg[r])
+
+
+def test_das_radar_matches_independent_bruteforce_numpy(oracle):
+    """C3-type case (radar, MAX_NOBS_PER_GRID(22) > 0, REF+RE0 merged budget, RTPS, boundary taper, radar lid):
+    das_letkf of the oracle against a restatement that shares NO code with oracle/ -- brute-force selection over all
+    observations (tests/golden/make_golden.py:select_bruteforce), LAPACK eigh for letkf_core, numpy for the rest."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import select_bruteforce
+    from helpers import radar_case
+    cfg, rig1, rjg1, hgt1, obs, gues = radar_case(member=6, nlon=24, nlat=24, nlev=5, max_nobs=12, seed=902, radius=5.0e3)
+    o = oracle.Oracle(cfg)
+    o.set_obs(obs)
+    o.set_grid(rig1, rjg1, hgt1)
+    k = cfg.MEMBER
+    g0 = gues.copy(order="F")
+    r = o.das_letkf(gues.copy(order="F"), want_nobsl=True)
+    assert r["status"] == 0
+    dzf = cfg.dist_zero_fac
+    zcut = cfg.RADAR_ZMAX + max(cfg.VERT_LOCAL[21], cfg.VERT_LOCAL_RADAR_VR) * dzf
+    nij1, nlev = hgt1.shape
+    checked = solved = 0
+    for il in range(nlev):
+        for ij in range(0, nij1, 13):
+            ri, rj, rz = rig1[ij], rjg1[ij], hgt1[ij, il]
+            if rz > zcut:
+                beta = 0.0
+            else:
+                d = min(min(ri - cfg.IHALO, cfg.nlon + cfg.IHALO + 1 - ri) * cfg.DX,
+                        min(rj - cfg.JHALO, cfg.nlat + cfg.JHALO + 1 - rj) * cfg.DY) / cfg.BOUNDARY_BUFFER_WIDTH
+                beta = 1.0 if d >= 1.0 else max(d, 0.0)
+            mean = g0[ij, il, k, :]
+            dx = g0[ij, il, :k, :] - mean                      # (k, nv)
+            got = r["anal3d"][ij, il, :k, :]
+            if beta == 0.0:
+                assert np.array_equal(got, mean + dx)
+                checked += 1
+                continue
+            pm = g0[ij, il, k, cfg.iv3d_p - 1]
+            ids = select_bruteforce(cfg, obs, (np.array([ri]), np.array([rj]), np.array([pm]), np.array([rz])), 1)[0]
+            assert len(ids) == r["nobsl"][ij, il]
+            if len(ids) == 0:
+                xa = mean + dx                                  # infl = 1: W = I, wbar = 0
+            else:
+                rdiag = []
+                for n in ids:
+                    e = obs["elm"][n]
+                    hl = cfg.HORI_LOCAL_RADAR_OBSNOREF if e == 4004 else cfg.HORI_LOCAL_RADAR_VR if e == 4002 else cfg.HORI_LOCAL[21]
+                    vl = cfg.VERT_LOCAL_RADAR_VR if e == 4002 else cfg.VERT_LOCAL[21]
+                    nd_v = abs(obs["lev"][n] - rz) / vl
+                    nd_h = np.sqrt(((ri - obs["ri"][n]) * cfg.DX) ** 2 + ((rj - obs["rj"][n]) * cfg.DY) ** 2) / hl
+                    rdiag.append(obs["err"][n] ** 2 / np.exp(-0.5 * (nd_h * nd_h + nd_v * nd_v)))
+                rdiag = np.array(rdiag)
+                y = obs["ensval"][ids, :k]
+                a = y.T @ (y / rdiag[:, None]) + (k - 1) * np.eye(k)
+                lam, v = np.linalg.eigh(a)
+                pa = (v / lam) @ v.T
+                w = (v * np.sqrt((k - 1) / lam)) @ v.T
+                wm = pa @ (y.T @ (obs["val"][ids] / rdiag))
+                xa = np.empty_like(dx)
+                for nvar in range(cfg.nv3d):
+                    x = dx[:, nvar]
+                    vg, va = x @ x, x @ pa @ x
+                    f = 0.95 * np.sqrt(vg / (va * (k - 1))) - 0.95 + 1.0 if (vg > 0 and va > 0) else 1.0
+                    t = (w * f + wm[:, None]) * beta + (1 - beta) * np.eye(k)
+                    xa[:, nvar] = mean[nvar] + x @ t
+                solved += 1
+            sc = np.maximum(np.abs(xa).max(axis=0), 1e-300)
+            assert (np.abs(got - xa) / sc).max() <= 1e-10, (ij, il)
+            checked += 1
+    assert checked > 40 and solved > 5
