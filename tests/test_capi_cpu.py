@@ -63,3 +63,17 @@ def test_create_rejects_bad_config(lib):
     h = C.c_void_p()
     assert lib.letkf_b200_create(C.byref(cfg), 0, C.byref(h)) == capi.EINVAL
     assert b"sm_100a" in lib.letkf_b200_build_info()
+
+
+def test_header_is_plain_c_and_example_compiles(tmp_path):
+    """include/letkf_b200.h must be consumable from C (the Fortran ISO_C_BINDING side sees exactly this ABI):
+    the C example compiles with -std=c99 -Wall -Werror and every function it calls is exported by the library."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    obj = str(tmp_path / "das_from_c.o")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), "-c",
+                           os.path.join(root, "examples", "das_from_c.c"), "-o", obj])
+    und = subprocess.check_output(["nm", "-u", obj], text=True)
+    wanted = {ln.split()[-1] for ln in und.splitlines() if "letkf_b200_" in ln}
+    assert wanted and all(hasattr(capi.load_library(), w) for w in wanted), wanted
