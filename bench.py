@@ -53,19 +53,37 @@ WORKLOADS = {
 }
 
 
-def make_workload(name, nprocs_e=1, myrank_e=0):
+def make_workload(name, nprocs_e=1, myrank_e=0, device=None, synth_kind="hx"):
+    """-> cfg, obs, rig1, rjg1, hgt1, ens.  synth_kind "hx" (default): members are smooth random fields + gridpoint
+    noise and ensval = H(x_m) by tri-linear interpolation of those members, one global
+    state whatever the rank count; "iid": the round-1 generator (independent rows, benign conditioning); "grid": no
+    observations (grid of a column sample only)."""
     from scale_letkf_b200 import synth
     w = WORKLOADS[name]
     if w["kind"] == "sonde":
         cfg = synth.config_c2(nlon=w["nlon"], nlat=w["nlat"], nlev=w["nlev"], member=w["member"])
-        obs = synth.make_sonde_obs(cfg, w["nsonde"], w["nsfc"], nlevobs=25, seed_no=2)
+        obs = None if synth_kind == "grid" else synth.make_sonde_obs(cfg, w["nsonde"], w["nsfc"], nlevobs=25, seed_no=2)
+        hlen, vlen = cfg.HORI_LOCAL[0] / cfg.DX, 3000.0
     else:
         cfg = synth.config_c3(nlon=w["nlon"], nlat=w["nlat"], nlev=w["nlev"], member=w["member"],
                               max_nobs=w["max_nobs"])
         rad = min(60.0e3, 0.47 * w["nlon"] * 500.0)
-        obs = synth.make_radar_obs(cfg, radius_m=rad, zmin=500.0, zmax=11000.0, dz=500.0, seed_no=3)
+        obs = None if synth_kind == "grid" else synth.make_radar_obs(cfg, radius_m=rad, zmin=500.0, zmax=11000.0, dz=500.0, seed_no=3)
+        hlen, vlen = cfg.HORI_LOCAL[21] / cfg.DX, 2000.0
     rig1, rjg1, hgt1 = synth.make_grid(cfg, nprocs_e=nprocs_e, myrank_e=myrank_e)
-    return cfg, obs, rig1, rjg1, hgt1
+    ens = None
+    if synth_kind == "hx":
+        ens = synth.SmoothEnsemble(cfg, seed_no=4, hlen=hlen, vlen=vlen, device=device)
+        obs = ens.attach(obs)
+    return cfg, obs, rig1, rjg1, hgt1, ens
+
+
+def host_threads():
+    """threads the CPU legs may use: the affinity mask, not OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def algorithmic_work(k, nv, npoints, nsolved, nobsl_sum):
@@ -156,12 +174,13 @@ class CpuSample:
     like letkf_tools.f90:289-320) on a cyclic-deal sample of the workload's columns: every
     `npe`-th column of the plane, all levels.  calibrate() sizes the sample for ~target_s."""
 
-    def __init__(self, name, nthreads=0):
+    def __init__(self, name, nthreads=0, synth_kind="hx"):
         from oracle import oracle_py
         oracle_py.build()
         self.name, self.w = name, WORKLOADS[name]
         self.oracle_py = oracle_py
-        self.nth = nthreads or oracle_py.max_threads()
+        self.nth = nthreads or host_threads()
+        self.synth_kind = synth_kind
         self.ncol = self.w["nlon"] * self.w["nlat"]
 
     def _deal_width(self, target_cols):   # coprime with nlon: spreads the sample over the plane
@@ -172,12 +191,19 @@ class CpuSample:
 
     def prepare(self, npe):
         from scale_letkf_b200 import synth
-        cfg, obs, rig1, rjg1, hgt1 = make_workload(self.name, nprocs_e=npe, myrank_e=npe // 3)
+        if getattr(self, "_obs", None) is None:   # the observation set does not depend on the column sample
+            _, self._obs, _, _, _, _ = make_workload(self.name, synth_kind=self.synth_kind)
+        cfg, _, rig1, rjg1, hgt1, ens = make_workload(self.name, nprocs_e=npe, myrank_e=npe // 3, synth_kind="grid")
         o = self.oracle_py.Oracle(cfg)
-        o.set_obs(obs)
+        o.set_obs(self._obs)
         o.set_grid(rig1, rjg1, hgt1)
         self.o, self.npe = o, npe
-        self.gues0 = synth.make_state(cfg, rig1, rjg1, hgt1, seed_no=4)
+        if self.synth_kind == "hx":
+            w = self.w
+            hl, vl = (cfg.HORI_LOCAL[0] / cfg.DX, 3000.0) if w["kind"] == "sonde" else (cfg.HORI_LOCAL[21] / cfg.DX, 2000.0)
+            self.gues0 = synth.SmoothEnsemble(cfg, seed_no=4, hlen=hl, vlen=vl).state(rig1, rjg1, as_numpy=True)
+        else:
+            self.gues0 = synth.make_state(cfg, rig1, rjg1, hgt1, seed_no=4)
 
     def run(self):
         g = self.gues0.copy(order="F")
@@ -261,7 +287,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     name = args.workload
-    cs = CpuSample(name)
+    cs = CpuSample(name, synth_kind=args.synth)
     cs.calibrate(args.cpu_seconds / 4.0)
     tot_pts, tot_s, nsolved, npts = 0, 0.0, 0, 0
     for i in range(args.warmup + args.steps):
@@ -297,11 +323,15 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=16.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-bench parity check against the oracle")
+    ap.add_argument("--parity-points", type=int, default=4000, help="points of the in-bench parity sample at k = 50")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
     ap.add_argument("--no-cycle", dest="cycle", action="store_false",
                     help="skip the full-cycle leg (transposes + bucketing + analysis)")
     ap.set_defaults(cycle=True)
     ap.add_argument("--cycle-steps", type=int, default=3)
+    ap.add_argument("--synth", default="hx", choices=["hx", "iid"],
+                    help="hx: smooth correlated members, ensval = H(x_m) (default); iid: round-1 generator")
     ap.add_argument("--subsample", type=int, default=1,
                     help="profiling aid: analyse only every S-th column of the plane (same per-point work)")
     args = ap.parse_args()
@@ -338,15 +368,19 @@ def main():
 
     name = args.workload
     w = WORKLOADS[name]
-    cfg, obs, rig1, rjg1, hgt1 = make_workload(name, nprocs_e=world * args.subsample, myrank_e=rank)
+    cfg, obs, rig1, rjg1, hgt1, ens = make_workload(name, nprocs_e=world * args.subsample, myrank_e=rank, device=dev,
+                                                    synth_kind=args.synth)
     k, nv, nlev = cfg.MEMBER, cfg.nv3d, cfg.nlev
     nij1 = len(rig1)
     eng = sl.LETKF(cfg, device=local)
     eng.set_letkf_obs(obs)
     eng.set_common_mpi_grid(rig1, rjg1, hgt1)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(20260102 + rank)
-    gues0 = synth.make_state(cfg, rig1, rjg1, hgt1, xp=torch, device=dev, gen=gen)
+    if ens is not None:      # one global state: every value is a function of the global grid index
+        gues0 = ens.state(rig1, rjg1)
+    else:
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(20260102 + rank)
+        gues0 = synth.make_state(cfg, rig1, rjg1, hgt1, xp=torch, device=dev, gen=gen)
     gues = torch.empty_like(gues0)
     anal = torch.empty_like(gues0)
     state_bytes = gues0.numel() * 8
@@ -390,6 +424,40 @@ def main():
     value = npoints * args.steps / (total_ms * 1e-3)
     ms_per_step = total_ms / args.steps
 
+    # ---- parity inside the bench: the analysis just timed against the oracle on a sample of this rank's columns ----
+    parity = None
+    if not args.no_parity:
+        try:
+            from oracle import oracle_py
+            oracle_py.build()
+            want_pts = max(nlev, int(args.parity_points * min(1.0, (50.0 / k) ** 3)))
+            ncs = max(1, min(nij1, want_pts // nlev))
+            cols = np.unique(np.linspace(0, nij1 - 1, ncs).astype(np.int64))
+            ct = torch.as_tensor(cols, device=dev)
+            g_s = np.asfortranarray(gues0[:, :, :, ct].cpu().numpy().T)          # (ncols, nlev, nens, nv3d)
+            gues.copy_(gues0)
+            nb = eng.das_letkf(gues, anal3d=anal, want_nobsl=True)["nobsl"][:, ct].cpu().numpy().T
+            a_gpu = anal[:, :k, :, ct].cpu().numpy().T                           # (ncols, nlev, k, nv3d)
+            o = oracle_py.Oracle(cfg)
+            o.set_obs(obs)
+            o.set_grid(rig1[cols], rjg1[cols], np.asfortranarray(hgt1[cols]))
+            ref = o.das_letkf(g_s, want_nobsl=True, nthreads=max(1, host_threads() // world))
+            b = ref["anal3d"][:, :, :k, :]
+            sc = np.maximum(np.abs(b).max(axis=(0, 1, 2), keepdims=True), 1e-300)
+            pv = torch.tensor([float((np.abs(a_gpu - b) / sc).max()), 0.0 if np.array_equal(nb, ref["nobsl"]) else 1.0,
+                               float(len(cols) * nlev)], dtype=torch.float64, device=dev)
+            if world > 1:
+                mx = pv.clone()
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                dist.all_reduce(pv, op=dist.ReduceOp.SUM)
+                pv[0], pv[1] = mx[0], mx[1]
+            parity = {"nobsl_equal": bool(pv[1] == 0.0), "max_rel_err": float(pv[0]), "points": int(pv[2]),
+                      "what": "GPU anal3d / nobsl of the timed workload vs the CPU oracle on a column sample of every rank, "
+                              "max |a-b| / max|b| per variable", "tolerance": 1e-10}
+            del o
+        except Exception as e:
+            parity = {"error": repr(e)[:300]}
+
     # ---- roofline of the dominant kernel (das_kernel; one launch per step per rank) -------------
     peaks, peaks_src = measured_peaks()
     flops, abytes = algorithmic_work(k, nv, npoints, nsolved, nobsl_sum)   # whole job, per step
@@ -409,9 +477,9 @@ def main():
             traffic = None
     roofline = {
         "kernel": "das_ns_kernel" if k <= 102 else "das_tiled", "bound": "tensor", "pipe": "fp64 DMMA (mma.sync m8n8k4.f64)", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": ach_tf / fp64_peak, "traffic": traffic,
+        "frac": ach_tf / fp64_peak, "traffic": traffic, "traffic_source": "ncu capture under profiles/ (bytes per point x points of this run), not measured in this run",
         "peak_source": fp64_src + "; MEASURED_PEAKS.json holds no FP64 figure",
-        "kernel_ms_per_launch": kms, "algorithmic_flops_per_launch": flops / world,
+        "kernel_ms_per_step": kms, "launches_per_step": int(launches / world), "algorithmic_flops_per_launch": flops / world,
         "algorithmic_bytes_per_launch": abytes / world,
         "hbm": {"achieved": ach_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "frac": ach_gbs / peaks.get("hbm_gbs"), "peak_source": peaks_src + " MEASURED_PEAKS.json"},
@@ -506,7 +574,7 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cs = CpuSample(name)
+        cs = CpuSample(name, synth_kind=args.synth)
         cs.calibrate(args.cpu_seconds)
         npts_c, dt_c, nsolved_c = cs.run()
         cpu = {"value": npts_c / dt_c, "unit": UNIT, "cores": cs.nth, "kind": "port",
@@ -523,7 +591,7 @@ def main():
                        "decomposition": f"cyclic column deal over {world} rank(s), obs replicated, no collective",
                        "l2": "inputs (%.1f GB state per rank) far larger than the 126 MB L2" % (state_bytes / 1e9)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches / world) * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "cycle": cycle,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "cycle": cycle,
             "kernel_ms_per_step": kms, "phase_share_rank0": phases,
         }
         if args.subsample > 1:

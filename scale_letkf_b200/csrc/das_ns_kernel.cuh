@@ -65,7 +65,7 @@ das_ns_kernel(const DasParams P) {
   __shared__ long long s_work;
   __shared__ long long s_ploff[kMaxNV];
   __shared__ int s_pln[kMaxNV];
-  const LaneOfs lo = lane_offsets(lane);
+  const LaneFrag lf = lane_frag(lane);
 
   LocalList L;
   L.cap = P.lcap;
@@ -312,70 +312,89 @@ das_ns_kernel(const DasParams P) {
           gram_circ<NB, LD>(acc, stage + (size_t)(c % 3) * CR * LD, wv + (c % 3) * CR, (nrows + 3) & ~3, w, lane);
         }
         __syncthreads();   // the staging buffers (Y among them) are free again
-        store_circ<NB>(acc, Yp, w, lo);
-        __syncthreads();
         const double cdiag = (double)(k - 1) / infl;   // (common_letkf.f90:140-143)
-        // ---- s = ||A||_1, b, bd (and the adaptive-inflation statistics) from the stored tiles -------
-        // lambda_max(A) = c0 + lambda_max(G) <= c0 + min(||G||_1, ||G||_F): the Frobenius norm is the tighter
-        // bound when the spectrum of G = Yr^T Y decays quickly, and a tighter s saves Newton-Schulz iterations
-        // four threads per row (NT = 4 KP): columns part, part + 4, ...; partial sums meet through two shuffles
-        double rs = 0.0, dgv = 0.0, fs = 0.0;
+        // ---- epilogue of the Gram in registers: ||G||_F, trace, b, bd (and the adaptive-inflation statistics) ----
+        // lambda_max(A) = c0 + lambda_max(G) <= c0 + ||G||_F (G = Yr^T Y is positive semi-definite, so the Frobenius
+        // norm is never above the trace and it is tight when the spectrum of G decays quickly -- the correlated-
+        // observation case that costs Newton-Schulz iterations)
+        double fs = 0.0, tr = 0.0;
         {
-          const int row = tid >> 2, part = tid & 3;
-          if (row < k) {
-            for (int col = part; col < k; col += 4) {
-              const double g = Yp[paddr(row, col)];
-              rs += fabs(g);
-              fs = fma(g, g, fs);
+          const int r = lane >> 2, q = lane & 3, row = w * 8 + r;
+#pragma unroll
+          for (int d = 0; d <= H; ++d) {
+            int jb = w + d;
+            if (jb >= NB) jb -= NB;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = jb * 8 + 2 * q + e;
+              const double v = acc[d][e];
+              if (row < k && col < k) {
+                fs = fma(d == 0 ? v : 2.0 * v, v, fs);
+                if (d == 0 && row == col) tr += v;
+              }
+              // dep / depd ride in columns k, k + 1; a block pair is stored once, as (w, jb) or as its mirror
+              if (row < k) {
+                if (col == k) bvec[row] = v;
+                if (col == k + 1 && P.det) bdvec[row] = v;
+              }
+              if (d != 0 && col < k) {
+                if (row == k) bvec[col] = v;
+                if (row == k + 1 && P.det) bdvec[col] = v;
+              }
+              if (d == 0 && row == k && col == k) red[3 * NB] = v;   // sum w dep^2
             }
           }
-          rs += __shfl_xor_sync(LETKF_FULL_MASK, rs, 1);
-          rs += __shfl_xor_sync(LETKF_FULL_MASK, rs, 2);
-          fs += __shfl_xor_sync(LETKF_FULL_MASK, fs, 1);
-          fs += __shfl_xor_sync(LETKF_FULL_MASK, fs, 2);
-          if (part != 0) fs = 0.0;   // one contribution per row
-          if (row < k && part == 0) {
-            dgv = Yp[paddr(row, row)];
-            bvec[row] = Yp[paddr(row, k)];
-            bdvec[row] = P.det ? Yp[paddr(row, k + 1)] : 0.0;
+          fs = warp_sum(fs);
+          tr = warp_sum(tr);
+          p3acc = warp_sum(p3acc);
+          if (lane == 0) {
+            red[w] = fs;
+            red[NB + w] = tr;
+            red[2 * NB + w] = p3acc;
           }
         }
-        const double g1 = block_max(rs, red);
-        const double gf = sqrt(block_sum(fs, red)) * (1.0 + 1.0e-12);   // (rounding guard)
-        const double s_norm = cdiag + fmin(g1, gf);
+        __syncthreads();
+        double gf2 = 0.0, trace = 0.0, parm3 = 0.0;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          gf2 += red[i];
+          trace += red[NB + i];
+          parm3 += red[2 * NB + i];
+        }
+        const double s_norm = cdiag + sqrt(gf2) * (1.0 + 1.0e-12);   // (rounding guard)
         if (P.INFL_MUL_ADAPTIVE) {   // (common_letkf.f90:229-254)
-          const double parm1 = Yp[paddr(k, k)];   // sum w dep^2
-          const double parm2 = block_sum(dgv, red) / (double)(k - 1);
-          const double parm3 = block_sum(p3acc, red);
+          const double parm1 = red[3 * NB];
+          const double parm2 = trace / (double)(k - 1);
           const double parm4 = (parm1 - parm3) / parm2 - infl;
           const double tq = (infl * parm2 + parm3) / parm2;
           const double sigma_o = 2.0 / parm3 * (tq * tq);
           const double gain = 0.04 * 0.04 / (sigma_o + 0.04 * 0.04);
           if (tid == 0) inflv[vtrig] = infl + gain * parm4;
         }
-        __syncthreads();
-        // ---- Y0 = (A + c0 I) / s on the leading k x k block, identity on the padding ----------------
+        // ---- M0 = (G + c0 I) / s on the leading k x k block, identity on the padding ------------------
         {
           const double is = 1.0 / s_norm;
-          for (int idx = tid; idx < PSZ; idx += blockDim.x) {
-            int bi, bj;
-            tile_coords(idx >> 6, bi, bj);
-            const int e = idx & 63, r = e >> 3, c = (e & 7) ^ ((r & 2) << 1);
-            const int row = bi * 8 + r, col = bj * 8 + c;
-            double v = Yp[idx];
-            if (row < k && col < k) v = (v + (row == col ? cdiag : 0.0)) * is;
-            else v = (row == col) ? 1.0 : 0.0;
-            Yp[idx] = v;
+          const int r = lane >> 2, q = lane & 3, row = w * 8 + r;
+#pragma unroll
+          for (int d = 0; d <= H; ++d) {
+            int jb = w + d;
+            if (jb >= NB) jb -= NB;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = jb * 8 + 2 * q + e;
+              const bool dg = (d == 0 && row == col);
+              acc[d][e] = (row < k && col < k) ? (acc[d][e] + (dg ? cdiag : 0.0)) * is : (dg ? 1.0 : 0.0);
+            }
           }
+          store_circ<NB>(acc, Yp, w, lf);
         }
-        __syncthreads();
         phase(2);
         // ---- Z = (A/s)^-1/2 --------------------------------------------------------------------------
-        const int its = newton_schulz_invsqrt<NB>(Yp, Zp, Tp, cdiag / s_norm, red, P.max_sweeps + 20);
+        const int its = newton_schulz_invsqrt<NB>(acc, Yp, Zp, Tp, cdiag / s_norm, red, P.max_sweeps + 20);
         if (its < 0) fail = true;
         c_iters += (unsigned long long)(its < 0 ? -its : its);
         // mtx_eigen zeroes eigenvalues below lambda_max*sqrt(eps) (common_mtx.f90:69) and letkf_core
-        // would then divide by zero; ||A||_1 <= k lambda_max bounds the same condition.
+        // would then divide by zero; ||A||_F <= sqrt(k) lambda_max bounds the same condition.
         if (!(cdiag * (double)k >= s_norm * 1.4901161193847656e-08)) fail = true;
         phase(4);
         // ---- Ts = Z [dX | b | bd]  (k x 16 skinny product on the tensor cores) --------------------
@@ -383,14 +402,17 @@ das_ns_kernel(const DasParams P) {
           double a2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
           const int r = lane >> 2, q = lane & 3;
           const double *pb = Xall + (size_t)r * LD + q;
-#pragma unroll 1
-          for (int l = 0; l < NB; ++l) {
+#pragma unroll
+          for (int e = 0; e < NB; ++e) {
+            int j = w + e;
+            if (j >= NB) j -= NB;
+            double a[2];
+            symm_afrag<NB>(a, Zp, w, e, j * C::RS, lf);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const double a = afrag(Zp, w, l, h, lo);
-              const int kk = l * 8 + h * 4;
-              dmma884(a2[0][0], a2[0][1], a, pb[kk]);
-              dmma884(a2[1][0], a2[1][1], a, pb[(size_t)8 * LD + kk]);
+              const int kk = j * 8 + h * 4;
+              dmma884(a2[0][0], a2[0][1], a[h], pb[kk]);
+              dmma884(a2[1][0], a2[1][1], a[h], pb[(size_t)8 * LD + kk]);
             }
           }
 #pragma unroll

@@ -4,23 +4,28 @@
 //
 // letkf_core only ever uses functions of A = Yr^T Y + (k-1)/rho I:
 //     Pa = A^-1,   trans = sqrt(k-1) A^-1/2,   transm = Pa Yr^T d
-// so no eigenvectors are needed.  Z = A^-1/2 is computed with the coupled Newton-Schulz iteration
-// (Higham, Functions of Matrices, eq. 6.35), interval-scaled each step:
-//     M = Z Y;  T = sqrt(c) (3 I - c M) / 2;  Z <- T Z;  Y <- T Y;      Y0 = A / s, Z0 = I
-// with s = ||A||_1 >= lambda_max, the eigenvalues of M bracketed by [a, b] (a0 = c0/s with the known
-// lowest eigenvalue bound c0 = (k-1)/rho, b0 = 1) and c = 3 / (a + sqrt(ab) + b), the scaling that
-// maps both interval ends onto the same image.  Every iterate is a polynomial in A, so all
-// matrices are symmetric and commute: the iteration is numerically stable and quadratically
-// convergent even with the (k-p)-fold degenerate eigenvalue c0 (p < k).  Once the residual ||I - Z Y|| is below
-// 2e-3 a single third- or fourth-order step (Z <- (I + E/2 + 3E^2/8 [+ 5E^3/16]) Z) finishes the solve: 3.9-4.7
-// iterations per solve on the BASELINE shapes instead of 5.3-6.4 with quadratic steps only.
+// so no eigenvectors are needed.  Z = A^-1/2 comes from a Newton-Schulz iteration in PRODUCT FORM:
+//     M_0 = A / s,  Z_0 = I;     T_j = sqrt(c_j) (3 I - c_j M_j) / 2;
+//     M_{j+1} = T_j M_j T_j,     Z_{j+1} = T_j Z_j                      (invariant M_j = Z_j (A/s) Z_j)
+// with s >= lambda_max(A), the eigenvalues of M_j bracketed by [a_j, 1] (a_0 = c0/s with the known lowest
+// eigenvalue c0 = (k-1)/rho) and c_j = 3 / (a_j + sqrt(a_j) + 1), the scaling that maps both ends of the
+// bracket onto the same image.  M_{j+1} is a function of the single matrix M_j (T_j is a polynomial in
+// M_j), so the iteration on M is self-correcting whatever the conditioning of A, and Z only accumulates the
+// factors: errors are never amplified.  (The textbook coupled form Z <- T Z, Y <- T Y with M = Z Y needs
+// Y <- Y T to be stable; with symmetric storage that cannot be expressed and rounding errors that do not
+// commute with A grow by ~sqrt(cond(A))/4 per step -- tools/ns_model.py)
+// Once ||I - M||_F < 1.5e-3 a single third- or fourth-order step (Z <- (I + E/2 + 3E^2/8 [+ 5E^3/16]) Z,
+// E = I - M) finishes the solve.
 //
 // All products are GEMMs on the FP64 tensor cores: mma.sync.aligned.m8n8k4.f64 (DMMA; tcgen05/TMEM
-// has no FP64 kind).  Because every matrix is symmetric, only the lower triangle of 8x8 tiles is
-// stored (packed, XOR-swizzled so that both the direct and the transposed fragment patterns are
-// bank-conflict free) and only one tile of each symmetric pair is computed: with NB (odd) row
-// blocks, warp w computes the "circulant" tiles (w, (w+d) mod NB), d = 0..(NB-1)/2, which covers
-// every unordered pair exactly once with perfect load balance.
+// has no FP64 kind).  Every matrix is symmetric, so only one 8x8 tile of each symmetric pair is stored and
+// computed: with NB (odd) row blocks, warp w owns the "circulant" tiles (w, (w+d) mod NB), d = 0..H,
+// H = (NB-1)/2, which covers every unordered pair exactly once with perfect load balance.  Tile (w, d)
+// lives at ((H+1) w + d) * 64 doubles, its elements in FRAGMENT ORDER: (r, c) at (c>>2)*32 + r*4 + (c&3),
+// so that a DMMA operand fragment of a stored tile is one bank-conflict-free, lane-contiguous load and the
+// fragment of its transpose is conflict-free as well.  Summing the inner index in circulant order
+// l = (w+e) mod NB makes every "stored or mirrored?" decision a function of (d, e) only -- resolved at compile
+// time in the fully unrolled product, leaving loads with immediate offsets and DMMAs in the inner loop.
 #pragma once
 #include "common.cuh"
 
@@ -35,12 +40,11 @@ struct NsCfg {
   static constexpr int LD = KP + 4;                // row stride of row-major staging / vector blocks
   static constexpr int NT = 32 * NB_;              // one warp per row block
   static constexpr int NTILE = NB_ * (NB_ + 1) / 2;
-  static constexpr int PSZ = NTILE * 64;           // doubles per packed symmetric matrix
+  static constexpr int PSZ = NTILE * 64;           // doubles per stored symmetric matrix
+  static constexpr int RS = (H + 1) * 64;          // doubles per warp-owned row of tiles
   static constexpr int CR = (PSZ / LD) & ~3;       // obs rows per staging chunk (three chunks fit in 3 PSZ); CR == 4 NB
   // resident CTAs per SM the register allocation is sized for
   static constexpr int MINB = NB_ <= 3 ? 8 : NB_ <= 5 ? 5 : NB_ <= 7 ? 4 : NB_ <= 9 ? 2 : 1;
-  // (registers: each of the 4 SM sub-partitions holds 16 K registers and ceil(NB MINB / 4) warps, which
-  // is what __launch_bounds__(NT, MINB) makes ptxas budget for -- 128 for NB = 13, 80 for NB = 7)
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -49,143 +53,116 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
       : "d"(a), "d"(b));
 }
 
-// ---- packed symmetric tile storage ---------------------------------------------------------------
-// tile (bi, bj), bi >= bj, at ((bi (bi+1))/2 + bj) * 64; element (r, c) of a stored tile at
-// r*8 + (c ^ ((r & 2) << 1)).
-__host__ __device__ __forceinline__ int ptile(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * 64; }
-__host__ __device__ __forceinline__ int pelem(int r, int c) { return r * 8 + (c ^ ((r & 2) << 1)); }
-// address of logical element (row, col) of a packed symmetric matrix
-__host__ __device__ __forceinline__ int paddr(int row, int col) {
+// ---- circulant, fragment-ordered tile storage -------------------------------------------------------
+__host__ __device__ __forceinline__ int fpos(int r, int c) { return (c >> 2) * 32 + r * 4 + (c & 3); }
+// address of logical element (row, col) of a stored symmetric matrix (element-wise passes only)
+template <int NB>
+__host__ __device__ __forceinline__ int caddr(int row, int col) {
+  constexpr int H = (NB - 1) / 2;
   const int bi = row >> 3, bj = col >> 3;
-  return (bi >= bj) ? ptile(bi, bj) + pelem(row & 7, col & 7) : ptile(bj, bi) + pelem(col & 7, row & 7);
+  int g = bj - bi;
+  if (g < 0) g += NB;
+  return (g <= H) ? (bi * (H + 1) + g) * 64 + fpos(row & 7, col & 7)
+                  : (bj * (H + 1) + (NB - g)) * 64 + fpos(col & 7, row & 7);
 }
 
-struct LaneOfs {   // per-lane offsets of the two fragment patterns, k-halves h = 0, 1
-  int p1[2];       // stored (r, 4h+q): direct A operand / transposed B operand
-  int p2[2];       // stored (4h+q, r): transposed A operand / direct B operand
-  int st_n;        // accumulator store, direct:     stored (r, 2q) [double2]
-  int st_t[2];     // accumulator store, transposed: stored (2q+e, r)
+struct LaneFrag {   // per-lane offsets inside a tile; lane = 4 r + q
+  int dir;          // element (r, 4h + q) at dir + 32 h   (operand fragment of the stored tile)
+  int trn;          // element (4h + q, r) at trn + 16 h   (operand fragment of its transpose)
+  int st;           // accumulator pair (r, 2q), (r, 2q + 1) at st, st + 1
 };
-__device__ __forceinline__ LaneOfs lane_offsets(int lane) {
+__device__ __forceinline__ LaneFrag lane_frag(int lane) {
   const int r = lane >> 2, q = lane & 3;
-  LaneOfs o;
-  o.p1[0] = pelem(r, q);
-  o.p1[1] = pelem(r, 4 + q);
-  o.p2[0] = pelem(q, r);
-  o.p2[1] = pelem(4 + q, r);
-  o.st_n = pelem(r, 2 * q);
-  o.st_t[0] = pelem(2 * q, r);
-  o.st_t[1] = pelem(2 * q + 1, r);
+  LaneFrag o;
+  o.dir = lane;
+  o.trn = (r >> 2) * 32 + q * 4 + (r & 3);
+  o.st = (q >> 1) * 32 + r * 4 + 2 * (q & 1);
   return o;
 }
-// A operand: logical block (bi, bl) of packed M, k-half h
-__device__ __forceinline__ double afrag(const double *M, int bi, int bl, int h, const LaneOfs &o) {
-  return (bi >= bl) ? M[ptile(bi, bl) + o.p1[h]] : M[ptile(bl, bi) + o.p2[h]];
-}
-// B operand: logical block (bl, bj) of packed M, k-half h
-__device__ __forceinline__ double bfrag(const double *M, int bl, int bj, int h, const LaneOfs &o) {
-  return (bl >= bj) ? M[ptile(bl, bj) + o.p2[h]] : M[ptile(bj, bl) + o.p1[h]];
-}
-// store / load one accumulator tile of logical block (bi, bj)
-__device__ __forceinline__ void store_tile(double *M, int bi, int bj, double c0, double c1, const LaneOfs &o) {
-  if (bi >= bj) {
-    *reinterpret_cast<double2 *>(M + ptile(bi, bj) + o.st_n) = make_double2(c0, c1);
-  } else {
-    double *t = M + ptile(bj, bi);
-    t[o.st_t[0]] = c0;
-    t[o.st_t[1]] = c1;
-  }
-}
-__device__ __forceinline__ void load_tile(const double *M, int bi, int bj, double &c0, double &c1,
-                                          const LaneOfs &o) {
-  if (bi >= bj) {
-    const double2 v = *reinterpret_cast<const double2 *>(M + ptile(bi, bj) + o.st_n);
-    c0 = v.x;
-    c1 = v.y;
-  } else {
-    const double *t = M + ptile(bj, bi);
-    c0 = t[o.st_t[0]];
-    c1 = t[o.st_t[1]];
-  }
-}
 
-// Operand fragments of one l-step of the circulant half-GEMM: A = X(w, l) (both k-halves) and
-// B = W(l, jd) for the warp's H + 1 column blocks.
-template <int NB>
-struct SymmFrag {
-  double a[2];
-  double b[(NB + 1) / 2][2];
-};
-// Running tile offsets (in doubles) of the operands.  Packed tile (bi, bj), bi >= bj, sits at
-// (bi (bi + 1) / 2 + bj) * 64, so walking l = 0, 1, ... along block-row x of a symmetric matrix adds
-// 64 per step up to the diagonal (stored row x) and (l + 1) * 64 per step below it (stored column x):
-// one compare + select + add per operand and step instead of re-deriving the tile address.
-template <int NB>
-struct SymmWalk {
-  int ta, tb[(NB + 1) / 2], j[(NB + 1) / 2];
-};
-template <int NB>
-__device__ __forceinline__ void symm_load(SymmFrag<NB> &f, SymmWalk<NB> &K, const double *X, const double *W,
-                                          int w, int l, const LaneOfs &o) {
-  {
-    const bool col = l > w;   // below the diagonal of block-row w: stored column w, transposed pattern
-    const double *t = X + K.ta;
-    f.a[0] = t[col ? o.p2[0] : o.p1[0]];
-    f.a[1] = t[col ? o.p2[1] : o.p1[1]];
-    K.ta += (l < w) ? 64 : (l + 1) * 64;
-  }
-#pragma unroll
-  for (int d = 0; d <= (NB - 1) / 2; ++d) {
-    const bool col = l >= K.j[d];
-    const double *t = W + K.tb[d];
-    f.b[d][0] = t[col ? o.p2[0] : o.p1[0]];
-    f.b[d][1] = t[col ? o.p2[1] : o.p1[1]];
-    K.tb[d] += (l < K.j[d]) ? 64 : (l + 1) * 64;
-  }
-}
-template <int NB>
-__device__ __forceinline__ void symm_mma(double (&acc)[(NB + 1) / 2][2], const SymmFrag<NB> &f) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int d = 0; d <= (NB - 1) / 2; ++d) dmma884(acc[d][0], acc[d][1], f.a[h], f.b[d][h]);
-}
-
-// acc[d] (+)= sum_l X(w, l) W(l, jd)   for the warp's circulant tiles jd = (w + d) mod NB.
-// Register double buffering: the fragments of step l + 1 are in flight while the DMMAs of step l issue.
+// acc[d] += sum_l X(w, l) W(l, jd)   for the warp's circulant tiles jd = (w + d) mod NB, X and W symmetric.
+// l runs in circulant order l = (w + e) mod NB.  With g = (d - e) mod NB:
+//   X(w, w+e):    e <= H: stored tile (w, e);                      else transpose of stored tile (w+e, NB-e)
+//   W(w+e, w+d):  g <= H: stored tile (w+e, g) [B operand = its "transposed" fragment pattern];
+//                 else transpose of stored tile (w+d, NB-g)
 template <int NB>
 __device__ __forceinline__ void symm_gemm(double (&acc)[(NB + 1) / 2][2], const double *X, const double *W,
-                                          int w, const LaneOfs &o) {
-  constexpr int H = (NB - 1) / 2;
-  SymmWalk<NB> K;
-  K.ta = (w * (w + 1) / 2) * 64;
+                                          int w, const LaneFrag &lf) {
+  constexpr int H = (NB - 1) / 2, RS = (H + 1) * 64;
+  int rb[NB];   // first tile of block-row (w + x) mod NB
 #pragma unroll
-  for (int d = 0; d <= H; ++d) {
-    int j = w + d;
+  for (int x = 0; x < NB; ++x) {
+    int j = w + x;
     if (j >= NB) j -= NB;
-    K.j[d] = j;
-    K.tb[d] = (j * (j + 1) / 2) * 64;
+    rb[x] = j * RS;
   }
-  SymmFrag<NB> f0, f1;
-  symm_load<NB>(f0, K, X, W, w, 0, o);
-#pragma unroll 1
-  for (int l = 0; l < NB - 1; l += 2) {   // NB is odd: pairs (l, l + 1), then the last step
-    symm_load<NB>(f1, K, X, W, w, l + 1, o);
-    symm_mma<NB>(acc, f0);
-    symm_load<NB>(f0, K, X, W, w, l + 2, o);
-    symm_mma<NB>(acc, f1);
+#pragma unroll
+  for (int e = 0; e < NB; ++e) {
+    double a[2], b[H + 1][2];
+    if (e <= H) {
+      const double *t = X + rb[0] + e * 64 + lf.dir;
+      a[0] = t[0];
+      a[1] = t[32];
+    } else {
+      const double *t = X + rb[e] + (NB - e) * 64 + lf.trn;
+      a[0] = t[0];
+      a[1] = t[16];
+    }
+#pragma unroll
+    for (int d = 0; d <= H; ++d) {
+      const int g = (d - e + NB) % NB;
+      if (g <= H) {
+        const double *t = W + rb[e] + g * 64 + lf.trn;
+        b[d][0] = t[0];
+        b[d][1] = t[16];
+      } else {
+        const double *t = W + rb[d] + (NB - g) * 64 + lf.dir;
+        b[d][0] = t[0];
+        b[d][1] = t[32];
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], a[h], b[d][h]);
   }
-  symm_mma<NB>(acc, f0);
 }
 
+// A operand fragments of block-row w of a stored symmetric matrix, inner block (w + e) mod NB
+template <int NB>
+__device__ __forceinline__ void symm_afrag(double (&a)[2], const double *X, int w, int e, int rb_e,
+                                           const LaneFrag &lf) {
+  constexpr int H = (NB - 1) / 2, RS = (H + 1) * 64;
+  if (e <= H) {
+    const double *t = X + w * RS + e * 64 + lf.dir;
+    a[0] = t[0];
+    a[1] = t[32];
+  } else {
+    const double *t = X + rb_e + (NB - e) * 64 + lf.trn;
+    a[0] = t[0];
+    a[1] = t[16];
+  }
+}
+
+// the warp's tiles <-> registers (accumulator layout)
 template <int NB>
 __device__ __forceinline__ void store_circ(const double (&acc)[(NB + 1) / 2][2], double *M, int w,
-                                           const LaneOfs &o) {
+                                           const LaneFrag &lf) {
+  constexpr int H = (NB - 1) / 2, RS = (H + 1) * 64;
+  double *t = M + w * RS + lf.st;
 #pragma unroll
-  for (int d = 0; d <= (NB - 1) / 2; ++d) {
-    int j = w + d;
-    if (j >= NB) j -= NB;
-    store_tile(M, w, j, acc[d][0], acc[d][1], o);
+  for (int d = 0; d <= H; ++d) *reinterpret_cast<double2 *>(t + d * 64) = make_double2(acc[d][0], acc[d][1]);
+}
+template <int NB>
+__device__ __forceinline__ void load_circ(double (&acc)[(NB + 1) / 2][2], const double *M, int w,
+                                          const LaneFrag &lf) {
+  constexpr int H = (NB - 1) / 2, RS = (H + 1) * 64;
+  const double *t = M + w * RS + lf.st;
+#pragma unroll
+  for (int d = 0; d <= H; ++d) {
+    const double2 v = *reinterpret_cast<const double2 *>(t + d * 64);
+    acc[d][0] = v.x;
+    acc[d][1] = v.y;
   }
 }
 
@@ -198,119 +175,62 @@ __device__ __forceinline__ void gram_circ(double (&acc)[(NB + 1) / 2][2], const 
   constexpr int H = (NB - 1) / 2;
   const int r = lane >> 2, q = lane & 3;
   const double *pa = Ys + (size_t)q * LD + w * 8 + r;
-  const double *pb = Ys + (size_t)q * LD + r;
-  int jo[H + 1];
+  const double *pw = wv + q;
+  const double *pb[H + 1];
 #pragma unroll
   for (int d = 0; d <= H; ++d) {
     int j = w + d;
     if (j >= NB) j -= NB;
-    jo[d] = j * 8;
+    pb[d] = Ys + (size_t)q * LD + j * 8 + r;
   }
 #pragma unroll 4
   for (int o = 0; o < nrows4; o += 4) {
-    const double a = pa[(size_t)o * LD] * wv[o + q];
-    const double *pbk = pb + (size_t)o * LD;
+    const double a = pa[(size_t)o * LD] * pw[o];
 #pragma unroll
-    for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], a, pbk[jo[d]]);
+    for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], a, pb[d][(size_t)o * LD]);
   }
 }
 
-// Coupled, interval-scaled Newton-Schulz on packed symmetric matrices.  On entry Yp holds
-// Y0 = A / s (leading k x k block; identity on the padding rows), c0s = c0 / s the lower eigenvalue
-// bound.  On exit Zp holds Z ~= (A/s)^-1/2.  Tp: scratch.  `red`: >= 32 doubles of shared scratch.
-// Returns the number of iterations, negative if the residual test was not met within max_iter.
+// Frobenius norm^2 contribution of (I - acc) held in the warp's tiles (off-diagonal tiles count twice)
+template <int NB>
+__device__ __forceinline__ double resid_fro2(const double (&acc)[(NB + 1) / 2][2], int lane) {
+  const int r = lane >> 2, q = lane & 3;
+  double s = 0.0;
+#pragma unroll
+  for (int d = 0; d <= (NB - 1) / 2; ++d) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const double v = ((d == 0 && r == 2 * q + e) ? 1.0 : 0.0) - acc[d][e];
+      s = fma(d == 0 ? v : 2.0 * v, v, s);
+    }
+  }
+  return s;
+}
+
+// Product-form, interval-scaled Newton-Schulz on stored symmetric matrices.  On entry `acc` holds the warp's
+// tiles of M0 = A / s (leading k x k block; identity on the padding rows) and the same tiles have been stored
+// to Mp (no barrier needed in between); c0s = c0 / s is the lower eigenvalue bound.  On exit Zp holds
+// Z ~= (A/s)^-1/2 (visible to all threads).  Tp: scratch.  `red`: >= NB doubles of shared scratch.
+// Returns the number of iterations, negative if max_iter was reached before the residual test was met.
 // All NT = 32 NB threads of the CTA must call.
 template <int NB>
-__device__ __forceinline__ int newton_schulz_invsqrt(double *Yp, double *Zp, double *Tp, double c0s,
-                                                     double *red, int max_iter) {
+__device__ __forceinline__ int newton_schulz_invsqrt(double (&acc)[(NB + 1) / 2][2], double *Mp, double *Zp,
+                                                     double *Tp, double c0s, double *red, int max_iter) {
   constexpr int H = (NB - 1) / 2;
   const int lane = threadIdx.x & 31;
   const int w = __shfl_sync(LETKF_FULL_MASK, threadIdx.x >> 5, 0);
   const int r = lane >> 2, q = lane & 3;
-  const LaneOfs o = lane_offsets(lane);
-  double a = c0s, b = 1.0;   // eigenvalue bracket of M = Z Y
-  double acc[H + 1][2], az[H + 1][2];
+  const LaneFrag lf = lane_frag(lane);
+  double a = c0s;            // eigenvalues of M in [a, 1]
+  double res = 1.0 - a;      // ||I - M||_2 <= 1 - a; later min(bound, measured Frobenius norm)
+  double az[H + 1][2];
   int it = 0;
-  bool first = true, done = false;
-  while (!done) {
+  bool have_z = false;       // Z0 = I is not stored
+  for (;;) {
     ++it;
-    if (first) {   // M = Z0 Y0 = Y0
-#pragma unroll
-      for (int d = 0; d <= H; ++d) {
-        int j = w + d;
-        if (j >= NB) j -= NB;
-        load_tile(Yp, w, j, acc[d][0], acc[d][1], o);
-      }
-    } else {
-#pragma unroll
-      for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
-      symm_gemm<NB>(acc, Zp, Yp, w, o);
-    }
-    // residual ||I - M||_max (the warp's diagonal tile is d = 0)
-    double res = 0.0;
-#pragma unroll
-    for (int d = 0; d <= H; ++d) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const double dg = (d == 0 && r == 2 * q + e) ? 1.0 : 0.0;
-        res = fmax(res, fabs(dg - acc[d][e]));
-      }
-    }
-    res = warp_max(res);
-    if (lane == 0) red[w] = res;
-    __syncthreads();
-    res = red[0];
-#pragma unroll
-    for (int i = 1; i < NB; ++i) res = fmax(res, red[i]);
-    const bool last = (res < 1.0e-7) || (it >= max_iter);
-    if (!last && !first && res < 2.0e-3) {
-      // Close to convergence one higher-order step finishes the job.  With E = I - Z Y (||E|| = res):
-      //   res < 2e-4:  Z <- (I + E/2 + 3 E^2/8) Z              residual ~ (5/16) res^3   <= 2.5e-12
-      //   res < 2e-3:  Z <- (I + E/2 + 3 E^2/8 + 5 E^3/16) Z   residual ~ (35/128) res^4 <= 4.4e-12
-      // i.e. 2 (3) half-GEMMs instead of the 3 + 2 (3 + 3 + 2) of further quadratic steps plus the final one.
-      // Y is no longer needed, its storage holds E^2.
-      const bool order4 = res >= 2.0e-4;
-#pragma unroll
-      for (int d = 0; d <= H; ++d) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) acc[d][e] = ((d == 0 && r == 2 * q + e) ? 1.0 : 0.0) - acc[d][e];
-      }
-      store_circ<NB>(acc, Tp, w, o);   // E
-      __syncthreads();
-#pragma unroll
-      for (int d = 0; d <= H; ++d) az[d][0] = az[d][1] = 0.0;
-      symm_gemm<NB>(az, Tp, Tp, w, o);   // E^2
-      if (order4) store_circ<NB>(az, Yp, w, o);
-#pragma unroll
-      for (int d = 0; d <= H; ++d) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-          az[d][e] = fma(0.375, az[d][e], fma(0.5, acc[d][e], (d == 0 && r == 2 * q + e) ? 1.0 : 0.0));
-      }
-      __syncthreads();   // E^2 visible; (order 3: all reads of E done)
-      if (order4) {
-#pragma unroll
-        for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
-        symm_gemm<NB>(acc, Yp, Tp, w, o);   // E^3
-#pragma unroll
-        for (int d = 0; d <= H; ++d) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) az[d][e] = fma(0.3125, acc[d][e], az[d][e]);
-        }
-        __syncthreads();   // all reads of E done
-      }
-      store_circ<NB>(az, Tp, w, o);
-      __syncthreads();
-#pragma unroll
-      for (int d = 0; d <= H; ++d) az[d][0] = az[d][1] = 0.0;
-      symm_gemm<NB>(az, Tp, Zp, w, o);   // Z' = T Z
-      __syncthreads();
-      store_circ<NB>(az, Zp, w, o);
-      __syncthreads();
-      return it;
-    }
+    if (res < 1.5e-3 || it >= max_iter) break;
     double c = 1.0;
-    if (!last && (b - a) > 1.0e-3) c = 3.0 / (a + sqrt(a * b) + b);
+    if (1.0 - a > 1.0e-3) c = 3.0 / (a + sqrt(a) + 1.0);
     const double sc = sqrt(c), h0 = 1.5 * sc, h1 = -0.5 * c * sc;
     // T = sqrt(c) (3 I - c M) / 2
 #pragma unroll
@@ -318,41 +238,93 @@ __device__ __forceinline__ int newton_schulz_invsqrt(double *Yp, double *Zp, dou
 #pragma unroll
       for (int e = 0; e < 2; ++e) acc[d][e] = fma(h1, acc[d][e], (d == 0 && r == 2 * q + e) ? h0 : 0.0);
     }
-    if (first) {
-      // Z1 = T ; Y1 = T Y0
-      store_circ<NB>(acc, Zp, w, o);
-      store_circ<NB>(acc, Tp, w, o);
-      __syncthreads();
+    store_circ<NB>(acc, Tp, w, lf);
+    if (!have_z) store_circ<NB>(acc, Zp, w, lf);   // Z1 = T0
+    __syncthreads();                               // T (and M, Z) visible
+#pragma unroll
+    for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
+    symm_gemm<NB>(acc, Tp, Mp, w, lf);             // U = T M
+    if (have_z) {
 #pragma unroll
       for (int d = 0; d <= H; ++d) az[d][0] = az[d][1] = 0.0;
-      symm_gemm<NB>(az, Tp, Yp, w, o);
-      __syncthreads();   // all reads of Y0 done (also protects red)
-      store_circ<NB>(az, Yp, w, o);
-      __syncthreads();
-    } else {
-      store_circ<NB>(acc, Tp, w, o);
-      __syncthreads();
-#pragma unroll
-      for (int d = 0; d <= H; ++d) az[d][0] = az[d][1] = 0.0;
-      symm_gemm<NB>(az, Tp, Zp, w, o);   // Z' = T Z
-      if (!last) {
-#pragma unroll
-        for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
-        symm_gemm<NB>(acc, Tp, Yp, w, o);   // Y' = T Y
-      }
-      __syncthreads();   // all reads of Z, Y, T done
-      store_circ<NB>(az, Zp, w, o);
-      if (!last) store_circ<NB>(acc, Yp, w, o);
-      __syncthreads();
+      symm_gemm<NB>(az, Tp, Zp, w, lf);            // Z' = T Z
     }
+    __syncthreads();                               // all reads of M and Z done
+    store_circ<NB>(acc, Mp, w, lf);
+    if (have_z) store_circ<NB>(az, Zp, w, lf);
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
+    symm_gemm<NB>(acc, Mp, Tp, w, lf);             // M' = U T
+    const double f2 = warp_sum(resid_fro2<NB>(acc, lane));
+    if (lane == 0) red[w] = f2;
+    __syncthreads();                               // all reads of U and T done; red visible
+    store_circ<NB>(acc, Mp, w, lf);                // (visible after the next barrier)
+    double fro2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) fro2 += red[i];
     const double t = c * a;   // image of the bracket under x -> c x (3 - c x)^2 / 4 is [g(c a), 1]
     a = t * (3.0 - t) * (3.0 - t) * 0.25;
-    b = 1.0;
-    first = false;
-    done = last;
-    if (last && !(res < 1.0e-7)) it = -it;
+    res = fmin(1.0 - a, sqrt(fro2));
+    have_z = true;
   }
-  return it;
+  const bool ok = res < 1.5e-3;
+  // Finishing step.  With E = I - M (||E||_2 <= res):
+  //   res < 1e-8  :  Z <- (I + E/2) Z                          residual ~ (3/8) res^2    < 4e-17
+  //   res < 1.5e-4:  Z <- (I + E/2 + 3 E^2/8) Z                residual ~ (5/16) res^3   < 1.1e-12
+  //   else        :  Z <- (I + E/2 + 3 E^2/8 + 5 E^3/16) Z     residual ~ (35/128) res^4 < 1.4e-12
+  const int order = res < 1.0e-8 ? 2 : res < 1.5e-4 ? 3 : 4;
+#pragma unroll
+  for (int d = 0; d <= H; ++d) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) acc[d][e] = ((d == 0 && r == 2 * q + e) ? 1.0 : 0.0) - acc[d][e];   // E
+  }
+  if (order == 2) {
+#pragma unroll
+    for (int d = 0; d <= H; ++d) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) az[d][e] = fma(0.5, acc[d][e], (d == 0 && r == 2 * q + e) ? 1.0 : 0.0);
+    }
+  } else {
+    store_circ<NB>(acc, Tp, w, lf);   // E
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d <= H; ++d) az[d][0] = az[d][1] = 0.0;
+    symm_gemm<NB>(az, Tp, Tp, w, lf);   // E^2
+    if (order == 4) store_circ<NB>(az, Mp, w, lf);   // M is dead (nobody reads Mp between the last barrier and here)
+#pragma unroll
+    for (int d = 0; d <= H; ++d) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        az[d][e] = fma(0.375, az[d][e], fma(0.5, acc[d][e], (d == 0 && r == 2 * q + e) ? 1.0 : 0.0));
+    }
+    __syncthreads();   // E^2 visible; (order 3: all reads of E done)
+    if (order == 4) {
+#pragma unroll
+      for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
+      symm_gemm<NB>(acc, Mp, Tp, w, lf);   // E^3
+#pragma unroll
+      for (int d = 0; d <= H; ++d) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) az[d][e] = fma(0.3125, acc[d][e], az[d][e]);
+      }
+      __syncthreads();   // all reads of E done
+    }
+  }
+  if (!have_z) {   // Z = T (A/s was already close to the identity)
+    store_circ<NB>(az, Zp, w, lf);
+    __syncthreads();
+  } else {
+    store_circ<NB>(az, Tp, w, lf);
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d <= H; ++d) az[d][0] = az[d][1] = 0.0;
+    symm_gemm<NB>(az, Tp, Zp, w, lf);   // Z' = T Z
+    __syncthreads();
+    store_circ<NB>(az, Zp, w, lf);
+    __syncthreads();
+  }
+  return ok ? it : -it;
 }
 
 }  // namespace letkf

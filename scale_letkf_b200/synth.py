@@ -255,3 +255,194 @@ def config_c3(nlon=256, nlat=256, nlev=60, member=100, max_nobs=500, **kw):
     for key, v in kw.items():
         setattr(c, key, v)
     return resolve_config(c)
+
+
+# ----------------------------------------------------------------------------- correlated ensemble + H(x)
+class SmoothEnsemble:
+    """Background ensemble and observation operator of the benchmark workloads ("gues3d =
+    smooth random fields + member noise; H(x) = linear interpolation of the synthetic members to the obs
+    location, so that ensval is consistent with gues3d").
+
+    Every draw d (members 0..k-1, deterministic run k, truth k+1) of variable n is a FUNCTION of the global grid
+    index, so any rank can evaluate any grid value without communication and 1/2/4/8 GPUs analyse the same
+    problem:
+        x_d(ri, rj, lev) = base_n + sigma_n [ rho S_d(ri, rj, z) + sqrt(1 - rho^2) W_d(ri, rj, lev) ]
+    S_d = sum_j (alpha_dj cos th_j + beta_dj sin th_j) / sqrt(J), th_j = kx_j ri + ky_j rj + kz_j z with Gaussian
+    wave numbers: a Gaussian random field of unit variance, horizontal correlation length `hlen` grid cells,
+    vertical `vlen` metres (the localisation scales).  W_d is white noise from an integer hash of
+    (ri, rj, lev, d, n).  Observations are y = H(x_truth) + err N(0,1), H = tri-linear interpolation of the
+    gridded draws (letkf_obs.f90:474-490 semantics: ensval = H(x_m) - mean, val = y - mean, DET row =
+    y - H(x_det)).  Local observations of one storm/sounding are therefore strongly correlated and
+    lambda_max(Yr^T Y) / c0 reaches 10^2-10^4, unlike i.i.d. rows.  torch is used as the array library (CPU or CUDA)."""
+
+    VAR_OF_ELM = {2819: 0, 2820: 1, 3073: 3, 3330: 5}   # U, V, T, Q -> iv3d - 1
+
+    def __init__(self, cfg, seed_no=4, rho=0.9, hlen=None, vlen=3000.0, nmodes=None, topo_amp=0.0, device=None):
+        import torch
+        self.torch, self.cfg, self.dev = torch, cfg, device
+        k = cfg.MEMBER
+        self.k, self.ndraw, self.rho, self.topo_amp = k, k + 2, float(rho), float(topo_amp)
+        J = nmodes or max(32, (k + 2) // 2 + 8)
+        g = rng(seed_no, 13)
+        hlen = hlen or cfg.HORI_LOCAL[0] / cfg.DX
+        self.kx = torch.as_tensor(g.normal(0.0, 1.0 / hlen, J), device=device)
+        self.ky = torch.as_tensor(g.normal(0.0, 1.0 / hlen, J), device=device)
+        self.kz = torch.as_tensor(g.normal(0.0, 1.0 / vlen, J), device=device)
+        self.coef = torch.as_tensor(g.standard_normal((cfg.nv3d, 2 * J, self.ndraw)) / np.sqrt(J), device=device)
+        self.zlev = torch.as_tensor(z_levels(cfg.nlev), device=device)
+        self.decay = torch.as_tensor(np.linspace(1.0, 0.0, cfg.nlev), device=device)
+        self.sigma = [float(_VAR_SCALE[n % 11]) for n in range(cfg.nv3d)]
+        self.mu = [float(_VAR_MEAN[n % 11]) for n in range(cfg.nv3d)]
+
+    # -- pieces -------------------------------------------------------------------------------
+    def hgt(self, ri, rj, lev):
+        """model-level height at (integer) grid coordinates, same formula as make_grid"""
+        t = self.torch
+        c = self.cfg
+        topo = self.topo_amp * (0.5 + 0.5 * t.sin(2 * np.pi * (ri - c.IHALO) / c.nlon) * t.cos(2 * np.pi * (rj - c.JHALO) / c.nlat))
+        return self.zlev[lev] + topo * self.decay[lev]
+
+    def _white(self, ri, rj, lev, n, draws):
+        """N(0,1) white noise, (npts, ndraws), from an integer hash of (ri, rj, lev, draw, variable)"""
+        t = self.torch
+        base = ((lev.to(t.int64) * 2097169 + rj.to(t.int64)) * 4194319 + ri.to(t.int64))[:, None]
+        x = base + (draws.to(t.int64)[None, :] + 4099 * n) * 1048583 * 8388617
+
+        def mix(v):
+            v = (v ^ (v >> 30)) * -4658895280553007687     # splitmix64 constants as signed int64
+            v = (v ^ (v >> 27)) * -7723592293110705685
+            return v ^ (v >> 31)
+
+        def unif(v):
+            return ((v >> 11) & ((1 << 53) - 1)).to(t.float64) * (2.0 ** -53) + 2.0 ** -54
+
+        u1 = unif(mix(x))
+        u2 = unif(mix(x + 0x632BE59BD9B4E019))
+        return t.sqrt(-2.0 * t.log(u1)) * t.cos(2.0 * np.pi * u2)
+
+    def base(self, n, ri, rj, z):
+        t = self.torch
+        if n + 1 == self.cfg.iv3d_p:
+            return 1.0e5 * t.exp(-z / 7500.0) + 50.0 * t.sin(0.03 * ri)
+        return self.mu[n] + self.sigma[n] * t.sin(0.07 * ri) * t.cos(0.05 * rj) + 0.0 * z
+
+    def values(self, n, ri, rj, lev, draws=None, chunk=1 << 18):
+        """x_d of variable n (0-based) at integer grid coordinates ri, rj (rig1-style, halo offset included) and
+        level indices lev (all 1-D, same length) -> (npts, ndraws)"""
+        t = self.torch
+        draws = t.arange(self.ndraw, device=self.dev) if draws is None else draws
+        out = t.empty((ri.numel(), draws.numel()), dtype=t.float64, device=self.dev)
+        cf = self.coef[n][:, draws]
+        for s in range(0, ri.numel(), chunk):
+            a, b, l = ri[s:s + chunk].to(t.float64), rj[s:s + chunk].to(t.float64), lev[s:s + chunk]
+            z = self.hgt(a, b, l)
+            th = a[:, None] * self.kx[None, :] + b[:, None] * self.ky[None, :] + z[:, None] * self.kz[None, :]
+            sm = t.cat([t.cos(th), t.sin(th)], dim=1) @ cf
+            w = self._white(a, b, l, n, draws)
+            out[s:s + chunk] = self.base(n, a, b, z)[:, None] + self.sigma[n] * (
+                self.rho * sm + np.sqrt(1.0 - self.rho ** 2) * w)
+        return out
+
+    # -- state -----------------------------------------------------------------------------------
+    def state(self, rig1, rjg1, as_numpy=False):
+        """gues3d of the columns (rig1, rjg1): torch (nv3d, nens, nlev, nij1) [the memory order of the Fortran
+        (nij1, nlev, nens, nv3d)] or, as_numpy, that Fortran-ordered numpy array.  Slot k = member mean summed in
+        member order like ensmean_grd, slot k+1 = deterministic run when DET_RUN."""
+        t = self.torch
+        c = self.cfg
+        k, nlev, nij1 = self.k, c.nlev, len(rig1)
+        nens = k + 2 if c.DET_RUN else k + 1
+        ri = t.as_tensor(np.asarray(rig1), device=self.dev).repeat(nlev)
+        rj = t.as_tensor(np.asarray(rjg1), device=self.dev).repeat(nlev)
+        lev = t.arange(nlev, device=self.dev).repeat_interleave(nij1)
+        draws = t.arange(k + 1 if c.DET_RUN else k, device=self.dev)
+        gues = t.empty((c.nv3d, nens, nlev, nij1), dtype=t.float64, device=self.dev)
+        for n in range(c.nv3d):
+            v = self.values(n, ri, rj, lev, draws)            # (nlev*nij1, ndraws)
+            gues[n, :k] = v[:, :k].T.reshape(k, nlev, nij1)
+            if c.DET_RUN:
+                gues[n, k + 1] = v[:, k].reshape(nlev, nij1)
+            m = gues[n, 0].clone()
+            for mm in range(1, k):
+                m += gues[n, mm]
+            gues[n, k] = m / k
+        if as_numpy:
+            return np.asfortranarray(gues.cpu().numpy().T)
+        return gues
+
+    # -- observation operator ---------------------------------------------------------------------
+    def _interp(self, n, ri, rj, rk, draws):
+        """tri-linear interpolation of variable n at real coordinates (ri, rj) and fractional level rk"""
+        t = self.torch
+        i0, j0 = t.floor(ri), t.floor(rj)
+        k0 = t.clamp(t.floor(rk), 0, self.cfg.nlev - 2) if self.cfg.nlev > 1 else t.zeros_like(rk)
+        fi, fj, fk = ri - i0, rj - j0, t.clamp(rk - k0, 0.0, 1.0)
+        out = None
+        for di in (0, 1):
+            for dj in (0, 1):
+                for dk in ((0, 1) if self.cfg.nlev > 1 else (0,)):
+                    wgt = (fi if di else 1 - fi) * (fj if dj else 1 - fj) * ((fk if dk else 1 - fk) if self.cfg.nlev > 1 else 1.0)
+                    v = self.values(n, i0 + di, j0 + dj, (k0 + dk).to(t.int64), draws) * wgt[:, None]
+                    out = v if out is None else out + v
+        return out
+
+    def hx(self, elm, ri, rj, lev, radar_xyz=None):
+        """H(x_d) for all draws: (nobs, ndraw).  lev = pressure (Pa) for conventional obs, height (m) for radar."""
+        t = self.torch
+        c = self.cfg
+        elm = np.asarray(elm)
+        ri_t = t.as_tensor(np.asarray(ri, dtype=np.float64), device=self.dev)
+        rj_t = t.as_tensor(np.asarray(rj, dtype=np.float64), device=self.dev)
+        lev_t = t.as_tensor(np.asarray(lev, dtype=np.float64), device=self.dev)
+        draws = t.arange(self.ndraw, device=self.dev)
+        radar = np.isin(elm, (capi.ID_RADAR_REF, capi.ID_RADAR_REF_ZERO, capi.ID_RADAR_VR))
+        zobs = t.where(t.as_tensor(radar, device=self.dev), lev_t, -7500.0 * t.log(t.clamp(lev_t, min=1.0) / 1.0e5))
+        idx = t.arange(c.nlev, dtype=t.float64, device=self.dev)
+        # fractional level index from the flat level heights (piecewise linear inverse)
+        pos = t.clamp(t.searchsorted(self.zlev, zobs.contiguous()), 1, max(c.nlev - 1, 1))
+        z0, z1 = self.zlev[pos - 1], self.zlev[t.clamp(pos, max=c.nlev - 1)]
+        rk = idx[pos - 1] + t.clamp((zobs - z0) / t.clamp(z1 - z0, min=1e-9), 0.0, 1.0)
+        out = t.empty((len(elm), self.ndraw), dtype=t.float64, device=self.dev)
+        cx, cy = radar_xyz if radar_xyz is not None else (c.nlon * 0.5 + c.IHALO + 0.5, c.nlat * 0.5 + c.JHALO + 0.5)
+        for e in np.unique(elm):
+            sel = t.as_tensor(np.nonzero(elm == e)[0], device=self.dev)
+            a, b, r = ri_t[sel], rj_t[sel], rk[sel]
+            if int(e) in self.VAR_OF_ELM:
+                v = self._interp(self.VAR_OF_ELM[int(e)], a, b, r, draws)
+            elif e == capi.ID_PS:
+                v = self._interp(c.iv3d_p - 1, a, b, t.zeros_like(r), draws)
+            elif e in (capi.ID_RADAR_REF, capi.ID_RADAR_REF_ZERO):   # linearised reflectivity (dBZ) of rain + snow + graupel
+                v = 25.0 + 4.0e4 * (self._interp(7, a, b, r, draws) + self._interp(9, a, b, r, draws)
+                                    + self._interp(10, a, b, r, draws) - 3.0e-4)
+            elif e == capi.ID_RADAR_VR:   # radial velocity seen from a radar at the domain centre, z = 0
+                dx, dy, dz = (a - cx) * c.DX, (b - cy) * c.DY, zobs[sel]
+                dist = t.sqrt(dx * dx + dy * dy + dz * dz).clamp(min=1.0)
+                v = (self._interp(0, a, b, r, draws) * (dx / dist)[:, None] + self._interp(1, a, b, r, draws) * (dy / dist)[:, None]
+                     + self._interp(2, a, b, r, draws) * (dz / dist)[:, None])
+            else:
+                raise ValueError(f"SmoothEnsemble.hx: element {e} not supported")
+            out[sel] = v
+        return out
+
+    def attach(self, obs, seed_no=5):
+        """replace the i.i.d. ensval / val / dat of an obs dict (make_sonde_obs / make_radar_obs positions) by
+        H(x)-consistent ones"""
+        t = self.torch
+        k, det = self.k, bool(self.cfg.DET_RUN)
+        h = self.hx(obs["elm"], obs["ri"], obs["rj"], obs["lev"])
+        g = rng(seed_no, 17)
+        err = t.as_tensor(np.asarray(obs["err"]), device=self.dev)
+        y = h[:, k + 1] + err * t.as_tensor(g.standard_normal(len(err)), device=self.dev)
+        mean = h[:, 0].clone()
+        for m in range(1, k):
+            mean += h[:, m]
+        mean /= k
+        ens = t.empty((len(err), k + 1 if det else k), dtype=t.float64, device=self.dev)
+        ens[:, :k] = h[:, :k] - mean[:, None]
+        if det:
+            ens[:, k] = y - h[:, k]
+        out = dict(obs)
+        out["ensval"] = np.ascontiguousarray(ens.cpu().numpy())
+        out["val"] = (y - mean).cpu().numpy()
+        out["dat"] = y.cpu().numpy()
+        return out

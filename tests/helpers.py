@@ -47,3 +47,46 @@ def sample_points(cfg, rig1, rjg1, hgt1, gues, stride=7):
             ri.append(rig1[ij]); rj.append(rjg1[ij])
             rlev.append(gues[ij, il, k, cfg.iv3d_p - 1]); rz.append(hgt1[ij, il])
     return tuple(np.array(x) for x in (ri, rj, rlev, rz))
+
+
+def truth_invsqrt(A):
+    """A^-1/2 of a symmetric positive definite matrix to long-double accuracy: double eigh, then Newton
+    corrections with the Sylvester equation solved in the (double) eigenbasis, all products in 80-bit."""
+    ld = np.longdouble
+    Al = A.astype(ld)
+    lam, V = np.linalg.eigh(A.astype(np.float64))
+    Vl, s = V.astype(ld), np.sqrt(lam.astype(ld))
+    Z = (Vl / s) @ Vl.T
+    I = np.eye(A.shape[0], dtype=ld)
+    for _ in range(4):
+        R = I - Z @ Al @ Z
+        Z = Z + Vl @ ((Vl.T @ R @ Vl) / (s[:, None] + s[None, :])) @ Vl.T
+        Z = (Z + Z.T) / 2
+    return Z
+
+
+def truth_analysis_point(cfg, y, rd, dep, dx, xm, infl=1.0):
+    """Long-double LETKF analysis of one grid point without relaxation or with RTPS (cfg.RELAX_ALPHA_SPREAD):
+    y (p, k) local obs-space perturbations, rd (p) rdiag, dep (p), dx (k, nv) state perturbations, xm (nv) mean.
+    Returns xa (k, nv) and the RTPS factors (nv).  (common_letkf.f90:111-226, letkf_tools.f90:457-486, 1971-2002)"""
+    ld = np.longdouble
+    k = y.shape[1]
+    yl, w = y.astype(ld), 1.0 / rd.astype(ld)
+    A = yl.T @ (yl * w[:, None]) + (ld(k - 1) / ld(infl)) * np.eye(k, dtype=ld)
+    Z = truth_invsqrt(A)
+    pa = Z @ Z
+    W = np.sqrt(ld(k - 1)) * Z
+    wm = pa @ (yl.T @ (dep.astype(ld) * w))
+    xa = np.empty(dx.shape, dtype=ld)
+    fac = np.ones(dx.shape[1], dtype=ld)
+    for n in range(dx.shape[1]):
+        d = dx[:, n].astype(ld)
+        f = ld(1)
+        if cfg.RELAX_ALPHA_SPREAD != 0.0:
+            vg, va = d @ d, d @ pa @ d
+            if vg > 0 and va > 0:
+                a = ld(cfg.RELAX_ALPHA_SPREAD)
+                f = a * np.sqrt(vg / (va * (k - 1))) - a + 1
+        fac[n] = f
+        xa[:, n] = ld(xm[n]) + d @ (W * f + wm[:, None])
+    return xa, fac
