@@ -24,17 +24,23 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: a variant build (e.g. out="libletkf_b200_x.so", defines=["LETKF_VARIANT_X"]) selected at run
+    time with LETKF_B200_LIB, for A/B measurements; the default build is the product."""
+    if out is None and not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    out = out or OUT
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a wrapper without libgomp specs; nvcc only needs a host g++
     subprocess.check_call(cmd, env=env)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=os.path.join(HERE, outs[0]) if outs else None,
+                defines=defs))

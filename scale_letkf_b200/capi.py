@@ -164,7 +164,8 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    # LETKF_B200_LIB: another build of the same library (A/B measurements of kernel variants)
+    p = path or os.environ.get("LETKF_B200_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} not found: the CUDA extension is not built and there is no CPU fallback. "

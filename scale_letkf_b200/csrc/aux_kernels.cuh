@@ -102,6 +102,11 @@ __global__ void fill_kernel(double *__restrict__ p, size_t n, double v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+// work3d = max(work3d, INFL_MUL_MIN) over the whole field (letkf_tools.f90:264-267)
+__global__ void clamp_min_kernel(double *__restrict__ p, size_t n, double lo) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = fmax(p[i], lo);
+}
+
 // ---- ensmean_grd ----------------------------------------------------------------------------
 // slot mem+1 = (x_1 + x_2 + ... + x_mem) / mem, summed in member order like the reference.
 __global__ void ensmean_kernel(int mem, int nens, size_t sl, int nvar, double *__restrict__ v) {

@@ -71,6 +71,7 @@ struct DasParams {
   unsigned long long *redo_count;
   const long long *point_list;
   const unsigned long long *point_count;
+  long long *trace;   // LETKF_EXP_TRACE builds only: (tag, clock64) pairs of CTA 0 / thread 0
 };
 
 __host__ __device__ inline size_t das_smem_bytes(int k, int nthreads) {

@@ -29,6 +29,7 @@ __host__ __device__ inline size_t das_ns_smem_bytes() {
   return d * sizeof(double) + (PRE ? 0 : sizeof(SearchSmem)) + 64;
 }
 
+// cp.async (LDGSTS) helpers of the tiled large-ensemble GEMM (tiled.cuh)
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
@@ -39,12 +40,62 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
+// ---- mbarrier + bulk-copy (TMA) primitives of the Gram staging pipeline ---------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// one contiguous row, global -> shared, completion (bytes) signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // PRE = true: every local list comes from presearch_kernel's pool; the kernel contains no search code at
 // all (fewer live registers, no SearchSmem).  A point whose list did not fit the pool is appended to
 // P.redo_list untouched and analysed afterwards by the PRE = false instantiation (P.point_list mode).
+#ifdef LETKF_EXP_TRACE
+#define LETKF_TRACE(tag)                                                              \
+  do {                                                                                \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && P.trace && s_ntrace < 4000) {          \
+      P.trace[2 * s_ntrace] = (tag);                                                  \
+      P.trace[2 * s_ntrace + 1] = clock64();                                          \
+      ++s_ntrace;                                                                     \
+    }                                                                                 \
+  } while (0)
+#else
+#define LETKF_TRACE(tag) do { } while (0)
+#endif
+
 template <int NB, bool PRE>
 __global__ void __launch_bounds__(NsCfg<NB>::NT, NsCfg<NB>::MINB)
 das_ns_kernel(const DasParams P) {
+#ifdef LETKF_EXP_TRACE
+  __shared__ int s_ntrace;
+  if (threadIdx.x == 0) s_ntrace = 0;
+#endif
   using C = NsCfg<NB>;
   constexpr int KP = C::KP, LD = C::LD, H = C::H, CR = C::CR, PSZ = C::PSZ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -62,10 +113,20 @@ das_ns_kernel(const DasParams P) {
   double *colsc = wv + 3 * CR;                  // [8][kMaxNV]
   double *red = colsc + 8 * kMaxNV;
   SearchSmem &S = *reinterpret_cast<SearchSmem *>((reinterpret_cast<uintptr_t>(red + 40) + 15) & ~(uintptr_t)15);
-  __shared__ long long s_work;
+  __shared__ long long s_work, s_next;
   __shared__ long long s_ploff[kMaxNV];
   __shared__ int s_pln[kMaxNV];
+  __shared__ __align__(8) unsigned long long s_full[3];   // mbarriers of the three Gram staging buffers
+  __shared__ int s_cnt[3];
   const LaneFrag lf = lane_frag(lane);
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&s_full[i], 1);   // one arrival (the requesting warp) + the bytes of the chunk's rows
+      s_cnt[i] = 0;               // warps that have consumed the chunk in buffer i
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned gchunk = 0;   // chunks staged so far by this CTA: buffer = gchunk % 3, mbarrier phase = (gchunk / 3) & 1
 
   LocalList L;
   L.cap = P.lcap;
@@ -77,28 +138,44 @@ das_ns_kernel(const DasParams P) {
   L.cpk = P.l_cpk + (size_t)blockIdx.x * P.ccap;
 
   const size_t sl = (size_t)P.nij1 * P.nlev;
-  unsigned long long c_points = 0, c_solved = 0, c_fail = 0, c_nobs = 0, c_over = 0, c_iters = 0;
-  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long tph = clock64();
+  // Statistics and phase clocks live in shared memory and are kept by thread 0 only: as per-thread registers they
+  // cost 30 registers that the software-pipelined tensor-core loops need (the kernel runs at 72 registers, 4 CTAs/SM).
+  __shared__ unsigned long long s_stat[6];   // points, solved, fail, nobs, overflow, solver iterations
+  __shared__ long long s_ph[9];              // [0..7] phase clocks, [8] time stamp of the last phase change
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i) s_stat[i] = 0;
+    for (int i = 0; i < 8; ++i) s_ph[i] = 0;
+    s_ph[8] = clock64();
+  }
   auto phase = [&](int i) {
-    const long long now = clock64();
-    ph[i] += now - tph;
-    tph = now;
+    if (tid == 0) {
+      const long long now = clock64();
+      s_ph[i] += now - s_ph[8];
+      s_ph[8] = now;
+    }
+  };
+  auto stat = [&](int i, unsigned long long v) {
+    if (tid == 0) s_stat[i] += v;
   };
   double *xm = colsc, *xdet = colsc + kMaxNV, *varg = colsc + 2 * kMaxNV, *vara = colsc + 3 * kMaxNV;
   double *ssum = colsc + 4 * kMaxNV, *sdsum = colsc + 5 * kMaxNV, *inflv = colsc + 6 * kMaxNV;
   double *parmv = colsc + 7 * kMaxNV;
   double *bvec = Xall + (size_t)(kMaxNV - 2) * LD, *bdvec = Xall + (size_t)(kMaxNV - 1) * LD;
 
+  // The work counter is fetched one point ahead (thread 0): the atomic's round trip overlaps the previous point.
+  unsigned long long nx_raw = 0;
+  if (tid == 0) nx_raw = atomicAdd(&P.counters[0], 1ull);
   for (;;) {
+    fence_proxy_async();   // generic-proxy writes to the staging buffers (matrices, Ts) before the next bulk copies
     __syncthreads();
     if (tid == 0) {
       long long v;
+      const long long i = (long long)nx_raw;
+      nx_raw = atomicAdd(&P.counters[0], 1ull);   // consumed at the top of the next iteration
       if (!PRE && P.point_list) {   // redo mode: explicit list of points, its length produced on the device
-        const long long i = (long long)atomicAdd(&P.counters[0], 1ull);
         v = (i < (long long)*P.point_count) ? P.point_list[i] : -2;
       } else {
-        v = P.point_begin + (long long)atomicAdd(&P.counters[0], 1ull);
+        v = P.point_begin + i;
         if (v >= P.point_end) v = -2;
         if (PRE && v >= 0) {   // all lists of the point must be in the pool
           bool ok = true;
@@ -118,11 +195,12 @@ das_ns_kernel(const DasParams P) {
     }
     __syncthreads();
     const long long wp = s_work;
+    LETKF_TRACE(1);
     if (wp == -2) break;      // no more work
     if (wp < 0) continue;     // handed to the redo pass
     phase(7);
     const int il = (int)(wp / P.nij1), ij = (int)(wp - (long long)il * P.nij1);
-    ++c_points;
+    stat(0, 1);
     const int nvtot = P.nv3d + (il == 0 ? P.nv2d : 0);
     const size_t pbase = (size_t)ij + (size_t)il * P.nij1;
 
@@ -136,6 +214,75 @@ das_ns_kernel(const DasParams P) {
           fmin(fmin(ri - P.IHALO, P.nlon + P.IHALO + 1 - ri) * P.DX,
                fmin(rj - P.JHALO, P.nlat + P.JHALO + 1 - rj) * P.DY) / P.BOUNDARY_BUFFER_WIDTH;
       if (dist_bdy < 1.0) beta = fmax(dist_bdy, 0.0);
+    }
+
+    // ---- Gram staging machinery of the point (used by every variable-localisation group) -------------------
+    int p_use = 0, nchunks = 0;   // local observations / staging chunks of the current group
+    double p3acc = 0.0;
+    constexpr int RPL = (CR + 31) / 32;   // rows per lane of a request
+    int cur_iob[RPL], nxt_iob[RPL];
+    double cur_rd[RPL], nxt_rd[RPL];
+    auto fetch_idx = [&](int c, int (&o_iob)[RPL], double (&o_rd)[RPL]) {
+      const int o0 = c * CR, nrows = (c < nchunks) ? min(CR, p_use - o0) : 0;
+#pragma unroll
+      for (int u = 0; u < RPL; ++u) {
+        const int row = lane + 32 * u;
+        o_iob[u] = -1;
+        o_rd[u] = 1.0;
+        if (row < nrows) {
+          o_iob[u] = L.iob[o0 + row];
+          o_rd[u] = L.rdiag[o0 + row];
+        }
+      }
+    };
+    auto request = [&](int c, const int (&iobs)[RPL], const double (&rds)[RPL]) {   // one warp, all lanes
+      const unsigned g = gchunk + (unsigned)c, st = g % 3u;
+      double *dst = stage + (size_t)st * CR * LD;
+      double *wdst = wv + st * CR;
+      const int o0 = c * CR, nrows = min(CR, p_use - o0), nrows4 = (nrows + 3) & ~3;
+      unsigned mine = 0;
+#pragma unroll
+      for (int u = 0; u < RPL; ++u) {
+        const int row = lane + 32 * u;
+        if (row < nrows) {
+          wdst[row] = 1.0 / rds[u];
+          if (P.INFL_MUL_ADAPTIVE) p3acc += L.rloc[o0 + row];
+        } else if (row < nrows4) {   // padding row of the last chunk: weight 0 and finite data
+          wdst[row] = 0.0;
+          for (int j = 0; j < KP; ++j) dst[(size_t)row * LD + j] = 0.0;
+        }
+        mine += __popc(__ballot_sync(LETKF_FULL_MASK, row < nrows));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(&s_full[st], mine * (unsigned)(KP * sizeof(double)));
+#pragma unroll
+      for (int u = 0; u < RPL; ++u) {
+        const int row = lane + 32 * u;
+        if (row < nrows)
+          bulk_g2s(dst + (size_t)row * LD, P.ensval + (size_t)iobs[u] * P.ldens, (unsigned)(KP * sizeof(double)), &s_full[st]);
+      }
+    };
+    auto gram_prologue = [&]() {   // chunks 0, 1, 2 are requested by warps 0, 1, 2
+      if (w < 3 && w < nchunks) {
+        fetch_idx(w, cur_iob, cur_rd);
+        request(w, cur_iob, cur_rd);
+      }
+      fetch_idx(3, nxt_iob, nxt_rd);
+    };
+    // With pre-searched lists the first group's observation rows are requested right away: their flight overlaps the
+    // member loads below.  (presearch_kernel stores an empty list for a group the solver skips: no stray request.)
+    bool pro_done = false;
+    if constexpr (PRE) {
+      const long long pl_off = s_ploff[0];
+      L.iob = P.pl_iob + pl_off;
+      L.rdiag = P.pl_rdiag + pl_off;
+      L.rloc = P.pl_rloc + pl_off;
+      p_use = max(s_pln[0], 0);
+      nchunks = (p_use + CR - 1) / CR;
+      if (p_use > 0) {
+        gram_prologue();
+        pro_done = true;
+      }
     }
 
     // ---- load members, form perturbations (letkf_tools.f90:209-230), destroy gues ----------
@@ -177,6 +324,7 @@ das_ns_kernel(const DasParams P) {
     }
     __syncthreads();
     phase(0);
+    LETKF_TRACE(2);
     auto store_anal = [&](int vv, int m, double v) {
       double *dst = (vv < P.nv3d) ? P.anal3d : P.anal2d;
       dst[gaddr(vv, m)] = v;
@@ -199,8 +347,7 @@ das_ns_kernel(const DasParams P) {
     bool solved_any = false;
 
     for (int vg = 0; vg < P.nvgroup; ++vg) {
-      int cols[kMaxNV];
-      int nc = 0;
+      unsigned colmask = 0;   // bit vv: variable vv belongs to this group and is analysed
       for (int vv = 0; vv < nvtot; ++vv) {
         if (P.vgroup[vv] != vg) continue;
         const bool masked = (vv < P.nv3d) && pmean < P.Q_UPDATE_TOP && (vv + 1) >= P.iv3d_q &&
@@ -210,11 +357,12 @@ das_ns_kernel(const DasParams P) {
           if (P.det && tid == 0) store_anal(vv, k + 1, xdet[vv]);
           if (P.infl3d && tid == 0 && vv < P.nv3d) P.infl3d[pbase + (size_t)vv * sl] = inflv[vv];
         } else {
-          cols[nc++] = vv;
+          colmask |= 1u << vv;
         }
       }
-      if (nc == 0) continue;
-      const int vtrig = cols[0];
+      if (colmask == 0) continue;
+      const int nc = __popc(colmask);
+      const int vtrig = __ffs(colmask) - 1;
       const double infl = inflv[vtrig];   // parm_infl handed to letkf_core (work3d(ij,ilev,n))
 
       // ---- local observations: pre-searched list (presearch_kernel) or in-kernel search ----------
@@ -229,11 +377,16 @@ das_ns_kernel(const DasParams P) {
       } else {
         nobsl = search_point(*P.T, P.rec, P.bstart, P.vlfac + (size_t)vg * P.T->nctype, pt, L, S);
       }
-      if (nobsl < 0) ++c_over;
-      const int p_use = nobsl < 0 ? 0 : nobsl;
+      if (nobsl < 0) stat(4, 1);
+      if (!pro_done) {
+        p_use = nobsl < 0 ? 0 : nobsl;
+        nchunks = (p_use + CR - 1) / CR;
+        p3acc = 0.0;
+      }
       phase(1);
+      LETKF_TRACE(3);
       if (P.nobsl_out && vg == 0 && tid == 0) P.nobsl_out[pbase] = p_use;
-      c_nobs += (unsigned long long)p_use;
+      stat(3, (unsigned long long)p_use);
       bool fail = false;
       double wscale = sqrt(infl);   // (W dx)_m = wscale * Ts[c][m];  p == 0: W = sqrt(infl) I
       double pscale = infl / (double)(k - 1);   // x^T Pa y = pscale * (t_x . t_y)
@@ -241,76 +394,51 @@ das_ns_kernel(const DasParams P) {
       if (p_use > 0) {
         solved_any = true;
         // ---- Gram [A | b | bd] = Yr^T [Y | dep | depd] (common_letkf.f90:111-128,182-195) on the
-        // tensor cores: raw obs rows [y_1..y_k, dep, depd, 0..] stream in with cp.async, the
+        // tensor cores: raw obs rows [y_1..y_k, dep, depd, 0..] stream in by TMA bulk copies, the
         // R^-1 weight is applied to the A operand.
         double acc[H + 1][2];
 #pragma unroll
         for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
-        double p3acc = 0.0;
-        const int nchunks = (p_use + CR - 1) / CR;
         static_assert(CR <= 4 * NB, "a warp stages at most four rows of a chunk");
-        // One warp per obs row (a row is KP/2 16-byte pieces), rows w, w + NB, w + 2 NB, w + 3 NB of a chunk.
-        // Chunks are requested strictly in order, and the sorted-obs indices of the NEXT chunk are fetched
-        // while the current one is requested, so that a request only pays the row latency, not index + row.
-        // The same holds for the R^-1 weights: the thread that owns row `tid` of a chunk loads rdiag one chunk
-        // ahead, otherwise its warp would sit out an L2 round trip inside every request while the other
-        // warps wait for it at the chunk barrier.
-        int nxt[4];
-        double rd_nxt = 0.0, rl_nxt = 0.0;
-        auto fetch_idx = [&](int c) {
-          const int o0 = c * CR, nrows = min(CR, p_use - o0);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) nxt[u] = (w + u * NB < nrows) ? L.iob[o0 + w + u * NB] : -1;
-          if (tid < nrows) {
-            rd_nxt = L.rdiag[o0 + tid];
-            if (P.INFL_MUL_ADAPTIVE) rl_nxt = L.rloc[o0 + tid];
-          }
-        };
-        fetch_idx(0);
-        auto issue = [&](int c) {
-          double *dst = stage + (size_t)(c % 3) * CR * LD;
-          double *wdst = wv + (c % 3) * CR;
-          const int o0 = c * CR;
-          const int nrows = min(CR, p_use - o0), nrows4 = (nrows + 3) & ~3;
-          const double rd_cur = rd_nxt, rl_cur = rl_nxt;
-          {
-            int iobs[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) iobs[u] = nxt[u];
-            fetch_idx(c + 1);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (iobs[u] < 0) continue;
-              const double *src = P.ensval + (size_t)iobs[u] * P.ldens;
-              double *drow = dst + (size_t)(w + u * NB) * LD;
-              for (int pc = lane; pc < KP / 2; pc += 32) cp_async16(drow + 2 * pc, src + 2 * pc);
-            }
-          }
-          for (int idx = tid; idx < (nrows4 - nrows) * KP; idx += blockDim.x)
-            dst[(size_t)(nrows + idx / KP) * LD + idx % KP] = 0.0;
-          if (tid < nrows4) {
-            double wt = 0.0;
-            if (tid < nrows) {
-              wt = 1.0 / rd_cur;
-              if (P.INFL_MUL_ADAPTIVE) p3acc += rl_cur;
-            }
-            wdst[tid] = wt;
-          }
-          cp_async_commit();
-        };
-        // three staging buffers (Y, Z and T are all free while the Gram accumulates in registers): chunk c+2 is
-        // requested while chunk c is consumed, and ONE barrier per chunk both publishes chunk c and retires
-        // the buffer of chunk c-1 that the next request overwrites
-        issue(0);
-        if (nchunks > 1) issue(1);
+        // Staging pipeline: three chunk buffers of CR obs rows (Y, Z and T are all free while the Gram accumulates in
+        // registers).  A chunk is requested by ONE warp: lane l stages row l (+32): one cp.async.bulk (TMA bulk copy, 8 KP
+        // bytes) per row lands on the chunk's `full` mbarrier together with the R^-1 weights.  "Last consumer refills":
+        // a warp that has consumed chunk c bumps a shared counter, and the warp that finds it was the last one requests
+        // chunk c + 3 into the same buffer -- nobody ever waits for a buffer to be released, and there is no CTA-wide
+        // barrier inside the loop.  Every warp keeps the (sorted-obs index, rdiag) of the rows of the chunk it may have to
+        // request next in registers, loaded one chunk ahead, so a request pays the row latency only, not index + row.
+        if (!pro_done) gram_prologue();
+        pro_done = false;
         for (int c = 0; c < nchunks; ++c) {
-          if (c + 1 < nchunks) cp_async_wait<1>();
-          else cp_async_wait<0>();
-          __syncthreads();
-          if (c + 2 < nchunks) issue(c + 2);
+          const unsigned g = gchunk + (unsigned)c, st = g % 3u;
+          LETKF_TRACE(10);
+          mbar_wait(&s_full[st], (g / 3u) & 1u);
+          LETKF_TRACE(11);
           const int nrows = min(CR, p_use - c * CR);
-          gram_circ<NB, LD>(acc, stage + (size_t)(c % 3) * CR * LD, wv + (c % 3) * CR, (nrows + 3) & ~3, w, lane);
+          if (nrows == CR) gram_circ_full<NB, LD>(acc, stage + (size_t)st * CR * LD, wv + st * CR, w, lane);
+          else gram_circ<NB, LD>(acc, stage + (size_t)st * CR * LD, wv + st * CR, (nrows + 3) & ~3, w, lane);
+          LETKF_TRACE(12);
+          // done with chunk c: the indices of chunk c + 3 (requested below by the last warp) are here, those of
+          // chunk c + 4 are requested now
+#pragma unroll
+          for (int u = 0; u < RPL; ++u) {
+            cur_iob[u] = nxt_iob[u];
+            cur_rd[u] = nxt_rd[u];
+          }
+          fetch_idx(c + 4, nxt_iob, nxt_rd);
+          __syncwarp();
+          int last = 0;
+          if (lane == 0) {
+            __threadfence_block();
+            last = (atomicAdd(&s_cnt[st], 1) == NB - 1);
+            if (last) s_cnt[st] = 0;
+          }
+          last = __shfl_sync(LETKF_FULL_MASK, last, 0);
+          LETKF_TRACE(13);
+          if (last && c + 3 < nchunks) request(c + 3, cur_iob, cur_rd);
+          LETKF_TRACE(14);
         }
+        gchunk += (unsigned)nchunks;
         __syncthreads();   // the staging buffers (Y among them) are free again
         const double cdiag = (double)(k - 1) / infl;   // (common_letkf.f90:140-143)
         // ---- epilogue of the Gram in registers: ||G||_F, trace, b, bd (and the adaptive-inflation statistics) ----
@@ -388,15 +516,43 @@ das_ns_kernel(const DasParams P) {
           }
           store_circ<NB>(acc, Yp, w, lf);
         }
+        if (tid == 0) {   // the next point of this CTA (its work counter was drawn at the top of this iteration)
+          long long nv = -1;
+          if (PRE || !P.point_list) {
+            nv = P.point_begin + (long long)nx_raw;
+            if (nv >= P.point_end) nv = -1;
+          }
+          s_next = nv;
+        }
         phase(2);
+        LETKF_TRACE(4);
         // ---- Z = (A/s)^-1/2 --------------------------------------------------------------------------
         const int its = newton_schulz_invsqrt<NB>(acc, Yp, Zp, Tp, cdiag / s_norm, red, P.max_sweeps + 20);
         if (its < 0) fail = true;
-        c_iters += (unsigned long long)(its < 0 ? -its : its);
+        stat(5, (unsigned long long)(its < 0 ? -its : its));
         // mtx_eigen zeroes eigenvalues below lambda_max*sqrt(eps) (common_mtx.f90:69) and letkf_core
         // would then divide by zero; ||A||_F <= sqrt(k) lambda_max bounds the same condition.
         if (!(cdiag * (double)k >= s_norm * 1.4901161193847656e-08)) fail = true;
         phase(4);
+        LETKF_TRACE(5);
+        {   // L2 prefetch of the next point's members (and its list header): their DRAM + TLB latency overlaps the
+            // rest of this point instead of opening the next one (s_next was published before the solve's barriers)
+          const long long nv = s_next;
+          if (nv >= 0) {
+            const int nil = (int)(nv / P.nij1), nij = (int)(nv - (long long)nil * P.nij1);
+            const size_t nbase = (size_t)nij + (size_t)nil * P.nij1;
+            for (int idx = tid; idx < P.nv3d * (k + 1 + P.det); idx += C::NT) {
+              const int vv = idx / (k + 1 + P.det), m = idx - vv * (k + 1 + P.det);
+              const double *a = P.gues3d + nbase + ((size_t)m + (size_t)vv * nens) * sl;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
+            if (PRE && tid == 0) {
+              const long long e = (nv - P.pl_base) * P.nvgroup;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pl_off + e));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pl_n + e));
+            }
+          }
+        }
         // ---- Ts = Z [dX | b | bd]  (k x 16 skinny product on the tensor cores) --------------------
         {
           double a2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
@@ -431,111 +587,101 @@ das_ns_kernel(const DasParams P) {
         }
         __syncthreads();
       }
-      // ---- per-column scalars: var_g = x.x, var_a = x^T Pa x, s = x^T Pa b, sd = x^T Pa bd ----------
-      {
-        const int nw = blockDim.x >> 5;
-        const double *tb = Ts + (size_t)(kMaxNV - 2) * LD, *tbd = Ts + (size_t)(kMaxNV - 1) * LD;
-        for (int c = w; c < nc; c += nw) {
-          const int vv = cols[c];
-          const double *x = Xall + (size_t)vv * LD, *t = Ts + (size_t)vv * LD;
-          double vg_ = 0.0, va_ = 0.0, s_ = 0.0, sdv_ = 0.0;
-          for (int m = lane; m < k; m += 32) {
-            const double xv = x[m], tv = t[m];
-            vg_ = fma(xv, xv, vg_);
-            va_ = fma(tv, tv, va_);
-            s_ = fma(tv, tb[m], s_);
-            sdv_ = fma(tv, tbd[m], sdv_);
-          }
-          vg_ = warp_sum(vg_);
-          va_ = warp_sum(va_);
-          s_ = warp_sum(s_);
-          sdv_ = warp_sum(sdv_);
-          if (lane == 0) {
-            // RTPS factor of the column (letkf_tools.f90:1971-2002), once per variable instead of per member
-            const double va = va_ * pscale;
-            double f = 1.0;
-            if (P.RELAX_ALPHA == 0.0 && P.RELAX_ALPHA_SPREAD != 0.0 && vg_ > 0.0 && va > 0.0)
-              f = P.RELAX_ALPHA_SPREAD * sqrt(vg_ * parmv[vv] / (va * (double)(k - 1))) - P.RELAX_ALPHA_SPREAD + 1.0;
-            varg[c] = vg_;
-            vara[c] = f;
-            ssum[c] = s_ * pscale;
-            sdsum[c] = P.det ? sdv_ * pscale : 0.0;
-          }
-        }
-      }
-      __syncthreads();
-      if (fail) ++c_fail;
+      if (fail) stat(2, 1);
       phase(5);
-
-      // ---- relaxation + update (letkf_tools.f90:457-513); result staged in Ts -------------------
-      for (int idx = tid; idx < nc * k; idx += blockDim.x) {
-        const int c = idx / k, m = idx - c * k;
-        const int vv = cols[c];
-        const double x = Xall[(size_t)vv * LD + m];
-        const double z = wscale * Ts[(size_t)vv * LD + m];   // (W dx)_m
-        const double parm = parmv[vv];
-        double wx;   // (W_rlx dx)_m
-        if (P.RELAX_ALPHA != 0.0) {
-          wx = (1.0 - P.RELAX_ALPHA) * z + P.RELAX_ALPHA * sqrt(parm) * x;
-        } else if (P.RELAX_ALPHA_SPREAD != 0.0) {
-          wx = vara[c] * z;
-        } else {
-          wx = z;
-        }
-        Ts[(size_t)vv * LD + m] = xm[vv] + (wx + ssum[c]) * beta + (1.0 - beta) * x;
-      }
-      __syncthreads();
-      if (P.Q_SPRD_MAX > 0.0) {   // (letkf_tools.f90:500-513)
-        for (int c = 0; c < nc; ++c) {
-          if (cols[c] != P.iv3d_q - 1) continue;
-          double *tq = Ts + (size_t)cols[c] * LD;
-          double part = 0.0;
-          for (int m = tid; m < k; m += blockDim.x) part += tq[m];
-          const double q_mean = block_sum(part, red) / (double)k;
-          part = 0.0;
-          for (int m = tid; m < k; m += blockDim.x) {
-            const double d = tq[m] - q_mean;
-            part = fma(d, d, part);
-          }
-          const double q_sprd = sqrt(block_sum(part, red) / (double)(k - 1)) / q_mean;
-          if (q_sprd > P.Q_SPRD_MAX) {
-            for (int m = tid; m < k; m += blockDim.x) {
-              const double d = tq[m] - q_mean;
-              tq[m] = q_mean + d * P.Q_SPRD_MAX / q_sprd;
+      LETKF_TRACE(6);
+      // ---- one HALF-warp per column: var_g = x.x, var_a = x^T Pa x, s = x^T Pa b, sd = x^T Pa bd, RTPP/RTPS
+      // relaxation, update (letkf_tools.f90:457-513), q-spread clamp and the store -- no CTA barrier, everything a
+      // column needs after the skinny product is local to its 16 lanes (2 NB half-warps >= the 11 columns: one round)
+      {
+        const double *tb = Ts + (size_t)(kMaxNV - 2) * LD, *tbd = Ts + (size_t)(kMaxNV - 1) * LD;
+        constexpr int MPL = (KP + 15) / 16;   // members per lane
+        const int hl = lane & 15;
+        auto hsum = [&](double v) {   // sum over the 16 lanes of the half-warp
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(LETKF_FULL_MASK, v, o);
+          return v;
+        };
+        for (int c0 = 2 * w; c0 < nc; c0 += 2 * NB) {
+          const int c = c0 + (lane >> 4);
+          const bool active = c < nc;
+          const int vv = active ? (int)__fns(colmask, 0, c + 1) : vtrig;   // c-th analysed variable of the group
+          const double *x = Xall + (size_t)vv * LD, *t = Ts + (size_t)vv * LD;
+          double xv[MPL], tv[MPL], xa[MPL];
+          double vg_ = 0.0, va_ = 0.0, s_ = 0.0, sdv_ = 0.0;
+#pragma unroll
+          for (int u = 0; u < MPL; ++u) {
+            const int m = hl + 16 * u;
+            xv[u] = tv[u] = 0.0;
+            if (m < k) {
+              xv[u] = x[m];
+              tv[u] = t[m];
+              vg_ = fma(xv[u], xv[u], vg_);
+              va_ = fma(tv[u], tv[u], va_);
+              s_ = fma(tv[u], tb[m], s_);
+              sdv_ = fma(tv[u], tbd[m], sdv_);
             }
           }
-          __syncthreads();
+          vg_ = hsum(vg_);
+          va_ = hsum(va_);
+          s_ = hsum(s_);
+          if (P.det) sdv_ = hsum(sdv_);
+          // RTPS factor of the column (letkf_tools.f90:1971-2002), once per variable instead of per member
+          const double va = va_ * pscale, parm = parmv[vv], xmv = xm[vv], ss = s_ * pscale;
+          double f = 1.0;
+          if (P.RELAX_ALPHA == 0.0 && P.RELAX_ALPHA_SPREAD != 0.0 && vg_ > 0.0 && va > 0.0)
+            f = P.RELAX_ALPHA_SPREAD * sqrt(vg_ * parm / (va * (double)(k - 1))) - P.RELAX_ALPHA_SPREAD + 1.0;
+          const double rpp = (P.RELAX_ALPHA != 0.0) ? P.RELAX_ALPHA * sqrt(parm) : 0.0;
+#pragma unroll
+          for (int u = 0; u < MPL; ++u) {
+            const double z = wscale * tv[u];   // (W dx)_m
+            double wx;                         // (W_rlx dx)_m
+            if (P.RELAX_ALPHA != 0.0) wx = (1.0 - P.RELAX_ALPHA) * z + rpp * xv[u];
+            else wx = f * z;
+            xa[u] = xmv + (wx + ss) * beta + (1.0 - beta) * xv[u];
+          }
+          if (P.Q_SPRD_MAX > 0.0) {   // (letkf_tools.f90:500-513); the shuffles are executed by every lane
+            double part = 0.0;
+#pragma unroll
+            for (int u = 0; u < MPL; ++u)
+              if (hl + 16 * u < k) part += xa[u];
+            const double q_mean = hsum(part) / (double)k;
+            part = 0.0;
+#pragma unroll
+            for (int u = 0; u < MPL; ++u)
+              if (hl + 16 * u < k) part = fma(xa[u] - q_mean, xa[u] - q_mean, part);
+            const double q_sprd = sqrt(hsum(part) / (double)(k - 1)) / q_mean;
+            if (vv == P.iv3d_q - 1 && q_sprd > P.Q_SPRD_MAX) {
+#pragma unroll
+              for (int u = 0; u < MPL; ++u) xa[u] = q_mean + (xa[u] - q_mean) * P.Q_SPRD_MAX / q_sprd;
+            }
+          }
+          if (active) {
+#pragma unroll
+            for (int u = 0; u < MPL; ++u)
+              if (hl + 16 * u < k) store_anal(vv, hl + 16 * u, xa[u]);
+            if (hl == 0) {
+              if (P.det) store_anal(vv, k + 1, xdet[vv] + sdv_ * pscale * beta);   // (:489-497)
+              if (P.rtps_out && vv < P.nv3d) P.rtps_out[pbase + (size_t)vv * sl] = f;
+              if (P.infl3d && vv < P.nv3d) {
+                const double v = (vv == vtrig || P.INFL_MUL_ADAPTIVE) ? inflv[P.INFL_MUL_ADAPTIVE ? P.vfirst[vv] : vv]
+                                                                       : inflv[vv];
+                P.infl3d[pbase + (size_t)vv * sl] = v;
+              }
+            }
+          }
         }
       }
-      for (int idx = tid; idx < nc * k; idx += blockDim.x) {
-        const int c = idx / k, m = idx - c * k;
-        store_anal(cols[c], m, Ts[(size_t)cols[c] * LD + m]);
-      }
-      if (tid < nc) {
-        const int vv = cols[tid];
-        if (P.det) store_anal(vv, k + 1, xdet[vv] + sdsum[tid] * beta);   // (:489-497)
-        if (P.rtps_out && vv < P.nv3d) {
-          P.rtps_out[pbase + (size_t)vv * sl] = vara[tid];
-        }
-        if (P.infl3d && vv < P.nv3d) {
-          const double v = (vv == vtrig || P.INFL_MUL_ADAPTIVE) ? inflv[P.INFL_MUL_ADAPTIVE ? P.vfirst[vv] : vv]
-                                                                 : inflv[vv];
-          P.infl3d[pbase + (size_t)vv * sl] = v;
-        }
-      }
+      fence_proxy_async();
       __syncthreads();
       phase(6);
+      LETKF_TRACE(7);
     }
-    if (solved_any) ++c_solved;
+    if (solved_any) stat(1, 1);
   }
   if (tid == 0) {
-    atomicAdd(&P.counters[1], c_points);
-    atomicAdd(&P.counters[2], c_solved);
-    atomicAdd(&P.counters[3], c_fail);
-    atomicAdd(&P.counters[4], c_nobs);
-    atomicAdd(&P.counters[5], c_over);
-    atomicAdd(&P.counters[6], c_iters);
-    for (int i = 0; i < 8; ++i) atomicAdd(&P.counters[8 + i], (unsigned long long)ph[i]);
+    for (int i = 0; i < 6; ++i) atomicAdd(&P.counters[1 + i], s_stat[i]);
+    for (int i = 0; i < 8; ++i) atomicAdd(&P.counters[8 + i], (unsigned long long)s_ph[i]);
   }
 }
 

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/letkf_b200.h"
@@ -100,6 +101,7 @@ struct letkf_b200_handle {
   SearchTables tables;
   std::vector<letkf_b200_ctype_info> ctinfo;
   std::vector<int> h_bstart, h_s2o;
+  std::vector<double> h_logp;   // host-computed ln(mean pressure) of the last host-buffer das call
   bool radar_only = true;
   int maxl = 1;
   DevBuf<SearchTables> d_tables;
@@ -132,6 +134,7 @@ struct letkf_b200_handle {
   float last_ms = 0.f;
   int last_launches = 0;
   TiledBufs *tiled = nullptr;
+  bool attr_gemm_big = false, attr_gemm_small = false;   // dynamic-shared-memory opt-in done on this handle's device
   // pre-search pipeline (presearch_kernel): two pools, chunk parity
   cudaStream_t s_search = nullptr;
   std::vector<cudaEvent_t> ev_s;
@@ -203,6 +206,7 @@ struct DasLaunch {
   int nt = 0;
   size_t smem = 0;
   long long grid = 0;
+  int occ = 1;
 };
 
 int plan_common(letkf_b200_handle *h, DasParams &P, DasLaunch &L, int occ, const char *what) {
@@ -243,6 +247,8 @@ int plan_das_ns(letkf_b200_handle *h, DasParams &P, DasLaunch &L) {
   CK(cudaFuncSetAttribute(das_ns_kernel<NB, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, das_ns_kernel<NB, PRE>, C::NT, L.smem));
+  if (const char *mo = std::getenv("LETKF_B200_MAXOCC")) occ = std::max(1, std::min(occ, std::atoi(mo)));   // experiments
+  L.occ = occ;
   return plan_common(h, P, L, occ, "das_ns_kernel does not fit on an SM");
 }
 template <bool PRE>
@@ -875,6 +881,10 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   const letkf_b200_config &c = h->cfg;
   if (c.nv2d > 0 && (!a->gues2d || !a->anal2d)) return fail(h, LETKF_B200_EINVAL, "gues2d/anal2d required when nv2d > 0");
   if (c.INFL_MUL <= 0.0 && !a->infl3d) return fail(h, LETKF_B200_EINVAL, "INFL_MUL <= 0 needs the infl3d field");
+  // 2-D variables take INFL_MUL: the reference's work2d field (read from the inflation file / adapted, letkf_tools.f90:
+  // 240-262, 546) has no counterpart in this interface yet
+  if (c.nv2d > 0 && (c.INFL_MUL <= 0.0 || c.INFL_MUL_ADAPTIVE))
+    return fail(h, LETKF_B200_EINVAL, "nv2d > 0 with INFL_MUL <= 0 or INFL_MUL_ADAPTIVE is not supported (no 2-D inflation field)");
   CK(cudaSetDevice(h->device));
   const int k = c.MEMBER, nens = c.DET_RUN ? k + 2 : k + 1;
   const size_t sl = (size_t)h->nij1 * c.nlev;
@@ -904,14 +914,38 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
     }
     if (a->rtps_infl_out) { CK(h->st_rtps.ensure(nf)); P.rtps_out = h->st_rtps.p; }
     if (a->nobsl_out) { CK(h->st_nobsl.ensure(sl)); P.nobsl_out = h->st_nobsl.p; }
-    if (a->logp) {
+    {
+      // ln(mean pressure) of every point on the HOST (letkf_tools.f90:1852-1866 takes log(rlev) with the host's libm):
+      // the vertical-distance tests then see bit-for-bit what a CPU run on this machine sees.  A caller-supplied
+      // table wins; with device-resident state and no table the kernels call CUDA's log() (<= 1 ulp).
+      const double *lp = a->logp;
+      if (!lp) {
+        h->h_logp.resize(sl);
+        const double *pm = a->gues3d + ((size_t)k + (size_t)(c.iv3d_p - 1) * nens) * sl;   // slot mmean of iv3d_p
+        const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        double *out = h->h_logp.data();
+        for (unsigned t = 0; t < nt; ++t)
+          th.emplace_back([=]() {
+            for (size_t i = sl * t / nt; i < sl * (t + 1) / nt; ++i) out[i] = std::log(pm[i]);
+          });
+        for (auto &x : th) x.join();
+        lp = out;
+      }
       CK(h->st_logp.ensure(sl));
-      CK(cudaMemcpyAsync(h->st_logp.p, a->logp, sizeof(double) * sl, cudaMemcpyHostToDevice, h->s_h2d));
+      CK(cudaMemcpyAsync(h->st_logp.p, lp, sizeof(double) * sl, cudaMemcpyHostToDevice, h->s_h2d));
       P.logp = h->st_logp.p;
     }
   } else {
     P.gues3d = a->gues3d; P.anal3d = a->anal3d; P.gues2d = a->gues2d; P.anal2d = a->anal2d;
     P.infl3d = a->infl3d; P.rtps_out = a->rtps_infl_out; P.nobsl_out = a->nobsl_out; P.logp = a->logp;
+  }
+  if (P.infl3d) {   // work3d = INFL_MUL (or the field read by the caller), clamped from below (letkf_tools.f90:240-267):
+                    // every point carries its value on return, also the ones the analysis skips
+    cudaStream_t sf = host ? h->s_h2d : h->stream;   // host mode: behind the upload of the field, before ev_in[0]
+    if (c.INFL_MUL > 0.0) fill_kernel<<<h->num_sms * 8, 256, 0, sf>>>(P.infl3d, nf, c.INFL_MUL);
+    if (c.INFL_MUL_MIN > 0.0) clamp_min_kernel<<<h->num_sms * 8, 256, 0, sf>>>(P.infl3d, nf, c.INFL_MUL_MIN);
+    CK(cudaGetLastError());
   }
   if (P.rtps_out) {   // work3da = 1 (letkf_tools.f90:271-276); skipped points keep 1
     fill_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(P.rtps_out, nf, 1.0);
@@ -938,6 +972,11 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   P.counters = h->counters.p;
   P.max_sweeps = 30;
   CK(cudaMemsetAsync(h->counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
+#ifdef LETKF_EXP_TRACE
+  CK(h->cb[9].ensure(8000));
+  CK(cudaMemsetAsync(h->cb[9].p, 0, sizeof(double) * 8000, h->stream));
+  P.trace = reinterpret_cast<long long *>(h->cb[9].p);
+#endif
   int r, nlaunch = 0;
   DasLaunch L;
   // MEMBER <= 102: tensor-core Newton-Schulz solve, one CTA per point (das_ns_kernel.cuh); larger
@@ -1092,7 +1131,7 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
         Q.point_begin = 0;
         Q.point_end = pe2 - pb;      // upper bound; the real length is *point_count
         CK(cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long), h->stream));
-        L.kern<<<(unsigned)std::min<long long>(L.grid, std::max<long long>(pe2 - pb, 1)), L.nt, L.smem, h->stream>>>(Q);
+              L.kern<<<(unsigned)std::min<long long>(L.grid, std::max<long long>(pe2 - pb, 1)), L.nt, L.smem, h->stream>>>(Q);
         CK(cudaGetLastError());
       }
       CK(cudaEventRecord(h->ev_k1[ch], h->stream));
@@ -1125,6 +1164,16 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   CK(cudaMemcpyAsync(cnt, h->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (host) CK(cudaStreamSynchronize(h->s_d2h));
+#ifdef LETKF_EXP_TRACE
+  if (const char *tp = std::getenv("LETKF_B200_TRACE")) {
+    std::vector<long long> tr(8000);
+    cudaMemcpy(tr.data(), h->cb[9].p, sizeof(long long) * 8000, cudaMemcpyDeviceToHost);
+    if (FILE *f = std::fopen(tp, "w")) {
+      for (int i = 0; i < 4000 && tr[2 * i] != 0; ++i) std::fprintf(f, "%lld %lld\n", tr[2 * i], tr[2 * i + 1]);
+      std::fclose(f);
+    }
+  }
+#endif
   h->last_ms = 0.f;
   for (int ch = 0; ch < nchunk; ++ch) {
     float ms = 0.f;
@@ -1386,11 +1435,8 @@ static int grd_buf_tiled(letkf_b200_handle *h, int np, const letkf_b200_thermo *
   }
   P.nv3d = c.nv3d; P.iv3d_q = c.iv3d_q;
   const size_t smem = (size_t)c.nv3d * 32 * 33 * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
-    CK(cudaFuncSetAttribute(grd_buf_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 32 * 33 * (int)sizeof(double)));
-    attr = true;
-  }
+  // (the attribute is per device: set it on every call, a process may hold handles on several GPUs)
+  CK(cudaFuncSetAttribute(grd_buf_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 32 * 33 * (int)sizeof(double)));
   const dim3 grid((unsigned)((d.nij1max + 31) / 32), (unsigned)((c.nlev + 31) / 32), (unsigned)np);
   grd_buf_tiled_kernel<<<grid, dim3(32, 8), smem, h->stream>>>(d, P, t ? 1 : 0, dir, v3dg, buf);
   if (c.nv2d > 0 && v2dg) grd_buf_2d_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(d, dir, v2dg, buf);

@@ -44,14 +44,29 @@ struct NsCfg {
   static constexpr int RS = (H + 1) * 64;          // doubles per warp-owned row of tiles
   static constexpr int CR = (PSZ / LD) & ~3;       // obs rows per staging chunk (three chunks fit in 3 PSZ); CR == 4 NB
   // resident CTAs per SM the register allocation is sized for
-  static constexpr int MINB = NB_ <= 3 ? 8 : NB_ <= 5 ? 5 : NB_ <= 7 ? 4 : NB_ <= 9 ? 2 : 1;
+#ifndef LETKF_MINB7
+#define LETKF_MINB7 4
+#endif
+  static constexpr int MINB = NB_ <= 3 ? 8 : NB_ <= 5 ? 5 : NB_ <= 7 ? LETKF_MINB7 : NB_ <= 9 ? 2 : 1;
 };
 
+// DMMA and the operand loads of the hot loops are volatile asm: the issue order is the source order, which is
+// written as an explicit software pipeline (fragments of step e + 1 are requested before the DMMAs of step e issue,
+// independent accumulator chains interleaved).  Left to itself ptxas placed every LDS right in front of the
+// DMMA that consumes it (one register recycled for all B fragments): latency-bound, 3x slower in the Gram.
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-      : "+d"(c0), "+d"(c1)
-      : "d"(a), "d"(b));
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
 }
+// shared-memory load at a 32-bit shared address + compile-time byte offset (folded into the LDS immediate)
+template <int OFF>
+__device__ __forceinline__ double lds_imm(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // ---- circulant, fragment-ordered tile storage -------------------------------------------------------
 __host__ __device__ __forceinline__ int fpos(int r, int c) { return (c >> 2) * 32 + r * 4 + (c & 3); }
@@ -86,46 +101,72 @@ __device__ __forceinline__ LaneFrag lane_frag(int lane) {
 //   W(w+e, w+d):  g <= H: stored tile (w+e, g) [B operand = its "transposed" fragment pattern];
 //                 else transpose of stored tile (w+d, NB-g)
 template <int NB>
+struct SymmAddr {   // 32-bit shared addresses (bytes) of the lane's element in the first tile of block-row (w + x) mod NB
+  unsigned xd0;              // X, direct pattern, block-row w
+  unsigned xt[NB];           // X, transposed pattern, block-row w + x   (used for x > H)
+  unsigned wt[NB];           // W, transposed pattern, block-row w + x
+  unsigned wd[(NB + 1) / 2]; // W, direct pattern, block-row w + d
+};
+template <int NB>
+struct SymmFrag {
+  double a[2], b[(NB + 1) / 2][2];
+};
+template <int NB, int E, int D>
+__device__ __forceinline__ void symm_load_b(SymmFrag<NB> &f, const SymmAddr<NB> &A);
+template <int NB, int E>
+__device__ __forceinline__ void symm_load(SymmFrag<NB> &f, const SymmAddr<NB> &A) {
+  constexpr int H = (NB - 1) / 2;
+  if constexpr (E <= H) {
+    f.a[0] = lds_imm<E * 512>(A.xd0);
+    f.a[1] = lds_imm<E * 512 + 256>(A.xd0);
+  } else {
+    f.a[0] = lds_imm<(NB - E) * 512>(A.xt[E]);
+    f.a[1] = lds_imm<(NB - E) * 512 + 128>(A.xt[E]);
+  }
+  symm_load_b<NB, E, 0>(f, A);
+}
+template <int NB, int E, int D>
+__device__ __forceinline__ void symm_load_b(SymmFrag<NB> &f, const SymmAddr<NB> &A) {
+  constexpr int H = (NB - 1) / 2, G = (D - E + NB) % NB;
+  if constexpr (G <= H) {
+    f.b[D][0] = lds_imm<G * 512>(A.wt[E]);
+    f.b[D][1] = lds_imm<G * 512 + 128>(A.wt[E]);
+  } else {
+    f.b[D][0] = lds_imm<(NB - G) * 512>(A.wd[D]);
+    f.b[D][1] = lds_imm<(NB - G) * 512 + 256>(A.wd[D]);
+  }
+  if constexpr (D < H) symm_load_b<NB, E, D + 1>(f, A);
+}
+template <int NB, int E>
+__device__ __forceinline__ void symm_steps(double (&acc)[(NB + 1) / 2][2], SymmFrag<NB> &cur, SymmFrag<NB> &nxt,
+                                           const SymmAddr<NB> &A) {
+  constexpr int H = (NB - 1) / 2;
+  if constexpr (E + 1 < NB) symm_load<NB, E + 1>(nxt, A);
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], cur.a[h], cur.b[d][h]);
+  if constexpr (E + 1 < NB) symm_steps<NB, E + 1>(acc, nxt, cur, A);
+}
+template <int NB>
 __device__ __forceinline__ void symm_gemm(double (&acc)[(NB + 1) / 2][2], const double *X, const double *W,
                                           int w, const LaneFrag &lf) {
   constexpr int H = (NB - 1) / 2, RS = (H + 1) * 64;
-  int rb[NB];   // first tile of block-row (w + x) mod NB
+  const unsigned xs = smem_addr(X), ws = smem_addr(W);
+  SymmAddr<NB> A;
 #pragma unroll
   for (int x = 0; x < NB; ++x) {
     int j = w + x;
     if (j >= NB) j -= NB;
-    rb[x] = j * RS;
+    const unsigned rb = (unsigned)(j * RS);
+    if (x == 0) A.xd0 = xs + 8u * (rb + lf.dir);
+    A.xt[x] = xs + 8u * (rb + lf.trn);
+    A.wt[x] = ws + 8u * (rb + lf.trn);
+    if (x <= H) A.wd[x] = ws + 8u * (rb + lf.dir);
   }
-#pragma unroll
-  for (int e = 0; e < NB; ++e) {
-    double a[2], b[H + 1][2];
-    if (e <= H) {
-      const double *t = X + rb[0] + e * 64 + lf.dir;
-      a[0] = t[0];
-      a[1] = t[32];
-    } else {
-      const double *t = X + rb[e] + (NB - e) * 64 + lf.trn;
-      a[0] = t[0];
-      a[1] = t[16];
-    }
-#pragma unroll
-    for (int d = 0; d <= H; ++d) {
-      const int g = (d - e + NB) % NB;
-      if (g <= H) {
-        const double *t = W + rb[e] + g * 64 + lf.trn;
-        b[d][0] = t[0];
-        b[d][1] = t[16];
-      } else {
-        const double *t = W + rb[d] + (NB - g) * 64 + lf.dir;
-        b[d][0] = t[0];
-        b[d][1] = t[32];
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-      for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], a[h], b[d][h]);
-  }
+  SymmFrag<NB> f0, f1;
+  symm_load<NB, 0>(f0, A);
+  symm_steps<NB, 0>(acc, f0, f1, A);
 }
 
 // A operand fragments of block-row w of a stored symmetric matrix, inner block (w + e) mod NB
@@ -189,6 +230,52 @@ __device__ __forceinline__ void gram_circ(double (&acc)[(NB + 1) / 2][2], const 
 #pragma unroll
     for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], a, pb[d][(size_t)o * LD]);
   }
+}
+
+// The same for a FULL chunk of 4 NB rows, as an explicit software pipeline over its NB four-row steps (operands
+// of step s + 1 requested before the DMMAs of step s issue; all offsets are LDS immediates).
+template <int NB>
+struct GramFrag {
+  double a, wt, b[(NB + 1) / 2];
+};
+template <int NB, int LD, int S, int D>
+__device__ __forceinline__ void gram_load_b(GramFrag<NB> &f, const unsigned (&pb)[(NB + 1) / 2]) {
+  f.b[D] = lds_imm<S * 4 * LD * 8>(pb[D]);
+  if constexpr (D < (NB - 1) / 2) gram_load_b<NB, LD, S, D + 1>(f, pb);
+}
+template <int NB, int LD, int S>
+__device__ __forceinline__ void gram_load(GramFrag<NB> &f, unsigned pa, unsigned pw, const unsigned (&pb)[(NB + 1) / 2]) {
+  f.a = lds_imm<S * 4 * LD * 8>(pa);
+  f.wt = lds_imm<S * 4 * 8>(pw);
+  gram_load_b<NB, LD, S, 0>(f, pb);
+}
+template <int NB, int LD, int S>
+__device__ __forceinline__ void gram_steps(double (&acc)[(NB + 1) / 2][2], GramFrag<NB> &cur, GramFrag<NB> &nxt, unsigned pa,
+                                           unsigned pw, const unsigned (&pb)[(NB + 1) / 2]) {
+  constexpr int H = (NB - 1) / 2;
+  if constexpr (S + 1 < NB) gram_load<NB, LD, S + 1>(nxt, pa, pw, pb);
+  const double a = cur.a * cur.wt;
+#pragma unroll
+  for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], a, cur.b[d]);
+  if constexpr (S + 1 < NB) gram_steps<NB, LD, S + 1>(acc, nxt, cur, pa, pw, pb);
+}
+template <int NB, int LD>
+__device__ __forceinline__ void gram_circ_full(double (&acc)[(NB + 1) / 2][2], const double *Ys, const double *wv, int w,
+                                               int lane) {
+  constexpr int H = (NB - 1) / 2;
+  const int r = lane >> 2, q = lane & 3;
+  const unsigned ys = smem_addr(Ys) + 8u * (unsigned)(q * LD + r);
+  const unsigned pa = ys + 64u * (unsigned)w, pw = smem_addr(wv) + 8u * (unsigned)q;
+  unsigned pb[H + 1];
+#pragma unroll
+  for (int d = 0; d <= H; ++d) {
+    int j = w + d;
+    if (j >= NB) j -= NB;
+    pb[d] = ys + 64u * (unsigned)j;
+  }
+  GramFrag<NB> f0, f1;
+  gram_load<NB, LD, 0>(f0, pa, pw, pb);
+  gram_steps<NB, LD, 0>(acc, f0, f1, pa, pw, pb);
 }
 
 // Frobenius norm^2 contribution of (I - acc) held in the warp's tiles (off-diagonal tiles count twice)

@@ -35,10 +35,9 @@ int tl_gemm(letkf_b200_handle *h, const GemmParams &P, int items) {
   if (big) {
     constexpr int BM = 128, BN = 128, ST = 3;
     const size_t smem = gemm_smem_bytes<BM, BN, ST>();
-    static bool attr = false;
-    if (!attr) {
+    if (!h->attr_gemm_big) {   // per handle, hence per device (the attribute is not process-wide)
       CK(cudaFuncSetAttribute(tl_gemm_kernel<BM, BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
+      h->attr_gemm_big = true;
     }
     const int tm = (mmax + BM - 1) / BM, tn = P.sym ? tm : (P.N + BN - 1) / BN;
     const int tiles = P.sym ? tm * (tm + 1) / 2 : tm * tn;
@@ -47,10 +46,9 @@ int tl_gemm(letkf_b200_handle *h, const GemmParams &P, int items) {
   } else {
     constexpr int BM = 64, BN = 64, ST = 3;
     const size_t smem = gemm_smem_bytes<BM, BN, ST>();
-    static bool attr = false;
-    if (!attr) {
+    if (!h->attr_gemm_small) {
       CK(cudaFuncSetAttribute(tl_gemm_kernel<BM, BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
+      h->attr_gemm_small = true;
     }
     const int tm = (mmax + BM - 1) / BM, tn = P.sym ? tm : (P.N + BN - 1) / BN;
     const int tiles = P.sym ? tm * (tm + 1) / 2 : tm * tn;

@@ -230,7 +230,7 @@ contains
   !-----------------------------------------------------------------------------
   subroutine letkf_b200_setup(device, nobs, nensobs, elm, typ, ri, rj, lev, dat, err, val, ensval)
     use common_nml          ! MEMBER, DET_RUN, INFL_MUL, ..., HORI_LOCAL(:), VAR_LOCAL_*(:)
-    use common_scale, only: nlon, nlat, nlev, nv3d, nv2d, iv3d_p, iv3d_q, iv3d_qg
+    use common_scale, only: nlong, nlatg, nlev, nv3d, nv2d, iv3d_p, iv3d_q, iv3d_qg
     use common_mpi_scale, only: nij1, rig1, rjg1, hgt1
     use letkf_obs, only: dist_zero_fac, dist_zero_fac_square
     use scale_grid, only: DX, DY
@@ -246,7 +246,13 @@ contains
     call c_config_defaults(cfg)
     cfg%MEMBER = MEMBER
     cfg%DET_RUN = merge(1, 0, DET_RUN)
-    cfg%nlon = nlon;  cfg%nlat = nlat;  cfg%nlev = nlev      ! this rank's sorting mesh (PRC subdomain)
+    ! The library works in GLOBAL grid-index space ("PRC 1x1 view"): rig1/rjg1 (common_mpi_scale.f90:303-308) and
+    ! obs%ri/rj (phys2ij) are global indices, so the sorting mesh and relax_beta take the global domain size.  On a
+    ! decomposed domain (PRC_NUM_X*PRC_NUM_Y > 1) hand letkf_b200_setup AT LEAST the observations of this rank's
+    ! extended subdomain (obsda_ext, letkf_obs.f90:918-1138); the local lists then hold the same observations as the
+    ! reference's (bucket scan order, i.e. summation order, may differ: 1e-10 class).  Passing the subdomain
+    ! nlon/nlat here would push every observation of ranks with iproc/jproc > 0 into the last bucket column/row.
+    cfg%nlon = nlong;  cfg%nlat = nlatg;  cfg%nlev = nlev
     cfg%nv3d = nv3d;  cfg%nv2d = nv2d
     cfg%IHALO = IHALO; cfg%JHALO = JHALO
     cfg%DX = DX; cfg%DY = DY
@@ -284,6 +290,12 @@ contains
     cfg%dist_zero_fac_square = dist_zero_fac_square
     call c_config_resolve(cfg)
 
+    ! namelist switches whose post-processing (letkf_tools.f90:693-932) is outside this wrapper: refuse loudly rather
+    ! than return a different analysis or silently skip an output file
+    if (INFL_ADD > 0.0d0) call unsupported('INFL_ADD > 0 (additive inflation, letkf_tools.f90:804-929)')
+    if (nv2d > 0 .and. (INFL_MUL <= 0.0d0 .or. INFL_MUL_ADAPTIVE)) &
+      call unsupported('2-D variables with INFL_MUL <= 0 or INFL_MUL_ADAPTIVE (no 2-D inflation field in the interface)')
+
     if (c_associated(handle)) call check(c_destroy(handle), 'destroy')
     call check(c_create(cfg, int(device, c_int), handle), 'create')
     call check(c_set_grid(handle, int(nij1, c_int), rig1, rjg1, hgt1, LETKF_B200_MEM_HOST), 'set_grid')
@@ -300,26 +312,59 @@ contains
   end subroutine
 
   !-----------------------------------------------------------------------------
-  ! Drop-in for das_letkf (letkf_tools.f90:50): same arguments, same INTENTs
-  ! (gues3d/gues2d are destroyed: perturbations in slots 1..MEMBER, mean in mmean).
+  ! Drop-in for das_letkf (letkf_tools.f90:50): same arguments, same INTENTs.
+  ! gues3d/gues2d are INTENT(INOUT) "destroyed" in the reference; PROGRAM letkf never reads them again
+  ! (letkf.f90:196-236), so the perturbations are NOT copied back from the device (reserved = 1) -- pass
+  ! copy_back = .true. if a caller does rely on slots 1..MEMBER holding dX on return.
+  ! Optional fields, all (nij1,nlev,nv3d) unless noted, replace the module-level work arrays of the reference:
+  !   infl3d   INOUT  work3d: multiplicative inflation.  Required when INFL_MUL <= 0 (the caller reads INFL_MUL_IN_BASENAME
+  !                   into it first, letkf_tools.f90:240-262) or INFL_MUL_ADAPTIVE (returns the adapted field for
+  !                   INFL_MUL_OUT_BASENAME, :693-720)
+  !   rtps3d   OUT    work3da: RTPS relaxation factors for RELAX_SPREAD_OUT (:722-750)
+  !   nobs2d   OUT    (nij1,nlev) number of local observations used, for NOBS_OUT (:752-802; per-type counts are not returned)
+  ! The gather / write_restart of these fields stays with the caller, exactly as in the reference.
   !-----------------------------------------------------------------------------
-  subroutine das_letkf_b200(gues3d, gues2d, anal3d, anal2d)
-    use common_scale, only: nlev, nv3d, nv2d
-    use common_mpi_scale, only: nij1, nens
+  subroutine das_letkf_b200(gues3d, gues2d, anal3d, anal2d, infl3d, rtps3d, nobs2d, copy_back)
+    use common_nml, only: INFL_MUL, INFL_MUL_ADAPTIVE, RELAX_SPREAD_OUT, NOBS_OUT
+    use common_scale, only: nlev, nv3d, nv2d, iv3d_p
+    use common_mpi_scale, only: nij1, nens, mmean
     real(c_double), intent(inout), target :: gues3d(nij1, nlev, nens, nv3d)
     real(c_double), intent(inout), target :: gues2d(nij1, nens, nv2d)
     real(c_double), intent(out), target :: anal3d(nij1, nlev, nens, nv3d)
     real(c_double), intent(out), target :: anal2d(nij1, nens, nv2d)
+    real(c_double), intent(inout), optional, target :: infl3d(nij1, nlev, nv3d)
+    real(c_double), intent(out), optional, target :: rtps3d(nij1, nlev, nv3d)
+    integer(c_int32_t), intent(out), optional, target :: nobs2d(nij1, nlev)
+    logical, intent(in), optional :: copy_back
+    real(c_double), allocatable, target :: logp(:, :)
     type(letkf_b200_das_args) :: a
+    if ((INFL_MUL <= 0.0d0 .or. INFL_MUL_ADAPTIVE) .and. .not. present(infl3d)) &
+      call unsupported('INFL_MUL <= 0 / INFL_MUL_ADAPTIVE without the infl3d argument of das_letkf_b200')
+    if (RELAX_SPREAD_OUT .and. .not. present(rtps3d)) &
+      call unsupported('RELAX_SPREAD_OUT without the rtps3d argument of das_letkf_b200')
+    if (NOBS_OUT .and. .not. present(nobs2d)) call unsupported('NOBS_OUT without the nobs2d argument of das_letkf_b200')
     a%gues3d = c_loc(gues3d); a%anal3d = c_loc(anal3d)
     a%gues2d = c_null_ptr;    a%anal2d = c_null_ptr
     if (nv2d > 0) then
       a%gues2d = c_loc(gues2d); a%anal2d = c_loc(anal2d)
     end if
-    a%infl3d = c_null_ptr; a%rtps_infl_out = c_null_ptr; a%nobsl_out = c_null_ptr; a%logp = c_null_ptr
+    a%infl3d = c_null_ptr; a%rtps_infl_out = c_null_ptr; a%nobsl_out = c_null_ptr
+    if (present(infl3d)) a%infl3d = c_loc(infl3d)
+    if (present(rtps3d)) a%rtps_infl_out = c_loc(rtps3d)
+    if (present(nobs2d)) a%nobsl_out = c_loc(nobs2d)
+    ! ln(mean pressure) with the HOST's log (the same libm as the reference's obs_local_cal, letkf_tools.f90:1852-1866):
+    ! local-observation selection is then bit-identical to a CPU run on this machine.  (Left null, the library
+    ! computes the same table on the host for host buffers; spelled out here so that the contract is visible.)
+    allocate (logp(nij1, nlev))
+    logp = log(gues3d(:, :, mmean, iv3d_p))
+    a%logp = c_loc(logp)
     a%mem_space = LETKF_B200_MEM_HOST
-    a%reserved = 0
+    a%reserved = 1
+    if (present(copy_back)) then
+      if (copy_back) a%reserved = 0
+    end if
     call check(c_das_letkf(handle, a), 'das_letkf')   ! the reference STOPs on eigensolver failure
+    deallocate (logp)
   end subroutine das_letkf_b200
 
   !-----------------------------------------------------------------------------
@@ -372,6 +417,12 @@ contains
     type(c_ptr), intent(in) :: d_bufr, d_v3dg, d_v2dg
     call check(c_buf_to_grd(handle, int(np, c_int), d_bufr, d_v3dg, d_v2dg), 'buf_to_grd')
   end subroutine
+
+  subroutine unsupported(what)
+    character(len=*), intent(in) :: what
+    write (6, '(2A)') '[Error] letkf_b200: not supported by this binding: ', what
+    stop 99
+  end subroutine unsupported
 
   subroutine check(status, what)
     integer(c_int), intent(in) :: status

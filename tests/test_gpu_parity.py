@@ -368,3 +368,66 @@ def test_set_obs_rejects_non_positive_pressure():
     assert ei.value.code == sl.capi.EINVAL
     e.set_letkf_obs(obs)   # the handle stays usable
     e.close()
+
+
+def test_das_without_logp_threshold_hits(oracle):
+    """logp = NULL through the host-buffer path: the library takes ln(mean pressure) with the HOST's libm, exactly like
+    a CPU run, so selection is bit-exact without a caller-supplied table -- also for observations constructed to sit
+    on the vertical cut-off (|ln p_obs - ln p| == dist_zero_fac * sigma_v up to rounding), where one ulp of the log
+    flips the decision.  > 10^6 candidate (point, observation) pairs."""
+    cfg, rig1, rjg1, hgt1, obs, gues = sonde_case(member=8, nlon=24, nlat=24, nlev=6, nsonde=40, nsfc=100, hloc=200.0e3)
+    k = cfg.MEMBER
+    g = synth.rng(77, 3)
+    nobs = len(obs["elm"])
+    sel = np.nonzero(obs["elm"] != 14593)[0]
+    nij1, nlev = hgt1.shape
+    dz = cfg.dist_zero_fac * cfg.VERT_LOCAL[0]
+    for n in sel[: 3000]:
+        ij, il = int(g.integers(0, nij1)), int(g.integers(0, nlev))
+        pm = gues[ij, il, k, cfg.iv3d_p - 1]
+        sgn = 1.0 if g.uniform() < 0.5 else -1.0
+        obs["lev"][n] = np.exp(np.log(pm) + sgn * dz * (1.0 + g.integers(-2, 3) * 2.2e-16))
+        obs["ri"][n] = rig1[ij] + g.uniform(-2.0, 2.0)
+        obs["rj"][n] = rjg1[ij] + g.uniform(-2.0, 2.0)
+    o, e = _engines(cfg, rig1, rjg1, hgt1, obs, oracle)
+    ref = o.das_letkf(gues.copy(order="F"), want_nobsl=True)
+    out = e.das_letkf(gues.copy(order="F"), want_nobsl=True)          # no logp
+    assert nij1 * nlev * nobs > 1e6
+    assert np.array_equal(out["nobsl"], ref["nobsl"])
+    a, b = out["anal3d"][:, :, :k, :], ref["anal3d"][:, :, :k, :]
+    assert relerr(a, b, axis=(0, 1, 2)) <= TOL
+    e.close()
+
+
+def test_das_infl3d_written_everywhere(oracle):
+    """radar-only case: points above RADAR_ZMAX + cut-off have beta == 0 and are skipped, yet the inflation field is
+    returned complete (work3d = INFL_MUL clamped by INFL_MUL_MIN at every point, letkf_tools.f90:240-267)"""
+    cfg, rig1, rjg1, hgt1, obs, gues = radar_case(member=10, max_nobs=30, nlon=24, nlat=24, nlev=8)
+    cfg.RADAR_ZMAX = 3000.0
+    cfg.INFL_MUL_ADAPTIVE = 1
+    cfg.INFL_MUL = 1.01
+    cfg.INFL_MUL_MIN = 1.03
+    o, e = _engines(cfg, rig1, rjg1, hgt1, obs, oracle)
+    shp = (gues.shape[0], gues.shape[1], gues.shape[3])
+    i1 = np.full(shp, max(cfg.INFL_MUL, cfg.INFL_MUL_MIN), order="F")
+    i2 = np.full(shp, np.nan, order="F")          # the library must overwrite every entry
+    ref = o.das_letkf(gues.copy(order="F"), infl3d=i1, want_nobsl=True)
+    out = e.das_letkf(gues.copy(order="F"), infl3d=i2, want_nobsl=True, logp=host_logp(cfg, gues))
+    assert (ref["nobsl"] == 0).any() and (ref["nobsl"] > 0).any()
+    assert np.isfinite(i2).all()
+    assert relerr(i2, i1) <= TOL
+    e.close()
+
+
+def test_das_rejects_2d_inflation_field():
+    cfg, rig1, rjg1, hgt1, obs, gues = sonde_case(member=6, nsonde=5, nsfc=10)
+    cfg.nv2d = 1
+    cfg.INFL_MUL_ADAPTIVE = 1
+    e = sl.LETKF(cfg, device=0)
+    e.set_letkf_obs(obs)
+    e.set_common_mpi_grid(rig1, rjg1, hgt1)
+    g2 = np.zeros((gues.shape[0], gues.shape[2], 1), order="F")
+    i3 = np.ones((gues.shape[0], gues.shape[1], gues.shape[3]), order="F")
+    with pytest.raises(sl.LetkfError):
+        e.das_letkf(gues.copy(order="F"), gues2d=g2, infl3d=i3)
+    e.close()
