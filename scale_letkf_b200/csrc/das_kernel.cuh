@@ -71,6 +71,7 @@ struct DasParams {
   unsigned long long *redo_count;
   const long long *point_list;
   const unsigned long long *point_count;
+  double *m0_scratch;   // [grid][PSZ]: M0 = A / s of ill-conditioned points, kept for the mean-weight refinement
   long long *trace;   // LETKF_EXP_TRACE builds only: (tag, clock64) pairs of CTA 0 / thread 0
 };
 

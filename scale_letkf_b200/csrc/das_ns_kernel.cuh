@@ -388,6 +388,7 @@ das_ns_kernel(const DasParams P) {
       if (P.nobsl_out && vg == 0 && tid == 0) P.nobsl_out[pbase] = p_use;
       stat(3, (unsigned long long)p_use);
       bool fail = false;
+      bool mean_by_x = false;   // rows 14/15 of Ts hold w = (A/s)^-1 b (refined) instead of Z b: dX wbar = (x . w) / s
       double wscale = sqrt(infl);   // (W dx)_m = wscale * Ts[c][m];  p == 0: W = sqrt(infl) I
       double pscale = infl / (double)(k - 1);   // x^T Pa y = pscale * (t_x . t_y)
 
@@ -516,6 +517,10 @@ das_ns_kernel(const DasParams P) {
           }
           store_circ<NB>(acc, Yp, w, lf);
         }
+        // Ill-conditioned point (lambda_max(A) / c0 above ~1e4): the mean weight wbar = Pa b is refined below against
+        // the ORIGINAL matrix, which is kept in global scratch for that purpose (rare: nothing is written otherwise).
+        const bool refine = (cdiag / s_norm) < 1.0e-4;
+        if (refine) store_circ<NB>(acc, P.m0_scratch + (size_t)blockIdx.x * PSZ, w, lf);
         if (tid == 0) {   // the next point of this CTA (its work counter was drawn at the top of this iteration)
           long long nv = -1;
           if (PRE || !P.point_list) {
@@ -577,6 +582,44 @@ das_ns_kernel(const DasParams P) {
             for (int e = 0; e < 2; ++e) Ts[(size_t)(nt * 8 + 2 * q + e) * LD + w * 8 + r] = a2[nt][e];
         }
         __syncthreads();
+        if (refine) {
+          // One step of iterative refinement of w = (A/s)^-1 b (and of the deterministic-run twin):
+          //   w0 = Z (Z b),  r = b - M0 w0,  w = w0 + Z (Z r),   then  dX wbar = (x . w) / s.
+          // Z carries a normwise error ~ eps sqrt(cond); b = Yr^T d is huge in the directions where A^-1 is tiny, so the
+          // product form (Z x).(Z b) loses ~10x against the eigen-decomposition of the reference above cond 1e6;
+          // the residual against the original matrix restores it (tools/ns_model.py, tests/test_gpu_illcond.py).
+          double *M0s = Yp;                                   // free since the last product of the solve
+          double *vw = Tp + (TS_ALIAS ? kMaxNV * LD : 0);     // [4][LD] vector scratch behind Ts
+          const double *m0g = P.m0_scratch + (size_t)blockIdx.x * PSZ;
+          for (int i = tid; i < PSZ; i += C::NT) M0s[i] = m0g[i];
+          const int nvec = P.det ? 2 : 1;
+          auto matvec = [&](const double *Mat, const double *x, double *y) {   // y = Mat x, leading k x k block
+            for (int i = tid; i < k; i += C::NT) {
+              double sacc = 0.0;
+              for (int j = 0; j < k; ++j) sacc = fma(Mat[caddr<NB>(i, j)], x[j], sacc);
+              y[i] = sacc;
+            }
+          };
+          __syncthreads();
+          for (int iv = 0; iv < nvec; ++iv) {
+            const double *bv = Xall + (size_t)(kMaxNV - 2 + iv) * LD;   // b (bd)
+            double *tbv = Ts + (size_t)(kMaxNV - 2 + iv) * LD;           // Z b -> (refined) w
+            double *w0 = vw, *rr = vw + LD, *t1 = vw + 2 * LD;
+            matvec(Zp, tbv, w0);
+            __syncthreads();
+            matvec(M0s, w0, rr);
+            __syncthreads();
+            for (int i = tid; i < k; i += C::NT) rr[i] = bv[i] - rr[i];
+            __syncthreads();
+            matvec(Zp, rr, t1);
+            __syncthreads();
+            matvec(Zp, t1, rr);
+            __syncthreads();
+            for (int i = tid; i < k; i += C::NT) tbv[i] = w0[i] + rr[i];
+            __syncthreads();
+          }
+        }
+        mean_by_x = refine;
         wscale = sqrt((double)(k - 1) / s_norm);
         pscale = 1.0 / s_norm;
       } else {
@@ -618,8 +661,8 @@ das_ns_kernel(const DasParams P) {
               tv[u] = t[m];
               vg_ = fma(xv[u], xv[u], vg_);
               va_ = fma(tv[u], tv[u], va_);
-              s_ = fma(tv[u], tb[m], s_);
-              sdv_ = fma(tv[u], tbd[m], sdv_);
+              s_ = fma(mean_by_x ? xv[u] : tv[u], tb[m], s_);
+              sdv_ = fma(mean_by_x ? xv[u] : tv[u], tbd[m], sdv_);
             }
           }
           vg_ = hsum(vg_);

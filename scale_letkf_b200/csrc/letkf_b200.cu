@@ -117,6 +117,7 @@ struct letkf_b200_handle {
   DevBuf<int> l_iob;
   DevBuf<double> l_rdiag, l_rloc, l_cnd;
   DevBuf<unsigned> l_cpk;
+  DevBuf<double> m0_scratch;   // das_ns_kernel: A / s of ill-conditioned points (mean-weight refinement)
   int ccap = 1;   // candidate-buffer entries per CTA (obs-number-limited search)
   DevBuf<unsigned long long> counters;
   DevBuf<double> st_gues, st_anal, st_gues2, st_anal2, st_infl, st_rtps, st_logp;
@@ -249,6 +250,8 @@ int plan_das_ns(letkf_b200_handle *h, DasParams &P, DasLaunch &L) {
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, das_ns_kernel<NB, PRE>, C::NT, L.smem));
   if (const char *mo = std::getenv("LETKF_B200_MAXOCC")) occ = std::max(1, std::min(occ, std::atoi(mo)));   // experiments
   L.occ = occ;
+  CK(h->m0_scratch.ensure((size_t)std::max(occ, 1) * h->num_sms * C::PSZ));
+  P.m0_scratch = h->m0_scratch.p;
   return plan_common(h, P, L, occ, "das_ns_kernel does not fit on an SM");
 }
 template <bool PRE>
@@ -432,7 +435,7 @@ int letkf_b200_destroy(letkf_b200_handle *h) {
   h->rig1.release(); h->rjg1.release(); h->hgt1.release();
   h->d_tables.release(); h->rec.release(); h->bstart.release(); h->s2o.release();
   h->sval.release(); h->sens.release(); h->vlfac_groups.release(); h->vlfac_one.release();
-  h->l_iob.release(); h->l_rdiag.release(); h->l_rloc.release(); h->l_cnd.release(); h->l_cpk.release(); h->counters.release();
+  h->l_iob.release(); h->l_rdiag.release(); h->l_rloc.release(); h->l_cnd.release(); h->l_cpk.release(); h->counters.release(); h->m0_scratch.release();
   h->st_gues.release(); h->st_anal.release(); h->st_gues2.release(); h->st_anal2.release();
   h->st_infl.release(); h->st_rtps.release(); h->st_logp.release(); h->st_nobsl.release();
   for (auto &b : h->cb) b.release();
