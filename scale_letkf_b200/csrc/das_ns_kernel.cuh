@@ -91,6 +91,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 template <int NB, bool PRE>
 __global__ void __launch_bounds__(NsCfg<NB>::NT, NsCfg<NB>::MINB)
+#ifdef LETKF_MAXNREG13
+__maxnreg__(NB == 13 ? LETKF_MAXNREG13 : (NB == 9 ? 112 : (NB == 7 ? 72 : (NB == 5 ? 72 : 80))))
+#endif
 das_ns_kernel(const DasParams P) {
 #ifdef LETKF_EXP_TRACE
   __shared__ int s_ntrace;

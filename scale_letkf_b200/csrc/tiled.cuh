@@ -515,6 +515,11 @@ __global__ void __launch_bounds__(256) tl_scale_kernel(const DasParams P, const 
     // mtx_eigen zeroes eigenvalues below lambda_max sqrt(eps) (common_mtx.f90:69) and letkf_core would
     // then divide by zero; ||A||_1 <= n lambda_max bounds the same condition.
     if (mode != 2 && !(B.cdiag[g] * (double)P.k >= s * 1.4901161193847656e-08)) B.fail[g] = 1;
+    // The tiled path still runs the COUPLED Newton-Schulz iteration (Z <- T Z, Y <- T Y on symmetric storage), whose
+    // rounding errors grow like sqrt(cond)/4 per step: accurate to ~2e-11 up to lambda_max/c0 = 2e3, 1e-9 class at
+    // 5e3 (tools/ns_model.py).  Beyond a bound of 4e3 the point is flagged (LETKF_B200_EEIGEN) instead of returning
+    // a silently degraded analysis; the one-CTA-per-point solver (MEMBER <= 102) uses the stable product form.
+    if (lo * is < 2.5e-4) B.fail[g] = 1;
   }
 }
 
