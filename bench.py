@@ -482,10 +482,20 @@ def measure(name, ctx, args, steps, warmup, legs):
                             "on this GPU count" % (state_bytes / 1e9)}
     elif "cycle" in legs and args.subsample == 1:
         try:
-            from scale_letkf_b200.transpose import EnsTranspose
+            from scale_letkf_b200.transpose import EnsTranspose, EnsTransposeP2P
             nens = gues0.shape[1]
             thermo = eng.thermo_defaults()
-            tr = EnsTranspose(eng, world, rank, nlev, nv, 0, group=None, device=dev, thermo=thermo)
+            if args.transpose == "p2p":   # one pass: local reads, stores straight into the receiving rank's array (NVLink)
+                p2p = EnsTransposeP2P(eng, world, rank, thermo=thermo)
+
+                class _Tr:   # the interface of EnsTranspose the loop below uses
+                    block = 0
+                    rounds = staticmethod(p2p.rounds)
+                    read_ens = staticmethod(lambda g3, g2, v3, v2, km, ne: p2p.read_ens(g3, v3, km, ne))
+                    write_ens = staticmethod(lambda v3, v2, g3, g2, km, ne: p2p.write_ens(v3, g3, km, ne))
+                tr = _Tr()
+            else:
+                tr = EnsTranspose(eng, world, rank, nlev, nv, 0, group=None, device=dev, thermo=thermo)
             gsz = nlev * w["nlon"] * w["nlat"] * nv
             rounds = list(tr.rounds(k))
             gin = [torch.empty(gsz, dtype=torch.float64, device=dev) if im is not None else None for _, im, _, _ in rounds]
@@ -530,7 +540,11 @@ def measure(name, ctx, args, steps, warmup, legs):
                 dist.all_reduce(rt, op=dist.ReduceOp.MAX)
             cycle = {"ms_median": float(tot.median()), "ms_min": float(tot.min()), "steps": args.cycle_steps,
                      "phases_ms_median": dict(zip(names, [round(float(x), 3) for x in arr.median(dim=0).values])),
-                     "bytes_all_to_all_per_rank": int(2 * tr.block * world * 8 * len(rounds)),
+                     "transposes": ("one pass over peer memory (letkf_b200_scatter_grd_p2p / _gather_grd_p2p: local reads, "
+                                    "NVLink stores into the receiving rank's array)") if args.transpose == "p2p" else
+                                   "CUDA pack + NCCL all_to_all_single + CUDA unpack",
+                     "transpose_gbs_per_gpu": {nm: round(2.0 * state_bytes * k / nens / (float(x) * 1e-3) * 1e-9, 1)
+                                               for nm, x in zip(names, arr.median(dim=0).values) if nm.startswith("transpose")},
                      "set_obs_host_ms_last": round(host_setobs_ms, 3),
                      "transpose_round_trip_max_rel_err": float(rt[0]), "input_checksum_rank0": chk_in,
                      "what": "restart variables -> transpose in (state_trans fused) + mean + obs bucketing + analysis + mean + transpose out (state_trans_inv fused), n_gpus ranks"}
@@ -616,6 +630,8 @@ def main():
                     help="skip the full-cycle leg (transposes + bucketing + analysis)")
     ap.set_defaults(cycle=True)
     ap.add_argument("--cycle-steps", type=int, default=3)
+    ap.add_argument("--transpose", default="p2p", choices=["p2p", "nccl"],
+                    help="member<->grid transposes of the cycle leg: one-pass peer-memory kernels (default) or pack + NCCL + unpack")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the secondary records of the default line (k100 = C3, c1, and at 8 GPUs c5_cycle and c4)")
     ap.add_argument("--synth", default="hx", choices=["hx", "iid"],

@@ -278,6 +278,36 @@ int letkf_b200_abi_size_qc(void);
 /* library build info (arch string, e.g. "sm_100a") */
 const char *letkf_b200_build_info(void);
 
+/* ---- one-pass member<->grid transposes over peer memory ---------------------
+ * Twins of scatter_grd_mpi_alltoall / gather_grd_mpi_alltoall (common_mpi_scale.f90:1279-1396) with the exchange
+ * INSIDE the kernel: every rank reads its own arrays and writes straight into the receiving rank's array -- its own
+ * memory or a peer GPU's over NVLink -- so grd_to_buf, MPI_ALLTOALL(V) and buf_to_grd (:1428-1476) are one pass.
+ * Ranks of one node, one process per GPU.  Peer arrays are made addressable with CUDA IPC:
+ *   peer_export  on the owner: 64-byte handle + offset of a device pointer (send it to the other ranks: MPI_Allgather,
+ *                torch.distributed.all_gather_object, ...)
+ *   peer_open    on every other rank: map it, get a device pointer valid on this rank's GPU (cached per handle)
+ * Synchronisation is the caller's, exactly as around the reference's blocking collective: all ranks must have
+ * finished the consumers of the destination arrays before the call (barrier), and the destination is complete
+ * once every rank's call has completed on its stream (stream synchronise, then barrier).
+ *   scatter: this rank holds the member that becomes slot `mslot` (1-based) as v3dg(nlev,nlon,nlat,nv3d) [v2dg(nlon,
+ *            nlat,nv2d)]; peer_v3d[m] = v3d(nij1_m,nlev,nens,nv3d) of rank m, m = 0..np-1 (own array included).  Ranks
+ *            without a member in this round do not call.
+ *   gather:  members mstart..mend (1-based; member mstart+q lives on rank q) leave this rank's v3d for
+ *            peer_v3dg[q] = v3dg of rank q, q = 0..mend-mstart.  Every rank calls.
+ * t != NULL applies state_trans (scatter) / state_trans_inv (gather) on the fly (common_scale.f90:1181-1280). */
+typedef struct letkf_b200_ipc {
+  unsigned char handle[64];
+  uint64_t offset;
+} letkf_b200_ipc;
+int letkf_b200_peer_export(letkf_b200_handle *h, const void *devptr, letkf_b200_ipc *out);
+int letkf_b200_peer_open(letkf_b200_handle *h, const letkf_b200_ipc *in, void **mapped);
+int letkf_b200_scatter_grd_p2p(letkf_b200_handle *h, int np, int myrank_e, int nens, int mslot,
+                               const letkf_b200_thermo *t, const double *v3dg, const double *v2dg,
+                               double *const *peer_v3d, double *const *peer_v2d);
+int letkf_b200_gather_grd_p2p(letkf_b200_handle *h, int np, int myrank_e, int nens, int mstart, int mend,
+                              const letkf_b200_thermo *t, const double *v3d, const double *v2d,
+                              double *const *peer_v3dg, double *const *peer_v2dg);
+
 #ifdef __cplusplus
 }
 #endif

@@ -310,3 +310,34 @@ class LETKF:
     def ens_to_buf(self, nprocs_e, myrank_e, nens, mstart, mend, v3d, v2d, bufs):
         self._ck(self.lib.letkf_b200_ens_to_buf(self.h, nprocs_e, myrank_e, nens, mstart, mend, _ptr(v3d),
                                                 _ptr(v2d), _ptr(bufs)))
+
+    # ---- one-pass transposes over peer memory ------------------------------------------------------
+    def peer_export(self, tensor):
+        """(handle bytes, offset) of a CUDA tensor's memory, to be sent to the other ranks"""
+        d = capi.Ipc()
+        self._ck(self.lib.letkf_b200_peer_export(self.h, _ptr(tensor), C.byref(d)))
+        return bytes(d.handle), int(d.offset)
+
+    def peer_open(self, desc):
+        """device address (int), valid on this rank's GPU, of a peer's exported tensor"""
+        d = capi.Ipc()
+        C.memmove(d.handle, desc[0], 64)
+        d.offset = desc[1]
+        out = C.c_void_p()
+        self._ck(self.lib.letkf_b200_peer_open(self.h, C.byref(d), C.byref(out)))
+        return out.value
+
+    def scatter_grd_p2p(self, nprocs_e, myrank_e, nens, mslot, v3dg, v2dg, peer_v3d, peer_v2d=None, thermo=None):
+        """peer_v3d: device addresses (ints) of v3d on ranks 0..np-1"""
+        a3 = (C.c_void_p * nprocs_e)(*peer_v3d)
+        a2 = (C.c_void_p * nprocs_e)(*peer_v2d) if peer_v2d else None
+        t = C.byref(thermo) if thermo is not None else None
+        self._ck(self.lib.letkf_b200_scatter_grd_p2p(self.h, nprocs_e, myrank_e, nens, mslot, t, _ptr(v3dg), _ptr(v2dg), a3, a2))
+
+    def gather_grd_p2p(self, nprocs_e, myrank_e, nens, mstart, mend, v3d, v2d, peer_v3dg, peer_v2dg=None, thermo=None):
+        """peer_v3dg: device addresses of the member-major grids of members mstart..mend (on ranks 0..mend-mstart)"""
+        n = mend - mstart + 1
+        a3 = (C.c_void_p * n)(*peer_v3dg)
+        a2 = (C.c_void_p * n)(*peer_v2dg) if peer_v2dg else None
+        t = C.byref(thermo) if thermo is not None else None
+        self._ck(self.lib.letkf_b200_gather_grd_p2p(self.h, nprocs_e, myrank_e, nens, mstart, mend, t, _ptr(v3d), _ptr(v2d), a3, a2))

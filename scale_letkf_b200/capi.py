@@ -96,6 +96,11 @@ class Thermo(C.Structure):
     ]
 
 
+class Ipc(C.Structure):
+    """letkf_b200_ipc: CUDA IPC handle + offset of a device pointer (one-pass transposes over peer memory)."""
+    _fields_ = [("handle", C.c_ubyte * 64), ("offset", C.c_uint64)]
+
+
 # QC codes (scale/common/common_obs_scale.f90:139-151)
 IQC_GOOD, IQC_GROSS_ERR, IQC_REF_MEM, IQC_OBS_BAD, IQC_OTYPE = 0, 5, 12, 50, 90
 UNDEF = -9.99e33   # common/common.f90:38
@@ -153,6 +158,10 @@ PROTOTYPES = {
     "letkf_b200_ens_to_buf": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "letkf_b200_buf_to_grd": (_i, [_vp, _i, _vp, _vp, _vp]),
     "letkf_b200_nij1": (_i, [_vp, _i, _i, _ip, _ip]),
+    "letkf_b200_peer_export": (_i, [_vp, _vp, C.POINTER(Ipc)]),
+    "letkf_b200_peer_open": (_i, [_vp, C.POINTER(Ipc), C.POINTER(_vp)]),
+    "letkf_b200_scatter_grd_p2p": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "letkf_b200_gather_grd_p2p": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "letkf_b200_abi_sizes": (None, [C.POINTER(C.c_int32 * 4)]),
     "letkf_b200_build_info": (C.c_char_p, []),
 }

@@ -433,6 +433,110 @@ __global__ void __launch_bounds__(256) grd_buf_tiled_kernel(TransposeDims d, Sta
       }
   }
 }
+// ---------------------------------------------------------------------------------------------
+// One-pass member <-> grid transposes over peer memory (scatter/gather_grd_mpi_alltoall twins,
+// common_mpi_scale.f90:1279-1396, with grd_to_buf / buf_to_grd :1428-1476 and the exchange folded in): every rank
+// READS its own arrays and WRITES straight into the receiving rank's array -- its own memory, or a peer's over
+// NVLink (CUDA IPC mapping) -- so pack, all-to-all and unpack are ONE pass over HBM and the transfer overlaps the
+// tile loop.  state_trans / state_trans_inv (common_scale.f90:1181-1280) are applied on the tile in shared memory.
+//   dir 0 (scatter): this rank holds the member that goes to slot `slot0` as v3dg(nlev,nlon,nlat,nv3d);
+//                    blockIdx.z = receiving rank m: columns j = m + np i  ->  v3d_m(i, k, slot0, n)
+//   dir 1 (gather):  this rank holds v3d(nij1,nlev,nens,nv3d); blockIdx.z = q: member slot0 + q lives on rank q:
+//                    v3d(i, k, slot0 + q, n) -> v3dg_q at column j = myrank + np i
+struct PeerPtrs {
+  double *p3[16];   // scatter: v3d of rank m;  gather: v3dg of rank q
+  double *p2[16];   // the 2-D twins (may be null)
+};
+__global__ void __launch_bounds__(256) grd_ens_p2p_kernel(TransposeDims d, StateTransParams T, int trans, int dir, int myrank,
+                                                          int nens, int slot0, const double *__restrict__ src, PeerPtrs peers) {
+  extern __shared__ double tile[];   // [nv3d][32 columns][33]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32, z = blockIdx.z;
+  const int colrank = dir == 0 ? z : myrank;          // whose columns this CTA moves
+  const int nij1 = nij1_of(d, colrank);
+  if (i0 >= nij1) return;
+  const size_t npts = (size_t)d.nlev * d.nlon * d.nlat;
+  constexpr int TS = 32 * 33;
+  auto gcol = [&](int i) -> size_t {   // first level of column i of rank `colrank` in a member-major field
+    const int j = colrank + d.np * i;
+    const int ilon = j % d.nlon, ilat = j / d.nlon;
+    return (size_t)d.nlev * (ilon + (size_t)d.nlon * ilat);
+  };
+  auto eidx = [&](int i, int k, int slot, int n) -> size_t {   // v3d(nij1, nlev, nens, nv3d) of rank `colrank`
+    return (size_t)i + (size_t)nij1 * ((size_t)k + (size_t)d.nlev * ((size_t)slot + (size_t)nens * n));
+  };
+  double *dst = peers.p3[z];
+  // every load of the tile is issued before the first shared-memory store (4 x nv3d values per thread in flight):
+  // the kernel is pure data movement and lives on bytes in flight
+  constexpr int NVU = 16;
+  double reg[NVU][4];
+  if (dir == 0) {
+    size_t gc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gc[q] = (i0 + ty + 8 * q < nij1 && k0 + tx < d.nlev) ? gcol(i0 + ty + 8 * q) + k0 + tx : (size_t)-1;
+#pragma unroll
+    for (int n = 0; n < NVU; ++n)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) reg[n][q] = (n < d.nv3d && gc[q] != (size_t)-1) ? src[gc[q] + npts * n] : 0.0;
+#pragma unroll
+    for (int n = 0; n < NVU; ++n)
+      if (n < d.nv3d) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tile[n * TS + (ty + 8 * q) * 33 + tx] = reg[n][q];
+      }
+  } else {
+    const bool oki = i0 + tx < nij1;
+#pragma unroll
+    for (int n = 0; n < NVU; ++n)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        reg[n][q] = (n < d.nv3d && oki && k0 + ty + 8 * q < d.nlev) ? src[eidx(i0 + tx, k0 + ty + 8 * q, slot0 + z, n)] : 0.0;
+#pragma unroll
+    for (int n = 0; n < NVU; ++n)
+      if (n < d.nv3d) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tile[n * TS + tx * 33 + ty + 8 * q] = reg[n][q];
+      }
+  }
+  __syncthreads();
+  if (trans) {
+    for (int e = ty * 32 + tx; e < 1024; e += 256) {
+      const int ii = e >> 5, kk = e & 31;
+      if (i0 + ii < nij1 && k0 + kk < d.nlev) state_trans_point(T, tile + ii * 33 + kk, TS, dir);
+    }
+    __syncthreads();
+  }
+  if (dir == 0) {
+    for (int n = 0; n < d.nv3d; ++n)
+      for (int kk = ty; kk < 32; kk += 8) {
+        const int i = i0 + tx, k = k0 + kk;
+        if (i < nij1 && k < d.nlev) dst[eidx(i, k, slot0, n)] = tile[n * TS + tx * 33 + kk];
+      }
+  } else {
+    for (int n = 0; n < d.nv3d; ++n)
+      for (int ii = ty; ii < 32; ii += 8) {
+        const int i = i0 + ii, k = k0 + tx;
+        if (i < nij1 && k < d.nlev) dst[gcol(i) + k + npts * n] = tile[n * TS + ii * 33 + tx];
+      }
+  }
+}
+// 2-D variables of the one-pass transposes: v2dg(nlon,nlat,nv2d) <-> v2d(nij1,nens,nv2d)
+__global__ void grd_ens_p2p_2d_kernel(TransposeDims d, int dir, int myrank, int nens, int slot0, int npeers,
+                                      const double *__restrict__ src, PeerPtrs peers) {
+  const size_t total = (size_t)d.nij1max * d.nv2d * npeers;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % d.nij1max);
+    const size_t t = idx / d.nij1max;
+    const int n = (int)(t % d.nv2d), z = (int)(t / d.nv2d);
+    const int colrank = dir == 0 ? z : myrank, nij1 = nij1_of(d, colrank);
+    if (i >= nij1 || !peers.p2[z]) continue;
+    const int j = colrank + d.np * i;
+    const size_t g = (j % d.nlon) + (size_t)d.nlon * ((j / d.nlon) + (size_t)d.nlat * n);
+    if (dir == 0) peers.p2[z][(size_t)i + (size_t)nij1 * ((size_t)slot0 + (size_t)nens * n)] = src[g];
+    else peers.p2[z][g] = src[(size_t)i + (size_t)nij1 * ((size_t)(slot0 + z) + (size_t)nens * n)];
+  }
+}
+
 // 2-D variables of the pack / unpack (v2dg(nlon,nlat,nv2d) <-> rows nlev*nv3d.. of the buffer)
 __global__ void grd_buf_2d_kernel(TransposeDims d, int dir, double *__restrict__ v2dg, double *__restrict__ buf) {
   const size_t total = (size_t)d.nij1max * d.nv2d * d.np;

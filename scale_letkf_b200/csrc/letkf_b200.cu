@@ -7,9 +7,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <cuda.h>
 
 #include "../../include/letkf_b200.h"
 #include "aux_kernels.cuh"
@@ -135,6 +138,7 @@ struct letkf_b200_handle {
   float last_ms = 0.f;
   int last_launches = 0;
   TiledBufs *tiled = nullptr;
+  std::map<std::string, void *> ipc_open;   // peer allocations mapped by letkf_b200_peer_open (by handle bytes)
   bool attr_gemm_big = false, attr_gemm_small = false;   // dynamic-shared-memory opt-in done on this handle's device
   // pre-search pipeline (presearch_kernel): two pools, chunk parity
   cudaStream_t s_search = nullptr;
@@ -457,6 +461,7 @@ int letkf_b200_destroy(letkf_b200_handle *h) {
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
   for (auto &pr : h->pinned) cudaHostUnregister(pr.first);
+  for (auto &kv : h->ipc_open) cudaIpcCloseMemHandle(kv.second);
   cudaGetLastError();
   delete h;
   return LETKF_B200_OK;
@@ -1487,6 +1492,91 @@ int letkf_b200_ens_to_buf(letkf_b200_handle *h, int np, int myrank_e, int nens, 
                                                           const_cast<double *>(v3d), const_cast<double *>(v2d), 1);
   CK(cudaGetLastError());
   return LETKF_B200_OK;
+}
+
+// ---- one-pass transposes over peer memory ------------------------------------------------------------------
+int letkf_b200_peer_export(letkf_b200_handle *h, const void *devptr, letkf_b200_ipc *out) {
+  if (!h || !devptr || !out) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  {   // the IPC handle names the whole allocation: find its base (driver entry point through the runtime, no -lcuda)
+    typedef CUresult (*range_fn)(CUdeviceptr *, size_t *, CUdeviceptr);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+    if (!fn || ((range_fn)fn)(&base, &size, (CUdeviceptr)devptr) != CUDA_SUCCESS)
+      return fail(h, LETKF_B200_ECUDA, "peer_export: cuMemGetAddressRange failed (not a device allocation?)");
+  }
+  cudaIpcMemHandle_t hd;
+  CK(cudaIpcGetMemHandle(&hd, (void *)base));
+  static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(out->handle, &hd, 64);
+  out->offset = (uint64_t)((CUdeviceptr)devptr - base);
+  return LETKF_B200_OK;
+}
+int letkf_b200_peer_open(letkf_b200_handle *h, const letkf_b200_ipc *in, void **mapped) {
+  if (!h || !in || !mapped) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const std::string key((const char *)in->handle, 64);
+  auto it = h->ipc_open.find(key);
+  void *base = nullptr;
+  if (it != h->ipc_open.end()) {
+    base = it->second;
+  } else {
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, in->handle, 64);
+    CK(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_open[key] = base;
+  }
+  *mapped = (char *)base + in->offset;
+  return LETKF_B200_OK;
+}
+
+static int grd_ens_p2p(letkf_b200_handle *h, int np, int myrank, int nens, int dir, int slot0, int npeers,
+                       const letkf_b200_thermo *t, const double *src3, const double *src2, double *const *peer3,
+                       double *const *peer2) {
+  CK(cudaSetDevice(h->device));
+  const letkf_b200_config &c = h->cfg;
+  if (np < 1 || np > 16 || npeers < 1 || npeers > np) return fail(h, LETKF_B200_EINVAL, "p2p transposes support 1..16 ranks");
+  if (t && (c.nv3d < 6 || c.iv3d_q != 6 || c.iv3d_p != 5))
+    return fail(h, LETKF_B200_EINVAL, "state_trans needs the u,v,w,T,p,q.. variable order");
+  const TransposeDims d = make_dims(h, np);
+  StateTransParams P;
+  std::memset(&P, 0, sizeof(P));
+  if (t) {
+    P.Rdry = t->Rdry; P.Rvap = t->Rvap; P.CVdry = t->CVdry; P.PRE00 = t->PRE00;
+    for (int i = 0; i < 16; ++i) P.tracer_cv[i] = t->TRACER_CV[i];
+    P.pos_q = t->POSITIVE_DEFINITE_Q; P.pos_qhyd = t->POSITIVE_DEFINITE_QHYD;
+  }
+  P.nv3d = c.nv3d; P.iv3d_q = c.iv3d_q;
+  PeerPtrs pp;
+  std::memset(&pp, 0, sizeof(pp));
+  for (int i = 0; i < npeers; ++i) {
+    if (!peer3[i]) return fail(h, LETKF_B200_EINVAL, "p2p transpose: null peer pointer");
+    pp.p3[i] = peer3[i];
+    pp.p2[i] = (peer2 && c.nv2d > 0) ? peer2[i] : nullptr;
+  }
+  const size_t smem = (size_t)c.nv3d * 32 * 33 * sizeof(double);
+  CK(cudaFuncSetAttribute(grd_ens_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 32 * 33 * (int)sizeof(double)));
+  const dim3 grid((unsigned)((d.nij1max + 31) / 32), (unsigned)((c.nlev + 31) / 32), (unsigned)npeers);
+  grd_ens_p2p_kernel<<<grid, dim3(32, 8), smem, h->stream>>>(d, P, t ? 1 : 0, dir, myrank, nens, slot0, src3, pp);
+  if (c.nv2d > 0 && src2 && peer2)
+    grd_ens_p2p_2d_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(d, dir, myrank, nens, slot0, npeers, src2, pp);
+  CK(cudaGetLastError());
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_scatter_grd_p2p(letkf_b200_handle *h, int np, int myrank_e, int nens, int mslot, const letkf_b200_thermo *t,
+                               const double *v3dg, const double *v2dg, double *const *peer_v3d, double *const *peer_v2d) {
+  if (!h || !v3dg || !peer_v3d || mslot < 1 || mslot > nens) return LETKF_B200_EINVAL;
+  return grd_ens_p2p(h, np, myrank_e, nens, 0, mslot - 1, np, t, v3dg, v2dg, peer_v3d, peer_v2d);
+}
+int letkf_b200_gather_grd_p2p(letkf_b200_handle *h, int np, int myrank_e, int nens, int mstart, int mend,
+                              const letkf_b200_thermo *t, const double *v3d, const double *v2d, double *const *peer_v3dg,
+                              double *const *peer_v2dg) {
+  if (!h || !v3d || !peer_v3dg || mstart < 1 || mend < mstart || mend > nens || mend - mstart + 1 > np) return LETKF_B200_EINVAL;
+  return grd_ens_p2p(h, np, myrank_e, nens, 1, mstart - 1, mend - mstart + 1, t, v3d, v2d, peer_v3dg, peer_v2dg);
 }
 
 }  // extern "C"

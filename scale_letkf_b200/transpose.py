@@ -107,3 +107,58 @@ class EnsTranspose:
             g3 = my_members3d[it] if im is not None else None
             g2 = my_members2d[it] if (im is not None and my_members2d is not None) else None
             self.gather_grd_mpi_alltoall(mstart, mend, v3d, v2d, g3, g2, nens)
+
+
+class EnsTransposeP2P:
+    """read_ens_mpi / write_ens_mpi twins on the ONE-PASS transposes (letkf_b200_scatter_grd_p2p / _gather_grd_p2p): every
+    rank reads its own arrays and writes straight into the receiving rank's array over NVLink, no pack buffer, no
+    collective call.  Ranks of one node; peer arrays are mapped once with CUDA IPC (handles exchanged through
+    torch.distributed.all_gather_object).  Barriers around the calls play the role of the blocking MPI_ALLTOALL."""
+
+    def __init__(self, eng, nprocs_e, myrank_e, group=None, thermo=None):
+        self.eng, self.np, self.rank, self.group, self.thermo = eng, int(nprocs_e), int(myrank_e), group, thermo
+        self._maps = {}
+
+    def _addresses(self, key, tensor):
+        """device addresses of `tensor` (same role on every rank) on all ranks, as seen from this GPU; None entries allowed"""
+        ptr = None if tensor is None else tensor.data_ptr()
+        if key in self._maps and self._maps[key][0] == ptr:
+            return self._maps[key][1]
+        if self.np == 1:
+            addrs = [ptr]
+        else:
+            desc = None if tensor is None else self.eng.peer_export(tensor)
+            allg = [None] * self.np
+            dist.all_gather_object(allg, desc, group=self.group)
+            addrs = [ptr if r == self.rank else (None if d is None else self.eng.peer_open(d)) for r, d in enumerate(allg)]
+        self._maps[key] = (ptr, addrs)
+        return addrs
+
+    def _barrier(self):
+        torch.cuda.synchronize()
+        if self.np > 1:
+            dist.barrier(group=self.group)
+
+    def rounds(self, nmem):
+        nit = (nmem + self.np - 1) // self.np
+        for it in range(nit):
+            im = self.rank + 1 + it * self.np
+            yield it, (im if im <= nmem else None), 1 + it * self.np, min((it + 1) * self.np, nmem)
+
+    def read_ens(self, my_members3d, v3d, nmem, nens):
+        """my_members3d[it]: member-major grid of the member this rank holds in round it (or None) -> v3d on every rank"""
+        peers = self._addresses("v3d", v3d)
+        self._barrier()                       # nobody still reads the previous contents of v3d
+        for it, im, mstart, mend in self.rounds(nmem):
+            if im is not None:
+                self.eng.scatter_grd_p2p(self.np, self.rank, nens, im, my_members3d[it], None, peers, thermo=self.thermo)
+        self._barrier()
+
+    def write_ens(self, v3d, my_members3d, nmem, nens):
+        """v3d (e.g. the analysis) on every rank -> member-major grids my_members3d[it] on the member-holding ranks"""
+        grids = [self._addresses(("g", it), my_members3d[it]) for it, _, _, _ in self.rounds(nmem)]
+        self._barrier()
+        for it, im, mstart, mend in self.rounds(nmem):
+            self.eng.gather_grd_p2p(self.np, self.rank, nens, mstart, mend, v3d, None, grids[it][:mend - mstart + 1],
+                                    thermo=self.thermo)
+        self._barrier()

@@ -194,6 +194,12 @@ def run_gpu(rank, world, port, q):
         mine = [None if im is None else F(grids[im - 1]) for _, im, _, _ in tr.rounds(k)]
         v3d = torch.zeros((nv3d, nens, nlev, nij1), dtype=torch.float64, device=dev)   # Fortran (nij1,nlev,nens,nv3d)
         tr.read_ens(mine, None, v3d, None, k, nens)
+        # the one-pass transposes over peer memory (CUDA IPC + NVLink stores) must give the same bits
+        from scale_letkf_b200.transpose import EnsTransposeP2P
+        p2p = EnsTransposeP2P(eng, world, rank)
+        v3d_p = torch.full_like(v3d, -7.0)
+        p2p.read_ens(mine, v3d_p, k, nens)
+        assert torch.equal(v3d_p[:, :k], v3d[:, :k]), "p2p scatter differs from the NCCL path"
         eng.ensmean_grd(v3d)
         # the same columns cut out of the whole-plane state
         ilon, ilat = synth.column_deal(nlon, nlat, world, rank)
@@ -216,6 +222,10 @@ def run_gpu(rank, world, port, q):
         # way back: analysis members as member-major grids on their owner ranks
         outg = [None if t is None else torch.zeros_like(t) for t in mine]
         tr.write_ens(anal, None, outg, None, k, nens)
+        outp = [None if t is None else torch.full_like(t, -7.0) for t in mine]
+        p2p.write_ens(anal, outp, k, nens)
+        for a_, b_ in zip(outp, outg):
+            assert (a_ is None and b_ is None) or torch.equal(a_, b_), "p2p gather differs from the NCCL path"
         # every rank gathers all analysis columns through the oracle to check its own members
         allb = [None] * world
         dist.all_gather_object(allb, (cols, b))

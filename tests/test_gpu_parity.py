@@ -431,3 +431,37 @@ def test_das_rejects_2d_inflation_field():
     with pytest.raises(sl.LetkfError):
         e.das_letkf(gues.copy(order="F"), gues2d=g2, infl3d=i3)
     e.close()
+
+
+def test_p2p_transposes_single_rank_match_three_pass(oracle):
+    """one-pass scatter / gather (letkf_b200_scatter_grd_p2p / _gather_grd_p2p, np = 1: the peer is the rank itself)
+    against the pack -> copy -> unpack path and the oracle's transposes, with and without the fused state transform"""
+    import torch
+    from scale_letkf_b200.transpose import EnsTranspose, EnsTransposeP2P
+    cfg = synth.config_c2(nlon=37, nlat=21, nlev=35, member=5)
+    rig1, rjg1, hgt1 = synth.make_grid(cfg)
+    e = sl.LETKF(cfg, device=0)
+    k, nens, nv, nlev = cfg.MEMBER, cfg.MEMBER + 1, cfg.nv3d, cfg.nlev
+    nij1 = cfg.nlon * cfg.nlat
+    g = synth.rng(5, 31)
+    dev = torch.device("cuda", 0)
+    for thermo in (None, e.thermo_defaults()):
+        grids = []
+        for m in range(k):
+            a = np.abs(g.standard_normal((nv, cfg.nlat, cfg.nlon, nlev))) + 0.5      # positive: valid restart variables
+            a[5:] *= 1e-3
+            grids.append(torch.from_numpy(a.reshape(-1)).to(dev))
+        ref = EnsTranspose(e, 1, 0, nlev, nv, 0, device=dev, thermo=thermo)
+        new = EnsTransposeP2P(e, 1, 0, thermo=thermo)
+        v_ref = torch.zeros((nv, nens, nlev, nij1), dtype=torch.float64, device=dev)
+        v_new = torch.full_like(v_ref, -1.0)
+        ref.read_ens(grids, None, v_ref, None, k, nens)
+        new.read_ens(grids, v_new, k, nens)
+        assert torch.equal(v_new[:, :k], v_ref[:, :k])
+        out_ref = [torch.zeros_like(x) for x in grids]
+        out_new = [torch.full_like(x, -1.0) for x in grids]
+        ref.write_ens(v_ref, None, out_ref, None, k, nens)
+        new.write_ens(v_new, out_new, k, nens)
+        for a, b in zip(out_new, out_ref):
+            assert torch.equal(a, b)
+    e.close()
