@@ -308,6 +308,32 @@ int letkf_b200_gather_grd_p2p(letkf_b200_handle *h, int np, int myrank_e, int ne
                               const letkf_b200_thermo *t, const double *v3d, const double *v2d,
                               double *const *peer_v3dg, double *const *peer_v2dg);
 
+/* ---- radar observation operator ----------------------
+ * Twin of the obsfmt_radar branch of obsope_cal (scale/obs/obsope_tools.f90:476-494): phys2ijkz (scale/common/
+ * common_obs_scale.f90:1116-1237), Trans_XtoY_radar (:342-493) and calc_ref_vr (:626-990, METHOD_REF_CALC 1/2/3), for ALL
+ * members at once, so that H(x_m) of a 30-second radar volume never leaves the GPU.
+ *   v3dgh[m]   member m's history grid WITH halos, v3dg(nlevh,nlonh,nlath,nv3dd) as read_ens_history_iter delivers
+ *              it (common_scale.f90:66-78: u,v,w,t,p,q,qc,qr,qi,qs,qg,rh,hgt), level fastest
+ *   ril, rjl   observation position in this subdomain's halo'ed index space (rij_g2l), lon/lat/lev as in obs(iof)
+ *   rotc       [2][nobs] MPRJ_rotcoef(lon,lat) of the SCALE-RM map projection (host library, un-vendored); NULL = (1,0)
+ *   yobs, qc   [nobs][ld_out], member fastest (the ensval(nensobs,nobs) layout of obs_da_value): H(x_m) and its QC flag
+ *              (iqc_good = 0, iqc_radar_vhi = 19, iqc_out_vhi = 20, iqc_out_vlo = 21, iqc_otype = 90, iqc_out_h = 98;
+ *              iqc_ref_low is reset to good exactly as obsope_cal does, :489) */
+typedef struct letkf_b200_radar_config {
+  int32_t METHOD_REF_CALC;        /* common_nml.f90:270 (default 3) */
+  int32_t USE_TERMINAL_VELOCITY;  /* :272 */
+  int32_t nlevh, nlonh, nlath, nlev, KHALO, nv3dd;
+  double MIN_RADAR_REF_DBZ;       /* :261 */
+  double LOW_REF_SHIFT;           /* :262 */
+  double RADAR_ZMAX;              /* common_nml.f90 PARAM_LETKF_RADAR */
+  double radar_lon, radar_lat, radar_z;   /* obs(iof)%meta(1:3) */
+} letkf_b200_radar_config;
+void letkf_b200_radar_config_defaults(letkf_b200_radar_config *r);
+int letkf_b200_obsope_radar(letkf_b200_handle *h, const letkf_b200_radar_config *r, int nobs, const int32_t *elm,
+                            const double *ril, const double *rjl, const double *lon, const double *lat,
+                            const double *lev, const double *rotc, int nmem, const double *const *v3dgh,
+                            int ld_out, double *yobs, int32_t *qc, int mem_space);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,6 +101,12 @@ void oracle_monit_dep(int nn, const int32_t *elm, const double *dep, const int32
                       double *bias, double *rmse);
 int oracle_max_threads(void);
 
+/* radar observation operator for all members (oracle_radar.cpp): obsope_tools.f90:476-494, common_obs_scale.f90:342-493,
+ * 626-990, 1116-1237; arguments as letkf_b200_obsope_radar (host pointers) */
+void oracle_obsope_radar(const letkf_b200_radar_config *r, int nobs, const int32_t *elm, const double *ril, const double *rjl,
+                         const double *lon, const double *lat, const double *lev, const double *rotc, int nmem,
+                         const double *const *v3dgh, int ld_out, double *yobs, int32_t *qc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,8 @@ def lib():
         L.oracle_enssprd_grd.argtypes = [i, i, i, i, i, vp, vp]
         L.oracle_state_trans.restype = None
         L.oracle_state_trans.argtypes = [C.POINTER(capi.Thermo), i, i, i, i, i, i, vp]
+        L.oracle_obsope_radar.restype = None
+        L.oracle_obsope_radar.argtypes = [C.POINTER(capi.RadarConfig), i, vp, vp, vp, vp, vp, vp, vp, i, C.POINTER(vp), i, vp, vp]
         L.oracle_monit_dep.restype = None
         L.oracle_monit_dep.argtypes = [i, vp, vp, vp, vp, vp, vp]
         L.oracle_max_threads.restype = i
@@ -303,3 +305,18 @@ def monit_dep(elm, dep, qc):
     n, b, r = np.zeros(16, dtype=np.int32), np.zeros(16), np.zeros(16)
     lib().oracle_monit_dep(len(elm), _p(elm), _p(_f64(dep)), _p(qc), _p(n), _p(b), _p(r))
     return n, b, r
+
+
+def obsope_radar(rcfg, elm, ril, rjl, lon, lat, lev, grids, rotc=None):
+    """oracle_radar.cpp: radar observation operator for all members; grids = list of F-order v3dg(nlevh,nlonh,nlath,nv3dd)"""
+    nobs, nmem = len(elm), len(grids)
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    elm = np.ascontiguousarray(elm, dtype=np.int32)
+    ril, rjl, lon, lat, lev = f(ril), f(rjl), f(lon), f(lat), f(lev)
+    rotc = None if rotc is None else f(rotc)
+    ptrs = (C.c_void_p * nmem)(*[g.ctypes.data for g in grids])
+    y = np.zeros((nobs, nmem))
+    q = np.zeros((nobs, nmem), dtype=np.int32)
+    lib().oracle_obsope_radar(C.byref(rcfg), nobs, _p(elm), _p(ril), _p(rjl), _p(lon), _p(lat), _p(lev), _p(rotc), nmem, ptrs,
+                              nmem, _p(y), _p(q))
+    return y, q

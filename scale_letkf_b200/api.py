@@ -341,3 +341,38 @@ class LETKF:
         a2 = (C.c_void_p * n)(*peer_v2dg) if peer_v2dg else None
         t = C.byref(thermo) if thermo is not None else None
         self._ck(self.lib.letkf_b200_gather_grd_p2p(self.h, nprocs_e, myrank_e, nens, mstart, mend, t, _ptr(v3d), _ptr(v2d), a3, a2))
+
+    # ---- radar observation operator ------------------------------------------------------------------
+    def radar_config_defaults(self):
+        r = capi.RadarConfig()
+        self.lib.letkf_b200_radar_config_defaults(C.byref(r))
+        return r
+
+    def obsope_radar(self, rcfg, elm, ril, rjl, lon, lat, lev, grids, rotc=None):
+        """H(x_m) of radar observations for all members (obsope_tools.f90:476-494 twin).  grids: list of member history
+        grids v3dg(nlevh,nlonh,nlath,nv3dd) -- numpy F-order (host) or torch CUDA tensors.  Returns (yobs, qc), shape
+        (nobs, nmem), as numpy arrays (host) or torch tensors (device)."""
+        nobs, nmem = len(elm), len(grids)
+        dev = _is_torch(grids[0])
+        ptrs = (C.c_void_p * nmem)(*[_ptr(g) for g in grids])
+        if dev:
+            import torch
+            d = grids[0].device
+            t = lambda a, dt: a if _is_torch(a) else torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=d)
+            elm, ril, rjl, lon, lat, lev = (t(elm, np.int32), t(ril, np.float64), t(rjl, np.float64), t(lon, np.float64),
+                                            t(lat, np.float64), t(lev, np.float64))
+            rotc = None if rotc is None else t(rotc, np.float64)
+            y = torch.empty((nobs, nmem), dtype=torch.float64, device=d)
+            q = torch.empty((nobs, nmem), dtype=torch.int32, device=d)
+            space = capi.MEM_DEVICE
+        else:
+            f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+            elm = np.ascontiguousarray(elm, dtype=np.int32)
+            ril, rjl, lon, lat, lev = f(ril), f(rjl), f(lon), f(lat), f(lev)
+            rotc = None if rotc is None else f(rotc)
+            y = np.zeros((nobs, nmem))
+            q = np.zeros((nobs, nmem), dtype=np.int32)
+            space = capi.MEM_HOST
+        self._ck(self.lib.letkf_b200_obsope_radar(self.h, C.byref(rcfg), nobs, _ptr(elm), _ptr(ril), _ptr(rjl), _ptr(lon),
+                                                  _ptr(lat), _ptr(lev), _ptr(rotc), nmem, ptrs, nmem, _ptr(y), _ptr(q), space))
+        return y, q

@@ -96,6 +96,17 @@ class Thermo(C.Structure):
     ]
 
 
+class RadarConfig(C.Structure):
+    """letkf_b200_radar_config (radar observation operator, common_nml.f90:257-272 + grid sizes + radar position)"""
+    _fields_ = [
+        ("METHOD_REF_CALC", C.c_int32), ("USE_TERMINAL_VELOCITY", C.c_int32),
+        ("nlevh", C.c_int32), ("nlonh", C.c_int32), ("nlath", C.c_int32), ("nlev", C.c_int32), ("KHALO", C.c_int32),
+        ("nv3dd", C.c_int32),
+        ("MIN_RADAR_REF_DBZ", C.c_double), ("LOW_REF_SHIFT", C.c_double), ("RADAR_ZMAX", C.c_double),
+        ("radar_lon", C.c_double), ("radar_lat", C.c_double), ("radar_z", C.c_double),
+    ]
+
+
 class Ipc(C.Structure):
     """letkf_b200_ipc: CUDA IPC handle + offset of a device pointer (one-pass transposes over peer memory)."""
     _fields_ = [("handle", C.c_ubyte * 64), ("offset", C.c_uint64)]
@@ -158,6 +169,9 @@ PROTOTYPES = {
     "letkf_b200_ens_to_buf": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "letkf_b200_buf_to_grd": (_i, [_vp, _i, _vp, _vp, _vp]),
     "letkf_b200_nij1": (_i, [_vp, _i, _i, _ip, _ip]),
+    "letkf_b200_radar_config_defaults": (None, [C.POINTER(RadarConfig)]),
+    "letkf_b200_obsope_radar": (_i, [_vp, C.POINTER(RadarConfig), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_vp), _i,
+                                     _vp, _vp, _i]),
     "letkf_b200_peer_export": (_i, [_vp, _vp, C.POINTER(Ipc)]),
     "letkf_b200_peer_open": (_i, [_vp, C.POINTER(Ipc), C.POINTER(_vp)]),
     "letkf_b200_scatter_grd_p2p": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp)]),

@@ -19,6 +19,7 @@
 #include "das_kernel.cuh"
 #include "das_ns_kernel.cuh"
 #include "tiled.cuh"
+#include "radar.cuh"
 
 using namespace letkf;
 
@@ -1049,8 +1050,20 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
     int maxlev = 0;
     for (int ch = 0; ch < nchunk; ++ch) maxlev = std::max(maxlev, lev0(ch + 1) - lev0(ch));
     pl_entries_max = (size_t)maxlev * h->nij1 * h->nvgroup;
+    // pool budget per buffer: what the longest chunk can need, within [2 GB, 8 GB] and a fifth of the free memory
+    // (a pool that overflows sends points to the redo pass, whose in-kernel search is ~2x slower: C3 on one GPU)
     const char *pm = std::getenv("LETKF_B200_POOL_MB");
-    const double budget = (pm ? std::atof(pm) : 2048.0) * 1048576.0;
+    double budget = 2048.0 * 1048576.0;
+    if (pm) {
+      budget = std::atof(pm) * 1048576.0;
+    } else {
+      size_t fr = 0, tot = 0;
+      if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+        double held = 0.0;   // what the two pools already hold counts as free
+        for (int b = 0; b < 2; ++b) held += (double)h->pl_iob[b].n * 4.0 + (double)h->pl_rdiag[b].n * 8.0 + (double)h->pl_rloc[b].n * 8.0;
+        budget = std::max(budget, std::min(8192.0 * 1048576.0, 0.2 * ((double)fr + held) / 2.0));
+      }
+    }
     const size_t per = c.INFL_MUL_ADAPTIVE ? 20 : 12;
     pl_cap = (long long)std::min<double>((double)pl_entries_max * (double)round_up(h->maxl, 4), budget / per);
     pl_cap = std::max<long long>(pl_cap, 4);
@@ -1577,6 +1590,76 @@ int letkf_b200_gather_grd_p2p(letkf_b200_handle *h, int np, int myrank_e, int ne
                               double *const *peer_v2dg) {
   if (!h || !v3d || !peer_v3dg || mstart < 1 || mend < mstart || mend > nens || mend - mstart + 1 > np) return LETKF_B200_EINVAL;
   return grd_ens_p2p(h, np, myrank_e, nens, 1, mstart - 1, mend - mstart + 1, t, v3d, v2d, peer_v3dg, peer_v2dg);
+}
+
+// ---- radar observation operator ------------------------------------------------------------------------------
+void letkf_b200_radar_config_defaults(letkf_b200_radar_config *r) {   // common_nml.f90:257-272
+  std::memset(r, 0, sizeof(*r));
+  r->METHOD_REF_CALC = 3;
+  r->USE_TERMINAL_VELOCITY = 0;
+  r->MIN_RADAR_REF_DBZ = 0.0;
+  r->LOW_REF_SHIFT = 0.0;
+  r->RADAR_ZMAX = 99.0e3;
+  r->nv3dd = 13;
+  r->KHALO = 2;
+}
+
+int letkf_b200_obsope_radar(letkf_b200_handle *h, const letkf_b200_radar_config *r, int nobs, const int32_t *elm,
+                            const double *ril, const double *rjl, const double *lon, const double *lat, const double *lev,
+                            const double *rotc, int nmem, const double *const *v3dgh, int ld_out, double *yobs, int32_t *qc,
+                            int mem_space) {
+  if (!h || !r || nobs < 0 || nmem < 1 || ld_out < nmem || !v3dgh) return LETKF_B200_EINVAL;
+  if (nobs == 0) return LETKF_B200_OK;
+  if (!elm || !ril || !rjl || !lon || !lat || !lev || !yobs || !qc) return LETKF_B200_EINVAL;
+  if (r->METHOD_REF_CALC < 1 || r->METHOD_REF_CALC > 3)
+    return fail(h, LETKF_B200_EINVAL, "Not recognized method for radar reflectivity and wind computation");
+  if (r->nv3dd < 13 || r->nlev + 2 * r->KHALO > r->nlevh) return fail(h, LETKF_B200_EINVAL, "obsope_radar: inconsistent grid sizes");
+  CK(cudaSetDevice(h->device));
+  const bool host = mem_space != LETKF_B200_MEM_DEVICE;
+  RadarParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.c.method = r->METHOD_REF_CALC; P.c.use_tv = r->USE_TERMINAL_VELOCITY;
+  P.c.min_ref = std::pow(10.0, r->MIN_RADAR_REF_DBZ / 10.0);   // common_obs_scale.f90:251 (host libm, like the reference)
+  P.c.min_ref_dbz = r->MIN_RADAR_REF_DBZ; P.c.low_ref_shift = r->LOW_REF_SHIFT;
+  P.nobs = nobs; P.nmem = nmem; P.nlevh = r->nlevh; P.nlonh = r->nlonh; P.nlath = r->nlath; P.nlev = r->nlev; P.khalo = r->KHALO;
+  P.nv3dd = r->nv3dd; P.ld_out = ld_out; P.zmax = r->RADAR_ZMAX;
+  P.radar_lon = r->radar_lon; P.radar_lat = r->radar_lat; P.radar_z = r->radar_z;
+  const size_t gsz = (size_t)r->nlevh * r->nlonh * r->nlath * r->nv3dd, no = (size_t)nobs * ld_out;
+  DevBuf<double> d_geo, d_grid, d_y;
+  DevBuf<int> d_elm, d_qc;
+  DevBuf<const double *> d_ptr;
+  CK(d_ptr.ensure(nmem));
+  std::vector<const double *> ptrs(nmem);
+  if (host) {
+    CK(d_geo.ensure((size_t)nobs * 7)); CK(d_elm.ensure(nobs)); CK(d_y.ensure(no)); CK(d_qc.ensure(no));
+    CK(d_grid.ensure(gsz * nmem));
+    const double *src[5] = {ril, rjl, lon, lat, lev};
+    for (int i = 0; i < 5; ++i)
+      CK(cudaMemcpyAsync(d_geo.p + (size_t)i * nobs, src[i], sizeof(double) * nobs, cudaMemcpyHostToDevice, h->stream));
+    if (rotc) CK(cudaMemcpyAsync(d_geo.p + (size_t)5 * nobs, rotc, sizeof(double) * 2 * nobs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_elm.p, elm, sizeof(int) * nobs, cudaMemcpyHostToDevice, h->stream));
+    for (int m = 0; m < nmem; ++m) {
+      CK(cudaMemcpyAsync(d_grid.p + gsz * m, v3dgh[m], sizeof(double) * gsz, cudaMemcpyHostToDevice, h->stream));
+      ptrs[m] = d_grid.p + gsz * m;
+    }
+    P.ril = d_geo.p; P.rjl = d_geo.p + nobs; P.lon = d_geo.p + 2 * (size_t)nobs; P.lat = d_geo.p + 3 * (size_t)nobs;
+    P.lev = d_geo.p + 4 * (size_t)nobs; P.rotc = rotc ? d_geo.p + 5 * (size_t)nobs : nullptr;
+    P.elm = d_elm.p; P.yobs = d_y.p; P.qc = d_qc.p;
+  } else {
+    for (int m = 0; m < nmem; ++m) ptrs[m] = v3dgh[m];
+    P.ril = ril; P.rjl = rjl; P.lon = lon; P.lat = lat; P.lev = lev; P.rotc = rotc; P.elm = elm; P.yobs = yobs; P.qc = qc;
+  }
+  CK(cudaMemcpyAsync(d_ptr.p, ptrs.data(), sizeof(double *) * nmem, cudaMemcpyHostToDevice, h->stream));
+  P.v3dgh = d_ptr.p;
+  obsope_radar_kernel<<<dim3((unsigned)((nobs + 127) / 128), (unsigned)nmem), 128, 0, h->stream>>>(P);
+  CK(cudaGetLastError());
+  if (host) {
+    CK(cudaMemcpyAsync(yobs, d_y.p, sizeof(double) * no, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(qc, d_qc.p, sizeof(int) * no, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  d_geo.release(); d_grid.release(); d_y.release(); d_elm.release(); d_qc.release(); d_ptr.release();
+  return LETKF_B200_OK;
 }
 
 }  // extern "C"
