@@ -308,6 +308,17 @@ int letkf_b200_gather_grd_p2p(letkf_b200_handle *h, int np, int myrank_e, int ne
                               const letkf_b200_thermo *t, const double *v3d, const double *v2d,
                               double *const *peer_v3dg, double *const *peer_v2dg);
 
+/* ---- device-resident observation chain -------------------
+ * set_obs_device: like set_obs, but every array of `obs` (and qc) is a DEVICE array of ALL observations as the
+ * observation operator (letkf_b200_obsope_radar) and the departure/QC kernel (letkf_b200_obs_departure_qc) leave them;
+ * the qc == iqc_good filter of the counting sort (letkf_obs.f90:752, 791), the combined-type lookup (:300-342) and
+ * the vertical coordinate are done on the device.  qc may be NULL (all accepted).  *nkept = accepted observations;
+ * get_kept_index returns their indices into the input arrays (arrival order), so that sorted_index can be mapped
+ * back.  ln(lev) of observations localised in ln p is CUDA's log() here (<= 1 ulp of the host's): radar
+ * observations (localised in height) are unaffected. */
+int letkf_b200_set_obs_device(letkf_b200_handle *h, const letkf_b200_obs *obs, const int32_t *qc, int32_t *nkept);
+int letkf_b200_get_kept_index(const letkf_b200_handle *h, int32_t *kept);
+
 /* ---- radar observation operator ----------------------
  * Twin of the obsfmt_radar branch of obsope_cal (scale/obs/obsope_tools.f90:476-494): phys2ijkz (scale/common/
  * common_obs_scale.f90:1116-1237), Trans_XtoY_radar (:342-493) and calc_ref_vr (:626-990, METHOD_REF_CALC 1/2/3), for ALL

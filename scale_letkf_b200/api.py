@@ -376,3 +376,36 @@ class LETKF:
         self._ck(self.lib.letkf_b200_obsope_radar(self.h, C.byref(rcfg), nobs, _ptr(elm), _ptr(ril), _ptr(rjl), _ptr(lon),
                                                   _ptr(lat), _ptr(lev), _ptr(rotc), nmem, ptrs, nmem, _ptr(y), _ptr(q), space))
         return y, q
+
+    # ---- device-resident observation chain --------------------------------------------------------------
+    def obs_departure_qc_device(self, elm, dat, err, qc, ensval, qcfg=None):
+        """departure + QC (letkf_obs.f90:355-560) in place on torch CUDA tensors: ensval (nobs, nensobs) H(x_m) ->
+        perturbations, qc updated; returns val (nobs)"""
+        import torch
+        if qcfg is None:
+            qcfg = capi.QcConfig()
+            self.lib.letkf_b200_qc_config_defaults(C.byref(qcfg))
+        val = torch.zeros(elm.shape[0], dtype=torch.float64, device=ensval.device)
+        self._ck(self.lib.letkf_b200_obs_departure_qc(self.h, C.byref(qcfg), elm.shape[0], ensval.shape[1], _ptr(elm), _ptr(dat),
+                                                      _ptr(err), _ptr(qc), _ptr(ensval), _ptr(val), capi.MEM_DEVICE))
+        return val
+
+    def set_letkf_obs_device(self, obs, qc=None):
+        """set_letkf_obs on torch CUDA tensors of ALL observations + their QC flags (int32, 0 = accepted): filter, combined
+        types, vertical coordinate and bucket sort on the device.  Returns the number of accepted observations."""
+        o = capi.Obs()
+        o.nobs = obs["elm"].shape[0]
+        o.nensobs = obs["ensval"].shape[1]
+        for kf in ("elm", "typ", "ri", "rj", "lev", "dat", "err", "val", "ensval"):
+            assert obs[kf].is_contiguous()
+            setattr(o, kf, obs[kf].data_ptr())
+        nk = C.c_int32()
+        self._obs_keepalive = obs
+        self._ck(self.lib.letkf_b200_set_obs_device(self.h, C.byref(o), _ptr(qc), C.byref(nk)))
+        return nk.value
+
+    def kept_index(self):
+        n, _ = self.obs_info()
+        a = np.zeros(n, dtype=np.int32)
+        self._ck(self.lib.letkf_b200_get_kept_index(self.h, _ptr(a)))
+        return a

@@ -169,6 +169,8 @@ PROTOTYPES = {
     "letkf_b200_ens_to_buf": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "letkf_b200_buf_to_grd": (_i, [_vp, _i, _vp, _vp, _vp]),
     "letkf_b200_nij1": (_i, [_vp, _i, _i, _ip, _ip]),
+    "letkf_b200_set_obs_device": (_i, [_vp, C.POINTER(Obs), _vp, _ip]),
+    "letkf_b200_get_kept_index": (_i, [_vp, _vp]),
     "letkf_b200_radar_config_defaults": (None, [C.POINTER(RadarConfig)]),
     "letkf_b200_obsope_radar": (_i, [_vp, C.POINTER(RadarConfig), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_vp), _i,
                                      _vp, _vp, _i]),

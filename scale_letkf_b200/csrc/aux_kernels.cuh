@@ -26,6 +26,62 @@ __global__ void bucket_key_kernel(const SearchTables *T, int nobs, const int *__
   atomicAdd(&count[b], 1);
 }
 
+// ---- device-resident front half of set_letkf_obs (letkf_obs.f90:300-342, 752, 791): which (element, type) pairs occur
+// among the accepted observations, their combined type, vertical coordinate and the compaction of qc == iqc_good ------
+__device__ __forceinline__ int dev_uid_obs(int elm) {   // common_obs_scale.f90:171-211 (0 = unknown)
+  switch (elm) {
+    case 2819: return 1; case 2820: return 2; case 3073: return 3; case 3074: return 4; case 3330: return 5; case 3331: return 6;
+    case 14593: return 7; case 19999: return 8; case 4001: return 9; case 4004: return 10; case 4002: return 11;
+    case 4003: return 12; case 8800: return 13; case 99991: return 14; case 99992: return 15; case 99993: return 16;
+    default: return 0;
+  }
+}
+// use[(ielm_u-1) * NOBTYPE + ityp-1] |= 1 for every accepted observation; err[0] |= 1 on an unknown element / type
+__global__ void obs_use_kernel(int nobs, int nobtype, const int *__restrict__ elm, const int *__restrict__ typ,
+                               const int *__restrict__ qc, int *__restrict__ use, int *__restrict__ err) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nobs || (qc && qc[n] != 0)) return;
+  const int u = dev_uid_obs(elm[n]), t = typ[n];
+  if (u < 1 || t < 1 || t > nobtype) {
+    atomicOr(err, 1);
+    return;
+  }
+  use[(u - 1) * nobtype + t - 1] = 1;
+}
+// keep[n] = accepted; ic[n] = combined type; vc[n] = vertical coordinate (ln p, ln ps, or height for vmode 3)
+__global__ void obs_prepare_kernel(int nobs, int nobtype, const int *__restrict__ elm, const int *__restrict__ typ,
+                                   const int *__restrict__ qc, const double *__restrict__ lev, const double *__restrict__ dat,
+                                   const int *__restrict__ ctype_elmtyp, const int *__restrict__ vmode, int *__restrict__ keep,
+                                   int *__restrict__ ic, double *__restrict__ vc, int *__restrict__ err) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nobs) return;
+  const bool k = !(qc && qc[n] != 0);
+  keep[n] = k ? 1 : 0;
+  if (!k) return;
+  const int c = ctype_elmtyp[(dev_uid_obs(elm[n]) - 1) * nobtype + typ[n] - 1] - 1;
+  ic[n] = c;
+  const int vm = vmode[c];
+  const double pr = (elm[n] == 14593) ? dat[n] : lev[n];
+  if (vm == 1 && !(pr > 0.0)) atomicOr(err, 2);   // ln of a non-positive pressure
+  vc[n] = (vm == 3) ? lev[n] : log(pr);
+}
+// stream compaction in arrival order (pos = exclusive scan of keep)
+__global__ void obs_compact_kernel(int nobs, int nensobs, const int *__restrict__ keep, const int *__restrict__ pos,
+                                   const int *__restrict__ ic, const double *__restrict__ vc, const double *__restrict__ ri,
+                                   const double *__restrict__ rj, const double *__restrict__ err, const double *__restrict__ val,
+                                   const double *__restrict__ ens, int *__restrict__ o_ic, double *__restrict__ o_vc,
+                                   double *__restrict__ o_ri, double *__restrict__ o_rj, double *__restrict__ o_err,
+                                   double *__restrict__ o_val, double *__restrict__ o_ens, int *__restrict__ kept_index) {
+  const int n = blockIdx.x, lane = threadIdx.x;
+  if (n >= nobs || !keep[n]) return;
+  const int d = pos[n];
+  if (lane == 0) {
+    o_ic[d] = ic[n]; o_vc[d] = vc[n]; o_ri[d] = ri[n]; o_rj[d] = rj[n]; o_err[d] = err[n]; o_val[d] = val[n];
+    kept_index[d] = n;
+  }
+  for (int m = lane; m < nensobs; m += blockDim.x) o_ens[(size_t)d * nensobs + m] = ens[(size_t)n * nensobs + m];
+}
+
 // single-CTA exclusive scan (setup path; nb up to a few million buckets)
 __global__ void exclusive_scan_kernel(const int *__restrict__ count, int *__restrict__ start, int nb) {
   __shared__ int red[kMaxWarps];

@@ -152,7 +152,8 @@ struct letkf_b200_handle {
   int ps_grid = 0;
   DevBuf<long long> redo_list;
   // scratch of set_obs
-  DevBuf<int> so_ic, so_key, so_count, so_fill, so_tmp;
+  DevBuf<int> so_ic, so_key, so_count, so_fill, so_tmp, so_use, so_keep, so_pos, so_ic0, so_kept;
+  DevBuf<double> so_vc0;
   DevBuf<double> so_ri, so_rj, so_vc, so_err, so_val, so_ens;
 };
 
@@ -451,6 +452,7 @@ int letkf_b200_destroy(letkf_b200_handle *h) {
   }
   h->ps_l_iob.release(); h->ps_l_rdiag.release(); h->ps_l_rloc.release(); h->ps_l_cnd.release(); h->ps_l_cpk.release();
   h->ps_counters.release(); h->redo_list.release();
+  h->so_use.release(); h->so_keep.release(); h->so_pos.release(); h->so_ic0.release(); h->so_kept.release(); h->so_vc0.release();
   h->so_ic.release(); h->so_key.release(); h->so_count.release(); h->so_fill.release(); h->so_tmp.release();
   h->so_ri.release(); h->so_rj.release(); h->so_vc.release(); h->so_err.release(); h->so_val.release(); h->so_ens.release();
   for (cudaEvent_t e : h->ev_s) cudaEventDestroy(e);
@@ -492,11 +494,18 @@ int letkf_b200_set_grid(letkf_b200_handle *h, int nij1, const double *rig1, cons
   return LETKF_B200_OK;
 }
 
-int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
+}  // extern "C"
+
+// set_letkf_obs twin.  device = false: every array of `obs` is a host array of accepted observations (the reference's
+// obsda after its QC filter).  device = true: device arrays straight out of the observation operator / departure-QC
+// kernels, with their QC flags; the filter qc == iqc_good (letkf_obs.f90:752, 791), the combined-type lookup and the
+// vertical coordinate are done on the device, nothing but a 1.5 KB occupancy table crosses PCIe.
+static int set_obs_impl(letkf_b200_handle *h, const letkf_b200_obs *obs, const int32_t *qc, bool device, int32_t *nkept_out) {
   if (!h || !obs || obs->nobs < 0) return LETKF_B200_EINVAL;
   CK(cudaSetDevice(h->device));
   const letkf_b200_config &c = h->cfg;
-  const int nobs = obs->nobs;
+  int nobs = obs->nobs;
+  const int nobs_in = obs->nobs;
   const int need = c.DET_RUN ? c.MEMBER + 1 : c.MEMBER;
   if (nobs > 0 && obs->nensobs < need) return fail(h, LETKF_B200_EINVAL, "nensobs < MEMBER (+1 with DET_RUN)");
   if (nobs >= (1 << 28)) return fail(h, LETKF_B200_EINVAL, "more than 2^28 observations");
@@ -504,10 +513,25 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
   // ---- ctype table (letkf_obs.f90:300-342) --------------------------------------------------
   bool use[LETKF_B200_NID_OBS][LETKF_B200_NOBTYPE];
   std::memset(use, 0, sizeof(use));
-  for (int n = 0; n < nobs; ++n) {
-    const int u = uid_obs(obs->elm[n]);
-    if (u < 1 || obs->typ[n] < 1 || obs->typ[n] > LETKF_B200_NOBTYPE) return fail(h, LETKF_B200_EINVAL, "unknown obs elm/typ");
-    use[u - 1][obs->typ[n] - 1] = true;
+  DevBuf<int> &d_use = h->so_use;   // [NID_OBS * NOBTYPE] occupancy, [.. + 1] error flags, then the lookup tables
+  if (!device) {
+    for (int n = 0; n < nobs; ++n) {
+      const int u = uid_obs(obs->elm[n]);
+      if (u < 1 || obs->typ[n] < 1 || obs->typ[n] > LETKF_B200_NOBTYPE) return fail(h, LETKF_B200_EINVAL, "unknown obs elm/typ");
+      use[u - 1][obs->typ[n] - 1] = true;
+    }
+  } else {
+    const int nu = LETKF_B200_NID_OBS * LETKF_B200_NOBTYPE;
+    CK(d_use.ensure(2 * nu + kMaxCtype + 8));
+    CK(cudaMemsetAsync(d_use.p, 0, sizeof(int) * (nu + 1), h->stream));
+    if (nobs > 0)
+      obs_use_kernel<<<(nobs + 255) / 256, 256, 0, h->stream>>>(nobs, LETKF_B200_NOBTYPE, obs->elm, obs->typ, qc, d_use.p, d_use.p + nu);
+    std::vector<int> hu(nu + 1);
+    CK(cudaMemcpyAsync(hu.data(), d_use.p, sizeof(int) * (nu + 1), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (hu[nu] & 1) return fail(h, LETKF_B200_EINVAL, "unknown obs elm/typ");
+    for (int u = 0; u < LETKF_B200_NID_OBS; ++u)
+      for (int t = 0; t < LETKF_B200_NOBTYPE; ++t) use[u][t] = hu[u * LETKF_B200_NOBTYPE + t] != 0;
   }
   int ctype_elmtyp[LETKF_B200_NID_OBS][LETKF_B200_NOBTYPE];
   std::memset(ctype_elmtyp, 0, sizeof(ctype_elmtyp));
@@ -574,9 +598,9 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
   T.IHALO = c.IHALO; T.JHALO = c.JHALO; T.nlon = c.nlon; T.nlat = c.nlat;
   T.DX = c.DX; T.DY = c.DY; T.dzf = c.dist_zero_fac; T.dzf2 = c.dist_zero_fac_square;
   // ---- per-obs ctype and vertical coordinate (host libm: same log() as a CPU run) ---------------
-  std::vector<int> ic_of(nobs);
-  std::vector<double> vc(nobs);
-  for (int n = 0; n < nobs; ++n) {
+  std::vector<int> ic_of(device ? 0 : nobs);
+  std::vector<double> vc(device ? 0 : nobs);
+  for (int n = 0; n < (device ? 0 : nobs); ++n) {
     const int ic = ctype_elmtyp[uid_obs(obs->elm[n]) - 1][obs->typ[n] - 1] - 1;
     ic_of[n] = ic;
     const CtypeDev &d = T.ct[ic];
@@ -607,11 +631,45 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
   CK(d_fill.ensure(boff + 1));
   CK(cudaMemsetAsync(d_count.p, 0, sizeof(int) * (boff + 1), h->stream));
   CK(cudaMemsetAsync(d_fill.p, 0, sizeof(int) * (boff + 1), h->stream));
+  if (device && nobs > 0) {
+    // combined type, vertical coordinate and the qc == 0 compaction on the device
+    const int nu = LETKF_B200_NID_OBS * LETKF_B200_NOBTYPE;
+    std::vector<int> tab(nu + kMaxCtype, 0);
+    for (int u = 0; u < LETKF_B200_NID_OBS; ++u)
+      for (int t = 0; t < LETKF_B200_NOBTYPE; ++t) tab[u * LETKF_B200_NOBTYPE + t] = ctype_elmtyp[u][t];
+    for (int ic = 0; ic < nct; ++ic) tab[nu + ic] = T.ct[ic].vmode;
+    int *d_tab = d_use.p + nu + 1, *d_err = d_use.p + nu;
+    CK(cudaMemcpyAsync(d_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(h->so_keep.ensure(nobs)); CK(h->so_pos.ensure((size_t)nobs + 1)); CK(h->so_ic0.ensure(nobs)); CK(h->so_vc0.ensure(nobs));
+    obs_prepare_kernel<<<(nobs + 255) / 256, 256, 0, h->stream>>>(nobs, LETKF_B200_NOBTYPE, obs->elm, obs->typ, qc, obs->lev, obs->dat,
+                                                                d_tab, d_tab + nu, h->so_keep.p, h->so_ic0.p, h->so_vc0.p, d_err);
+    exclusive_scan_kernel<<<1, 256, 0, h->stream>>>(h->so_keep.p, h->so_pos.p, nobs);
+    int hk[2] = {0, 0};
+    CK(cudaMemcpyAsync(&hk[0], h->so_pos.p + nobs, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&hk[1], d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (hk[1] & 2) return fail(h, LETKF_B200_EINVAL, "non-positive pressure in an observation localised in ln p");
+    nobs = hk[0];
+    h->nobstotal = nobs;
+    CK(h->s2o.ensure(std::max(nobs, 1))); CK(h->rec.ensure(std::max(nobs, 1))); CK(h->sval.ensure(std::max(nobs, 1)));
+    CK(h->sens.ensure((size_t)std::max(nobs, 1) * h->ldens));
+    CK(h->so_kept.ensure(std::max(nobs, 1)));
+  }
+  if (nobs_in > 0 && nobs == 0 && device) {   // everything rejected: empty tables
+    exclusive_scan_kernel<<<1, 256, 0, h->stream>>>(d_count.p, h->bstart.p, boff);
+    CK(cudaGetLastError());
+  } else
   if (nobs > 0) {
     CK(d_ic.ensure(nobs)); CK(d_key.ensure(nobs)); CK(d_tmp.ensure(nobs));
     CK(d_ri.ensure(nobs)); CK(d_rj.ensure(nobs)); CK(d_vc.ensure(nobs)); CK(d_err.ensure(nobs));
     CK(d_val.ensure(nobs)); CK(d_ens.ensure((size_t)nobs * obs->nensobs));
     const size_t nb = sizeof(double) * nobs;
+    if (device) {
+      obs_compact_kernel<<<nobs_in, 64, 0, h->stream>>>(nobs_in, obs->nensobs, h->so_keep.p, h->so_pos.p, h->so_ic0.p, h->so_vc0.p,
+                                                       obs->ri, obs->rj, obs->err, obs->val, obs->ensval, d_ic.p, d_vc.p, d_ri.p,
+                                                       d_rj.p, d_err.p, d_val.p, d_ens.p, h->so_kept.p);
+      CK(cudaGetLastError());
+    } else {
     CK(cudaMemcpyAsync(d_ic.p, ic_of.data(), sizeof(int) * nobs, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_ri.p, obs->ri, nb, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_rj.p, obs->rj, nb, cudaMemcpyHostToDevice, h->stream));
@@ -622,6 +680,7 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
     // (cached per handle) so that the copy runs at PCIe speed instead of the pageable-memory staging rate
     if (nb * obs->nensobs >= ((size_t)32 << 20)) ensure_pinned(h, const_cast<double *>(obs->ensval), nb * obs->nensobs);
     CK(cudaMemcpyAsync(d_ens.p, obs->ensval, nb * obs->nensobs, cudaMemcpyHostToDevice, h->stream));
+    }
     const int tb = 256, gb = (nobs + tb - 1) / tb;
     bucket_key_kernel<<<gb, tb, 0, h->stream>>>(h->d_tables.p, nobs, d_ic.p, d_ri.p, d_rj.p, d_key.p, d_count.p);
     exclusive_scan_kernel<<<1, 256, 0, h->stream>>>(d_count.p, h->bstart.p, boff);
@@ -697,6 +756,23 @@ int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) {
   CK(cudaMemcpyAsync(h->vlfac_groups.p, vg.data(), sizeof(double) * vg.size(), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->obs_set = true;
+  if (nkept_out) *nkept_out = nobs;
+  return LETKF_B200_OK;
+}
+
+extern "C" {
+
+int letkf_b200_set_obs(letkf_b200_handle *h, const letkf_b200_obs *obs) { return set_obs_impl(h, obs, nullptr, false, nullptr); }
+
+int letkf_b200_set_obs_device(letkf_b200_handle *h, const letkf_b200_obs *obs, const int32_t *qc, int32_t *nkept) {
+  return set_obs_impl(h, obs, qc, true, nkept);
+}
+
+int letkf_b200_get_kept_index(const letkf_b200_handle *h, int32_t *kept) {
+  if (!h || !h->obs_set || !kept) return LETKF_B200_ESTATE;
+  if (h->so_kept.n < (size_t)std::max(h->nobstotal, 1)) return LETKF_B200_ESTATE;   // not a set_obs_device table
+  if (h->nobstotal > 0 && cudaMemcpy(kept, h->so_kept.p, sizeof(int) * h->nobstotal, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return LETKF_B200_ECUDA;
   return LETKF_B200_OK;
 }
 

@@ -225,3 +225,49 @@ def test_set_letkf_obs_raw_pipeline(oracle):
     n2, b2, r2 = oracle.monit_dep(raw["elm"], val, qc)
     assert np.array_equal(info["nobs"], n2)
     e.close()
+
+
+@pytest.mark.gpu
+def test_device_obs_chain_matches_host_chain(oracle):
+    """letkf_b200_obs_departure_qc(DEVICE) -> letkf_b200_set_obs_device (qc filter, combined types, vertical coordinate
+    and bucket sort on the device) gives the tables of the host chain (host filter + letkf_b200_set_obs), and the
+    same analysis."""
+    import torch
+    import scale_letkf_b200 as sl
+    from scale_letkf_b200 import synth
+    cfg = synth.config_c3(nlon=24, nlat=24, nlev=6, member=12, max_nobs=40)
+    rig1, rjg1, hgt1 = synth.make_grid(cfg)
+    gues = synth.make_state(cfg, rig1, rjg1, hgt1, seed_no=71)
+    pos = synth.make_radar_obs(cfg, radius_m=5.0e3, zmin=500.0, zmax=6000.0, dz=1000.0, seed_no=72)
+    n = len(pos["elm"])
+    raw = synth.make_raw_obs(member=12, nobs=n, seed_no=73)
+    radar = np.isin(pos["elm"], (4001, 4004))
+    raw["elm"] = pos["elm"]                      # radar elements at radar positions, H(x_m) / data of the raw generator
+    raw["ensval"] = np.where(radar[:, None], np.abs(raw["ensval"]) + 8.0, raw["ensval"])
+    raw["dat"] = np.where(radar, np.abs(raw["dat"]) + 8.0, raw["dat"])
+    raw.update({kf: pos[kf] for kf in ("typ", "ri", "rj", "lev")})
+    e1 = sl.LETKF(cfg, device=0)
+    r1 = e1.set_letkf_obs_raw(raw, qc_in=raw["qc"].astype(np.int32))
+    e1.set_common_mpi_grid(rig1, rjg1, hgt1)
+    e2 = sl.LETKF(cfg, device=0)
+    dev = torch.device("cuda", 0)
+    t = {kf: torch.as_tensor(np.ascontiguousarray(raw[kf]), device=dev) for kf in ("elm", "typ", "ri", "rj", "lev", "dat", "err")}
+    t["ensval"] = torch.as_tensor(np.ascontiguousarray(raw["ensval"]), device=dev)
+    qc = torch.as_tensor(raw["qc"].astype(np.int32), device=dev)
+    t["val"] = e2.obs_departure_qc_device(t["elm"], t["dat"], t["err"], qc, t["ensval"])
+    nk = e2.set_letkf_obs_device(t, qc)
+    e2.set_common_mpi_grid(rig1, rjg1, hgt1)
+    assert nk == r1["kept"] and 0 < nk < n
+    assert np.array_equal(qc.cpu().numpy(), r1["qc"])
+    assert e1.obs_info() == e2.obs_info()
+    for ic in range(e1.obs_info()[1]):
+        assert np.array_equal(e1.ac_ext(ic), e2.ac_ext(ic))
+    kept = e2.kept_index()
+    assert np.array_equal(kept, np.nonzero(r1["qc"] == 0)[0])
+    assert np.array_equal(e1.sorted_index(), e2.sorted_index())
+    a = e1.das_letkf(gues.copy(order="F"), want_nobsl=True)
+    b = e2.das_letkf(gues.copy(order="F"), want_nobsl=True)
+    assert np.array_equal(a["nobsl"], b["nobsl"]) and a["nsolved"] > 0
+    assert np.array_equal(a["anal3d"][:, :, :12, :], b["anal3d"][:, :, :12, :])
+    e1.close()
+    e2.close()

@@ -54,7 +54,7 @@ def make_case(nobs=4000, nmem=3, nlev=20, nlon=18, nlat=16, halo=2, seed=5, meth
     r = capi.RadarConfig()
     r.METHOD_REF_CALC, r.USE_TERMINAL_VELOCITY = method, use_tv
     r.nlevh, r.nlonh, r.nlath, r.nlev, r.KHALO, r.nv3dd = nlevh, nlonh, nlath, nlev, halo, 13
-    r.MIN_RADAR_REF_DBZ, r.LOW_REF_SHIFT, r.RADAR_ZMAX = 5.0, -2.0, 9000.0
+    r.MIN_RADAR_REF_DBZ, r.LOW_REF_SHIFT, r.RADAR_ZMAX = 5.0, -2.0, float(zlev[halo + nlev - 1] * 1.05)
     r.radar_lon, r.radar_lat, r.radar_z = radar_lon, radar_lat, radar_z
     return r, elm, ril, rjl, lon, lat, lev, grids, rotc
 
