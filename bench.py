@@ -414,6 +414,8 @@ def measure(name, ctx, args, steps, warmup, legs):
     # ---- parity inside the bench: the analysis just timed against the oracle on a sample of this rank's columns ----
     parity = None
     if "parity" in legs:
+        perr = None
+        pv = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=torch.float64, device=dev)   # err, nobsl mismatch, points, failed
         try:
             from oracle import oracle_py
             oracle_py.build()
@@ -438,18 +440,21 @@ def measure(name, ctx, args, steps, warmup, legs):
             sc = np.maximum(np.abs(b[sel]).max(axis=(0, 1), keepdims=True), 1e-300)
             pv = torch.tensor([float((np.abs(a_gpu[sel] - b[sel]) / sc).max()),
                                0.0 if np.array_equal(nb[sel], ref["nobsl"][sel]) else 1.0,
-                               float(sel.sum())], dtype=torch.float64, device=dev)
-            if world > 1:
-                mx = pv.clone()
-                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-                dist.all_reduce(pv, op=dist.ReduceOp.SUM)
-                pv[0], pv[1] = mx[0], mx[1]
+                               float(sel.sum()), 0.0], dtype=torch.float64, device=dev)
+            del o
+        except Exception as e:
+            perr = repr(e)[:300]
+        if world > 1:   # outside the try block: every rank takes part whatever happened on it
+            mx = pv.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(pv, op=dist.ReduceOp.SUM)
+            pv[0], pv[1], pv[3] = mx[0], mx[1], mx[3]
+        if float(pv[3]) != 0.0:
+            parity = {"error": perr or "the parity leg failed on another rank"}
+        else:
             parity = {"nobsl_equal": bool(pv[1] == 0.0), "max_rel_err": float(pv[0]), "points": int(pv[2]),
                       "what": "GPU anal3d / nobsl of the timed workload vs the CPU oracle on a column sample of every rank, "
                               "max |a-b| / max|b| per variable", "tolerance": 1e-10}
-            del o
-        except Exception as e:
-            parity = {"error": repr(e)[:300]}
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
     peaks, peaks_src = measured_peaks()
@@ -483,6 +488,10 @@ def measure(name, ctx, args, steps, warmup, legs):
     # ---- full analysis cycle (SURVEY.md section 8d metric ii) ----------------------------------------
     cycle = None
     free_b, _ = torch.cuda.mem_get_info()
+    if world > 1:   # one decision for all ranks: the cycle leg is full of collectives
+        fb = torch.tensor([float(free_b)], dtype=torch.float64, device=dev)
+        dist.all_reduce(fb, op=dist.ReduceOp.MIN)
+        free_b = float(fb[0])
     if "cycle" in legs and args.subsample == 1 and free_b < 2.2 * state_bytes:
         cycle = {"skipped": "member-major input and output grids (2 x %.1f GB) do not fit next to the three state arrays "
                             "on this GPU count" % (state_bytes / 1e9)}
@@ -651,6 +660,9 @@ def main():
                     help="member<->grid transposes of the cycle leg: one-pass peer-memory kernels (default) or pack + NCCL + unpack")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the secondary records of the default line (k100 = C3, c1, and at 8 GPUs c5_cycle and c4)")
+    ap.add_argument("--all-extra", action="store_true", help="run the 8-GPU secondary records (c5_cycle, c4) at any rank count")
+    ap.add_argument("--extra-deadline", type=float, default=480.0,
+                    help="seconds after which the secondary records are abandoned and the line is printed without them")
     ap.add_argument("--synth", default="hx", choices=["hx", "iid"],
                     help="hx: smooth correlated members, ensval = H(x_m) (default); iid: round-1 generator")
     ap.add_argument("--subsample", type=int, default=1,
@@ -698,26 +710,15 @@ def main():
         legs.add("cpu")
     r = measure(args.workload, ctx, args, args.steps, args.warmup, legs)
 
-    # ---- secondary records of the default line (the other BASELINE.json shapes) ------------------------
+    # ---- the line (rank 0); emitted once, by the main thread or -- if a secondary record hangs -- by the deadline thread ----
     extra = {}
-    if args.workload == "c2" and not args.no_extra and args.subsample == 1:
-        def sub(key, name, steps, warmup, lg):
-            try:
-                extra[key] = brief(measure(name, ctx, args, steps, warmup, lg), steps)
-            except Exception as e:
-                extra[key] = {"error": repr(e)[:300]}
-                torch.cuda.empty_cache()
-        sub("k100", "c3", 3, 1, {"parity", "cycle"})            # C3: 256x256x60, k = 100, dense radar
-        if world >= 8:
-            sub("c5_cycle", "c5", 2, 1, {"cycle"})              # C5: 400x400x60 full cycle
-            sub("c4", "c4", 1, 1, {"parity"})                   # C4: 128x128x40, k = 1000, one full-size pass
-        if rank == 0:
-            try:
-                extra["c1"] = c1_record()
-            except Exception as e:
-                extra["c1"] = {"error": repr(e)[:300]}
+    emitted = threading.Lock()
 
-    if rank == 0:
+    def emit(note=None):
+        if not emitted.acquire(blocking=False):
+            return
+        if rank != 0:
+            return
         line = {
             "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
@@ -734,13 +735,44 @@ def main():
             "roofline": r["roofline"], "cpu_baseline": r["cpu"], "parity": r["parity"], "cycle": r["cycle"],
             "kernel_ms_per_step": r["kms"], "phase_share_rank0": r["phases"],
         }
-        line.update(extra)
+        line.update(dict(extra))
+        if note:
+            line["extras_note"] = note
         if args.subsample > 1:
             line["config"]["subsample"] = f"every {args.subsample}-th column only (profiling aid, not a bench value)"
         if world > 1:
             sys.stdout.flush()
             os.dup2(saved_stdout_fd, 1)
         print(json.dumps(line), flush=True)
+
+    # ---- secondary records of the default line (the other BASELINE.json shapes) ------------------------
+    if args.workload == "c2" and not args.no_extra and args.subsample == 1:
+        done = threading.Event()
+
+        def deadline():   # the main measurement is never lost to a secondary record that hangs in a collective
+            if not done.wait(args.extra_deadline):
+                emit("secondary records stopped after %.0f s (deadline); the records present are complete" % args.extra_deadline)
+                sys.stdout.flush()
+                os._exit(0)
+        threading.Thread(target=deadline, daemon=True).start()
+
+        def sub(key, name, steps, warmup, lg):
+            try:
+                extra[key] = brief(measure(name, ctx, args, steps, warmup, lg), steps)
+            except Exception as e:
+                extra[key] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
+        sub("k100", "c3", 3, 1, {"parity", "cycle"})            # C3: 256x256x60, k = 100, dense radar
+        if world >= 8 or args.all_extra:
+            sub("c5_cycle", "c5", 2, 1, {"cycle"})              # C5: 400x400x60 full cycle
+            sub("c4", "c4", 1, 1, {"parity"})                   # C4: 128x128x40, k = 1000, one full-size pass
+        if rank == 0:
+            try:
+                extra["c1"] = c1_record()
+            except Exception as e:
+                extra["c1"] = {"error": repr(e)[:300]}
+        done.set()
+    emit()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -119,11 +119,20 @@ class EnsTransposeP2P:
         self.eng, self.np, self.rank, self.group, self.thermo = eng, int(nprocs_e), int(myrank_e), group, thermo
         self._maps = {}
 
-    def _addresses(self, key, tensor):
-        """device addresses of `tensor` (same role on every rank) on all ranks, as seen from this GPU; None entries allowed"""
+    def _addresses(self, key, owner, tensor):
+        """device addresses of `tensor` (same role on every rank) on all ranks, as seen from this GPU; None entries allowed.
+
+        The handle exchange is a COLLECTIVE, so whether it runs must be decided identically on every rank: the cache is
+        keyed by `key` and validated by the identity of `owner` (the Python object the caller passed: the same object on
+        every rank at the same point of the program), never by this rank's pointer alone -- a rank that holds no member
+        in a round (tensor None) would otherwise skip an exchange its peers enter (hang at 4 / 8 ranks with 50 members)."""
         ptr = None if tensor is None else tensor.data_ptr()
-        if key in self._maps and self._maps[key][0] == ptr:
-            return self._maps[key][1]
+        hit = self._maps.get(key)
+        if hit is not None and hit[0] is owner:
+            if hit[1] != ptr:
+                raise RuntimeError("EnsTransposeP2P: tensor %r of a registered owner was re-allocated; pass a new owner "
+                                   "object (a new list / tensor) on every rank instead" % (key,))
+            return hit[2]
         if self.np == 1:
             addrs = [ptr]
         else:
@@ -131,7 +140,7 @@ class EnsTransposeP2P:
             allg = [None] * self.np
             dist.all_gather_object(allg, desc, group=self.group)
             addrs = [ptr if r == self.rank else (None if d is None else self.eng.peer_open(d)) for r, d in enumerate(allg)]
-        self._maps[key] = (ptr, addrs)
+        self._maps[key] = (owner, ptr, addrs)   # the strong reference to `owner` keeps its id from being reused
         return addrs
 
     def _barrier(self):
@@ -147,7 +156,7 @@ class EnsTransposeP2P:
 
     def read_ens(self, my_members3d, v3d, nmem, nens):
         """my_members3d[it]: member-major grid of the member this rank holds in round it (or None) -> v3d on every rank"""
-        peers = self._addresses("v3d", v3d)
+        peers = self._addresses("v3d", v3d, v3d)
         self._barrier()                       # nobody still reads the previous contents of v3d
         for it, im, mstart, mend in self.rounds(nmem):
             if im is not None:
@@ -156,7 +165,7 @@ class EnsTransposeP2P:
 
     def write_ens(self, v3d, my_members3d, nmem, nens):
         """v3d (e.g. the analysis) on every rank -> member-major grids my_members3d[it] on the member-holding ranks"""
-        grids = [self._addresses(("g", it), my_members3d[it]) for it, _, _, _ in self.rounds(nmem)]
+        grids = [self._addresses(("g", it), my_members3d, my_members3d[it]) for it, _, _, _ in self.rounds(nmem)]
         self._barrier()
         for it, im, mstart, mend in self.rounds(nmem):
             self.eng.gather_grd_p2p(self.np, self.rank, nens, mstart, mend, v3d, None, grids[it][:mend - mstart + 1],

@@ -246,3 +246,73 @@ def run_gpu(rank, world, port, q):
         q.put((rank, "FAIL " + repr(e) + traceback.format_exc()))
     finally:
         dist.destroy_process_group()
+
+
+class _StubP2PEngine:
+    """Stand-in of the engine for EnsTransposeP2P on CPU: 'exports' a tensor as (rank, data_ptr), 'opens' it as an
+    integer, counts the calls.  The p2p kernels themselves need CUDA IPC (covered by the 2-GPU test)."""
+
+    def __init__(self, rank):
+        self.rank, self.exports, self.calls = rank, 0, []
+
+    def peer_export(self, t):
+        self.exports += 1
+        return (self.rank, t.data_ptr())
+
+    def peer_open(self, d):
+        return 1000 + d[0]
+
+    def scatter_grd_p2p(self, np_, rank, nens, im, g3, g2, peers, thermo=None):
+        assert g3 is not None and len(peers) == np_ and all(p is not None for p in peers)
+        self.calls.append(("s", im))
+
+    def gather_grd_p2p(self, np_, rank, nens, mstart, mend, v3d, v2d, peers, thermo=None):
+        assert len(peers) == mend - mstart + 1 and all(p is not None for p in peers), peers
+        self.calls.append(("g", mstart, mend))
+
+
+def run_p2p_bookkeeping(rank, world, port, nmem, q):
+    """EnsTransposeP2P's handle exchange is a collective: every rank must enter it the same number of times, also when
+    the rank holds no member in the last round (its grid is None) and the caller switches between two grid lists --
+    the sequence bench.py's cycle leg produces (write gin, read gin, write gout, ...).  A mismatch hangs: the test
+    harness times out."""
+    try:
+        import datetime
+        import torch
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=60))
+        from scale_letkf_b200.transpose import EnsTransposeP2P
+        orig = dist.all_gather_object
+        ncoll = [0]
+
+        def counting(*a, **kw):
+            ncoll[0] += 1
+            return orig(*a, **kw)
+        dist.all_gather_object = counting
+        eng = _StubP2PEngine(rank)
+        tr = EnsTransposeP2P(eng, world, rank)
+        torch.cuda.synchronize = lambda *a, **kw: None      # CPU-only process
+        rounds = list(tr.rounds(nmem))
+        mk = lambda: [torch.zeros(4, dtype=torch.float64) if im is not None else None for _, im, _, _ in rounds]
+        gin, gout = mk(), mk()
+        v3d, anal = torch.zeros(8, dtype=torch.float64), torch.zeros(8, dtype=torch.float64)
+        tr.write_ens(v3d, gin, nmem, nmem + 1)
+        for _ in range(3):
+            tr.read_ens(gin, v3d, nmem, nmem + 1)
+            tr.write_ens(anal, gout, nmem, nmem + 1)
+        tr.read_ens(gin, v3d, nmem, nmem + 1)
+        tr.write_ens(v3d, gout, nmem, nmem + 1)
+        n = torch.tensor([ncoll[0]], dtype=torch.int64)
+        lo, hi = n.clone(), n.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert int(lo) == int(hi) == 1 + 2 * len(rounds), (int(lo), int(hi), len(rounds))   # v3d, gin[it], gout[it]: once each
+        mine = sum(1 for _, im, _, _ in rounds if im is not None)
+        assert sum(1 for c in eng.calls if c[0] == "s") == 4 * mine
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:   # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL " + repr(e) + traceback.format_exc()))

@@ -49,6 +49,28 @@ def test_transposes_with_fused_state_trans_world2_gloo():
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
 
 
+@pytest.mark.parametrize("world,nmem", [(2, 3), (4, 6), (4, 8)])   # (4, 6): ranks 2, 3 hold no member in the last round
+def test_p2p_handle_exchange_is_rank_consistent_gloo(world, nmem):
+    """EnsTransposeP2P exchanges CUDA IPC handles with a collective; every rank must take part in every exchange even
+    when its own grid of the round is None (50 members on 4 or 8 ranks) -- otherwise the cycle leg of bench.py hangs."""
+    import torch.multiprocessing as mp
+    import mr_worker
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=mr_worker.run_p2p_bookkeeping, args=(r, world, port, nmem, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        res = [q.get(timeout=150) for _ in procs]
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.terminate()
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_column_deal_partitions_the_plane(world):
     """every (ilon, ilat) column is analysed by exactly one rank; nij1 follows set_common_mpi_grid"""
