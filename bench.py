@@ -399,6 +399,7 @@ def measure(name, ctx, args, steps, warmup, legs):
     phases = dict(zip(["load", "search", "gram", "factor", "eigen", "apply", "store", "sched"],
                       (ph / max(ph.sum(), 1.0)).round(4).tolist()))
     phases["solver_iterations_per_solve"] = out["solver_iterations"] / max(out["nsolved"], 1)
+    phases["refined_share_of_solves"] = out.get("nrefined", 0) / max(out["nsolved"], 1)   # ill-conditioned path (explicit Z + refinement)
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms, float(sum(kern_ms))], dtype=torch.float64, device=dev)
     cnt = torch.tensor([out["npoints"], out["nsolved"], out["nobsl_sum"], out["launches"]], dtype=torch.float64,

@@ -209,6 +209,9 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *args);
 /* counters of the last das call: points analysed, points solved (nobsl>0), eigensolve failures */
 int letkf_b200_das_stats(const letkf_b200_handle *h, int64_t *npoints, int64_t *nsolved,
                          int64_t *nfail, int64_t *nobsl_sum);
+/* solves of the last das call that took the ill-conditioned path (lambda_max(A) / c0 above ~1e4: explicit A^-1/2 and one
+ * step of iterative refinement of the mean weight against the original matrix; MEMBER <= 102 only) */
+int letkf_b200_das_refined(const letkf_b200_handle *h, int64_t *nrefined);
 /* CUDA-event time (ms) of the dominant kernel in the last das call (bench roofline) */
 int letkf_b200_das_kernel_ms(const letkf_b200_handle *h, float *analysis_ms, int *launches);
 

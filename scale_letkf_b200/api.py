@@ -240,9 +240,11 @@ class LETKF:
         ph = (C.c_int64 * 8)()
         it = C.c_int64()
         self.lib.letkf_b200_das_phase_clocks(self.h, ph, C.byref(it))
+        nref = C.c_int64()
+        self.lib.letkf_b200_das_refined(self.h, C.byref(nref))
         return dict(status=r, anal3d=anal3d, anal2d=anal2d, rtps=rtps, nobsl=nobsl, npoints=st[0].value,
                     nsolved=st[1].value, nfail=st[2].value, nobsl_sum=st[3].value, kernel_ms=ms.value,
-                    launches=nl.value, phase_clocks=list(ph), solver_iterations=it.value)
+                    launches=nl.value, phase_clocks=list(ph), solver_iterations=it.value, nrefined=nref.value)
 
     def ensmean_grd(self, v3d, v2d=None):
         """Fill slot MEMBER+1 with the member mean (in place)."""

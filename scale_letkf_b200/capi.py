@@ -156,6 +156,7 @@ PROTOTYPES = {
     "letkf_b200_das_letkf": (_i, [_vp, C.POINTER(DasArgs)]),
     "letkf_b200_das_stats": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "letkf_b200_das_refined": (_i, [_vp, C.POINTER(C.c_int64)]),
     "letkf_b200_das_kernel_ms": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "letkf_b200_das_phase_clocks": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "letkf_b200_ensmean_grd": (_i, [_vp, _i, _i, _i, _vp, _vp, _i]),

@@ -18,14 +18,21 @@
 
 namespace letkf {
 
+// A/B aid: -DLETKF_NS_ZPATH forces the explicit-Z Newton-Schulz (the ill-conditioned path) on every point
+#ifdef LETKF_NS_ZPATH
+constexpr bool kForceZPath = true;
+#else
+constexpr bool kForceZPath = false;
+#endif
+
 template <int NB, bool PRE = false>
 __host__ __device__ inline size_t das_ns_smem_bytes() {
   using C = NsCfg<NB>;
   size_t d = 3 * (size_t)C::PSZ;          // packed Y, Z, T (together: the three obs-chunk staging buffers of the Gram)
   d += (size_t)kMaxNV * C::LD;            // Xall
   if (kMaxNV * C::LD > C::PSZ) d += (size_t)kMaxNV * C::LD;   // Ts (else it aliases T: the Newton-Schulz scratch is free by then)
-  d += 3 * (size_t)C::CR;                 // per-row weights of the three staged chunks
-  d += 8 * kMaxNV + 40;                   // per-column scalars, reductions
+  d += 4 * (size_t)C::CR;                 // per-row weights of the four staged chunks
+  d += 8 * kMaxNV + 56;                   // per-column scalars, reductions (3 NW + 1 <= 49 doubles)
   return d * sizeof(double) + (PRE ? 0 : sizeof(SearchSmem)) + 64;
 }
 
@@ -33,6 +40,10 @@ __host__ __device__ inline size_t das_ns_smem_bytes() {
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
@@ -71,23 +82,16 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                "l"(src), "r"(bytes), "r"(smem_u32(b))
                : "memory");
 }
+// the executing thread arrives on the mbarrier once all its earlier cp.async copies have landed (the pending count
+// must already include this arrival: mbarrier.init with one count per thread)
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long *b) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // PRE = true: every local list comes from presearch_kernel's pool; the kernel contains no search code at
 // all (fewer live registers, no SearchSmem).  A point whose list did not fit the pool is appended to
 // P.redo_list untouched and analysed afterwards by the PRE = false instantiation (P.point_list mode).
-#ifdef LETKF_EXP_TRACE
-#define LETKF_TRACE(tag)                                                              \
-  do {                                                                                \
-    if (threadIdx.x == 0 && blockIdx.x == 0 && P.trace && s_ntrace < 4000) {          \
-      P.trace[2 * s_ntrace] = (tag);                                                  \
-      P.trace[2 * s_ntrace + 1] = clock64();                                          \
-      ++s_ntrace;                                                                     \
-    }                                                                                 \
-  } while (0)
-#else
-#define LETKF_TRACE(tag) do { } while (0)
-#endif
 
 template <int NB, bool PRE>
 __global__ void __launch_bounds__(NsCfg<NB>::NT, NsCfg<NB>::MINB)
@@ -96,40 +100,42 @@ __maxnreg__(NB == 13 ? LETKF_MAXNREG13 : (NB == 9 ? 112 : (NB == 7 ? 72 : (NB ==
 #endif
 das_ns_kernel(const DasParams P) {
 #ifdef LETKF_EXP_TRACE
-  __shared__ int s_ntrace;
-  if (threadIdx.x == 0) s_ntrace = 0;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    g_trace_buf = P.trace;
+    g_trace_n = 0;
+  }
 #endif
   using C = NsCfg<NB>;
   constexpr int KP = C::KP, LD = C::LD, H = C::H, CR = C::CR, PSZ = C::PSZ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = P.k, nens = P.nens;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int w = __shfl_sync(LETKF_FULL_MASK, tid >> 5, 0);   // warp-uniform: tile addressing on the uniform datapath
+  const int wid = __shfl_sync(LETKF_FULL_MASK, tid >> 5, 0);   // warp of the CTA (warp-uniform: tile addressing on the uniform datapath)
+  const int w = wid < NB ? wid : NB - 1;                       // its row block
+  const TileOwn own = tile_own<NB>(wid);                       // the tiles of that row block it owns (ns_solver.cuh)
+  const bool rowown = wid < NB;                                // it also carries the vector rows of the block
+  constexpr int NW = C::NW;
   double *Yp = reinterpret_cast<double *>(smem_raw);
   double *Zp = Yp + PSZ;
   double *Tp = Zp + PSZ;
-  double *stage = Yp;                           // 3 x CR x LD doubles inside Yp..Tp
+  double *stage = Yp;                           // 4 x CR x LD doubles inside Yp..Tp
   double *Xall = Tp + PSZ;                      // [kMaxNV][LD]: perturbations of variable vv; rows 14/15: b, bd
   constexpr bool TS_ALIAS = kMaxNV * LD <= PSZ;   // [kMaxNV][LD]: Z Xall -- lives in T's storage when it fits
   double *Ts = TS_ALIAS ? Tp : Xall + (size_t)kMaxNV * LD;
-  double *wv = Xall + (size_t)(TS_ALIAS ? 1 : 2) * kMaxNV * LD;      // [2][CR]
-  double *colsc = wv + 3 * CR;                  // [8][kMaxNV]
+  double *wv = Xall + (size_t)(TS_ALIAS ? 1 : 2) * kMaxNV * LD;      // [4][CR]
+  double *colsc = wv + 4 * CR;                  // [8][kMaxNV]
   double *red = colsc + 8 * kMaxNV;
-  SearchSmem &S = *reinterpret_cast<SearchSmem *>((reinterpret_cast<uintptr_t>(red + 40) + 15) & ~(uintptr_t)15);
+  SearchSmem &S = *reinterpret_cast<SearchSmem *>((reinterpret_cast<uintptr_t>(red + 56) + 15) & ~(uintptr_t)15);
   __shared__ long long s_work, s_next;
   __shared__ long long s_ploff[kMaxNV];
   __shared__ int s_pln[kMaxNV];
-  __shared__ __align__(8) unsigned long long s_full[3];   // mbarriers of the three Gram staging buffers
-  __shared__ int s_cnt[3];
+  __shared__ __align__(8) unsigned long long s_full[4];   // mbarriers of the four Gram staging buffers
   const LaneFrag lf = lane_frag(lane);
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(&s_full[i], 1);   // one arrival (the requesting warp) + the bytes of the chunk's rows
-      s_cnt[i] = 0;               // warps that have consumed the chunk in buffer i
-    }
+    for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], C::NT);   // every thread arrives once its copies of the chunk have landed
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  unsigned gchunk = 0;   // chunks staged so far by this CTA: buffer = gchunk % 3, mbarrier phase = (gchunk / 3) & 1
+  unsigned gchunk = 0;   // chunks staged so far by this CTA: buffer = gchunk % 4, mbarrier phase = (gchunk / 4) & 1
 
   LocalList L;
   L.cap = P.lcap;
@@ -143,10 +149,10 @@ das_ns_kernel(const DasParams P) {
   const size_t sl = (size_t)P.nij1 * P.nlev;
   // Statistics and phase clocks live in shared memory and are kept by thread 0 only: as per-thread registers they
   // cost 30 registers that the software-pipelined tensor-core loops need (the kernel runs at 72 registers, 4 CTAs/SM).
-  __shared__ unsigned long long s_stat[6];   // points, solved, fail, nobs, overflow, solver iterations
+  __shared__ unsigned long long s_stat[7];   // points, solved, fail, nobs, overflow, solver iterations, refined solves
   __shared__ long long s_ph[9];              // [0..7] phase clocks, [8] time stamp of the last phase change
   if (tid == 0) {
-    for (int i = 0; i < 6; ++i) s_stat[i] = 0;
+    for (int i = 0; i < 7; ++i) s_stat[i] = 0;
     for (int i = 0; i < 8; ++i) s_ph[i] = 0;
     s_ph[8] = clock64();
   }
@@ -222,55 +228,44 @@ das_ns_kernel(const DasParams P) {
     // ---- Gram staging machinery of the point (used by every variable-localisation group) -------------------
     int p_use = 0, nchunks = 0;   // local observations / staging chunks of the current group
     double p3acc = 0.0;
-    constexpr int RPL = (CR + 31) / 32;   // rows per lane of a request
-    int cur_iob[RPL], nxt_iob[RPL];
-    double cur_rd[RPL], nxt_rd[RPL];
-    auto fetch_idx = [&](int c, int (&o_iob)[RPL], double (&o_rd)[RPL]) {
-      const int o0 = c * CR, nrows = (c < nchunks) ? min(CR, p_use - o0) : 0;
-#pragma unroll
-      for (int u = 0; u < RPL; ++u) {
-        const int row = lane + 32 * u;
-        o_iob[u] = -1;
-        o_rd[u] = 1.0;
-        if (row < nrows) {
-          o_iob[u] = L.iob[o0 + row];
-          o_rd[u] = L.rdiag[o0 + row];
-        }
-      }
+    // Every warp requests ITS rows of a chunk (row = wid + NW * r, r < RPW <= 4): the warp copies one row per step with
+    // 16-byte cp.async (LDGSTS; lane l moves bytes 16 l ..), lane r also the row's R^-1 weight.  The lists are padded
+    // to a multiple of four entries (weight 0), so every staged row is a list entry: no special cases in here.
+    constexpr int RPW = C::RPW;
+    static_assert(RPW <= 32, "one row index per lane");
+    int cur_iob = 0;         // sorted-obs index of row wid + NW * lane of the chunk this warp requests next
+    int p4 = 0;              // list length rounded up to a multiple of four
+    auto fetch_idx = [&](int c, int &o_iob) {
+      const int o0 = c * CR, row = wid + NW * lane;
+      o_iob = 0;
+      if (lane < RPW && row < min(CR, p4 - o0)) o_iob = L.iob[o0 + row];   // (c >= nchunks: p4 - o0 <= 0)
     };
-    auto request = [&](int c, const int (&iobs)[RPL], const double (&rds)[RPL]) {   // one warp, all lanes
-      const unsigned g = gchunk + (unsigned)c, st = g % 3u;
+    auto request = [&](int c, int iob) {   // every warp, all lanes
+      const unsigned g = gchunk + (unsigned)c, st = g & 3u;
       double *dst = stage + (size_t)st * CR * LD;
       double *wdst = wv + st * CR;
-      const int o0 = c * CR, nrows = min(CR, p_use - o0), nrows4 = (nrows + 3) & ~3;
-      unsigned mine = 0;
+      const int o0 = c * CR, nrows4 = min(CR, p4 - o0);
 #pragma unroll
-      for (int u = 0; u < RPL; ++u) {
-        const int row = lane + 32 * u;
-        if (row < nrows) {
-          wdst[row] = 1.0 / rds[u];
-          if (P.INFL_MUL_ADAPTIVE) p3acc += L.rloc[o0 + row];
-        } else if (row < nrows4) {   // padding row of the last chunk: weight 0 and finite data
-          wdst[row] = 0.0;
-          for (int j = 0; j < KP; ++j) dst[(size_t)row * LD + j] = 0.0;
+      for (int r = 0; r < RPW; ++r) {
+        const int row = wid + NW * r;
+        const int ib = __shfl_sync(LETKF_FULL_MASK, iob, r);
+        if (row < nrows4) {
+          const double *src = P.ensval + (size_t)ib * P.ldens;
+          double *d = dst + (size_t)row * LD;
+#pragma unroll
+          for (int pc = lane; pc < KP / 2; pc += 32) cp_async16(d + 2 * pc, src + 2 * pc);
+          if (lane == r) cp_async8(wdst + row, L.rdiag + o0 + row);   // (the list holds 1 / rdiag)
         }
-        mine += __popc(__ballot_sync(LETKF_FULL_MASK, row < nrows));
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_expect_tx(&s_full[st], mine * (unsigned)(KP * sizeof(double)));
-#pragma unroll
-      for (int u = 0; u < RPL; ++u) {
-        const int row = lane + 32 * u;
-        if (row < nrows)
-          bulk_g2s(dst + (size_t)row * LD, P.ensval + (size_t)iobs[u] * P.ldens, (unsigned)(KP * sizeof(double)), &s_full[st]);
-      }
+      cp_async_mbar_arrive(&s_full[st]);
     };
-    auto gram_prologue = [&]() {   // chunks 0, 1, 2 are requested by warps 0, 1, 2
-      if (w < 3 && w < nchunks) {
-        fetch_idx(w, cur_iob, cur_rd);
-        request(w, cur_iob, cur_rd);
-      }
-      fetch_idx(3, nxt_iob, nxt_rd);
+    auto gram_prologue = [&]() {   // chunks 0 and 1; the indices of chunk 2 wait in registers
+      int i1;
+      fetch_idx(0, cur_iob);
+      fetch_idx(1, i1);
+      if (nchunks > 0) request(0, cur_iob);
+      if (nchunks > 1) request(1, i1);
+      fetch_idx(2, cur_iob);
     };
     // With pre-searched lists the first group's observation rows are requested right away: their flight overlaps the
     // member loads below.  (presearch_kernel stores an empty list for a group the solver skips: no stray request.)
@@ -281,6 +276,7 @@ das_ns_kernel(const DasParams P) {
       L.rdiag = P.pl_rdiag + pl_off;
       L.rloc = P.pl_rloc + pl_off;
       p_use = max(s_pln[0], 0);
+      p4 = (p_use + 3) & ~3;
       nchunks = (p_use + CR - 1) / CR;
       if (p_use > 0) {
         gram_prologue();
@@ -379,13 +375,28 @@ das_ns_kernel(const DasParams P) {
         L.rloc = P.pl_rloc + pl_off;   // only dereferenced when INFL_MUL_ADAPTIVE (then the pool exists)
       } else {
         nobsl = search_point(*P.T, P.rec, P.bstart, P.vlfac + (size_t)vg * P.T->nctype, pt, L, S);
+        // the Gram wants what presearch_kernel leaves in the pool: 1 / rdiag, padded to a multiple of four entries
+        // with weight 0 (the padding rows repeat the first observation: finite data)
+        const int n = max(nobsl, 0), n4 = (n + 3) & ~3;   // (lcap is a multiple of four)
+        for (int i = tid; i < n4; i += C::NT) {
+          if (i < n) {
+            L.rdiag[i] = 1.0 / L.rdiag[i];
+          } else {
+            L.rdiag[i] = 0.0;
+            L.iob[i] = L.iob[0];
+          }
+        }
+        __syncthreads();
       }
       if (nobsl < 0) stat(4, 1);
       if (!pro_done) {
         p_use = nobsl < 0 ? 0 : nobsl;
+        p4 = (p_use + 3) & ~3;
         nchunks = (p_use + CR - 1) / CR;
-        p3acc = 0.0;
       }
+      p3acc = 0.0;
+      if (P.INFL_MUL_ADAPTIVE)   // sum of the localisation weights (common_letkf.f90:233)
+        for (int i = tid; i < p_use; i += C::NT) p3acc += L.rloc[i];
       phase(1);
       LETKF_TRACE(3);
       if (P.nobsl_out && vg == 0 && tid == 0) P.nobsl_out[pbase] = p_use;
@@ -398,48 +409,33 @@ das_ns_kernel(const DasParams P) {
       if (p_use > 0) {
         solved_any = true;
         // ---- Gram [A | b | bd] = Yr^T [Y | dep | depd] (common_letkf.f90:111-128,182-195) on the
-        // tensor cores: raw obs rows [y_1..y_k, dep, depd, 0..] stream in by TMA bulk copies, the
-        // R^-1 weight is applied to the A operand.
+        // tensor cores: raw obs rows [y_1..y_k, dep, depd, 0..] stream in by cp.async, the R^-1 weight is applied
+        // to the A operand.
         double acc[H + 1][2];
 #pragma unroll
         for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
-        static_assert(CR <= 4 * NB, "a warp stages at most four rows of a chunk");
-        // Staging pipeline: three chunk buffers of CR obs rows (Y, Z and T are all free while the Gram accumulates in
-        // registers).  A chunk is requested by ONE warp: lane l stages row l (+32): one cp.async.bulk (TMA bulk copy, 8 KP
-        // bytes) per row lands on the chunk's `full` mbarrier together with the R^-1 weights.  "Last consumer refills":
-        // a warp that has consumed chunk c bumps a shared counter, and the warp that finds it was the last one requests
-        // chunk c + 3 into the same buffer -- nobody ever waits for a buffer to be released, and there is no CTA-wide
-        // barrier inside the loop.  Every warp keeps the (sorted-obs index, rdiag) of the rows of the chunk it may have to
-        // request next in registers, loaded one chunk ahead, so a request pays the row latency only, not index + row.
+        // Staging pipeline: FOUR chunk buffers of CR obs rows (Y, Z and T are all free while the Gram accumulates in
+        // registers).  Every warp requests its own rows of a chunk (16-byte cp.async; per-row TMA bulk copies cost
+        // ~500 clocks of issue each at four CTAs per SM -- profiles/r02_trace_notes.md), and every thread arrives on
+        // the chunk's `full` mbarrier when its copies have landed (cp.async.mbarrier.arrive).  A warp that has finished
+        // chunk c requests its rows of chunk c + 2 into buffer (c + 2) % 4: that buffer held chunk c - 2, and passing the
+        // wait on chunk c proves that every warp had finished chunk c - 2 (it arrived on chunk c's barrier only after
+        // that).  So there is no release barrier, no counter and no CTA-wide barrier in the loop.  The sorted-obs index
+        // of the row a lane requests next is loaded one chunk ahead, so a request pays the row latency only.
         if (!pro_done) gram_prologue();
         pro_done = false;
         for (int c = 0; c < nchunks; ++c) {
-          const unsigned g = gchunk + (unsigned)c, st = g % 3u;
+          const unsigned g = gchunk + (unsigned)c, st = g & 3u;
           LETKF_TRACE(10);
-          mbar_wait(&s_full[st], (g / 3u) & 1u);
+          mbar_wait(&s_full[st], (g >> 2) & 1u);
           LETKF_TRACE(11);
-          const int nrows = min(CR, p_use - c * CR);
-          if (nrows == CR) gram_circ_full<NB, LD>(acc, stage + (size_t)st * CR * LD, wv + st * CR, w, lane);
-          else gram_circ<NB, LD>(acc, stage + (size_t)st * CR * LD, wv + st * CR, (nrows + 3) & ~3, w, lane);
+          const int nrows4 = min(CR, p4 - c * CR);
+          if (nrows4 == CR) gram_circ_full<NB, LD, C::NSTEP>(acc, stage + (size_t)st * CR * LD, wv + st * CR, w, lane, own);
+          else gram_circ<NB, LD>(acc, stage + (size_t)st * CR * LD, wv + st * CR, nrows4, w, lane, own);
           LETKF_TRACE(12);
-          // done with chunk c: the indices of chunk c + 3 (requested below by the last warp) are here, those of
-          // chunk c + 4 are requested now
-#pragma unroll
-          for (int u = 0; u < RPL; ++u) {
-            cur_iob[u] = nxt_iob[u];
-            cur_rd[u] = nxt_rd[u];
-          }
-          fetch_idx(c + 4, nxt_iob, nxt_rd);
-          __syncwarp();
-          int last = 0;
-          if (lane == 0) {
-            __threadfence_block();
-            last = (atomicAdd(&s_cnt[st], 1) == NB - 1);
-            if (last) s_cnt[st] = 0;
-          }
-          last = __shfl_sync(LETKF_FULL_MASK, last, 0);
+          if (c + 2 < nchunks) request(c + 2, cur_iob);
           LETKF_TRACE(13);
-          if (last && c + 3 < nchunks) request(c + 3, cur_iob, cur_rd);
+          fetch_idx(c + 3, cur_iob);
           LETKF_TRACE(14);
         }
         gchunk += (unsigned)nchunks;
@@ -454,6 +450,7 @@ das_ns_kernel(const DasParams P) {
           const int r = lane >> 2, q = lane & 3, row = w * 8 + r;
 #pragma unroll
           for (int d = 0; d <= H; ++d) {
+            if (!owns<NB>(own, d)) continue;
             int jb = w + d;
             if (jb >= NB) jb -= NB;
 #pragma unroll
@@ -473,29 +470,29 @@ das_ns_kernel(const DasParams P) {
                 if (row == k) bvec[col] = v;
                 if (row == k + 1 && P.det) bdvec[col] = v;
               }
-              if (d == 0 && row == k && col == k) red[3 * NB] = v;   // sum w dep^2
+              if (d == 0 && row == k && col == k) red[3 * NW] = v;   // sum w dep^2
             }
           }
           fs = warp_sum(fs);
           tr = warp_sum(tr);
           p3acc = warp_sum(p3acc);
           if (lane == 0) {
-            red[w] = fs;
-            red[NB + w] = tr;
-            red[2 * NB + w] = p3acc;
+            red[wid] = fs;
+            red[NW + wid] = tr;
+            red[2 * NW + wid] = p3acc;
           }
         }
         __syncthreads();
         double gf2 = 0.0, trace = 0.0, parm3 = 0.0;
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
+        for (int i = 0; i < NW; ++i) {
           gf2 += red[i];
-          trace += red[NB + i];
-          parm3 += red[2 * NB + i];
+          trace += red[NW + i];
+          parm3 += red[2 * NW + i];
         }
         const double s_norm = cdiag + sqrt(gf2) * (1.0 + 1.0e-12);   // (rounding guard)
         if (P.INFL_MUL_ADAPTIVE) {   // (common_letkf.f90:229-254)
-          const double parm1 = red[3 * NB];
+          const double parm1 = red[3 * NW];
           const double parm2 = trace / (double)(k - 1);
           const double parm4 = (parm1 - parm3) / parm2 - infl;
           const double tq = (infl * parm2 + parm3) / parm2;
@@ -518,12 +515,12 @@ das_ns_kernel(const DasParams P) {
               acc[d][e] = (row < k && col < k) ? (acc[d][e] + (dg ? cdiag : 0.0)) * is : (dg ? 1.0 : 0.0);
             }
           }
-          store_circ<NB>(acc, Yp, w, lf);
+          store_circ<NB>(acc, Yp, w, lf, own);
         }
         // Ill-conditioned point (lambda_max(A) / c0 above ~1e4): the mean weight wbar = Pa b is refined below against
         // the ORIGINAL matrix, which is kept in global scratch for that purpose (rare: nothing is written otherwise).
         const bool refine = (cdiag / s_norm) < 1.0e-4;
-        if (refine) store_circ<NB>(acc, P.m0_scratch + (size_t)blockIdx.x * PSZ, w, lf);
+        if (refine) store_circ<NB>(acc, P.m0_scratch + (size_t)blockIdx.x * PSZ, w, lf, own);
         if (tid == 0) {   // the next point of this CTA (its work counter was drawn at the top of this iteration)
           long long nv = -1;
           if (PRE || !P.point_list) {
@@ -534,8 +531,17 @@ das_ns_kernel(const DasParams P) {
         }
         phase(2);
         LETKF_TRACE(4);
-        // ---- Z = (A/s)^-1/2 --------------------------------------------------------------------------
-        const int its = newton_schulz_invsqrt<NB>(acc, Yp, Zp, Tp, cdiag / s_norm, red, P.max_sweeps + 20);
+        // ---- Ts = (A/s)^-1/2 [dX | b | bd] ------------------------------------------------------------
+        // Normal path: the Newton-Schulz factors are applied to the 16 vectors directly (newton_schulz_apply), Z is
+        // never formed.  Ill-conditioned points need Z itself for the refinement of the mean weight below.
+        int its;
+        if (!kForceZPath && !refine) {
+          its = newton_schulz_apply<NB, LD>(acc, Yp, Zp, Xall, Ts, TS_ALIAS ? Zp : Tp, Yp, cdiag / s_norm, red,
+                                            P.max_sweeps + 20);
+        } else {
+          stat(6, 1);
+          its = newton_schulz_invsqrt<NB>(acc, Yp, Zp, Tp, cdiag / s_norm, red, P.max_sweeps + 20);
+        }
         if (its < 0) fail = true;
         stat(5, (unsigned long long)(its < 0 ? -its : its));
         // mtx_eigen zeroes eigenvalues below lambda_max*sqrt(eps) (common_mtx.f90:69) and letkf_core
@@ -561,8 +567,8 @@ das_ns_kernel(const DasParams P) {
             }
           }
         }
-        // ---- Ts = Z [dX | b | bd]  (k x 16 skinny product on the tensor cores) --------------------
-        {
+        // ---- refine path: Ts = Z [dX | b | bd]  (k x 16 skinny product on the tensor cores) ----------
+        if ((kForceZPath || refine) && rowown) {
           double a2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
           const int r = lane >> 2, q = lane & 3;
           const double *pb = Xall + (size_t)r * LD + q;
@@ -648,7 +654,7 @@ das_ns_kernel(const DasParams P) {
           for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(LETKF_FULL_MASK, v, o);
           return v;
         };
-        for (int c0 = 2 * w; c0 < nc; c0 += 2 * NB) {
+        for (int c0 = 2 * wid; c0 < nc; c0 += 2 * NW) {
           const int c = c0 + (lane >> 4);
           const bool active = c < nc;
           const int vv = active ? (int)__fns(colmask, 0, c + 1) : vtrig;   // c-th analysed variable of the group
@@ -726,7 +732,7 @@ das_ns_kernel(const DasParams P) {
     if (solved_any) stat(1, 1);
   }
   if (tid == 0) {
-    for (int i = 0; i < 6; ++i) atomicAdd(&P.counters[1 + i], s_stat[i]);
+    for (int i = 0; i < 7; ++i) atomicAdd(&P.counters[1 + i], s_stat[i]);
     for (int i = 0; i < 8; ++i) atomicAdd(&P.counters[8 + i], (unsigned long long)s_ph[i]);
   }
 }
@@ -808,10 +814,13 @@ __global__ void __launch_bounds__(128) presearch_kernel(const DasParams P, int *
       __syncthreads();
       const long long off = s_off;
       if (n > 0 && off >= 0) {
-        for (int i = tid; i < n; i += blockDim.x) {
-          P.pl_iob[off + i] = L.iob[i];
-          P.pl_rdiag[off + i] = L.rdiag[i];
-          if (P.pl_rloc) P.pl_rloc[off + i] = L.rloc[i];
+        // what the solver's Gram stages: 1 / rdiag, the list padded to four entries with weight 0 (the padding
+        // rows repeat the first observation: finite data)
+        const int n4 = (n + 3) & ~3;
+        for (int i = tid; i < n4; i += blockDim.x) {
+          P.pl_iob[off + i] = L.iob[i < n ? i : 0];
+          P.pl_rdiag[off + i] = i < n ? 1.0 / L.rdiag[i] : 0.0;
+          if (P.pl_rloc) P.pl_rloc[off + i] = i < n ? L.rloc[i] : 0.0;
         }
       }
     }

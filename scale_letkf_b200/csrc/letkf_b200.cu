@@ -134,7 +134,7 @@ struct letkf_b200_handle {
   std::vector<cudaEvent_t> ev_in, ev_k0, ev_k1;
   std::vector<std::pair<void *, size_t>> pinned;   // caller buffers page-locked by ensure_pinned
   // stats of the last das call
-  long long st_points = 0, st_solved = 0, st_fail = 0, st_nobs = 0, st_sweeps = 0;
+  long long st_points = 0, st_solved = 0, st_fail = 0, st_nobs = 0, st_sweeps = 0, st_refined = 0;
   long long st_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float last_ms = 0.f;
   int last_launches = 0;
@@ -729,7 +729,7 @@ static int set_obs_impl(letkf_b200_handle *h, const letkf_b200_obs *obs, const i
     maxl += (G.limit > 0) ? std::min(G.limit, tot) : tot;
   }
   for (int ic = 0; ic < nct; ++ic) h->ctinfo[ic].n_merge = n_merge[ic];
-  h->maxl = std::max(maxl, 1);
+  h->maxl = (std::max(maxl, 1) + 3) & ~3;   // a multiple of four: the solver pads its lists to four-row steps
   {   // Candidate buffer entries per CTA.  Slices are laid out by candidate position (search.cuh), so the
       // buffer must span the candidates of one search rectangle although only the survivors are
       // written: 32 K entries cover a radar rectangle of ~3 search increments; pages never touched cost
@@ -1058,8 +1058,8 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   P.max_sweeps = 30;
   CK(cudaMemsetAsync(h->counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
 #ifdef LETKF_EXP_TRACE
-  CK(h->cb[9].ensure(8000));
-  CK(cudaMemsetAsync(h->cb[9].p, 0, sizeof(double) * 8000, h->stream));
+  CK(h->cb[9].ensure(32000));
+  CK(cudaMemsetAsync(h->cb[9].p, 0, sizeof(double) * 32000, h->stream));
   P.trace = reinterpret_cast<long long *>(h->cb[9].p);
 #endif
   int r, nlaunch = 0;
@@ -1263,10 +1263,10 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   if (host) CK(cudaStreamSynchronize(h->s_d2h));
 #ifdef LETKF_EXP_TRACE
   if (const char *tp = std::getenv("LETKF_B200_TRACE")) {
-    std::vector<long long> tr(8000);
-    cudaMemcpy(tr.data(), h->cb[9].p, sizeof(long long) * 8000, cudaMemcpyDeviceToHost);
+    std::vector<long long> tr(32000);
+    cudaMemcpy(tr.data(), h->cb[9].p, sizeof(long long) * 32000, cudaMemcpyDeviceToHost);
     if (FILE *f = std::fopen(tp, "w")) {
-      for (int i = 0; i < 4000 && tr[2 * i] != 0; ++i) std::fprintf(f, "%lld %lld\n", tr[2 * i], tr[2 * i + 1]);
+      for (int i = 0; i < 16000 && tr[2 * i] != 0; ++i) std::fprintf(f, "%lld %lld\n", tr[2 * i], tr[2 * i + 1]);
       std::fclose(f);
     }
   }
@@ -1278,6 +1278,7 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
     h->last_ms += ms;
   }
   h->st_sweeps = (long long)cnt[6];
+  h->st_refined = (long long)cnt[7];
   for (int i = 0; i < 8; ++i) h->st_phase[i] = (long long)cnt[8 + i];
   h->st_points = (long long)cnt[1];
   h->st_solved = (long long)cnt[2];
@@ -1295,6 +1296,11 @@ int letkf_b200_das_stats(const letkf_b200_handle *h, int64_t *npoints, int64_t *
   if (nsolved) *nsolved = h->st_solved;
   if (nfail) *nfail = h->st_fail;
   if (nobsl_sum) *nobsl_sum = h->st_nobs;
+  return LETKF_B200_OK;
+}
+int letkf_b200_das_refined(const letkf_b200_handle *h, int64_t *nrefined) {
+  if (!h || !nrefined) return LETKF_B200_EINVAL;
+  *nrefined = h->st_refined;
   return LETKF_B200_OK;
 }
 int letkf_b200_das_kernel_ms(const letkf_b200_handle *h, float *ms, int *launches) {

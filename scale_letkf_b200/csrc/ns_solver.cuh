@@ -29,6 +29,24 @@
 #pragma once
 #include "common.cuh"
 
+// LETKF_EXP_TRACE builds only (profiling aid): (tag, clock64) pairs of CTA 0 / thread 0, 16000 entries
+#ifdef LETKF_EXP_TRACE
+namespace letkf {
+__device__ long long *g_trace_buf;
+__device__ int g_trace_n;
+}
+#define LETKF_TRACE(tag)                                                                       \
+  do {                                                                                         \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && letkf::g_trace_buf && letkf::g_trace_n < 16000) { \
+      letkf::g_trace_buf[2 * letkf::g_trace_n] = (tag);                                        \
+      letkf::g_trace_buf[2 * letkf::g_trace_n + 1] = clock64();                                \
+      ++letkf::g_trace_n;                                                                      \
+    }                                                                                          \
+  } while (0)
+#else
+#define LETKF_TRACE(tag) do { } while (0)
+#endif
+
 namespace letkf {
 
 template <int NB_>
@@ -38,17 +56,51 @@ struct NsCfg {
   static constexpr int H = (NB_ - 1) / 2;          // warp w owns tiles (w, w+d mod NB), d = 0..H
   static constexpr int KP = 8 * NB_;               // padded ensemble size (>= k + 2)
   static constexpr int LD = KP + 4;                // row stride of row-major staging / vector blocks
-  static constexpr int NT = 32 * NB_;              // one warp per row block
+  // Warps of the CTA.  Normally one per row block.  NB = 13 runs 16 warps, four per SM sub-partition: with 13 the
+  // sub-partitions would issue 28 / 21 / 21 / 21 of the 91 tile products of every GEMM and the first one sets the pace
+  // (measured: every DMMA phase of the k = 100 solver ran at the pipe limit of that sub-partition).  Warps 0..11 own
+  // their whole row block; the seven tiles of row block 12 are shared out to warps 12..15 (2 + 2 + 2 + 1): 23/23/23/22.
+#ifdef LETKF_SPLIT13
+  static constexpr int NW = NB_ == 13 ? 16 : NB_;
+#else
+  static constexpr int NW = NB_;
+#endif
+  static constexpr bool SPLIT = NW != NB_;
+  static constexpr int NT = 32 * NW;
   static constexpr int NTILE = NB_ * (NB_ + 1) / 2;
   static constexpr int PSZ = NTILE * 64;           // doubles per stored symmetric matrix
   static constexpr int RS = (H + 1) * 64;          // doubles per warp-owned row of tiles
-  static constexpr int CR = (PSZ / LD) & ~3;       // obs rows per staging chunk (three chunks fit in 3 PSZ); CR == 4 NB
+  static constexpr int CR = ((3 * PSZ) / (4 * LD)) & ~3;   // obs rows per staging chunk: FOUR chunk buffers share the 3 PSZ doubles of Y, Z, T
+  static constexpr int NSTEP = CR / 4;             // four-row DMMA steps of a full chunk
+  static constexpr int RPW = (CR + NW - 1) / NW;   // rows of a chunk one warp requests (row = warp + NW * r, r < RPW)
   // resident CTAs per SM the register allocation is sized for
 #ifndef LETKF_MINB7
 #define LETKF_MINB7 4
 #endif
   static constexpr int MINB = NB_ <= 3 ? 8 : NB_ <= 5 ? 5 : NB_ <= 7 ? LETKF_MINB7 : NB_ <= 9 ? 2 : 1;
 };
+
+// Tiles (w, d), d in [lo, hi) of row block w that the calling warp owns (accumulates, updates, stores)
+struct TileOwn {
+  int lo, hi;
+  __device__ __forceinline__ unsigned bit(int d) const { return (d >= lo && d < hi) ? 1u : 0u; }
+};
+template <int NB>
+__device__ __forceinline__ TileOwn tile_own(int warp) {
+  constexpr int H = (NB - 1) / 2;
+  if constexpr (!NsCfg<NB>::SPLIT) {
+    return TileOwn{0, H + 1};
+  } else {
+    if (warp < NB - 1) return TileOwn{0, H + 1};
+    const int i = warp - (NB - 1);
+    return TileOwn{2 * i, 2 * i + 2 < H + 1 ? 2 * i + 2 : H + 1};
+  }
+}
+template <int NB>
+__device__ __forceinline__ bool owns(const TileOwn &o, int d) {
+  if constexpr (!NsCfg<NB>::SPLIT) return true;
+  else return d >= o.lo && d < o.hi;
+}
 
 // DMMA and the operand loads of the hot loops are volatile asm: the issue order is the source order, which is
 // written as an explicit software pipeline (fragments of step e + 1 are requested before the DMMAs of step e issue,
@@ -67,6 +119,29 @@ __device__ __forceinline__ double lds_imm(unsigned addr) {
   return v;
 }
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// Predicated forms (warp-uniform predicate `on`): straight-line code for warps that own only some of the tiles of a
+// row block -- a C++ `if` around volatile asm becomes a branch per tile and breaks the software pipeline apart.
+__device__ __forceinline__ void dmma884_if(double &c0, double &c1, double a, double b, unsigned on) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %4, 0;\n"
+      "@p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      "}"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b), "r"(on));
+}
+template <int OFF>
+__device__ __forceinline__ void lds_imm_if(double &v, unsigned addr, unsigned on) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %2, 0;\n"
+      "@p ld.shared.f64 %0, [%1+%3];\n"
+      "}"
+      : "+d"(v)
+      : "r"(addr), "r"(on), "n"(OFF));
+}
 
 // ---- circulant, fragment-ordered tile storage -------------------------------------------------------
 __host__ __device__ __forceinline__ int fpos(int r, int c) { return (c >> 2) * 32 + r * 4 + (c & 3); }
@@ -112,9 +187,9 @@ struct SymmFrag {
   double a[2], b[(NB + 1) / 2][2];
 };
 template <int NB, int E, int D>
-__device__ __forceinline__ void symm_load_b(SymmFrag<NB> &f, const SymmAddr<NB> &A);
+__device__ __forceinline__ void symm_load_b(SymmFrag<NB> &f, const SymmAddr<NB> &A, const TileOwn &own);
 template <int NB, int E>
-__device__ __forceinline__ void symm_load(SymmFrag<NB> &f, const SymmAddr<NB> &A) {
+__device__ __forceinline__ void symm_load(SymmFrag<NB> &f, const SymmAddr<NB> &A, const TileOwn &own) {
   constexpr int H = (NB - 1) / 2;
   if constexpr (E <= H) {
     f.a[0] = lds_imm<E * 512>(A.xd0);
@@ -123,34 +198,48 @@ __device__ __forceinline__ void symm_load(SymmFrag<NB> &f, const SymmAddr<NB> &A
     f.a[0] = lds_imm<(NB - E) * 512>(A.xt[E]);
     f.a[1] = lds_imm<(NB - E) * 512 + 128>(A.xt[E]);
   }
-  symm_load_b<NB, E, 0>(f, A);
+  symm_load_b<NB, E, 0>(f, A, own);
 }
 template <int NB, int E, int D>
-__device__ __forceinline__ void symm_load_b(SymmFrag<NB> &f, const SymmAddr<NB> &A) {
+__device__ __forceinline__ void symm_load_b(SymmFrag<NB> &f, const SymmAddr<NB> &A, const TileOwn &own) {
   constexpr int H = (NB - 1) / 2, G = (D - E + NB) % NB;
-  if constexpr (G <= H) {
-    f.b[D][0] = lds_imm<G * 512>(A.wt[E]);
-    f.b[D][1] = lds_imm<G * 512 + 128>(A.wt[E]);
+  if constexpr (!NsCfg<NB>::SPLIT) {
+    if constexpr (G <= H) {
+      f.b[D][0] = lds_imm<G * 512>(A.wt[E]);
+      f.b[D][1] = lds_imm<G * 512 + 128>(A.wt[E]);
+    } else {
+      f.b[D][0] = lds_imm<(NB - G) * 512>(A.wd[D]);
+      f.b[D][1] = lds_imm<(NB - G) * 512 + 256>(A.wd[D]);
+    }
   } else {
-    f.b[D][0] = lds_imm<(NB - G) * 512>(A.wd[D]);
-    f.b[D][1] = lds_imm<(NB - G) * 512 + 256>(A.wd[D]);
+    const unsigned on = own.bit(D);
+    if constexpr (G <= H) {
+      lds_imm_if<G * 512>(f.b[D][0], A.wt[E], on);
+      lds_imm_if<G * 512 + 128>(f.b[D][1], A.wt[E], on);
+    } else {
+      lds_imm_if<(NB - G) * 512>(f.b[D][0], A.wd[D], on);
+      lds_imm_if<(NB - G) * 512 + 256>(f.b[D][1], A.wd[D], on);
+    }
   }
-  if constexpr (D < H) symm_load_b<NB, E, D + 1>(f, A);
+  if constexpr (D < H) symm_load_b<NB, E, D + 1>(f, A, own);
 }
 template <int NB, int E>
 __device__ __forceinline__ void symm_steps(double (&acc)[(NB + 1) / 2][2], SymmFrag<NB> &cur, SymmFrag<NB> &nxt,
-                                           const SymmAddr<NB> &A) {
+                                           const SymmAddr<NB> &A, const TileOwn &own) {
   constexpr int H = (NB - 1) / 2;
-  if constexpr (E + 1 < NB) symm_load<NB, E + 1>(nxt, A);
+  if constexpr (E + 1 < NB) symm_load<NB, E + 1>(nxt, A, own);
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
-    for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], cur.a[h], cur.b[d][h]);
-  if constexpr (E + 1 < NB) symm_steps<NB, E + 1>(acc, nxt, cur, A);
+    for (int d = 0; d <= H; ++d) {
+      if constexpr (!NsCfg<NB>::SPLIT) dmma884(acc[d][0], acc[d][1], cur.a[h], cur.b[d][h]);
+      else dmma884_if(acc[d][0], acc[d][1], cur.a[h], cur.b[d][h], own.bit(d));
+    }
+  if constexpr (E + 1 < NB) symm_steps<NB, E + 1>(acc, nxt, cur, A, own);
 }
 template <int NB>
 __device__ __forceinline__ void symm_gemm(double (&acc)[(NB + 1) / 2][2], const double *X, const double *W,
-                                          int w, const LaneFrag &lf) {
+                                          int w, const LaneFrag &lf, const TileOwn &own) {
   constexpr int H = (NB - 1) / 2, RS = (H + 1) * 64;
   const unsigned xs = smem_addr(X), ws = smem_addr(W);
   SymmAddr<NB> A;
@@ -165,8 +254,10 @@ __device__ __forceinline__ void symm_gemm(double (&acc)[(NB + 1) / 2][2], const 
     if (x <= H) A.wd[x] = ws + 8u * (rb + lf.dir);
   }
   SymmFrag<NB> f0, f1;
-  symm_load<NB, 0>(f0, A);
-  symm_steps<NB, 0>(acc, f0, f1, A);
+#pragma unroll
+  for (int d = 0; d <= H; ++d) f0.b[d][0] = f0.b[d][1] = f1.b[d][0] = f1.b[d][1] = 0.0;   // (tiles the warp does not own are never loaded)
+  symm_load<NB, 0>(f0, A, own);
+  symm_steps<NB, 0>(acc, f0, f1, A, own);
 }
 
 // A operand fragments of block-row w of a stored symmetric matrix, inner block (w + e) mod NB
@@ -188,19 +279,21 @@ __device__ __forceinline__ void symm_afrag(double (&a)[2], const double *X, int 
 // the warp's tiles <-> registers (accumulator layout)
 template <int NB>
 __device__ __forceinline__ void store_circ(const double (&acc)[(NB + 1) / 2][2], double *M, int w,
-                                           const LaneFrag &lf) {
+                                           const LaneFrag &lf, const TileOwn &own) {
   constexpr int H = (NB - 1) / 2, RS = (H + 1) * 64;
   double *t = M + w * RS + lf.st;
 #pragma unroll
-  for (int d = 0; d <= H; ++d) *reinterpret_cast<double2 *>(t + d * 64) = make_double2(acc[d][0], acc[d][1]);
+  for (int d = 0; d <= H; ++d)
+    if (owns<NB>(own, d)) *reinterpret_cast<double2 *>(t + d * 64) = make_double2(acc[d][0], acc[d][1]);
 }
 template <int NB>
 __device__ __forceinline__ void load_circ(double (&acc)[(NB + 1) / 2][2], const double *M, int w,
-                                          const LaneFrag &lf) {
+                                          const LaneFrag &lf, const TileOwn &own) {
   constexpr int H = (NB - 1) / 2, RS = (H + 1) * 64;
   const double *t = M + w * RS + lf.st;
 #pragma unroll
   for (int d = 0; d <= H; ++d) {
+    if (!owns<NB>(own, d)) continue;
     const double2 v = *reinterpret_cast<const double2 *>(t + d * 64);
     acc[d][0] = v.x;
     acc[d][1] = v.y;
@@ -212,7 +305,7 @@ __device__ __forceinline__ void load_circ(double (&acc)[(NB + 1) / 2][2], const 
 //   acc[d] += sum_o wv[o] Ys[o][w-block]^T Ys[o][jd-block]
 template <int NB, int LD>
 __device__ __forceinline__ void gram_circ(double (&acc)[(NB + 1) / 2][2], const double *Ys, const double *wv,
-                                          int nrows4, int w, int lane) {
+                                          int nrows4, int w, int lane, const TileOwn &own) {
   constexpr int H = (NB - 1) / 2;
   const int r = lane >> 2, q = lane & 3;
   const double *pa = Ys + (size_t)q * LD + w * 8 + r;
@@ -228,40 +321,48 @@ __device__ __forceinline__ void gram_circ(double (&acc)[(NB + 1) / 2][2], const 
   for (int o = 0; o < nrows4; o += 4) {
     const double a = pa[(size_t)o * LD] * pw[o];
 #pragma unroll
-    for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], a, pb[d][(size_t)o * LD]);
+    for (int d = 0; d <= H; ++d) {
+      if constexpr (!NsCfg<NB>::SPLIT) dmma884(acc[d][0], acc[d][1], a, pb[d][(size_t)o * LD]);
+      else dmma884_if(acc[d][0], acc[d][1], a, pb[d][(size_t)o * LD], own.bit(d));
+    }
   }
 }
 
-// The same for a FULL chunk of 4 NB rows, as an explicit software pipeline over its NB four-row steps (operands
+// The same for a FULL chunk of 4 NSTEP rows, as an explicit software pipeline over its four-row steps (operands
 // of step s + 1 requested before the DMMAs of step s issue; all offsets are LDS immediates).
 template <int NB>
 struct GramFrag {
   double a, wt, b[(NB + 1) / 2];
 };
 template <int NB, int LD, int S, int D>
-__device__ __forceinline__ void gram_load_b(GramFrag<NB> &f, const unsigned (&pb)[(NB + 1) / 2]) {
-  f.b[D] = lds_imm<S * 4 * LD * 8>(pb[D]);
-  if constexpr (D < (NB - 1) / 2) gram_load_b<NB, LD, S, D + 1>(f, pb);
+__device__ __forceinline__ void gram_load_b(GramFrag<NB> &f, const unsigned (&pb)[(NB + 1) / 2], const TileOwn &own) {
+  if constexpr (!NsCfg<NB>::SPLIT) f.b[D] = lds_imm<S * 4 * LD * 8>(pb[D]);
+  else lds_imm_if<S * 4 * LD * 8>(f.b[D], pb[D], own.bit(D));
+  if constexpr (D < (NB - 1) / 2) gram_load_b<NB, LD, S, D + 1>(f, pb, own);
 }
 template <int NB, int LD, int S>
-__device__ __forceinline__ void gram_load(GramFrag<NB> &f, unsigned pa, unsigned pw, const unsigned (&pb)[(NB + 1) / 2]) {
+__device__ __forceinline__ void gram_load(GramFrag<NB> &f, unsigned pa, unsigned pw, const unsigned (&pb)[(NB + 1) / 2],
+                                          const TileOwn &own) {
   f.a = lds_imm<S * 4 * LD * 8>(pa);
   f.wt = lds_imm<S * 4 * 8>(pw);
-  gram_load_b<NB, LD, S, 0>(f, pb);
+  gram_load_b<NB, LD, S, 0>(f, pb, own);
 }
-template <int NB, int LD, int S>
+template <int NB, int LD, int NSTEP, int S>
 __device__ __forceinline__ void gram_steps(double (&acc)[(NB + 1) / 2][2], GramFrag<NB> &cur, GramFrag<NB> &nxt, unsigned pa,
-                                           unsigned pw, const unsigned (&pb)[(NB + 1) / 2]) {
+                                           unsigned pw, const unsigned (&pb)[(NB + 1) / 2], const TileOwn &own) {
   constexpr int H = (NB - 1) / 2;
-  if constexpr (S + 1 < NB) gram_load<NB, LD, S + 1>(nxt, pa, pw, pb);
+  if constexpr (S + 1 < NSTEP) gram_load<NB, LD, S + 1>(nxt, pa, pw, pb, own);
   const double a = cur.a * cur.wt;
 #pragma unroll
-  for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], a, cur.b[d]);
-  if constexpr (S + 1 < NB) gram_steps<NB, LD, S + 1>(acc, nxt, cur, pa, pw, pb);
+  for (int d = 0; d <= H; ++d) {
+    if constexpr (!NsCfg<NB>::SPLIT) dmma884(acc[d][0], acc[d][1], a, cur.b[d]);
+    else dmma884_if(acc[d][0], acc[d][1], a, cur.b[d], own.bit(d));
+  }
+  if constexpr (S + 1 < NSTEP) gram_steps<NB, LD, NSTEP, S + 1>(acc, nxt, cur, pa, pw, pb, own);
 }
-template <int NB, int LD>
+template <int NB, int LD, int NSTEP>
 __device__ __forceinline__ void gram_circ_full(double (&acc)[(NB + 1) / 2][2], const double *Ys, const double *wv, int w,
-                                               int lane) {
+                                               int lane, const TileOwn &own) {
   constexpr int H = (NB - 1) / 2;
   const int r = lane >> 2, q = lane & 3;
   const unsigned ys = smem_addr(Ys) + 8u * (unsigned)(q * LD + r);
@@ -274,17 +375,20 @@ __device__ __forceinline__ void gram_circ_full(double (&acc)[(NB + 1) / 2][2], c
     pb[d] = ys + 64u * (unsigned)j;
   }
   GramFrag<NB> f0, f1;
-  gram_load<NB, LD, 0>(f0, pa, pw, pb);
-  gram_steps<NB, LD, 0>(acc, f0, f1, pa, pw, pb);
+#pragma unroll
+  for (int d = 0; d <= H; ++d) f0.b[d] = f1.b[d] = 0.0;   // (tiles the warp does not own are never loaded)
+  gram_load<NB, LD, 0>(f0, pa, pw, pb, own);
+  gram_steps<NB, LD, NSTEP, 0>(acc, f0, f1, pa, pw, pb, own);
 }
 
 // Frobenius norm^2 contribution of (I - acc) held in the warp's tiles (off-diagonal tiles count twice)
 template <int NB>
-__device__ __forceinline__ double resid_fro2(const double (&acc)[(NB + 1) / 2][2], int lane) {
+__device__ __forceinline__ double resid_fro2(const double (&acc)[(NB + 1) / 2][2], int lane, const TileOwn &own) {
   const int r = lane >> 2, q = lane & 3;
   double s = 0.0;
 #pragma unroll
   for (int d = 0; d <= (NB - 1) / 2; ++d) {
+    if (!owns<NB>(own, d)) continue;
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const double v = ((d == 0 && r == 2 * q + e) ? 1.0 : 0.0) - acc[d][e];
@@ -305,7 +409,9 @@ __device__ __forceinline__ int newton_schulz_invsqrt(double (&acc)[(NB + 1) / 2]
                                                      double *Tp, double c0s, double *red, int max_iter) {
   constexpr int H = (NB - 1) / 2;
   const int lane = threadIdx.x & 31;
-  const int w = __shfl_sync(LETKF_FULL_MASK, threadIdx.x >> 5, 0);
+  const int wid = __shfl_sync(LETKF_FULL_MASK, threadIdx.x >> 5, 0);   // warp of the CTA
+  const int w = wid < NB ? wid : NB - 1;                               // its row block
+  const TileOwn own = tile_own<NB>(wid);
   const int r = lane >> 2, q = lane & 3;
   const LaneFrag lf = lane_frag(lane);
   double a = c0s;            // eigenvalues of M in [a, 1]
@@ -325,31 +431,31 @@ __device__ __forceinline__ int newton_schulz_invsqrt(double (&acc)[(NB + 1) / 2]
 #pragma unroll
       for (int e = 0; e < 2; ++e) acc[d][e] = fma(h1, acc[d][e], (d == 0 && r == 2 * q + e) ? h0 : 0.0);
     }
-    store_circ<NB>(acc, Tp, w, lf);
-    if (!have_z) store_circ<NB>(acc, Zp, w, lf);   // Z1 = T0
+    store_circ<NB>(acc, Tp, w, lf, own);
+    if (!have_z) store_circ<NB>(acc, Zp, w, lf, own);   // Z1 = T0
     __syncthreads();                               // T (and M, Z) visible
 #pragma unroll
     for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
-    symm_gemm<NB>(acc, Tp, Mp, w, lf);             // U = T M
+    symm_gemm<NB>(acc, Tp, Mp, w, lf, own);             // U = T M
     if (have_z) {
 #pragma unroll
       for (int d = 0; d <= H; ++d) az[d][0] = az[d][1] = 0.0;
-      symm_gemm<NB>(az, Tp, Zp, w, lf);            // Z' = T Z
+      symm_gemm<NB>(az, Tp, Zp, w, lf, own);            // Z' = T Z
     }
     __syncthreads();                               // all reads of M and Z done
-    store_circ<NB>(acc, Mp, w, lf);
-    if (have_z) store_circ<NB>(az, Zp, w, lf);
+    store_circ<NB>(acc, Mp, w, lf, own);
+    if (have_z) store_circ<NB>(az, Zp, w, lf, own);
     __syncthreads();
 #pragma unroll
     for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
-    symm_gemm<NB>(acc, Mp, Tp, w, lf);             // M' = U T
-    const double f2 = warp_sum(resid_fro2<NB>(acc, lane));
-    if (lane == 0) red[w] = f2;
+    symm_gemm<NB>(acc, Mp, Tp, w, lf, own);             // M' = U T
+    const double f2 = warp_sum(resid_fro2<NB>(acc, lane, own));
+    if (lane == 0) red[wid] = f2;
     __syncthreads();                               // all reads of U and T done; red visible
-    store_circ<NB>(acc, Mp, w, lf);                // (visible after the next barrier)
+    store_circ<NB>(acc, Mp, w, lf, own);                // (visible after the next barrier)
     double fro2 = 0.0;
 #pragma unroll
-    for (int i = 0; i < NB; ++i) fro2 += red[i];
+    for (int i = 0; i < NsCfg<NB>::NW; ++i) fro2 += red[i];
     const double t = c * a;   // image of the bracket under x -> c x (3 - c x)^2 / 4 is [g(c a), 1]
     a = t * (3.0 - t) * (3.0 - t) * 0.25;
     res = fmin(1.0 - a, sqrt(fro2));
@@ -373,12 +479,12 @@ __device__ __forceinline__ int newton_schulz_invsqrt(double (&acc)[(NB + 1) / 2]
       for (int e = 0; e < 2; ++e) az[d][e] = fma(0.5, acc[d][e], (d == 0 && r == 2 * q + e) ? 1.0 : 0.0);
     }
   } else {
-    store_circ<NB>(acc, Tp, w, lf);   // E
+    store_circ<NB>(acc, Tp, w, lf, own);   // E
     __syncthreads();
 #pragma unroll
     for (int d = 0; d <= H; ++d) az[d][0] = az[d][1] = 0.0;
-    symm_gemm<NB>(az, Tp, Tp, w, lf);   // E^2
-    if (order == 4) store_circ<NB>(az, Mp, w, lf);   // M is dead (nobody reads Mp between the last barrier and here)
+    symm_gemm<NB>(az, Tp, Tp, w, lf, own);   // E^2
+    if (order == 4) store_circ<NB>(az, Mp, w, lf, own);   // M is dead (nobody reads Mp between the last barrier and here)
 #pragma unroll
     for (int d = 0; d <= H; ++d) {
 #pragma unroll
@@ -389,7 +495,7 @@ __device__ __forceinline__ int newton_schulz_invsqrt(double (&acc)[(NB + 1) / 2]
     if (order == 4) {
 #pragma unroll
       for (int d = 0; d <= H; ++d) acc[d][0] = acc[d][1] = 0.0;
-      symm_gemm<NB>(acc, Mp, Tp, w, lf);   // E^3
+      symm_gemm<NB>(acc, Mp, Tp, w, lf, own);   // E^3
 #pragma unroll
       for (int d = 0; d <= H; ++d) {
 #pragma unroll
@@ -399,17 +505,181 @@ __device__ __forceinline__ int newton_schulz_invsqrt(double (&acc)[(NB + 1) / 2]
     }
   }
   if (!have_z) {   // Z = T (A/s was already close to the identity)
-    store_circ<NB>(az, Zp, w, lf);
+    store_circ<NB>(az, Zp, w, lf, own);
     __syncthreads();
   } else {
-    store_circ<NB>(az, Tp, w, lf);
+    store_circ<NB>(az, Tp, w, lf, own);
     __syncthreads();
 #pragma unroll
     for (int d = 0; d <= H; ++d) az[d][0] = az[d][1] = 0.0;
-    symm_gemm<NB>(az, Tp, Zp, w, lf);   // Z' = T Z
+    symm_gemm<NB>(az, Tp, Zp, w, lf, own);   // Z' = T Z
     __syncthreads();
-    store_circ<NB>(az, Zp, w, lf);
+    store_circ<NB>(az, Zp, w, lf, own);
     __syncthreads();
+  }
+  return ok ? it : -it;
+}
+
+// ---- the same iteration APPLIED to a block of vectors (the normal path of das_ns_kernel) -----------------------------
+// das_letkf never needs Z = (A/s)^-1/2 itself, only Z [dX | b | bd] (at most 16 columns).  Z is the product of the
+// factors T_j = h0_j I + h1_j M_j, so the factors are applied to the vector block as they appear,
+//     V_j = h0_j V_{j-1} + h1_j (M_j V_{j-1}),
+// one skinny product (4 NB DMMAs per warp) instead of the symmetric half-GEMM Z <- T Z ((NB + 1) NB DMMAs), T is never
+// stored (U = T M = h0 M + h1 M M, M' = U T = h0 U + h1 U M), and the finishing polynomial is evaluated on the vectors
+// in Horner form (order - 1 skinny products instead of E^2, E^3 and T Z).  Per iteration: two half-GEMMs, one skinny
+// product, three CTA barriers (product form on Z: three half-GEMMs, four barriers).
+//
+// Vector blocks are [16][LD] (column c of the block contiguous over the members); a warp owns the 8 members of its
+// row block in every column.
+template <int LD>
+__device__ __forceinline__ void load_vown(double (&v)[2][2], const double *V, int w, int lane) {
+  const int r = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) v[nt][e] = V[(size_t)(nt * 8 + 2 * q + e) * LD + w * 8 + r];
+}
+template <int LD>
+__device__ __forceinline__ void store_vown(const double (&v)[2][2], double *V, int w, int lane) {
+  const int r = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) V[(size_t)(nt * 8 + 2 * q + e) * LD + w * 8 + r] = v[nt][e];
+}
+// a2[nt] += Mat(row block w, :) V(:, column tile nt), Mat a stored symmetric matrix
+template <int NB, int LD>
+__device__ __forceinline__ void skinny_mv(double (&a2)[2][2], const double *Mat, const double *V, int w,
+                                          const LaneFrag &lf, int lane) {
+  constexpr int RS = ((NB - 1) / 2 + 1) * 64;
+  const int r = lane >> 2, q = lane & 3;
+  const double *pb = V + (size_t)r * LD + q;
+  double a[2], an[2];
+  symm_afrag<NB>(a, Mat, w, 0, w * RS, lf);
+#pragma unroll
+  for (int e = 0; e < NB; ++e) {
+    int j = w + e;
+    if (j >= NB) j -= NB;
+    if (e + 1 < NB) {   // A fragments one step ahead
+      int jn = j + 1;
+      if (jn >= NB) jn -= NB;
+      symm_afrag<NB>(an, Mat, w, e + 1, jn * RS, lf);
+    }
+    const double b00 = pb[j * 8], b01 = pb[j * 8 + 4], b10 = pb[(size_t)8 * LD + j * 8], b11 = pb[(size_t)8 * LD + j * 8 + 4];
+    dmma884(a2[0][0], a2[0][1], a[0], b00);
+    dmma884(a2[1][0], a2[1][1], a[0], b10);
+    dmma884(a2[0][0], a2[0][1], a[1], b01);
+    dmma884(a2[1][0], a2[1][1], a[1], b11);
+    a[0] = an[0];
+    a[1] = an[1];
+  }
+}
+
+// On entry `acc` holds the warp's tiles of M0 = A / s, also stored to Ma; V0: the vectors.  On exit V = (A/s)^-1/2 V0
+// (visible to all threads).  Mb: matrix scratch; Eb: where the finishing step stores E = I - M (may be Mb); tmp: one
+// vector block of scratch (may overlay Ma, and Mb when Eb != Mb).  V0 is only read.  All threads of the CTA must call.
+// Returns the number of iterations, negative if max_iter was reached before the residual test was met.
+template <int NB, int LD>
+__device__ __forceinline__ int newton_schulz_apply(double (&acc)[(NB + 1) / 2][2], double *Ma, double *Mb, const double *V0,
+                                                   double *V, double *Eb, double *tmp, double c0s, double *red,
+                                                   int max_iter) {
+  constexpr int H = (NB - 1) / 2;
+  const int lane = threadIdx.x & 31;
+  const int wid = __shfl_sync(LETKF_FULL_MASK, threadIdx.x >> 5, 0);   // warp of the CTA
+  const int w = wid < NB ? wid : NB - 1;                               // its row block
+  const TileOwn own = tile_own<NB>(wid);
+  const int r = lane >> 2, q = lane & 3;
+  const LaneFrag lf = lane_frag(lane);
+  double a = c0s;            // eigenvalues of M in [a, 1]
+  double res = 1.0 - a;      // ||I - M||_2 <= 1 - a; later min(bound, measured Frobenius norm)
+  double au[H + 1][2];
+  const bool rowown = wid < NB;   // this warp also carries the vector rows of its row block
+  const double *Vs = V0;
+  int it = 0;
+  __syncthreads();           // M0 (stored by the caller) visible: the first product reads every tile
+  LETKF_TRACE(20);
+  for (;;) {
+    ++it;
+    if (res < 1.5e-3 || it >= max_iter) break;
+    double c = 1.0;
+    if (1.0 - a > 1.0e-3) c = 3.0 / (a + sqrt(a) + 1.0);
+    const double sc = sqrt(c), h0 = 1.5 * sc, h1 = -0.5 * c * sc;   // T = h0 I + h1 M
+#pragma unroll
+    for (int d = 0; d <= H; ++d) au[d][0] = au[d][1] = 0.0;
+    symm_gemm<NB>(au, Ma, Ma, w, lf, own);                // M M
+    double pv[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, vo[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    if (rowown) {
+      skinny_mv<NB, LD>(pv, Ma, Vs, w, lf, lane);    // M V
+      load_vown<LD>(vo, Vs, w, lane);
+    }
+#pragma unroll
+    for (int d = 0; d <= H; ++d) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) acc[d][e] = fma(h1, au[d][e], h0 * acc[d][e]);   // U = T M
+    }
+    store_circ<NB>(acc, Mb, w, lf, own);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) pv[nt][e] = fma(h1, pv[nt][e], h0 * vo[nt][e]);   // V' = T V
+    LETKF_TRACE(21);
+    __syncthreads();                                 // U visible; all reads of V done
+    LETKF_TRACE(22);
+    if (rowown) store_vown<LD>(pv, V, w, lane);
+#pragma unroll
+    for (int d = 0; d <= H; ++d) au[d][0] = au[d][1] = 0.0;
+    symm_gemm<NB>(au, Mb, Ma, w, lf, own);                // U M
+#pragma unroll
+    for (int d = 0; d <= H; ++d) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) acc[d][e] = fma(h1, au[d][e], h0 * acc[d][e]);   // M' = U T
+    }
+    const double f2 = warp_sum(resid_fro2<NB>(acc, lane, own));
+    if (lane == 0) red[wid] = f2;
+    LETKF_TRACE(23);
+    __syncthreads();                                 // all reads of M and U done; red visible
+    LETKF_TRACE(24);
+    store_circ<NB>(acc, Ma, w, lf, own);
+    double fro2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NsCfg<NB>::NW; ++i) fro2 += red[i];
+    __syncthreads();                                 // M' and V' visible (red may be rewritten)
+    LETKF_TRACE(25);
+    const double t = c * a;   // image of the bracket under x -> c x (3 - c x)^2 / 4 is [g(c a), 1]
+    a = t * (3.0 - t) * (3.0 - t) * 0.25;
+    res = fmin(1.0 - a, sqrt(fro2));
+    Vs = V;
+  }
+  const bool ok = res < 1.5e-3;
+  // Finishing step (same orders and thresholds as newton_schulz_invsqrt), Horner form on the vectors:
+  //   V <- Vs + E (1/2 Vs + E (3/8 Vs + E (5/16 Vs)))
+  const int order = res < 1.0e-8 ? 2 : res < 1.5e-4 ? 3 : 4;
+#pragma unroll
+  for (int d = 0; d <= H; ++d) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) acc[d][e] = ((d == 0 && r == 2 * q + e) ? 1.0 : 0.0) - acc[d][e];   // E
+  }
+  store_circ<NB>(acc, Eb, w, lf, own);
+  __syncthreads();
+  LETKF_TRACE(26);
+  const double *ts = Vs;
+  for (int jj = order - 1; jj >= 1; --jj) {
+    double pv[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, vo[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    if (rowown) {
+      skinny_mv<NB, LD>(pv, Eb, ts, w, lf, lane);
+      load_vown<LD>(vo, Vs, w, lane);
+    }
+    const double cm = jj == 1 ? 1.0 : jj == 2 ? 0.5 : 0.375;                           // coefficient of Vs at this level
+    const double sp = jj != order - 1 ? 1.0 : jj == 1 ? 0.5 : jj == 2 ? 0.375 : 0.3125;   // E (c Vs) = c (E Vs)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) pv[nt][e] = fma(sp, pv[nt][e], cm * vo[nt][e]);
+    double *dst = jj == 1 ? V : tmp;
+    if (dst == ts) __syncthreads();   // in place: every warp has read the block
+    if (rowown) store_vown<LD>(pv, dst, w, lane);
+    __syncthreads();
+    ts = tmp;
   }
   return ok ? it : -it;
 }
