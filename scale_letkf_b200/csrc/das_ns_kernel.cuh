@@ -113,7 +113,7 @@ das_ns_kernel(const DasParams P) {
   const int wid = __shfl_sync(LETKF_FULL_MASK, tid >> 5, 0);   // warp of the CTA (warp-uniform: tile addressing on the uniform datapath)
   const int w = wid < NB ? wid : NB - 1;                       // its row block
   const TileOwn own = tile_own<NB>(wid);                       // the tiles of that row block it owns (ns_solver.cuh)
-  const bool rowown = wid < NB;                                // it also carries the vector rows of the block
+  const bool rowown = carries_vectors<NB>(wid);                // it also carries the vector rows of the block
   constexpr int NW = C::NW;
   double *Yp = reinterpret_cast<double *>(smem_raw);
   double *Zp = Yp + PSZ;
@@ -430,7 +430,8 @@ das_ns_kernel(const DasParams P) {
           mbar_wait(&s_full[st], (g >> 2) & 1u);
           LETKF_TRACE(11);
           const int nrows4 = min(CR, p4 - c * CR);
-          if (nrows4 == CR) gram_circ_full<NB, LD, C::NSTEP>(acc, stage + (size_t)st * CR * LD, wv + st * CR, w, lane, own);
+          if (nrows4 == CR && owns_row<NB>(own))
+            gram_circ_full<NB, LD, C::NSTEP>(acc, stage + (size_t)st * CR * LD, wv + st * CR, w, lane);
           else gram_circ<NB, LD>(acc, stage + (size_t)st * CR * LD, wv + st * CR, nrows4, w, lane, own);
           LETKF_TRACE(12);
           if (c + 2 < nchunks) request(c + 2, cur_iob);
@@ -450,27 +451,28 @@ das_ns_kernel(const DasParams P) {
           const int r = lane >> 2, q = lane & 3, row = w * 8 + r;
 #pragma unroll
           for (int d = 0; d <= H; ++d) {
-            if (!owns<NB>(own, d)) continue;
-            int jb = w + d;
+            if (!has<NB>(own, d)) continue;
+            const bool dgt = dact<NB>(own, d) == 0;   // the diagonal tile of the row block
+            int jb = w + dact<NB>(own, d);
             if (jb >= NB) jb -= NB;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int col = jb * 8 + 2 * q + e;
               const double v = acc[d][e];
               if (row < k && col < k) {
-                fs = fma(d == 0 ? v : 2.0 * v, v, fs);
-                if (d == 0 && row == col) tr += v;
+                fs = fma(dgt ? v : 2.0 * v, v, fs);
+                if (dgt && row == col) tr += v;
               }
               // dep / depd ride in columns k, k + 1; a block pair is stored once, as (w, jb) or as its mirror
               if (row < k) {
                 if (col == k) bvec[row] = v;
                 if (col == k + 1 && P.det) bdvec[row] = v;
               }
-              if (d != 0 && col < k) {
+              if (!dgt && col < k) {
                 if (row == k) bvec[col] = v;
                 if (row == k + 1 && P.det) bdvec[col] = v;
               }
-              if (d == 0 && row == k && col == k) red[3 * NW] = v;   // sum w dep^2
+              if (dgt && row == k && col == k) red[3 * NW] = v;   // sum w dep^2
             }
           }
           fs = warp_sum(fs);
@@ -506,12 +508,12 @@ das_ns_kernel(const DasParams P) {
           const int r = lane >> 2, q = lane & 3, row = w * 8 + r;
 #pragma unroll
           for (int d = 0; d <= H; ++d) {
-            int jb = w + d;
+            int jb = w + dact<NB>(own, d);
             if (jb >= NB) jb -= NB;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int col = jb * 8 + 2 * q + e;
-              const bool dg = (d == 0 && row == col);
+              const bool dg = (dact<NB>(own, d) == 0 && row == col);
               acc[d][e] = (row < k && col < k) ? (acc[d][e] + (dg ? cdiag : 0.0)) * is : (dg ? 1.0 : 0.0);
             }
           }

@@ -56,14 +56,16 @@ struct NsCfg {
   static constexpr int H = (NB_ - 1) / 2;          // warp w owns tiles (w, w+d mod NB), d = 0..H
   static constexpr int KP = 8 * NB_;               // padded ensemble size (>= k + 2)
   static constexpr int LD = KP + 4;                // row stride of row-major staging / vector blocks
-  // Warps of the CTA.  Normally one per row block.  NB = 13 runs 16 warps, four per SM sub-partition: with 13 the
-  // sub-partitions would issue 28 / 21 / 21 / 21 of the 91 tile products of every GEMM and the first one sets the pace
-  // (measured: every DMMA phase of the k = 100 solver ran at the pipe limit of that sub-partition).  Warps 0..11 own
-  // their whole row block; the seven tiles of row block 12 are shared out to warps 12..15 (2 + 2 + 2 + 1): 23/23/23/22.
-#ifdef LETKF_SPLIT13
-  static constexpr int NW = NB_ == 13 ? 16 : NB_;
-#else
+  // Warps of the CTA.  Normally one per row block, owning the H + 1 circulant tiles of that block.  NB = 13 runs 16
+  // warps, four per SM sub-partition: with 13 the sub-partitions would issue 28 / 21 / 21 / 21 of the 91 tile products
+  // of every GEMM and the first one sets the pace (measured: every DMMA phase of the k = 100 solver ran at the pipe
+  // limit of that sub-partition).  Warps 0..11 own their whole row block (compile-time addressing, as everywhere); the
+  // seven tiles of row block 12 are shared out to warps 12..15 (2 + 2 + 2 + 1, run-time addressing): 23/23/23/22.
+  // The last warp also carries the vector rows of block 12.
+#ifdef LETKF_NOSPLIT13   // A/B aid: 13 warps, one per row block
   static constexpr int NW = NB_;
+#else
+  static constexpr int NW = NB_ == 13 ? 16 : NB_;
 #endif
   static constexpr bool SPLIT = NW != NB_;
   static constexpr int NT = 32 * NW;
@@ -80,10 +82,10 @@ struct NsCfg {
   static constexpr int MINB = NB_ <= 3 ? 8 : NB_ <= 5 ? 5 : NB_ <= 7 ? LETKF_MINB7 : NB_ <= 9 ? 2 : 1;
 };
 
-// Tiles (w, d), d in [lo, hi) of row block w that the calling warp owns (accumulates, updates, stores)
+// The tiles of its row block w that the calling warp owns (accumulates, updates, stores): (w, dbase + s), s < nd,
+// held in acc[s].  Without the split: all H + 1 of them, dbase = 0 (everything below folds at compile time).
 struct TileOwn {
-  int lo, hi;
-  __device__ __forceinline__ unsigned bit(int d) const { return (d >= lo && d < hi) ? 1u : 0u; }
+  int dbase, nd;
 };
 template <int NB>
 __device__ __forceinline__ TileOwn tile_own(int warp) {
@@ -93,13 +95,28 @@ __device__ __forceinline__ TileOwn tile_own(int warp) {
   } else {
     if (warp < NB - 1) return TileOwn{0, H + 1};
     const int i = warp - (NB - 1);
-    return TileOwn{2 * i, 2 * i + 2 < H + 1 ? 2 * i + 2 : H + 1};
+    return TileOwn{2 * i, (H + 1 - 2 * i) < 2 ? (H + 1 - 2 * i) : 2};
   }
 }
 template <int NB>
-__device__ __forceinline__ bool owns(const TileOwn &o, int d) {
+__device__ __forceinline__ bool has(const TileOwn &o, int s) {
   if constexpr (!NsCfg<NB>::SPLIT) return true;
-  else return d >= o.lo && d < o.hi;
+  else return s < o.nd;
+}
+template <int NB>
+__device__ __forceinline__ int dact(const TileOwn &o, int s) {   // circulant offset of the tile in acc[s]
+  if constexpr (!NsCfg<NB>::SPLIT) return s;
+  else return o.dbase + s;
+}
+template <int NB>
+__device__ __forceinline__ bool owns_row(const TileOwn &o) {    // the whole row block: compile-time addressed code
+  if constexpr (!NsCfg<NB>::SPLIT) return true;
+  else return o.nd == (NB + 1) / 2;
+}
+template <int NB>
+__device__ __forceinline__ bool carries_vectors(int warp) {      // the warp that holds the vector rows of its row block
+  if constexpr (!NsCfg<NB>::SPLIT) return true;
+  else return warp < NB - 1 || warp == NsCfg<NB>::NW - 1;
 }
 
 // DMMA and the operand loads of the hot loops are volatile asm: the issue order is the source order, which is
@@ -119,30 +136,6 @@ __device__ __forceinline__ double lds_imm(unsigned addr) {
   return v;
 }
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-// Predicated forms (warp-uniform predicate `on`): straight-line code for warps that own only some of the tiles of a
-// row block -- a C++ `if` around volatile asm becomes a branch per tile and breaks the software pipeline apart.
-__device__ __forceinline__ void dmma884_if(double &c0, double &c1, double a, double b, unsigned on) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.u32 p, %4, 0;\n"
-      "@p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-      "}"
-      : "+d"(c0), "+d"(c1)
-      : "d"(a), "d"(b), "r"(on));
-}
-template <int OFF>
-__device__ __forceinline__ void lds_imm_if(double &v, unsigned addr, unsigned on) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.u32 p, %2, 0;\n"
-      "@p ld.shared.f64 %0, [%1+%3];\n"
-      "}"
-      : "+d"(v)
-      : "r"(addr), "r"(on), "n"(OFF));
-}
-
 // ---- circulant, fragment-ordered tile storage -------------------------------------------------------
 __host__ __device__ __forceinline__ int fpos(int r, int c) { return (c >> 2) * 32 + r * 4 + (c & 3); }
 // address of logical element (row, col) of a stored symmetric matrix (element-wise passes only)
@@ -187,9 +180,9 @@ struct SymmFrag {
   double a[2], b[(NB + 1) / 2][2];
 };
 template <int NB, int E, int D>
-__device__ __forceinline__ void symm_load_b(SymmFrag<NB> &f, const SymmAddr<NB> &A, const TileOwn &own);
+__device__ __forceinline__ void symm_load_b(SymmFrag<NB> &f, const SymmAddr<NB> &A);
 template <int NB, int E>
-__device__ __forceinline__ void symm_load(SymmFrag<NB> &f, const SymmAddr<NB> &A, const TileOwn &own) {
+__device__ __forceinline__ void symm_load(SymmFrag<NB> &f, const SymmAddr<NB> &A) {
   constexpr int H = (NB - 1) / 2;
   if constexpr (E <= H) {
     f.a[0] = lds_imm<E * 512>(A.xd0);
@@ -198,48 +191,34 @@ __device__ __forceinline__ void symm_load(SymmFrag<NB> &f, const SymmAddr<NB> &A
     f.a[0] = lds_imm<(NB - E) * 512>(A.xt[E]);
     f.a[1] = lds_imm<(NB - E) * 512 + 128>(A.xt[E]);
   }
-  symm_load_b<NB, E, 0>(f, A, own);
+  symm_load_b<NB, E, 0>(f, A);
 }
 template <int NB, int E, int D>
-__device__ __forceinline__ void symm_load_b(SymmFrag<NB> &f, const SymmAddr<NB> &A, const TileOwn &own) {
+__device__ __forceinline__ void symm_load_b(SymmFrag<NB> &f, const SymmAddr<NB> &A) {
   constexpr int H = (NB - 1) / 2, G = (D - E + NB) % NB;
-  if constexpr (!NsCfg<NB>::SPLIT) {
-    if constexpr (G <= H) {
-      f.b[D][0] = lds_imm<G * 512>(A.wt[E]);
-      f.b[D][1] = lds_imm<G * 512 + 128>(A.wt[E]);
-    } else {
-      f.b[D][0] = lds_imm<(NB - G) * 512>(A.wd[D]);
-      f.b[D][1] = lds_imm<(NB - G) * 512 + 256>(A.wd[D]);
-    }
+  if constexpr (G <= H) {
+    f.b[D][0] = lds_imm<G * 512>(A.wt[E]);
+    f.b[D][1] = lds_imm<G * 512 + 128>(A.wt[E]);
   } else {
-    const unsigned on = own.bit(D);
-    if constexpr (G <= H) {
-      lds_imm_if<G * 512>(f.b[D][0], A.wt[E], on);
-      lds_imm_if<G * 512 + 128>(f.b[D][1], A.wt[E], on);
-    } else {
-      lds_imm_if<(NB - G) * 512>(f.b[D][0], A.wd[D], on);
-      lds_imm_if<(NB - G) * 512 + 256>(f.b[D][1], A.wd[D], on);
-    }
+    f.b[D][0] = lds_imm<(NB - G) * 512>(A.wd[D]);
+    f.b[D][1] = lds_imm<(NB - G) * 512 + 256>(A.wd[D]);
   }
-  if constexpr (D < H) symm_load_b<NB, E, D + 1>(f, A, own);
+  if constexpr (D < H) symm_load_b<NB, E, D + 1>(f, A);
 }
 template <int NB, int E>
 __device__ __forceinline__ void symm_steps(double (&acc)[(NB + 1) / 2][2], SymmFrag<NB> &cur, SymmFrag<NB> &nxt,
-                                           const SymmAddr<NB> &A, const TileOwn &own) {
+                                           const SymmAddr<NB> &A) {
   constexpr int H = (NB - 1) / 2;
-  if constexpr (E + 1 < NB) symm_load<NB, E + 1>(nxt, A, own);
+  if constexpr (E + 1 < NB) symm_load<NB, E + 1>(nxt, A);
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
-    for (int d = 0; d <= H; ++d) {
-      if constexpr (!NsCfg<NB>::SPLIT) dmma884(acc[d][0], acc[d][1], cur.a[h], cur.b[d][h]);
-      else dmma884_if(acc[d][0], acc[d][1], cur.a[h], cur.b[d][h], own.bit(d));
-    }
-  if constexpr (E + 1 < NB) symm_steps<NB, E + 1>(acc, nxt, cur, A, own);
+    for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], cur.a[h], cur.b[d][h]);
+  if constexpr (E + 1 < NB) symm_steps<NB, E + 1>(acc, nxt, cur, A);
 }
 template <int NB>
-__device__ __forceinline__ void symm_gemm(double (&acc)[(NB + 1) / 2][2], const double *X, const double *W,
-                                          int w, const LaneFrag &lf, const TileOwn &own) {
+__device__ __forceinline__ void symm_gemm_row(double (&acc)[(NB + 1) / 2][2], const double *X, const double *W,
+                                              int w, const LaneFrag &lf) {
   constexpr int H = (NB - 1) / 2, RS = (H + 1) * 64;
   const unsigned xs = smem_addr(X), ws = smem_addr(W);
   SymmAddr<NB> A;
@@ -254,10 +233,8 @@ __device__ __forceinline__ void symm_gemm(double (&acc)[(NB + 1) / 2][2], const 
     if (x <= H) A.wd[x] = ws + 8u * (rb + lf.dir);
   }
   SymmFrag<NB> f0, f1;
-#pragma unroll
-  for (int d = 0; d <= H; ++d) f0.b[d][0] = f0.b[d][1] = f1.b[d][0] = f1.b[d][1] = 0.0;   // (tiles the warp does not own are never loaded)
-  symm_load<NB, 0>(f0, A, own);
-  symm_steps<NB, 0>(acc, f0, f1, A, own);
+  symm_load<NB, 0>(f0, A);
+  symm_steps<NB, 0>(acc, f0, f1, A);
 }
 
 // A operand fragments of block-row w of a stored symmetric matrix, inner block (w + e) mod NB
@@ -276,6 +253,41 @@ __device__ __forceinline__ void symm_afrag(double (&a)[2], const double *X, int 
   }
 }
 
+// The same product for a warp that owns only the tiles (w, dbase + s), s < nd <= 2 of its row block: run-time
+// addressing (the split of NB = 13; these warps issue 4 instead of 14 DMMAs per inner block).
+template <int NB>
+__device__ __forceinline__ void symm_gemm_part(double (&acc)[(NB + 1) / 2][2], const double *X, const double *W, int w,
+                                               const LaneFrag &lf, const TileOwn &own) {
+  constexpr int H = (NB - 1) / 2, RS = (H + 1) * 64;
+#pragma unroll
+  for (int e = 0; e < NB; ++e) {
+    int j = w + e;
+    if (j >= NB) j -= NB;
+    double a[2];
+    symm_afrag<NB>(a, X, w, e, j * RS, lf);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (s < own.nd) {
+        const int d = own.dbase + s;
+        int g = d - e, jd = w + d;
+        if (g < 0) g += NB;
+        if (jd >= NB) jd -= NB;
+        const bool stored = g <= H;   // W(w+e, w+d) is the stored tile (w+e, g); else the transpose of tile (w+d, NB-g)
+        const double *t = stored ? W + j * RS + g * 64 + lf.trn : W + jd * RS + (NB - g) * 64 + lf.dir;
+        const double b0 = t[0], b1 = t[stored ? 16 : 32];
+        dmma884(acc[s][0], acc[s][1], a[0], b0);
+        dmma884(acc[s][0], acc[s][1], a[1], b1);
+      }
+    }
+  }
+}
+template <int NB>
+__device__ __forceinline__ void symm_gemm(double (&acc)[(NB + 1) / 2][2], const double *X, const double *W,
+                                          int w, const LaneFrag &lf, const TileOwn &own) {
+  if (owns_row<NB>(own)) symm_gemm_row<NB>(acc, X, W, w, lf);
+  else symm_gemm_part<NB>(acc, X, W, w, lf, own);
+}
+
 // the warp's tiles <-> registers (accumulator layout)
 template <int NB>
 __device__ __forceinline__ void store_circ(const double (&acc)[(NB + 1) / 2][2], double *M, int w,
@@ -284,7 +296,7 @@ __device__ __forceinline__ void store_circ(const double (&acc)[(NB + 1) / 2][2],
   double *t = M + w * RS + lf.st;
 #pragma unroll
   for (int d = 0; d <= H; ++d)
-    if (owns<NB>(own, d)) *reinterpret_cast<double2 *>(t + d * 64) = make_double2(acc[d][0], acc[d][1]);
+    if (has<NB>(own, d)) *reinterpret_cast<double2 *>(t + dact<NB>(own, d) * 64) = make_double2(acc[d][0], acc[d][1]);
 }
 template <int NB>
 __device__ __forceinline__ void load_circ(double (&acc)[(NB + 1) / 2][2], const double *M, int w,
@@ -293,8 +305,8 @@ __device__ __forceinline__ void load_circ(double (&acc)[(NB + 1) / 2][2], const 
   const double *t = M + w * RS + lf.st;
 #pragma unroll
   for (int d = 0; d <= H; ++d) {
-    if (!owns<NB>(own, d)) continue;
-    const double2 v = *reinterpret_cast<const double2 *>(t + d * 64);
+    if (!has<NB>(own, d)) continue;
+    const double2 v = *reinterpret_cast<const double2 *>(t + dact<NB>(own, d) * 64);
     acc[d][0] = v.x;
     acc[d][1] = v.y;
   }
@@ -302,7 +314,8 @@ __device__ __forceinline__ void load_circ(double (&acc)[(NB + 1) / 2][2], const 
 
 // Gram of a staged chunk: raw obs rows Ys[o][m] (row-major, leading dimension LD, nrows4 rows, a
 // multiple of 4) with per-row weights wv[o] (0 for padding rows):
-//   acc[d] += sum_o wv[o] Ys[o][w-block]^T Ys[o][jd-block]
+//   acc[s] += sum_o wv[o] Ys[o][w-block]^T Ys[o][jd-block],   jd = w + dbase + s, s < nd
+// (run-time loop: the partial last chunk of a list, and every chunk of a warp that owns only part of its row block)
 template <int NB, int LD>
 __device__ __forceinline__ void gram_circ(double (&acc)[(NB + 1) / 2][2], const double *Ys, const double *wv,
                                           int nrows4, int w, int lane, const TileOwn &own) {
@@ -310,59 +323,66 @@ __device__ __forceinline__ void gram_circ(double (&acc)[(NB + 1) / 2][2], const 
   const int r = lane >> 2, q = lane & 3;
   const double *pa = Ys + (size_t)q * LD + w * 8 + r;
   const double *pw = wv + q;
-  const double *pb[H + 1];
-#pragma unroll
-  for (int d = 0; d <= H; ++d) {
-    int j = w + d;
-    if (j >= NB) j -= NB;
-    pb[d] = Ys + (size_t)q * LD + j * 8 + r;
-  }
-#pragma unroll 4
-  for (int o = 0; o < nrows4; o += 4) {
-    const double a = pa[(size_t)o * LD] * pw[o];
+  if (owns_row<NB>(own)) {
+    const double *pb[H + 1];
 #pragma unroll
     for (int d = 0; d <= H; ++d) {
-      if constexpr (!NsCfg<NB>::SPLIT) dmma884(acc[d][0], acc[d][1], a, pb[d][(size_t)o * LD]);
-      else dmma884_if(acc[d][0], acc[d][1], a, pb[d][(size_t)o * LD], own.bit(d));
+      int j = w + d;
+      if (j >= NB) j -= NB;
+      pb[d] = Ys + (size_t)q * LD + j * 8 + r;
+    }
+#pragma unroll 4
+    for (int o = 0; o < nrows4; o += 4) {
+      const double a = pa[(size_t)o * LD] * pw[o];
+#pragma unroll
+      for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], a, pb[d][(size_t)o * LD]);
+    }
+  } else {
+    int j0 = w + own.dbase, j1 = w + own.dbase + 1;
+    if (j0 >= NB) j0 -= NB;
+    if (j1 >= NB) j1 -= NB;
+    const double *pb0 = Ys + (size_t)q * LD + j0 * 8 + r, *pb1 = Ys + (size_t)q * LD + j1 * 8 + r;
+    const bool two = own.nd > 1;
+#pragma unroll 2
+    for (int o = 0; o < nrows4; o += 4) {
+      const double a = pa[(size_t)o * LD] * pw[o];
+      dmma884(acc[0][0], acc[0][1], a, pb0[(size_t)o * LD]);
+      if (two) dmma884(acc[1][0], acc[1][1], a, pb1[(size_t)o * LD]);
     }
   }
 }
 
-// The same for a FULL chunk of 4 NSTEP rows, as an explicit software pipeline over its four-row steps (operands
-// of step s + 1 requested before the DMMAs of step s issue; all offsets are LDS immediates).
+// The same for a FULL chunk of 4 NSTEP rows and a warp that owns its whole row block, as an explicit software pipeline
+// over its four-row steps (operands of step s + 1 requested before the DMMAs of step s issue; all offsets are LDS
+// immediates).
 template <int NB>
 struct GramFrag {
   double a, wt, b[(NB + 1) / 2];
 };
 template <int NB, int LD, int S, int D>
-__device__ __forceinline__ void gram_load_b(GramFrag<NB> &f, const unsigned (&pb)[(NB + 1) / 2], const TileOwn &own) {
-  if constexpr (!NsCfg<NB>::SPLIT) f.b[D] = lds_imm<S * 4 * LD * 8>(pb[D]);
-  else lds_imm_if<S * 4 * LD * 8>(f.b[D], pb[D], own.bit(D));
-  if constexpr (D < (NB - 1) / 2) gram_load_b<NB, LD, S, D + 1>(f, pb, own);
+__device__ __forceinline__ void gram_load_b(GramFrag<NB> &f, const unsigned (&pb)[(NB + 1) / 2]) {
+  f.b[D] = lds_imm<S * 4 * LD * 8>(pb[D]);
+  if constexpr (D < (NB - 1) / 2) gram_load_b<NB, LD, S, D + 1>(f, pb);
 }
 template <int NB, int LD, int S>
-__device__ __forceinline__ void gram_load(GramFrag<NB> &f, unsigned pa, unsigned pw, const unsigned (&pb)[(NB + 1) / 2],
-                                          const TileOwn &own) {
+__device__ __forceinline__ void gram_load(GramFrag<NB> &f, unsigned pa, unsigned pw, const unsigned (&pb)[(NB + 1) / 2]) {
   f.a = lds_imm<S * 4 * LD * 8>(pa);
   f.wt = lds_imm<S * 4 * 8>(pw);
-  gram_load_b<NB, LD, S, 0>(f, pb, own);
+  gram_load_b<NB, LD, S, 0>(f, pb);
 }
 template <int NB, int LD, int NSTEP, int S>
 __device__ __forceinline__ void gram_steps(double (&acc)[(NB + 1) / 2][2], GramFrag<NB> &cur, GramFrag<NB> &nxt, unsigned pa,
-                                           unsigned pw, const unsigned (&pb)[(NB + 1) / 2], const TileOwn &own) {
+                                           unsigned pw, const unsigned (&pb)[(NB + 1) / 2]) {
   constexpr int H = (NB - 1) / 2;
-  if constexpr (S + 1 < NSTEP) gram_load<NB, LD, S + 1>(nxt, pa, pw, pb, own);
+  if constexpr (S + 1 < NSTEP) gram_load<NB, LD, S + 1>(nxt, pa, pw, pb);
   const double a = cur.a * cur.wt;
 #pragma unroll
-  for (int d = 0; d <= H; ++d) {
-    if constexpr (!NsCfg<NB>::SPLIT) dmma884(acc[d][0], acc[d][1], a, cur.b[d]);
-    else dmma884_if(acc[d][0], acc[d][1], a, cur.b[d], own.bit(d));
-  }
-  if constexpr (S + 1 < NSTEP) gram_steps<NB, LD, NSTEP, S + 1>(acc, nxt, cur, pa, pw, pb, own);
+  for (int d = 0; d <= H; ++d) dmma884(acc[d][0], acc[d][1], a, cur.b[d]);
+  if constexpr (S + 1 < NSTEP) gram_steps<NB, LD, NSTEP, S + 1>(acc, nxt, cur, pa, pw, pb);
 }
 template <int NB, int LD, int NSTEP>
 __device__ __forceinline__ void gram_circ_full(double (&acc)[(NB + 1) / 2][2], const double *Ys, const double *wv, int w,
-                                               int lane, const TileOwn &own) {
+                                               int lane) {
   constexpr int H = (NB - 1) / 2;
   const int r = lane >> 2, q = lane & 3;
   const unsigned ys = smem_addr(Ys) + 8u * (unsigned)(q * LD + r);
@@ -375,10 +395,8 @@ __device__ __forceinline__ void gram_circ_full(double (&acc)[(NB + 1) / 2][2], c
     pb[d] = ys + 64u * (unsigned)j;
   }
   GramFrag<NB> f0, f1;
-#pragma unroll
-  for (int d = 0; d <= H; ++d) f0.b[d] = f1.b[d] = 0.0;   // (tiles the warp does not own are never loaded)
-  gram_load<NB, LD, 0>(f0, pa, pw, pb, own);
-  gram_steps<NB, LD, NSTEP, 0>(acc, f0, f1, pa, pw, pb, own);
+  gram_load<NB, LD, 0>(f0, pa, pw, pb);
+  gram_steps<NB, LD, NSTEP, 0>(acc, f0, f1, pa, pw, pb);
 }
 
 // Frobenius norm^2 contribution of (I - acc) held in the warp's tiles (off-diagonal tiles count twice)
@@ -388,11 +406,12 @@ __device__ __forceinline__ double resid_fro2(const double (&acc)[(NB + 1) / 2][2
   double s = 0.0;
 #pragma unroll
   for (int d = 0; d <= (NB - 1) / 2; ++d) {
-    if (!owns<NB>(own, d)) continue;
+    if (!has<NB>(own, d)) continue;
+    const bool dg = dact<NB>(own, d) == 0;   // the diagonal tile (the others stand for two tiles of the full matrix)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const double v = ((d == 0 && r == 2 * q + e) ? 1.0 : 0.0) - acc[d][e];
-      s = fma(d == 0 ? v : 2.0 * v, v, s);
+      const double v = ((dg && r == 2 * q + e) ? 1.0 : 0.0) - acc[d][e];
+      s = fma(dg ? v : 2.0 * v, v, s);
     }
   }
   return s;
@@ -429,7 +448,7 @@ __device__ __forceinline__ int newton_schulz_invsqrt(double (&acc)[(NB + 1) / 2]
 #pragma unroll
     for (int d = 0; d <= H; ++d) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) acc[d][e] = fma(h1, acc[d][e], (d == 0 && r == 2 * q + e) ? h0 : 0.0);
+      for (int e = 0; e < 2; ++e) acc[d][e] = fma(h1, acc[d][e], (dact<NB>(own, d) == 0 && r == 2 * q + e) ? h0 : 0.0);
     }
     store_circ<NB>(acc, Tp, w, lf, own);
     if (!have_z) store_circ<NB>(acc, Zp, w, lf, own);   // Z1 = T0
@@ -470,13 +489,13 @@ __device__ __forceinline__ int newton_schulz_invsqrt(double (&acc)[(NB + 1) / 2]
 #pragma unroll
   for (int d = 0; d <= H; ++d) {
 #pragma unroll
-    for (int e = 0; e < 2; ++e) acc[d][e] = ((d == 0 && r == 2 * q + e) ? 1.0 : 0.0) - acc[d][e];   // E
+    for (int e = 0; e < 2; ++e) acc[d][e] = ((dact<NB>(own, d) == 0 && r == 2 * q + e) ? 1.0 : 0.0) - acc[d][e];   // E
   }
   if (order == 2) {
 #pragma unroll
     for (int d = 0; d <= H; ++d) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) az[d][e] = fma(0.5, acc[d][e], (d == 0 && r == 2 * q + e) ? 1.0 : 0.0);
+      for (int e = 0; e < 2; ++e) az[d][e] = fma(0.5, acc[d][e], (dact<NB>(own, d) == 0 && r == 2 * q + e) ? 1.0 : 0.0);
     }
   } else {
     store_circ<NB>(acc, Tp, w, lf, own);   // E
@@ -489,7 +508,7 @@ __device__ __forceinline__ int newton_schulz_invsqrt(double (&acc)[(NB + 1) / 2]
     for (int d = 0; d <= H; ++d) {
 #pragma unroll
       for (int e = 0; e < 2; ++e)
-        az[d][e] = fma(0.375, az[d][e], fma(0.5, acc[d][e], (d == 0 && r == 2 * q + e) ? 1.0 : 0.0));
+        az[d][e] = fma(0.375, az[d][e], fma(0.5, acc[d][e], (dact<NB>(own, d) == 0 && r == 2 * q + e) ? 1.0 : 0.0));
     }
     __syncthreads();   // E^2 visible; (order 3: all reads of E done)
     if (order == 4) {
@@ -593,7 +612,7 @@ __device__ __forceinline__ int newton_schulz_apply(double (&acc)[(NB + 1) / 2][2
   double a = c0s;            // eigenvalues of M in [a, 1]
   double res = 1.0 - a;      // ||I - M||_2 <= 1 - a; later min(bound, measured Frobenius norm)
   double au[H + 1][2];
-  const bool rowown = wid < NB;   // this warp also carries the vector rows of its row block
+  const bool rowown = carries_vectors<NB>(wid);   // this warp also carries the vector rows of its row block
   const double *Vs = V0;
   int it = 0;
   __syncthreads();           // M0 (stored by the caller) visible: the first product reads every tile
@@ -657,7 +676,7 @@ __device__ __forceinline__ int newton_schulz_apply(double (&acc)[(NB + 1) / 2][2
 #pragma unroll
   for (int d = 0; d <= H; ++d) {
 #pragma unroll
-    for (int e = 0; e < 2; ++e) acc[d][e] = ((d == 0 && r == 2 * q + e) ? 1.0 : 0.0) - acc[d][e];   // E
+    for (int e = 0; e < 2; ++e) acc[d][e] = ((dact<NB>(own, d) == 0 && r == 2 * q + e) ? 1.0 : 0.0) - acc[d][e];   // E
   }
   store_circ<NB>(acc, Eb, w, lf, own);
   __syncthreads();

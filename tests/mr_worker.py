@@ -157,7 +157,7 @@ def run_thermo(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def run_gpu(rank, world, port, q):
+def run_gpu(rank, world, port, q, k=6):
     """One rank per GPU, NCCL: members -> (CUDA pack, all-to-all, CUDA unpack) -> ensmean_grd ->
     das_letkf on this rank's columns -> the way back; checked against the single-domain oracle."""
     import torch
@@ -172,7 +172,6 @@ def run_gpu(rank, world, port, q):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        k = 6
         cfg = synth.config_c2(nlon=12, nlat=12, nlev=4, member=k)
         for t in range(24):
             cfg.HORI_LOCAL[t] = 60.0e3
@@ -226,6 +225,13 @@ def run_gpu(rank, world, port, q):
         p2p.write_ens(anal, outp, k, nens)
         for a_, b_ in zip(outp, outg):
             assert (a_ is None and b_ is None) or torch.equal(a_, b_), "p2p gather differs from the NCCL path"
+        # a second set of output grids (what bench.py's cycle leg does): the handle exchange runs again on EVERY rank,
+        # also on one that holds no member in the last round (k odd)
+        outp2 = [None if t is None else torch.full_like(t, -9.0) for t in mine]
+        p2p.write_ens(anal, outp2, k, nens)
+        p2p.write_ens(anal, outp, k, nens)
+        for a_, b_ in zip(outp2, outg):
+            assert (a_ is None and b_ is None) or torch.equal(a_, b_), "p2p gather into a second set of grids"
         # every rank gathers all analysis columns through the oracle to check its own members
         allb = [None] * world
         dist.all_gather_object(allb, (cols, b))

@@ -89,7 +89,8 @@ def test_column_deal_partitions_the_plane(world):
 
 
 @pytest.mark.gpu
-def test_cycle_two_gpus_nccl():
+@pytest.mark.parametrize("k", [6, 5])   # 5: rank 1 holds no member in the last round
+def test_cycle_two_gpus_nccl(k):
     """2 GPUs: NCCL all-to-all transposes + per-rank das_letkf == single-domain oracle (<= 1e-10)"""
     import torch
     if torch.cuda.device_count() < 2:
@@ -99,7 +100,7 @@ def test_cycle_two_gpus_nccl():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=mr_worker.run_gpu, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=mr_worker.run_gpu, args=(r, 2, port, q, k)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
