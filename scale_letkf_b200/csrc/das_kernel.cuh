@@ -38,6 +38,8 @@ struct DasParams {
   int nvgroup;
   int vgroup[kMaxNV];     // group of variable vv (0-based)
   int vfirst[kMaxNV];     // var_local_n2n - 1: first variable of vv's group
+  unsigned gmask[kMaxNV]; // bit vv: variable vv belongs to group vg (das_ns_kernel: no per-point loop over the variables)
+  unsigned qmask;         // bit vv: 3-D moisture variable iv3d_q .. iv3d_qg (left alone above Q_UPDATE_TOP)
   const double *vlfac;    // [nvgroup][nctype]
   // namelist scalars
   double INFL_MUL, INFL_MUL_MIN, RELAX_ALPHA, RELAX_ALPHA_SPREAD, Q_UPDATE_TOP, Q_SPRD_MAX;
@@ -57,6 +59,7 @@ struct DasParams {
   unsigned long long *counters;   // [0] work, [1] npoints, [2] nsolved, [3] nfail, [4] nobsl_sum, [5] overflow, [6] Jacobi sweeps, [8..15] phase clocks
   long long point_begin, point_end;   // (ij, ilev) points [begin, end) of this launch, ilev-major
   int max_sweeps;
+  int stagger_ns, stagger_div;   // experiments (LETKF_B200_STAGGER_US): CTA b sleeps (b / stagger_div) * stagger_ns at kernel start
   // Local lists produced ahead of time by presearch_kernel (das_ns_kernel.cuh) for the points
   // [pl_base, ...): entry (wp - pl_base) * nvgroup + vg holds the count (pl_n, -1 = list overflow) and
   // the offset into the pools (pl_off, -1 = not pre-searched: the solver searches by itself).

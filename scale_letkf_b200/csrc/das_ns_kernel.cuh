@@ -45,6 +45,19 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
 }
+// the same with a 32-bit shared address (no generic -> shared conversion in the request path of the Gram)
+__device__ __forceinline__ void cp_async16_s(unsigned s, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4_s(unsigned s, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8_s(unsigned s, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_s(unsigned b) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(b) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -130,12 +143,17 @@ das_ns_kernel(const DasParams P) {
   __shared__ long long s_ploff[kMaxNV];
   __shared__ int s_pln[kMaxNV];
   __shared__ __align__(8) unsigned long long s_full[4];   // mbarriers of the four Gram staging buffers
+  __shared__ int s_idx[C::NW][2][4];                      // sorted-obs indices of the rows a warp requests next (two chunks)
   const LaneFrag lf = lane_frag(lane);
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], C::NT);   // every thread arrives once its copies of the chunk have landed
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   unsigned gchunk = 0;   // chunks staged so far by this CTA: buffer = gchunk % 4, mbarrier phase = (gchunk / 4) & 1
+  if (P.stagger_ns > 0) {   // experiment: de-phase the CTAs that share an SM (they all start a launch in the same phase)
+    const long long t_end = clock64() + 2ll * (long long)(blockIdx.x / P.stagger_div) * P.stagger_ns;   // ~2 clocks per ns
+    while (clock64() < t_end) __nanosleep(1000);
+  }
 
   LocalList L;
   L.cap = P.lcap;
@@ -233,39 +251,54 @@ das_ns_kernel(const DasParams P) {
     // to a multiple of four entries (weight 0), so every staged row is a list entry: no special cases in here.
     constexpr int RPW = C::RPW;
     static_assert(RPW <= 32, "one row index per lane");
-    int cur_iob = 0;         // sorted-obs index of row wid + NW * lane of the chunk this warp requests next
+    static_assert(RPW <= 4, "s_idx holds four row indices per warp and chunk");
     int p4 = 0;              // list length rounded up to a multiple of four
-    auto fetch_idx = [&](int c, int &o_iob) {
+    // Everything the request path needs is kept as 32-bit shared addresses / warp-uniform values: the path runs once
+    // per chunk in every warp and, at four CTAs per SM, its instruction count weighs as much as the DMMAs of the chunk.
+    const unsigned stage_s = smem_u32(stage), wv_s = smem_u32(wv), full_s = smem_u32(&s_full[0]);
+    const unsigned idx_s = smem_u32(&s_idx[wid][0][0]);
+    // The sorted-obs indices of the rows a warp will request travel global -> shared by cp.async as well (lane r: row
+    // wid + NW r of chunk c, slot c & 1), one chunk ahead of the request that reads them: no register holds them across
+    // the DMMA loop (it was spilled, which exposed the full load latency twice per chunk).
+    auto fetch_idx = [&](int c) {
       const int o0 = c * CR, row = wid + NW * lane;
-      o_iob = 0;
-      if (lane < RPW && row < min(CR, p4 - o0)) o_iob = L.iob[o0 + row];   // (c >= nchunks: p4 - o0 <= 0)
+      if (lane < RPW && row < p4 - o0 && row < CR) cp_async4_s(idx_s + 16u * (unsigned)(c & 1) + 4u * (unsigned)lane, L.iob + o0 + row);
+      cp_async_commit();
     };
-    auto request = [&](int c, int iob) {   // every warp, all lanes
-      const unsigned g = gchunk + (unsigned)c, st = g & 3u;
-      double *dst = stage + (size_t)st * CR * LD;
-      double *wdst = wv + st * CR;
-      const int o0 = c * CR, nrows4 = min(CR, p4 - o0);
+    auto request = [&](int c) {   // every warp, all lanes
+      const unsigned st = __shfl_sync(LETKF_FULL_MASK, (gchunk + (unsigned)c) & 3u, 0);   // (uniform for the compiler too)
+      // this lane's 16 bytes of row 0 of the buffer / of observation 0 (rows are KP doubles: P.ldens == KP); made opaque
+      // so that the compiler keeps them in registers for the three rows instead of recomputing them from scratch
+      unsigned buf_l = stage_s + st * (unsigned)(CR * LD * 8) + 16u * (unsigned)lane;
+      unsigned long long ens_l = reinterpret_cast<unsigned long long>(P.ensval) + 16ull * (unsigned)lane;
+      asm volatile("" : "+r"(buf_l), "+l"(ens_l));
+      const int o0 = c * CR, left = p4 - o0;   // rows of the list from this chunk on (a multiple of four)
+      cp_async_wait<0>();   // this thread's index copy (and its row copies of the previous request) have landed
+      __syncwarp();
 #pragma unroll
       for (int r = 0; r < RPW; ++r) {
         const int row = wid + NW * r;
-        const int ib = __shfl_sync(LETKF_FULL_MASK, iob, r);
-        if (row < nrows4) {
-          const double *src = P.ensval + (size_t)ib * P.ldens;
-          double *d = dst + (size_t)row * LD;
-#pragma unroll
-          for (int pc = lane; pc < KP / 2; pc += 32) cp_async16(d + 2 * pc, src + 2 * pc);
-          if (lane == r) cp_async8(wdst + row, L.rdiag + o0 + row);   // (the list holds 1 / rdiag)
+        if (row < left && row < CR) {
+          const int ib = s_idx[wid][c & 1][r];
+          const char *src = reinterpret_cast<const char *>(ens_l + (unsigned long long)ib * (KP * 8));
+          const unsigned d = buf_l + (unsigned)row * (unsigned)(LD * 8);
+          if (KP / 2 >= 32 || lane < KP / 2) cp_async16_s(d, src);
+          if (KP / 2 > 32 && lane < KP / 2 - 32) cp_async16_s(d + 512u, src + 512);
         }
       }
-      cp_async_mbar_arrive(&s_full[st]);
+      {
+        const int row = wid + NW * lane;   // lane r < RPW copies the R^-1 weight of the warp's r-th row (the list holds 1 / rdiag)
+        if (lane < RPW && row < left && row < CR) cp_async8_s(wv_s + 8u * (st * (unsigned)CR + (unsigned)row), L.rdiag + o0 + row);
+      }
+      cp_async_mbar_arrive_s(full_s + 8u * st);
+      __syncwarp();   // every lane has read the slot before fetch_idx overwrites it
     };
-    auto gram_prologue = [&]() {   // chunks 0 and 1; the indices of chunk 2 wait in registers
-      int i1;
-      fetch_idx(0, cur_iob);
-      fetch_idx(1, i1);
-      if (nchunks > 0) request(0, cur_iob);
-      if (nchunks > 1) request(1, i1);
-      fetch_idx(2, cur_iob);
+    auto gram_prologue = [&]() {   // chunks 0 and 1; the indices of chunk 2 are on their way
+      fetch_idx(0);
+      fetch_idx(1);
+      if (nchunks > 0) request(0);
+      if (nchunks > 1) request(1);
+      fetch_idx(2);
     };
     // With pre-searched lists the first group's observation rows are requested right away: their flight overlaps the
     // member loads below.  (presearch_kernel stores an empty list for a group the solver skips: no stray request.)
@@ -346,18 +379,15 @@ das_ns_kernel(const DasParams P) {
     bool solved_any = false;
 
     for (int vg = 0; vg < P.nvgroup; ++vg) {
-      unsigned colmask = 0;   // bit vv: variable vv belongs to this group and is analysed
-      for (int vv = 0; vv < nvtot; ++vv) {
-        if (P.vgroup[vv] != vg) continue;
-        const bool masked = (vv < P.nv3d) && pmean < P.Q_UPDATE_TOP && (vv + 1) >= P.iv3d_q &&
-                            (vv + 1) <= P.iv3d_qg;
-        if (masked) {   // (letkf_tools.f90:371-385)
-          for (int m = tid; m < k; m += blockDim.x) store_anal(vv, m, xm[vv] + Xall[(size_t)vv * LD + m]);
-          if (P.det && tid == 0) store_anal(vv, k + 1, xdet[vv]);
-          if (P.infl3d && tid == 0 && vv < P.nv3d) P.infl3d[pbase + (size_t)vv * sl] = inflv[vv];
-        } else {
-          colmask |= 1u << vv;
-        }
+      // bit vv: variable vv belongs to this group (masks prepared by the host) ...
+      const unsigned gm = P.gmask[vg] & ((1u << nvtot) - 1u);
+      const unsigned skip = (pmean < P.Q_UPDATE_TOP) ? (gm & P.qmask) : 0u;   // ... moisture above Q_UPDATE_TOP: left alone
+      const unsigned colmask = gm & ~skip;                                     // ... and is analysed
+      for (unsigned rest = skip; rest; rest &= rest - 1) {   // (letkf_tools.f90:371-385)
+        const int vv = __ffs(rest) - 1;
+        for (int m = tid; m < k; m += blockDim.x) store_anal(vv, m, xm[vv] + Xall[(size_t)vv * LD + m]);
+        if (P.det && tid == 0) store_anal(vv, k + 1, xdet[vv]);
+        if (P.infl3d && tid == 0 && vv < P.nv3d) P.infl3d[pbase + (size_t)vv * sl] = inflv[vv];
       }
       if (colmask == 0) continue;
       const int nc = __popc(colmask);
@@ -425,7 +455,7 @@ das_ns_kernel(const DasParams P) {
         if (!pro_done) gram_prologue();
         pro_done = false;
         for (int c = 0; c < nchunks; ++c) {
-          const unsigned g = gchunk + (unsigned)c, st = g & 3u;
+          const unsigned g = __shfl_sync(LETKF_FULL_MASK, gchunk + (unsigned)c, 0), st = g & 3u;
           LETKF_TRACE(10);
           mbar_wait(&s_full[st], (g >> 2) & 1u);
           LETKF_TRACE(11);
@@ -434,9 +464,9 @@ das_ns_kernel(const DasParams P) {
             gram_circ_full<NB, LD, C::NSTEP>(acc, stage + (size_t)st * CR * LD, wv + st * CR, w, lane);
           else gram_circ<NB, LD>(acc, stage + (size_t)st * CR * LD, wv + st * CR, nrows4, w, lane, own);
           LETKF_TRACE(12);
-          if (c + 2 < nchunks) request(c + 2, cur_iob);
+          if (c + 2 < nchunks) request(c + 2);
           LETKF_TRACE(13);
-          fetch_idx(c + 3, cur_iob);
+          fetch_idx(c + 3);
           LETKF_TRACE(14);
         }
         gchunk += (unsigned)nchunks;
@@ -477,7 +507,7 @@ das_ns_kernel(const DasParams P) {
           }
           fs = warp_sum(fs);
           tr = warp_sum(tr);
-          p3acc = warp_sum(p3acc);
+          if (P.INFL_MUL_ADAPTIVE) p3acc = warp_sum(p3acc);
           if (lane == 0) {
             red[wid] = fs;
             red[NW + wid] = tr;

@@ -248,6 +248,7 @@ int plan_das(letkf_b200_handle *h, DasParams &P, DasLaunch &L) {
 template <int NB, bool PRE>
 int plan_das_ns(letkf_b200_handle *h, DasParams &P, DasLaunch &L) {
   using C = NsCfg<NB>;
+  if (P.ldens != C::KP) return fail(h, LETKF_B200_ESTATE, "observation rows were laid out for another ensemble size (call set_obs again)");
   L.kern = das_ns_kernel<NB, PRE>;
   L.nt = C::NT;
   L.smem = das_ns_smem_bytes<NB, PRE>();
@@ -976,7 +977,7 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   const size_t n3 = sl * nens * c.nv3d, n2 = (size_t)h->nij1 * nens * c.nv2d, nf = sl * c.nv3d;
   const bool host = a->mem_space != LETKF_B200_MEM_DEVICE;
   const bool back = !(a->reserved & 1);   // hand the destroyed gues (perturbations, mean) back to the host
-  DasParams P;
+  DasParams P = {};
   std::memset(&P, 0, sizeof(P));
   if (host) {
     CK(h->st_gues.ensure(n3));
@@ -1042,7 +1043,11 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   P.rig1 = h->rig1.p; P.rjg1 = h->rjg1.p; P.hgt1 = h->hgt1.p;
   P.T = h->d_tables.p; P.rec = h->rec.p; P.bstart = h->bstart.p; P.ensval = h->sens.p; P.val = h->sval.p; P.ldens = h->ldens;
   P.nvgroup = h->nvgroup;
-  for (int n = 0; n < kMaxNV; ++n) { P.vgroup[n] = h->vgroup[n]; P.vfirst[n] = h->vfirst[n]; }
+  for (int n = 0; n < kMaxNV; ++n) { P.vgroup[n] = h->vgroup[n]; P.vfirst[n] = h->vfirst[n]; P.gmask[n] = 0; }
+  for (int n = 0; n < c.nv3d + c.nv2d; ++n) P.gmask[h->vgroup[n]] |= 1u << n;
+  P.qmask = 0;
+  for (int n = 0; n < c.nv3d; ++n)
+    if (n + 1 >= c.iv3d_q && n + 1 <= c.iv3d_qg) P.qmask |= 1u << n;
   P.vlfac = h->vlfac_groups.p;
   P.INFL_MUL = c.INFL_MUL; P.INFL_MUL_MIN = c.INFL_MUL_MIN; P.RELAX_ALPHA = c.RELAX_ALPHA;
   P.RELAX_ALPHA_SPREAD = c.RELAX_ALPHA_SPREAD; P.Q_UPDATE_TOP = c.Q_UPDATE_TOP; P.Q_SPRD_MAX = c.Q_SPRD_MAX;
@@ -1056,6 +1061,9 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   P.lcap = h->maxl;
   P.counters = h->counters.p;
   P.max_sweeps = 30;
+  P.stagger_ns = 0;
+  P.stagger_div = std::max(h->num_sms, 1);
+  if (const char *sg = std::getenv("LETKF_B200_STAGGER_US")) P.stagger_ns = (int)(1000.0 * std::atof(sg));
   CK(cudaMemsetAsync(h->counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
 #ifdef LETKF_EXP_TRACE
   CK(h->cb[9].ensure(32000));
