@@ -86,6 +86,37 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank (and hence the pinned host buffers it allocates afterwards: first touch) to the CPUs of the NUMA
+    node its GPU hangs off.  Round 1 ran all eight ranks on node 0: the host-buffer (e2e) leg moved 35 GB through one
+    socket's memory at 131 GB/s aggregate.  Returns a small record for the JSON line; never raises."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:   # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"node": None, "note": "the platform reports no NUMA node for this GPU"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return {"node": node, "note": "no allowed CPU on the GPU's node"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except Exception as e:
+        return {"node": None, "note": repr(e)[:120]}
+
+
 def algorithmic_work(k, nv, npoints, nsolved, nobsl_sum):
     """F(k,p) = 2pk^2 + 9k^3 + 4k^3 + (2pk + 2k^2) + nv(2k^2 + 2k^2) per
     solved point, B(k,p) = 2 nv (k+1) 8 per analysed point + p (k+4) 8 per solved point."""
@@ -699,6 +730,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    numa = bind_to_gpu_numa(local) if world > 1 else None   # (one rank: keep every core for the CPU baseline leg)
     ctx = dict(world=world, rank=rank, local=local, dev=dev, barrier=barrier)
     legs = set()
     if not args.no_parity:
@@ -736,6 +768,8 @@ def main():
             "roofline": r["roofline"], "cpu_baseline": r["cpu"], "parity": r["parity"], "cycle": r["cycle"],
             "kernel_ms_per_step": r["kms"], "phase_share_rank0": r["phases"],
         }
+        if numa is not None:
+            line["numa_rank0"] = numa
         line.update(dict(extra))
         if note:
             line["extras_note"] = note

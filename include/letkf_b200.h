@@ -322,6 +322,23 @@ int letkf_b200_gather_grd_p2p(letkf_b200_handle *h, int np, int myrank_e, int ne
 int letkf_b200_set_obs_device(letkf_b200_handle *h, const letkf_b200_obs *obs, const int32_t *qc, int32_t *nkept);
 int letkf_b200_get_kept_index(const letkf_b200_handle *h, int32_t *kept);
 
+/* ---- additive inflation block of das_letkf (scale/letkf/letkf_tools.f90:804-929) --------
+ * anal(i,k,m,n) += (addi(i,k,ishuf(m),n) - mean_m addi(i,k,:,n)) * INFL_ADD * addinfl_weight(i)
+ *                  [* gues3d(i,k,mmean,n) for the moisture variables iv3d_q..iv3d_qg when INFL_ADD_Q_RATIO]
+ *   addi3d/2d  the additive-inflation ensemble as read_ens_mpi_addiinfl delivers it, laid out like gues3d/gues2d
+ *              (members 1..MEMBER are read; the arrays are NOT modified: the reference turns them into perturbations in place,
+ *              nothing reads them afterwards)
+ *   gues3d     background array of das_letkf: only its mean slot is read, only with q_ratio (may be NULL otherwise)
+ *   ishuf      INFL_ADD_SHUFFLE: permutation of 1..MEMBER drawn by the caller (Knuth_Shuffle + MPI_BCAST in the reference);
+ *              NULL = identity
+ *   ref_only   INFL_ADD_REF_ONLY: addinfl_weight(i) = exp(-d^2/2) of the nearest radar-reflectivity observation (combined
+ *              type REF/PHARAD of the tables of the last set_obs) in units of its localisation scale, 0 beyond dist_zero_fac;
+ *              otherwise 1.  weight_out (nij1, optional) receives the weights.
+ * Arithmetic in the reference's order without FMA contraction: identical to the CPU except for exp() (<= 1 ulp). */
+int letkf_b200_additive_inflation(letkf_b200_handle *h, double infl_add, int q_ratio, int ref_only, const int32_t *ishuf,
+                                  const double *addi3d, const double *addi2d, const double *gues3d, double *anal3d,
+                                  double *anal2d, double *weight_out, int mem_space);
+
 /* ---- radar observation operator ----------------------
  * Twin of the obsfmt_radar branch of obsope_cal (scale/obs/obsope_tools.f90:476-494): phys2ijkz (scale/common/
  * common_obs_scale.f90:1116-1237), Trans_XtoY_radar (:342-493) and calc_ref_vr (:626-990, METHOD_REF_CALC 1/2/3), for ALL

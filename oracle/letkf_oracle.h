@@ -97,6 +97,11 @@ void oracle_enssprd_grd(int mem, int nens, int nij, int nlev, int nv3d, const do
 void oracle_state_trans(const letkf_b200_thermo *t, int inverse, int nlev, int nlon, int nlat, int nv3d,
                         int iv3d_q, double *v3dg);
 /* scale/common/common_obs_scale.f90:1851-1895 (serial sums in observation order) */
+void oracle_additive_inflation(int mem, int nens, int nij, int nlev, int nv3d, int nv2d, double infl_add, int q_ratio,
+                               int ref_only, int iv3d_q, int iv3d_qg, const int32_t *ishuf, double *addi3d, double *addi2d,
+                               const double *gues3d, double *anal3d, double *anal2d, const double *rig1, const double *rjg1,
+                               int nref, const double *obs_ri, const double *obs_rj, double hloc, double DX, double DY,
+                               double dist_zero_fac_square, double *weight);
 void oracle_monit_dep(int nn, const int32_t *elm, const double *dep, const int32_t *qc, int32_t *nobs,
                       double *bias, double *rmse);
 int oracle_max_threads(void);

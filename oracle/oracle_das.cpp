@@ -958,6 +958,64 @@ void oracle_enssprd_grd(int mem, int nens, int nij, int nlev, int nv3d, const do
     }
 }
 
+// Additive inflation block of das_letkf, letkf_tools.f90:804-929 (the ensemble arrives as an argument instead of
+// read_ens_mpi_addiinfl; ishuf comes from the caller instead of Knuth_Shuffle).  addi3d/addi2d are turned into
+// perturbations in place like the reference's gues3d/gues2d.  obs_ri/obs_rj: positions of the radar-reflectivity
+// observations of combined type (REF, PHARAD) -- the loop :822-830 over obsgrd(ic)%ac_ext -- hloc its hori_loc_ctype.
+void oracle_additive_inflation(int mem, int nens, int nij, int nlev, int nv3d, int nv2d, double infl_add, int q_ratio,
+                               int ref_only, int iv3d_q, int iv3d_qg, const int32_t *ishuf, double *addi3d, double *addi2d,
+                               const double *gues3d, double *anal3d, double *anal2d, const double *rig1, const double *rjg1,
+                               int nref, const double *obs_ri, const double *obs_rj, double hloc, double DX, double DY,
+                               double dist_zero_fac_square, double *weight) {
+  const size_t sl = (size_t)nij * nlev;
+  std::vector<double> w((size_t)nij, 1.0);
+  if (ref_only) {   // :816-840
+    for (int ij = 0; ij < nij; ++ij) {
+      double ref_min_dist = 1.0e33;
+      for (int o = 0; o < nref; ++o) {
+        const double rdx = (rig1[ij] - obs_ri[o]) * DX, rdy = (rjg1[ij] - obs_rj[o]) * DY;
+        const double rdxy = rdx * rdx + rdy * rdy;
+        if (rdxy < ref_min_dist) ref_min_dist = rdxy;
+      }
+      ref_min_dist = ref_min_dist / (hloc * hloc);
+      w[ij] = (ref_min_dist <= dist_zero_fac_square) ? std::exp(-0.5 * ref_min_dist) : 0.0;
+    }
+  }
+  if (weight) std::copy(w.begin(), w.end(), weight);
+  oracle_ensmean_grd(mem, nens, nij, nlev, nv3d, addi2d ? nv2d : 0, addi3d, addi2d);   // :849
+  for (int n = 0; n < nv3d; ++n)   // :869-877
+    for (int m = 0; m < mem; ++m)
+      for (size_t p = 0; p < sl; ++p) addi3d[p + ((size_t)m + (size_t)n * nens) * sl] -= addi3d[p + ((size_t)mem + (size_t)n * nens) * sl];
+  if (addi2d)
+    for (int n = 0; n < nv2d; ++n)
+      for (int m = 0; m < mem; ++m)
+        for (int i = 0; i < nij; ++i) addi2d[i + ((size_t)m + (size_t)n * nens) * nij] -= addi2d[i + ((size_t)mem + (size_t)n * nens) * nij];
+  for (int n = 0; n < nv3d; ++n) {   // :889-912
+    const bool moist = (n + 1) >= iv3d_q && (n + 1) <= iv3d_qg;   // q, qc, qr, qi, qs, qg: contiguous variable indices
+    for (int m = 0; m < mem; ++m) {
+      const int ms = ishuf ? ishuf[m] - 1 : m;
+      for (size_t p = 0; p < sl; ++p) {
+        const double g = addi3d[p + ((size_t)ms + (size_t)n * nens) * sl];
+        double &a = anal3d[p + ((size_t)m + (size_t)n * nens) * sl];
+        if (moist) {
+          const double work = q_ratio ? gues3d[p + ((size_t)mem + (size_t)n * nens) * sl] : 1.0;   // work3d (:807-811)
+          a = a + g * infl_add * w[p % nij] * work;
+        } else {
+          a = a + g * infl_add * w[p % nij];
+        }
+      }
+    }
+  }
+  if (addi2d && anal2d)
+    for (int n = 0; n < nv2d; ++n)   // :914-925
+      for (int m = 0; m < mem; ++m) {
+        const int ms = ishuf ? ishuf[m] - 1 : m;
+        for (int i = 0; i < nij; ++i)
+          anal2d[i + ((size_t)m + (size_t)n * nens) * nij] =
+              anal2d[i + ((size_t)m + (size_t)n * nens) * nij] + addi2d[i + ((size_t)ms + (size_t)n * nens) * nij] * infl_add * w[i];
+      }
+}
+
 // state_trans (common_scale.f90:1181-1224) and state_trans_inv (:1229-1280), in place.
 void oracle_state_trans(const letkf_b200_thermo *t, int inverse, int nlev, int nlon, int nlat, int nv3d,
                         int iv3d_q, double *v3dg) {

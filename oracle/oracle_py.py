@@ -79,6 +79,9 @@ def lib():
         L.oracle_state_trans.argtypes = [C.POINTER(capi.Thermo), i, i, i, i, i, i, vp]
         L.oracle_obsope_radar.restype = None
         L.oracle_obsope_radar.argtypes = [C.POINTER(capi.RadarConfig), i, vp, vp, vp, vp, vp, vp, vp, i, C.POINTER(vp), i, vp, vp]
+        L.oracle_additive_inflation.restype = None
+        d = C.c_double
+        L.oracle_additive_inflation.argtypes = [i, i, i, i, i, i, d, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, i, vp, vp, d, d, d, d, vp]
         L.oracle_monit_dep.restype = None
         L.oracle_monit_dep.argtypes = [i, vp, vp, vp, vp, vp, vp]
         L.oracle_max_threads.restype = i
@@ -296,6 +299,24 @@ def enssprd_grd(mem, v3d):
     out = np.zeros((nij, nlev, nv3d), order="F")
     lib().oracle_enssprd_grd(mem, nens, nij, nlev, nv3d, _p(v3d), _p(out))
     return out
+
+
+def additive_inflation(cfg, addi3d, anal3d, infl_add, gues3d=None, q_ratio=False, ref_only=False, ishuf=None, addi2d=None,
+                       anal2d=None, rig1=None, rjg1=None, ref_ri=None, ref_rj=None, hloc=1.0):
+    """letkf_tools.f90:804-929 on F-order arrays shaped like gues3d (nij, nlev, nens, nv3d); addi* become perturbations and
+    anal* are updated in place.  ref_ri/ref_rj: positions of the (REF, PHARAD) observations.  Returns addinfl_weight."""
+    nij, nlev, nens, nv3d = addi3d.shape
+    nv2d = 0 if addi2d is None else addi2d.shape[2]
+    sh = None if ishuf is None else np.ascontiguousarray(ishuf, dtype=np.int32)
+    w = np.zeros(nij)
+    rr = None if ref_ri is None else _f64(ref_ri)
+    rj = None if ref_rj is None else _f64(ref_rj)
+    lib().oracle_additive_inflation(cfg.MEMBER, nens, nij, nlev, nv3d, nv2d, float(infl_add), int(bool(q_ratio)), int(bool(ref_only)),
+                                    cfg.iv3d_q, cfg.iv3d_qg, _p(sh), _p(addi3d), _p(addi2d), _p(gues3d), _p(anal3d), _p(anal2d),
+                                    _p(None if rig1 is None else _f64(rig1)), _p(None if rjg1 is None else _f64(rjg1)),
+                                    0 if rr is None else len(rr), _p(rr), _p(rj), float(hloc), float(cfg.DX), float(cfg.DY),
+                                    float(cfg.dist_zero_fac_square), _p(w))
+    return w
 
 
 def monit_dep(elm, dep, qc):

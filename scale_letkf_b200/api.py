@@ -274,6 +274,24 @@ class LETKF:
         self._ck(self.lib.letkf_b200_enssprd_grd(self.h, k, nens, nij, _ptr(v3d), None, _ptr(out), None, space))
         return out
 
+    def additive_inflation(self, addi3d, anal3d, infl_add, gues3d=None, q_ratio=False, ref_only=False, ishuf=None,
+                           addi2d=None, anal2d=None, want_weight=False):
+        """Additive inflation block of das_letkf (letkf_tools.f90:804-929), in place on anal3d (anal2d): numpy F-order
+        host arrays shaped like gues3d, or torch CUDA tensors with the same memory.  ishuf: permutation of 1..MEMBER."""
+        dev = _is_torch(addi3d)
+        sh = None if ishuf is None else np.ascontiguousarray(ishuf, dtype=np.int32)
+        w = None
+        if want_weight:
+            if dev:
+                import torch
+                w = torch.zeros(self.nij1, dtype=torch.float64, device=addi3d.device)
+            else:
+                w = np.zeros(self.nij1)
+        self._ck(self.lib.letkf_b200_additive_inflation(self.h, float(infl_add), int(bool(q_ratio)), int(bool(ref_only)), _ptr(sh),
+                                                        _ptr(addi3d), _ptr(addi2d), _ptr(gues3d), _ptr(anal3d), _ptr(anal2d), _ptr(w),
+                                                        capi.MEM_DEVICE if dev else capi.MEM_HOST))
+        return w
+
     def thermo_defaults(self):
         t = capi.Thermo()
         self.lib.letkf_b200_thermo_defaults(C.byref(t))

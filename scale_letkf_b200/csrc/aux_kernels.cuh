@@ -193,6 +193,62 @@ __global__ void enssprd_kernel(int mem, int nens, size_t sl, int nvar, const dou
   out[i] = __dsqrt_rn(__ddiv_rn(a, (double)(mem - 1)));
 }
 
+// ---- additive inflation block of das_letkf (letkf_tools.f90:804-929) ------------------------------
+// addinfl_weight(ij) of INFL_ADD_REF_ONLY (:816-840): exp(-d^2 / 2) of the nearest radar-reflectivity observation in units
+// of its horizontal localisation scale, 0 beyond dist_zero_fac.  Brute force over all observations [b0, b1) of the
+// combined type like the reference; observation positions are staged through shared memory 256 at a time.
+__global__ void __launch_bounds__(256) addinfl_weight_kernel(int nij, const double *__restrict__ rig1, const double *__restrict__ rjg1,
+                                                            const ObsRec *__restrict__ rec, int b0, int b1, double DX, double DY,
+                                                            double hloc, double dzf2, double *__restrict__ w) {
+  __shared__ double sri[256], srj[256];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const double ri = i < nij ? rig1[i] : 0.0, rj = i < nij ? rjg1[i] : 0.0;
+  double best = 1.0e33;
+  for (int base = b0; base < b1; base += 256) {
+    const int n = min(256, b1 - base);
+    __syncthreads();
+    if ((int)threadIdx.x < n) {
+      sri[threadIdx.x] = rec[base + threadIdx.x].ri;
+      srj[threadIdx.x] = rec[base + threadIdx.x].rj;
+    }
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+      const double rdx = __dmul_rn(__dsub_rn(ri, sri[j]), DX), rdy = __dmul_rn(__dsub_rn(rj, srj[j]), DY);
+      const double d = __dadd_rn(__dmul_rn(rdx, rdx), __dmul_rn(rdy, rdy));
+      if (d < best) best = d;
+    }
+  }
+  if (i >= nij) return;
+  best = __ddiv_rn(best, __dmul_rn(hloc, hloc));
+  w[i] = (best <= dzf2) ? exp(-0.5 * best) : 0.0;
+}
+// anal(p, m, n) += (addi(p, ishuf(m), n) - mean_m addi(p, :, n)) * INFL_ADD * weight(i) [* gues mean(p, n) for the moisture
+// variables with INFL_ADD_Q_RATIO] (:869-925): the ensemble mean of the additive ensemble is summed in member order like
+// ensmean_grd, the products are taken left to right without FMA contraction -> bit-identical to the CPU.  One thread
+// per (point, variable); HBM-bound: the additive members are read twice (mean, update), the analysis once each way.
+__global__ void additive_inflation_kernel(int mem, int nens, int nij, size_t sl, int nvar, const double *__restrict__ addi,
+                                          double *__restrict__ anal, const double *__restrict__ gues_mean, size_t gm_vstride,
+                                          size_t gm_off, const double *__restrict__ w, const int *__restrict__ ishuf,
+                                          double infl_add, int q_lo, int q_hi) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sl * nvar) return;
+  const size_t n = i / sl, p = i - n * sl;
+  const double *b = addi + p + n * (size_t)nens * sl;
+  double *a = anal + p + n * (size_t)nens * sl;
+  double s = b[0];
+  for (int m = 1; m < mem; ++m) s = __dadd_rn(s, b[(size_t)m * sl]);
+  const double mean = __ddiv_rn(s, (double)mem);
+  const double wi = w ? w[p % (size_t)nij] : 1.0;
+  const bool q = gues_mean != nullptr && (int)n >= q_lo && (int)n <= q_hi;
+  const double qf = q ? gues_mean[p + n * gm_vstride + gm_off] : 1.0;   // background mean: slot `mem` of gues3d, or staged planes
+  for (int m = 0; m < mem; ++m) {
+    const int ms = ishuf ? ishuf[m] - 1 : m;
+    double t = __dmul_rn(__dmul_rn(__dsub_rn(b[(size_t)ms * sl], mean), infl_add), wi);
+    if (q) t = __dmul_rn(t, qf);
+    a[(size_t)m * sl] = __dadd_rn(a[(size_t)m * sl], t);
+  }
+}
+
 // ---- transposes -----------------------------------------------------------------------------
 struct TransposeDims {
   int nlon, nlat, nlev, nv3d, nv2d, np, nij1max, nlevall;

@@ -1466,6 +1466,91 @@ int letkf_b200_enssprd_grd(letkf_b200_handle *h, int mem, int nens, int nij, con
   return LETKF_B200_OK;
 }
 
+int letkf_b200_additive_inflation(letkf_b200_handle *h, double infl_add, int q_ratio, int ref_only, const int32_t *ishuf,
+                                  const double *addi3d, const double *addi2d, const double *gues3d, double *anal3d,
+                                  double *anal2d, double *weight_out, int mem_space) {
+  if (!h || !addi3d || !anal3d || !(infl_add > 0.0) || (q_ratio && !gues3d)) return LETKF_B200_EINVAL;
+  if (h->nij1 < 1) return fail(h, LETKF_B200_ESTATE, "additive_inflation: set_grid has not been called");
+  CK(cudaSetDevice(h->device));
+  const letkf_b200_config &c = h->cfg;
+  const int k = c.MEMBER, nens = c.DET_RUN ? k + 2 : k + 1, nij = h->nij1;
+  const size_t sl = (size_t)nij * c.nlev, n3 = sl * nens * c.nv3d, n2 = (size_t)nij * nens * c.nv2d, o3 = sl * c.nv3d;
+  const bool host = mem_space != LETKF_B200_MEM_DEVICE, two = c.nv2d > 0 && addi2d && anal2d;
+  if (ishuf)
+    for (int m = 0; m < k; ++m)
+      if (ishuf[m] < 1 || ishuf[m] > k) return fail(h, LETKF_B200_EINVAL, "additive_inflation: ishuf is not a permutation of 1..MEMBER");
+  // ---- addinfl_weight (:812-842) ----
+  const double *d_w = nullptr;
+  if (ref_only) {
+    if (h->nobstotal < 0 || h->h_bstart.empty()) return fail(h, LETKF_B200_ESTATE, "additive_inflation: INFL_ADD_REF_ONLY needs set_obs");
+    CK(h->st_logp.ensure((size_t)nij));
+    int b0 = 0, b1 = 0;
+    double hloc = 1.0;
+    for (int ic = 0; ic < h->tables.nctype; ++ic) {   // ctype_elmtyp(uid_obs(id_radar_ref_obs), 22)
+      const CtypeDev &d = h->tables.ct[ic];
+      if (d.elm_u == uid_obs(ID_REF) && d.typ == 22) {
+        b0 = h->h_bstart[d.boff];
+        b1 = h->h_bstart[d.boff + d.ngrdext_i * d.ngrdext_j];
+        hloc = d.hori_loc;
+      }
+    }
+    addinfl_weight_kernel<<<(nij + 255) / 256, 256, 0, h->stream>>>(nij, h->rig1.p, h->rjg1.p, h->rec.p, b0, b1, c.DX, c.DY, hloc,
+                                                                   c.dist_zero_fac_square, h->st_logp.p);
+    CK(cudaGetLastError());
+    d_w = h->st_logp.p;
+    if (weight_out) {
+      CK(cudaMemcpyAsync(weight_out, d_w, sizeof(double) * nij, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+    }
+  } else if (weight_out) {
+    std::vector<double> ones((size_t)nij, 1.0);
+    CK(cudaMemcpyAsync(weight_out, ones.data(), sizeof(double) * nij, host ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  // ---- the update (:869-925) ----
+  const double *d_add3 = addi3d, *d_add2 = addi2d;
+  double *d_an3 = anal3d, *d_an2 = anal2d;
+  if (host) {
+    CK(h->st_gues.ensure(n3)); CK(h->st_anal.ensure(n3));
+    CK(cudaMemcpyAsync(h->st_gues.p, addi3d, sizeof(double) * n3, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->st_anal.p, anal3d, sizeof(double) * n3, cudaMemcpyHostToDevice, h->stream));
+    d_add3 = h->st_gues.p; d_an3 = h->st_anal.p;
+    if (q_ratio) {   // only the mean slot of the background is read: one plane per variable, at its place in a gues3d-shaped view
+      CK(h->st_rtps.ensure(o3));
+      CK(cudaMemcpy2DAsync(h->st_rtps.p, sizeof(double) * sl, gues3d + (size_t)k * sl, sizeof(double) * sl * nens, sizeof(double) * sl,
+                           c.nv3d, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (two) {
+      CK(h->st_gues2.ensure(n2)); CK(h->st_anal2.ensure(n2));
+      CK(cudaMemcpyAsync(h->st_gues2.p, addi2d, sizeof(double) * n2, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(h->st_anal2.p, anal2d, sizeof(double) * n2, cudaMemcpyHostToDevice, h->stream));
+      d_add2 = h->st_gues2.p; d_an2 = h->st_anal2.p;
+    }
+  }
+  DevBuf<int> &d_sh = h->so_tmp;   // (scratch of set_obs, free between calls)
+  const int *d_ishuf = nullptr;
+  if (ishuf) {
+    CK(d_sh.ensure((size_t)k));
+    CK(cudaMemcpyAsync(d_sh.p, ishuf, sizeof(int) * k, cudaMemcpyHostToDevice, h->stream));
+    d_ishuf = d_sh.p;
+  }
+  const int q_lo = c.iv3d_q - 1, q_hi = c.iv3d_qg - 1;   // (the moisture variables q, qc, qr, qi, qs, qg are contiguous)
+  // background mean = slot MEMBER of gues3d on the device, or the nv3d planes staged above
+  const double *d_gm = !q_ratio ? nullptr : host ? h->st_rtps.p : gues3d;
+  const size_t gm_vs = host ? sl : sl * nens, gm_off = host ? 0 : (size_t)k * sl;
+  additive_inflation_kernel<<<(unsigned)((o3 + 255) / 256), 256, 0, h->stream>>>(k, nens, nij, sl, c.nv3d, d_add3, d_an3, d_gm, gm_vs, gm_off, d_w,
+                                                                                 d_ishuf, infl_add, q_lo, q_hi);
+  if (two)
+    additive_inflation_kernel<<<(unsigned)(((size_t)nij * c.nv2d + 255) / 256), 256, 0, h->stream>>>(k, nens, nij, (size_t)nij, c.nv2d, d_add2, d_an2,
+                                                                                                     nullptr, 0, 0, d_w, d_ishuf, infl_add, -1, -2);
+  CK(cudaGetLastError());
+  if (host) {
+    CK(cudaMemcpyAsync(anal3d, d_an3, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+    if (two) CK(cudaMemcpyAsync(anal2d, d_an2, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return LETKF_B200_OK;
+}
+
 void letkf_b200_thermo_defaults(letkf_b200_thermo *t) {   // SCALE-RM scale_const / scale_tracer values
   std::memset(t, 0, sizeof(*t));
   t->Rdry = 287.04;
