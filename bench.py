@@ -517,6 +517,12 @@ def measure(name, ctx, args, steps, warmup, legs):
                 "frac": ach_gbs / peaks.get("hbm_gbs"), "peak_source": peaks_src + " MEASURED_PEAKS.json"},
     }
 
+    if ctx.get("on_partial") is not None:   # from here on only optional legs follow (cycle, e2e, cpu): a watchdog may print this
+        ctx["on_partial"](dict(value=value, ms_per_step=ms_per_step, clocks=clocks, phases=phases, parity=parity, roofline=roofline,
+                               cycle={"error": "the leg did not finish before the deadline"}, e2e=None, cpu=None, launches=launches,
+                               npoints=npoints, nsolved=nsolved, nobsl_sum=nobsl_sum, kms=kms, state_bytes=state_bytes, k=k,
+                               nobs=int(len(obs["elm"])), desc=w["desc"], grid=[w["nlon"], w["nlat"], w["nlev"]]))
+
     # ---- full analysis cycle (SURVEY.md section 8d metric ii) ----------------------------------------
     cycle = None
     free_b, _ = torch.cuda.mem_get_info()
@@ -693,6 +699,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the secondary records of the default line (k100 = C3, c1, and at 8 GPUs c5_cycle and c4)")
     ap.add_argument("--all-extra", action="store_true", help="run the 8-GPU secondary records (c5_cycle, c4) at any rank count")
+    ap.add_argument("--main-deadline", type=float, default=420.0,
+                    help="seconds the optional legs of the main workload (cycle, e2e, cpu) may take before the line is printed without them")
     ap.add_argument("--extra-deadline", type=float, default=480.0,
                     help="seconds after which the secondary records are abandoned and the line is printed without them")
     ap.add_argument("--synth", default="hx", choices=["hx", "iid"],
@@ -741,17 +749,17 @@ def main():
         legs.add("e2e")
     if not args.no_cpu:
         legs.add("cpu")
-    r = measure(args.workload, ctx, args, args.steps, args.warmup, legs)
-
-    # ---- the line (rank 0); emitted once, by the main thread or -- if a secondary record hangs -- by the deadline thread ----
+    # ---- the line (rank 0); emitted once, by the main thread or -- if an optional leg hangs -- by a deadline thread ----
     extra = {}
     emitted = threading.Lock()
+    res = {}
 
     def emit(note=None):
         if not emitted.acquire(blocking=False):
             return
         if rank != 0:
             return
+        r = res["r"]
         line = {
             "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
@@ -779,6 +787,26 @@ def main():
             sys.stdout.flush()
             os.dup2(saved_stdout_fd, 1)
         print(json.dumps(line), flush=True)
+
+    # The device-timed measurement and its parity check are never lost to an optional leg (cycle: peer-memory transposes
+    # and barriers; e2e; cpu baseline) that hangs in a collective: every rank arms the same deadline when measure() hands out
+    # the partial result, rank 0 prints the line without the unfinished legs, every rank exits 0.
+    main_done = threading.Event()
+
+    def on_partial(rp):
+        res["r"] = rp
+
+        def main_deadline():
+            if not main_done.wait(args.main_deadline):
+                emit("optional legs (cycle / e2e / cpu_baseline) stopped after %.0f s (deadline); value, roofline and parity "
+                     "are complete" % args.main_deadline)
+                sys.stdout.flush()
+                os._exit(0)
+        threading.Thread(target=main_deadline, daemon=True).start()
+    ctx["on_partial"] = on_partial
+    res["r"] = measure(args.workload, ctx, args, args.steps, args.warmup, legs)
+    main_done.set()
+    ctx["on_partial"] = None
 
     # ---- secondary records of the default line (the other BASELINE.json shapes) ------------------------
     if args.workload == "c2" and not args.no_extra and args.subsample == 1:

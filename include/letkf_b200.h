@@ -190,6 +190,20 @@ int letkf_b200_obs_local(letkf_b200_handle *h, int npts, const double *ri, const
                          int32_t *idx, double *rdiag, double *rloc, int max_out,
                          int mem_space);
 
+/* ---- NOBS_OUT fields of das_letkf (letkf_tools.f90:281-284, 399-401, 440-447, 767-778) ------
+ * obs_local's optional outputs nobsl_t / cutd_t (:1342-1343) at every analysis point (set_grid), for the variable-localisation
+ * group of the 3-D model variable nvar (1-based; the reference writes those of iv3d_t), reduced to the eleven fields the
+ * reference writes to NOBS_OUT_BASENAME, out(nij1,nlev,11):
+ *   1..5  number of local observations of report types 1 (ADPUPA), 3, 4, 8 and 22 (PHARAD), summed over the elements
+ *   6..8  nobsl_t(REF | RE0 | VR, PHARAD)        9..11  cutd_t(REF | RE0 | VR, PHARAD)
+ * Points with relax_beta = 0 keep zeros.  pmean = gues3d(:,:,mmean,iv3d_p) (nij1,nlev); logp optional as in das_letkf (host
+ * buffers: ln p is always taken by the host libm).  Counts are identical to the reference's, including its quirk that an
+ * unlimited merged group (REF + RE0) reports cumulative counts.  cutd_t is the criterion value of the worst selected
+ * observation of a group that filled MAX_NOBS_PER_GRID -- what the reference's quickselect leaves in the last slot -- and
+ * differs from the reference only when its last incremental search pass found EXACTLY the limit (no quickselect: the
+ * reference then reports the last SCANNED observation, which depends on the level-to-level search_q0 history). */
+int letkf_b200_nobs_out(letkf_b200_handle *h, int nvar, const double *pmean, const double *logp, double *out, int mem_space);
+
 /* ---- das_letkf twin (letkf_tools.f90:50) ----------------------------------- */
 typedef struct letkf_b200_das_args {
   double *gues3d;        /* (nij1,nlev,nens,nv3d) INOUT: destroyed -> perturbations, slot MEMBER+1 = mean */

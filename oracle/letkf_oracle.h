@@ -72,6 +72,9 @@ int oracle_das_letkf(oracle_state *s, double *gues3d, double *gues2d, double *an
                      double *anal2d, double *infl3d, double *rtps_infl_out,
                      int32_t *nobsl_out, const uint8_t *point_mask, int nthreads,
                      int64_t *npoints, int64_t *nsolved);
+/* NOBS_OUT fields of das_letkf (letkf_tools.f90:281-284, 399-401, 440-447, 767-778) for model variable nvar: out (nij1,nlev,11),
+ * exact_hits (nij1,nlev) optional */
+void oracle_nobs_out(oracle_state *s, int nvar, const double *pmean, double *out, int32_t *exact_hits, int nthreads);
 /* scale/common/common_scale.f90:1513-1552 */
 void oracle_ensmean_grd(int mem, int nens, int nij, int nlev, int nv3d, int nv2d, double *v3d,
                         double *v2d);

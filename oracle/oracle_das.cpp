@@ -207,11 +207,29 @@ struct Scratch {   // per-thread work arrays of obs_local (:1347-1351, 1400-1417
   std::vector<int> touched;   // entries of rloc_tmp written in this call (reset lazily)
 };
 
+// optional outputs nobsl_t / cutd_t of obs_local (letkf_tools.f90:1342-1343): [elm_u - 1][typ - 1]
+struct LocalDiag {
+  int nobsl_t[LETKF_B200_NID_OBS][LETKF_B200_NOBTYPE];
+  double cutd_t[LETKF_B200_NID_OBS][LETKF_B200_NOBTYPE];
+  // a limited group whose last search pass found EXACTLY the limit: no quickselect ran, so the reference's cutd_t is the
+  // value of the LAST SCANNED observation (which depends on the srch_q0 history), not that of the worst selected one
+  int exact_hits;
+};
+
 // obs_local, letkf_tools.f90:1325-1759.  srch_q0 may be NULL (then q starts at 1).
 // brute: candidates are ALL observations of the ctype (semantic definition).
 void obs_local(const oracle_state &s, double ri, double rj, double rlev, double rz, int nvar,
-               LocalOut &out, Scratch &w, int *srch_q0, bool brute) {
+               LocalOut &out, Scratch &w, int *srch_q0, bool brute, LocalDiag *dg = nullptr) {
   out.clear();
+  if (dg) {   // (:1380-1390)
+    std::memset(dg->nobsl_t, 0, sizeof(dg->nobsl_t));
+    for (auto &r : dg->cutd_t)
+      for (double &v : r) v = 0.0;
+    dg->exact_hits = 0;
+    if (s.cfg.MAX_NOBS_PER_GRID_CRITERION == 1)
+      for (int ic = 0; ic < s.nctype; ++ic)
+        dg->cutd_t[s.elm_u_ctype[ic] - 1][s.typ_ctype[ic] - 1] = s.hori_loc_ctype[ic] * s.cfg.dist_zero_fac;
+  }
   if (s.nobstotal == 0) return;
   int maxlimit = 0;
   for (int t = 0; t < NOBTYPE; ++t) maxlimit = std::max(maxlimit, s.cfg.MAX_NOBS_PER_GRID[t]);
@@ -241,12 +259,17 @@ void obs_local(const oracle_state &s, double ri, double rj, double rlev, double 
   };
 
   for (int ic = 0; ic < s.nctype; ++ic) {
-    if (s.n_merge[ic] == 0) continue;
+    if (s.n_merge[ic] == 0) {
+      if (dg) dg->cutd_t[s.elm_u_ctype[ic] - 1][s.typ_ctype[ic] - 1] = 0.0;   // (:1427-1431)
+      continue;
+    }
     const int nobsl_max_master = s.cfg.MAX_NOBS_PER_GRID[s.typ_ctype[ic] - 1];
     const int nm = s.n_merge[ic];
+    const int eu_master = s.elm_u_ctype[ic] - 1, ty_master = s.typ_ctype[ic] - 1;
 
     if (nobsl_max_master <= 0) {
       // no obs-number limit (:1438-1476)
+      const size_t nobsl_prev = out.iob.size();   // (:1444: set once, before the loop over the merged types)
       for (int icm = 0; icm < nm; ++icm) {
         const int ic2 = s.ic_merge[ic][icm];
         if (s.obsgrd[ic2].tot_ext > 0) {
@@ -261,6 +284,8 @@ void obs_local(const oracle_state &s, double ri, double rj, double rlev, double 
             out.push(iob, nrdiag, nrloc);
           }
         }
+        // (:1473-1475) nobsl - nobsl_prev with nobsl_prev from BEFORE the merged loop: cumulative over the merged types
+        if (dg) dg->nobsl_t[s.elm_u_ctype[ic2] - 1][s.typ_ctype[ic2] - 1] = (int)(out.iob.size() - nobsl_prev);
       }
     } else if (s.cfg.MAX_NOBS_PER_GRID_CRITERION == 1) {
       // incremental search + N nearest (:1479-1660)
@@ -348,6 +373,7 @@ void obs_local(const oracle_state &s, double ri, double rj, double rlev, double 
         }
       }
       if (nobsl_incr == 0) continue;
+      if (dg && nobsl_incr == nobsl_max_master) dg->exact_hits++;
       if (nobsl_incr > nobsl_max_master) {
         oracle_quickselect_arg(w.dist_tmp.data(), w.nobs_use2.data(), 1, nobsl_incr, nobsl_max_master);
         nobsl_incr = nobsl_max_master;
@@ -355,6 +381,11 @@ void obs_local(const oracle_state &s, double ri, double rj, double rlev, double 
       for (int n = 0; n < nobsl_incr; ++n) {
         const int iob = w.nobs_use2[n] - 1;
         out.push(iob, w.rdiag_tmp[iob], w.rloc_tmp[iob]);
+      }
+      if (dg) {   // (:1653-1660)
+        dg->nobsl_t[eu_master][ty_master] = nobsl_incr;
+        if (nobsl_incr == nobsl_max_master)
+          dg->cutd_t[eu_master][ty_master] = s.hori_loc_ctype[ic] * std::sqrt(w.dist_tmp[w.nobs_use2[nobsl_incr - 1] - 1]);
       }
     } else {
       // criterion 2 / 3: select over everything inside the cut-off (:1663-1729)
@@ -378,6 +409,7 @@ void obs_local(const oracle_state &s, double ri, double rj, double rlev, double 
         }
       }
       if (nobsl_incr == 0) continue;
+      if (dg && nobsl_incr == nobsl_max_master) dg->exact_hits++;
       if (nobsl_incr > nobsl_max_master) {
         if (s.cfg.MAX_NOBS_PER_GRID_CRITERION == 2) {
           oracle_quickselect_desc_arg(w.rloc_tmp.data(), w.nobs_use2.data(), 1, nobsl_incr, nobsl_max_master);
@@ -389,6 +421,14 @@ void obs_local(const oracle_state &s, double ri, double rj, double rlev, double 
       for (int n = 0; n < nobsl_incr; ++n) {
         const int iob = w.nobs_use2[n] - 1;
         out.push(iob, w.rdiag_tmp[iob], w.rloc_tmp[iob]);
+      }
+      if (dg) {   // (:1718-1729)
+        dg->nobsl_t[eu_master][ty_master] = nobsl_incr;
+        if (nobsl_incr == nobsl_max_master) {
+          const int last = w.nobs_use2[nobsl_incr - 1] - 1;
+          if (s.cfg.MAX_NOBS_PER_GRID_CRITERION == 2) dg->cutd_t[eu_master][ty_master] = w.rloc_tmp[last];
+          else if (s.cfg.MAX_NOBS_PER_GRID_CRITERION == 3) dg->cutd_t[eu_master][ty_master] = w.rdiag_tmp[last];
+        }
       }
     }
   }
@@ -667,6 +707,56 @@ int oracle_obs_local(oracle_state *s, int npts, const double *ri, const double *
     }
   }
   return status;
+}
+
+// NOBS_OUT fields of das_letkf for the 3-D model variable nvar (the reference writes those of iv3d_t): work3dn
+// (letkf_tools.f90:281-284 zero-initialised, :399-401 copied inside a variable-localisation group, :440-447 filled from
+// nobsl_t / cutd_t of obs_local) and the eleven fields the reference writes to NOBS_OUT_BASENAME (:767-778):
+//   out(:,:,1..5)  = sum over elements of nobsl_t(:, type) for report types 1, 3, 4, 8, 22
+//   out(:,:,6..8)  = nobsl_t(REF | RE0 | VR, PHARAD);   out(:,:,9..11) = cutd_t(REF | RE0 | VR, PHARAD)
+// Levels run sequentially per column (search_q0 carry, :194-195, :313); points with relax_beta = 0 keep the zeros.
+// pmean (nij1, nlev) = gues3d(:,:,mmean,iv3d_p).  exact_hits (nij1, nlev), optional: number of obs-number-limited groups whose
+// last search pass found exactly the limit (see LocalDiag).
+void oracle_nobs_out(oracle_state *sp, int nvar, const double *pmean, double *out, int32_t *exact_hits, int nthreads) {
+  oracle_state &s = *sp;
+  const int nij1 = s.nij1, nlev = s.cfg.nlev;
+  const size_t sl = (size_t)nij1 * nlev;
+  std::fill(out, out + sl * 11, 0.0);
+  if (exact_hits) std::fill(exact_hits, exact_hits + sl, 0);
+  const int nrep = s.var_local_n2n[nvar - 1];   // the variable whose obs_local call fills the group's work3dn
+  std::vector<int> search_q0((size_t)std::max(s.nctype, 1) * nij1, 1);
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+  nthreads = 1;
+#endif
+  static const int rep_types[5] = {1, 3, 4, 8, 22};
+  const int eu[3] = {9, 10, 11};   // uid_obs of id_radar_ref_obs, id_radar_ref_zero_obs, id_radar_vr_obs
+#pragma omp parallel num_threads(nthreads)
+  {
+    LocalOut lo;
+    Scratch w;
+    LocalDiag dg;
+    for (int il = 0; il < nlev; ++il) {
+#pragma omp for schedule(dynamic, 4)
+      for (int ij = 0; ij < nij1; ++ij) {
+        const size_t p = ij + (size_t)il * nij1;
+        if (relax_beta(s, s.rig1[ij], s.rjg1[ij], s.hgt1[p]) == 0.0) continue;   // (:323-352)
+        obs_local(s, s.rig1[ij], s.rjg1[ij], pmean[p], s.hgt1[p], nrep, lo, w, &search_q0[(size_t)ij * std::max(s.nctype, 1)],
+                  false, &dg);
+        for (int f = 0; f < 5; ++f) {
+          int sum = 0;
+          for (int e = 0; e < LETKF_B200_NID_OBS; ++e) sum += dg.nobsl_t[e][rep_types[f] - 1];
+          out[p + sl * f] = (double)sum;
+        }
+        for (int f = 0; f < 3; ++f) {
+          out[p + sl * (5 + f)] = (double)dg.nobsl_t[eu[f] - 1][21];
+          out[p + sl * (8 + f)] = dg.cutd_t[eu[f] - 1][21];
+        }
+        if (exact_hits) exact_hits[p] = dg.exact_hits;
+      }
+    }
+  }
 }
 
 // das_letkf, letkf_tools.f90:50-932 (live path).  nv2d variables follow :528-660.

@@ -82,6 +82,8 @@ def lib():
         L.oracle_additive_inflation.restype = None
         d = C.c_double
         L.oracle_additive_inflation.argtypes = [i, i, i, i, i, i, d, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, i, vp, vp, d, d, d, d, vp]
+        L.oracle_nobs_out.restype = None
+        L.oracle_nobs_out.argtypes = [vp, i, vp, vp, vp, i]
         L.oracle_monit_dep.restype = None
         L.oracle_monit_dep.argtypes = [i, vp, vp, vp, vp, vp, vp]
         L.oracle_max_threads.restype = i
@@ -238,6 +240,16 @@ class Oracle:
         if r != 0:
             raise RuntimeError("oracle_obs_local: max_out too small")
         return nobsl, idx, rdiag, rloc
+
+    def nobs_out(self, nvar, pmean, nthreads=0):
+        """NOBS_OUT fields of das_letkf (letkf_tools.f90:440-447, 767-778) for model variable nvar (the reference: iv3d_t).
+        pmean: F-order (nij1, nlev) mean pressure.  -> out (nij1, nlev, 11) F-order, exact_hits (nij1, nlev)"""
+        pm = np.asfortranarray(pmean, dtype=np.float64)
+        nij1, nlev = pm.shape
+        out = np.zeros((nij1, nlev, 11), order="F")
+        hits = np.zeros((nij1, nlev), dtype=np.int32, order="F")
+        lib().oracle_nobs_out(self.h, int(nvar), _p(pm), _p(out), _p(hits), int(nthreads))
+        return out, hits
 
     def das_letkf(self, gues3d, gues2d=None, infl3d=None, want_rtps=False, want_nobsl=False,
                   point_mask=None, nthreads=0):

@@ -292,6 +292,20 @@ class LETKF:
                                                         capi.MEM_DEVICE if dev else capi.MEM_HOST))
         return w
 
+    def nobs_out(self, nvar, pmean, logp=None):
+        """NOBS_OUT fields of das_letkf (letkf_tools.f90:440-447, 767-778) for model variable nvar: pmean (nij1, nlev) F-order
+        numpy (host) or a torch CUDA tensor with the same memory (nlev, nij1) -> (nij1, nlev, 11) / torch (11, nlev, nij1)."""
+        if _is_torch(pmean):
+            import torch
+            out = torch.empty((11,) + tuple(pmean.shape), dtype=torch.float64, device=pmean.device)
+            space = capi.MEM_DEVICE
+        else:
+            pmean = np.asfortranarray(pmean, dtype=np.float64)
+            out = np.zeros(pmean.shape + (11,), order="F")
+            space = capi.MEM_HOST
+        self._ck(self.lib.letkf_b200_nobs_out(self.h, int(nvar), _ptr(pmean), _ptr(logp), _ptr(out), space))
+        return out
+
     def thermo_defaults(self):
         t = capi.Thermo()
         self.lib.letkf_b200_thermo_defaults(C.byref(t))

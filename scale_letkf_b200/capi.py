@@ -160,6 +160,7 @@ PROTOTYPES = {
     "letkf_b200_das_kernel_ms": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "letkf_b200_das_phase_clocks": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "letkf_b200_ensmean_grd": (_i, [_vp, _i, _i, _i, _vp, _vp, _i]),
+    "letkf_b200_nobs_out": (_i, [_vp, _i, _vp, _vp, _vp, _i]),
     "letkf_b200_additive_inflation": (_i, [_vp, C.c_double, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "letkf_b200_enssprd_grd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "letkf_b200_thermo_defaults": (None, [C.POINTER(Thermo)]),

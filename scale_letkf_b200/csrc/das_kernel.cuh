@@ -574,6 +574,153 @@ __global__ void __launch_bounds__(128) search_kernel(const SearchParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// NOBS_OUT fields of das_letkf (letkf_tools.f90:281-284, 440-447, 767-778) at every analysis point, for the
+// variable-localisation group of one model variable: obs_local with its optional outputs nobsl_t / cutd_t
+// (:1380-1390, 1427-1431, 1473-1475, 1653-1660, 1718-1729) reduced to the eleven fields the reference writes:
+//   out(:,:,0..4) = sum over elements of nobsl_t(:, type) for report types 1, 3, 4, 8, 22
+//   out(:,:,5..7) = nobsl_t(REF | RE0 | VR, PHARAD),  out(:,:,8..10) = cutd_t(REF | RE0 | VR, PHARAD)
+// The search is search_point (the list das_letkf analyses with); the epilogue classifies the selected observations by
+// combined type (ranges of the sorted order) and, for obs-number-limited groups that filled their budget, takes the worst
+// criterion key of the selected set (criterion 1: normalised distance recomputed with obs_geom's exact arithmetic).
+// Reference quirks kept: nobsl_t of an UNLIMITED merged group is cumulative over its members (nobsl_prev is set once,
+// :1444); merged non-master types report cutd_t = 0.
+struct NobsOutParams {
+  const SearchTables *T;
+  const ObsRec *rec;
+  const int *bstart;
+  const double *vlfac;
+  const double *rig1, *rjg1, *hgt1, *logp, *pmean;   // logp (nij1,nlev) or NULL -> log(pmean)
+  int nij1, nlev, radar_only, IHALO, JHALO, nlon, nlat;
+  double zcut, BOUNDARY_BUFFER_WIDTH, DX, DY;
+  double *out;   // (nij1, nlev, 11)
+  int *l_iob;
+  double *l_rdiag, *l_rloc;
+  int lcap;
+  double *l_cnd;
+  unsigned *l_cpk;
+  int ccap;
+  unsigned long long *counters;
+};
+
+__global__ void __launch_bounds__(128) nobs_out_kernel(const NobsOutParams P) {
+  __shared__ SearchSmem S;
+  __shared__ long long s_work;
+  __shared__ int s_cnt[kMaxCtype], s_cstart[kMaxCtype];
+  __shared__ unsigned long long s_key[kMaxGroup];
+  __shared__ unsigned char s_grp[kMaxCtype];
+  const SearchTables &T = *P.T;
+  const int tid = threadIdx.x;
+  LocalList L;
+  L.cap = P.lcap;
+  L.iob = P.l_iob + (size_t)blockIdx.x * P.lcap;
+  L.rdiag = P.l_rdiag + (size_t)blockIdx.x * P.lcap;
+  L.rloc = P.l_rloc + (size_t)blockIdx.x * P.lcap;
+  L.ccap = P.ccap;
+  L.cnd = P.l_cnd + (size_t)blockIdx.x * P.ccap;
+  L.cpk = P.l_cpk + (size_t)blockIdx.x * P.ccap;
+  const long long npts = (long long)P.nij1 * P.nlev;
+  const size_t sl = (size_t)npts;
+  if (tid < T.nctype) s_cstart[tid] = P.bstart[T.ct[tid].boff];   // first sorted index of the combined type
+  if (tid < T.ngroup)
+    for (int m = 0; m < T.grp[tid].n; ++m) s_grp[T.grp[tid].ic[m]] = (unsigned char)tid;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_work = (long long)atomicAdd(&P.counters[0], 1ull);
+    if (tid < kMaxCtype) s_cnt[tid] = 0;
+    if (tid < kMaxGroup) s_key[tid] = (T.criterion == 2) ? ~0ull : 0ull;
+    __syncthreads();
+    const long long wp = s_work;
+    if (wp >= npts) break;
+    const int il = (int)(wp / P.nij1), ij = (int)(wp - (long long)il * P.nij1);
+    const size_t pbase = (size_t)ij + (size_t)il * P.nij1;
+    const double ri = P.rig1[ij], rj = P.rjg1[ij], rz = P.hgt1[pbase];
+    double beta = 1.0;   // relax_beta (letkf_tools.f90:1911-1948), as in the das kernels
+    if (P.radar_only && rz > P.zcut) {
+      beta = 0.0;
+    } else if (P.BOUNDARY_BUFFER_WIDTH > 0.0) {
+      const double dist_bdy =
+          fmin(fmin(ri - P.IHALO, P.nlon + P.IHALO + 1 - ri) * P.DX,
+               fmin(rj - P.JHALO, P.nlat + P.JHALO + 1 - rj) * P.DY) / P.BOUNDARY_BUFFER_WIDTH;
+      if (dist_bdy < 1.0) beta = fmax(dist_bdy, 0.0);
+    }
+    if (beta == 0.0) {   // no obs_local call: work3dn keeps its zeros (:283, :323-352)
+      if (tid < 11) P.out[pbase + sl * tid] = 0.0;
+      continue;
+    }
+    Point pt;
+    pt.ri = ri;
+    pt.rj = rj;
+    pt.rz = rz;
+    pt.lp = P.logp ? P.logp[pbase] : log(P.pmean[pbase]);
+    const int n = search_point(T, P.rec, P.bstart, P.vlfac, pt, L, S);
+    __syncthreads();
+    if (n < 0) {   // list capacity exceeded (cannot happen with maxl from set_obs): flagged, the host returns an error
+      if (tid == 0) atomicAdd(&P.counters[5], 1ull);
+      if (tid < 11) P.out[pbase + sl * tid] = -1.0;
+      continue;
+    }
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int iob = L.iob[i];
+      int ic = T.nctype - 1;
+      while (ic > 0 && s_cstart[ic] > iob) --ic;
+      atomicAdd(&s_cnt[ic], 1);
+      const int g = s_grp[ic];
+      if (T.grp[g].limit > 0) {
+        if (T.criterion == 1) {
+          double nd = 0.0;
+          obs_geom(T, T.ct[ic], pt, P.rec[iob], nd);
+          atomicMax(&s_key[g], (unsigned long long)__double_as_longlong(nd));     // non-negative doubles order like integers
+        } else if (T.criterion == 2) {
+          atomicMin(&s_key[g], (unsigned long long)__double_as_longlong(L.rloc[i]));
+        } else {
+          atomicMax(&s_key[g], (unsigned long long)__double_as_longlong(L.rdiag[i]));
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int rep[5] = {0, 0, 0, 0, 0}, nt[3] = {0, 0, 0};
+      double cut[3] = {0.0, 0.0, 0.0};
+      auto put = [&](const CtypeDev &c, int cnt, double cutd) {
+        const int slot = c.typ == 1 ? 0 : c.typ == 3 ? 1 : c.typ == 4 ? 2 : c.typ == 8 ? 3 : c.typ == 22 ? 4 : -1;
+        if (slot >= 0) rep[slot] += cnt;
+        if (c.typ == 22 && c.elm_u >= 9 && c.elm_u <= 11) {
+          nt[c.elm_u - 9] = cnt;
+          cut[c.elm_u - 9] = cutd;
+        }
+      };
+      for (int g = 0; g < T.ngroup; ++g) {
+        const GroupDev &G = T.grp[g];
+        const CtypeDev &cm = T.ct[G.ic[0]];
+        const double cut0 = (T.criterion == 1) ? __dmul_rn(cm.hori_loc, T.dzf) : 0.0;   // (:1385-1389)
+        int tot = 0;
+        for (int m = 0; m < G.n; ++m) tot += s_cnt[G.ic[m]];
+        if (G.limit <= 0) {
+          int cum = 0;
+          for (int m = 0; m < G.n; ++m) {
+            cum += s_cnt[G.ic[m]];
+            put(T.ct[G.ic[m]], cum, m == 0 ? cut0 : 0.0);
+          }
+        } else {
+          double cutd = cut0;
+          if (tot == G.limit) {
+            const double key = __longlong_as_double((long long)s_key[g]);
+            cutd = (T.criterion == 1) ? __dmul_rn(cm.hori_loc, __dsqrt_rn(key)) : key;
+          }
+          put(cm, tot, cutd);
+          for (int m = 1; m < G.n; ++m) put(T.ct[G.ic[m]], 0, 0.0);
+        }
+      }
+      for (int f = 0; f < 5; ++f) P.out[pbase + sl * f] = (double)rep[f];
+      for (int f = 0; f < 3; ++f) {
+        P.out[pbase + sl * (5 + f)] = (double)nt[f];
+        P.out[pbase + sl * (8 + f)] = cut[f];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Batched letkf_core twin (common/common_letkf.f90:52-257): explicit trans / transm / pao.
 struct CoreParams {
   int ne, nobs, npts, ld, ldk, npairs, ncols;

@@ -960,6 +960,66 @@ int letkf_b200_obs_local(letkf_b200_handle *h, int npts, const double *ri, const
   return LETKF_B200_OK;
 }
 
+int letkf_b200_nobs_out(letkf_b200_handle *h, int nvar, const double *pmean, const double *logp, double *out, int mem_space) {
+  if (!h || !out || (!pmean && !logp)) return LETKF_B200_EINVAL;
+  if (!h->obs_set) return fail(h, LETKF_B200_ESTATE, "set_obs has not been called");
+  if (h->nij1 < 1) return fail(h, LETKF_B200_ESTATE, "set_grid has not been called");
+  const letkf_b200_config &c = h->cfg;
+  if (nvar < 1 || nvar > c.nv3d) return fail(h, LETKF_B200_EINVAL, "nobs_out: nvar must be a 3-D variable (1..nv3d)");
+  CK(cudaSetDevice(h->device));
+  const bool host = mem_space != LETKF_B200_MEM_DEVICE;
+  const size_t sl = (size_t)h->nij1 * c.nlev;
+  const int nct = std::max(h->nctype, 1);
+  CK(h->vlfac_one.ensure(nct));
+  CK(cudaMemcpyAsync(h->vlfac_one.p, h->h_vlfac.data() + (size_t)(nvar - 1) * h->nctype, sizeof(double) * h->nctype,
+                     cudaMemcpyHostToDevice, h->stream));
+  NobsOutParams P;
+  std::memset(&P, 0, sizeof(P));
+  std::vector<double> lp;
+  if (host) {   // ln p by the host libm (selection thresholds bit-identical to a CPU run), like obs_local
+    CK(h->st_logp.ensure(sl));
+    const double *src = logp;
+    if (!src) {
+      lp.resize(sl);
+      for (size_t i = 0; i < sl; ++i) lp[i] = std::log(pmean[i]);
+      src = lp.data();
+    }
+    CK(cudaMemcpyAsync(h->st_logp.p, src, sizeof(double) * sl, cudaMemcpyHostToDevice, h->stream));
+    P.logp = h->st_logp.p;
+    CK(h->cb[4].ensure(sl * 11));
+    P.out = h->cb[4].p;
+  } else {
+    P.logp = logp;
+    P.pmean = pmean;
+    P.out = out;
+  }
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>(sl, (size_t)h->num_sms * 8));
+  CK(h->l_iob.ensure((size_t)grid * h->maxl));
+  CK(h->l_rdiag.ensure((size_t)grid * h->maxl));
+  CK(h->l_rloc.ensure((size_t)grid * h->maxl));
+  CK(h->l_cnd.ensure((size_t)grid * h->ccap));
+  CK(h->l_cpk.ensure((size_t)grid * h->ccap));
+  CK(cudaMemsetAsync(h->counters.p, 0, 16 * sizeof(unsigned long long), h->stream));
+  P.T = h->d_tables.p; P.rec = h->rec.p; P.bstart = h->bstart.p; P.vlfac = h->vlfac_one.p;
+  P.rig1 = h->rig1.p; P.rjg1 = h->rjg1.p; P.hgt1 = h->hgt1.p;
+  P.nij1 = h->nij1; P.nlev = c.nlev;
+  P.radar_only = h->radar_only ? 1 : 0;
+  P.zcut = c.RADAR_ZMAX + std::max(c.VERT_LOCAL[21], c.VERT_LOCAL_RADAR_VR) * c.dist_zero_fac;
+  P.BOUNDARY_BUFFER_WIDTH = c.BOUNDARY_BUFFER_WIDTH; P.DX = c.DX; P.DY = c.DY;
+  P.IHALO = c.IHALO; P.JHALO = c.JHALO; P.nlon = c.nlon; P.nlat = c.nlat;
+  P.l_iob = h->l_iob.p; P.l_rdiag = h->l_rdiag.p; P.l_rloc = h->l_rloc.p; P.lcap = h->maxl;
+  P.l_cnd = h->l_cnd.p; P.l_cpk = h->l_cpk.p; P.ccap = h->ccap;
+  P.counters = h->counters.p;
+  nobs_out_kernel<<<grid, 128, 0, h->stream>>>(P);
+  CK(cudaGetLastError());
+  unsigned long long cnt[16];
+  CK(cudaMemcpyAsync(cnt, h->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+  if (host) CK(cudaMemcpyAsync(out, P.out, sizeof(double) * sl * 11, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (cnt[5] != 0) return fail(h, LETKF_B200_EINVAL, "nobs_out: a local list exceeded the capacity sized by set_obs");
+  return LETKF_B200_OK;
+}
+
 int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
   if (!h || !a || !a->gues3d || !a->anal3d) return LETKF_B200_EINVAL;
   if (!h->obs_set) return fail(h, LETKF_B200_ESTATE, "set_obs has not been called");

@@ -105,6 +105,9 @@ def select_bruteforce(cfg, obs, pts, nvar):
                     cand.append((nd, int(n)))
             cand.sort()
             N = cfg.MAX_NOBS_PER_GRID[21]
+            if N <= 0:                      # no obs-number limit (:1438-1476): everything inside the cut-off
+                sel += [n for _, n in cand]
+                continue
             if len(cand) > N:
                 assert cand[N - 1][0] < cand[N][0], "tie at the N-th distance: change the seed"
             sel += [n for _, n in cand[:N]]

@@ -71,43 +71,66 @@ def main():
             r["note"] = note
         rows.append(r)
 
-    val = v3d.numel() // nens                        # values of one member slot
-    # ensmean_grd: reads k member slots, writes the mean slot
-    rec("ensmean_kernel", "ensmean_grd (common_scale.f90:1513)", (k + 1) * val * 8, timed(lambda: eng.ensmean_grd(v3d)))
-    # enssprd_grd: reads k members + the mean, writes one spread field
-    rec("enssprd_kernel", "enssprd_grd (common_scale.f90:1557)", (k + 2) * val * 8, timed(lambda: eng.enssprd_grd(v3d)))
-    # one-pass transposes, np = 1 (local peer): every value read once and written once, state_trans fused
-    thermo = eng.thermo_defaults()
-    p2p = EnsTransposeP2P(eng, 1, 0, thermo=thermo)
-    gsz = nlev * cfg.nlon * cfg.nlat * nv
-    nm = min(k, 8)                                   # a block of members is enough to time the kernels
-    grids = [torch.empty(gsz, dtype=torch.float64, device=dev) for _ in range(nm)]
-    outg = [torch.empty(gsz, dtype=torch.float64, device=dev) for _ in range(nm)]
-    p2p.write_ens(v3d, grids, nm, nens)              # physically sensible restart variables for state_trans
-    rec("scatter_grd_p2p_kernel", "scatter_grd_mpi_alltoall + state_trans, one pass (common_mpi_scale.f90:1279)", 2 * nm * gsz * 8,
-        timed(lambda: p2p.read_ens(grids, v3d, nm, nens)), note="%d members, np = 1" % nm)
-    rec("gather_grd_p2p_kernel", "gather_grd_mpi_alltoall + state_trans_inv, one pass (common_mpi_scale.f90:1340)", 2 * nm * gsz * 8,
-        timed(lambda: p2p.write_ens(v3d, outg, nm, nens)), note="%d members, np = 1" % nm)
-    # stand-alone state_trans on one member-major grid (in place: read + write, +5 derived reads)
-    g0 = grids[0].clone()
-    rec("state_trans_kernel", "state_trans (common_scale.f90:1181), in place on one member", 2 * gsz * 8, timed(lambda: eng.state_trans(g0, thermo)))
-    # observation chain on the device: departure + QC, then filter / sort / gather
-    od = {kf: torch.as_tensor(np.ascontiguousarray(obs[kf], dtype=np.int32 if kf in ("elm", "typ") else np.float64), device=dev)
-          for kf in ("elm", "typ", "ri", "rj", "lev", "dat", "err", "val", "ensval")}
-    nobs, nensobs = od["ensval"].shape
-    hx = od["ensval"] + od["dat"][:, None]           # H(x_m) again (the generator stored perturbation-like rows)
-    qc = torch.zeros(nobs, dtype=torch.int32, device=dev)
+    def guard(what, fn):   # one failing section must not lose the others
+        try:
+            fn()
+        except Exception as e:
+            rows.append({"kernel": what, "error": repr(e)[:300]})
+            torch.cuda.empty_cache()
 
-    def dep():
-        e = hx.clone()
-        q = qc.clone()
-        eng.obs_departure_qc_device(od["elm"], od["dat"], od["err"], q, e)
-    t_clone = timed(lambda: (hx.clone(), qc.clone()))
-    rec("obs_departure_qc_kernel", "departure + QC of set_letkf_obs (letkf_obs.f90:355-560)", 2 * nobs * nensobs * 8,
-        max(timed(dep) - t_clone, 1e-4), note="clone of the input subtracted; %d observations x %d" % (nobs, nensobs))
-    rec("set_obs_device (obs_prepare/compact/bucket_*/obs_gather kernels)", "qc filter + combined types + bucket sort + row gather "
-        "(letkf_obs.f90:308-342, 747-805)", nobs * (nensobs * 8 + (k + 6) * 8 + 6 * 8), timed(lambda: eng.set_letkf_obs_device(od, None)),
-        note="whole call incl. two small D2H synchronisations; latency-bound for %d observations" % nobs)
+    def _means():
+        val = v3d.numel() // nens                        # values of one member slot
+        # ensmean_grd: reads k member slots, writes the mean slot
+        rec("ensmean_kernel", "ensmean_grd (common_scale.f90:1513)", (k + 1) * val * 8, timed(lambda: eng.ensmean_grd(v3d)))
+        # enssprd_grd: reads k members + the mean, writes one spread field
+        rec("enssprd_kernel", "enssprd_grd (common_scale.f90:1557)", (k + 2) * val * 8, timed(lambda: eng.enssprd_grd(v3d)))
+    guard("means", _means)
+
+    def _additive():
+        val = v3d.numel() // nens
+        an = torch.zeros_like(v3d)
+        # additive inflation: the additive ensemble read (mean + update: the second read of a column comes from L2 at best),
+        # the analysis members read and written
+        rec("additive_inflation_kernel", "additive inflation block of das_letkf (letkf_tools.f90:869-925)", 3 * k * val * 8,
+            timed(lambda: eng.additive_inflation(v3d, an, 0.1)))
+        del an
+    guard("additive", _additive)
+    def _transposes():
+        # one-pass transposes, np = 1 (local peer): every value read once and written once, state_trans fused
+        thermo = eng.thermo_defaults()
+        p2p = EnsTransposeP2P(eng, 1, 0, thermo=thermo)
+        gsz = nlev * cfg.nlon * cfg.nlat * nv
+        nm = min(k, 8)                                   # a block of members is enough to time the kernels
+        grids = [torch.empty(gsz, dtype=torch.float64, device=dev) for _ in range(nm)]
+        outg = [torch.empty(gsz, dtype=torch.float64, device=dev) for _ in range(nm)]
+        p2p.write_ens(v3d, grids, nm, nens)              # physically sensible restart variables for state_trans
+        rec("scatter_grd_p2p_kernel", "scatter_grd_mpi_alltoall + state_trans, one pass (common_mpi_scale.f90:1279)", 2 * nm * gsz * 8,
+            timed(lambda: p2p.read_ens(grids, v3d, nm, nens)), note="%d members, np = 1" % nm)
+        rec("gather_grd_p2p_kernel", "gather_grd_mpi_alltoall + state_trans_inv, one pass (common_mpi_scale.f90:1340)", 2 * nm * gsz * 8,
+            timed(lambda: p2p.write_ens(v3d, outg, nm, nens)), note="%d members, np = 1" % nm)
+        # stand-alone state_trans on one member-major grid (in place: read + write, +5 derived reads)
+        g0 = grids[0].clone()
+        rec("state_trans_kernel", "state_trans (common_scale.f90:1181), in place on one member", 2 * gsz * 8, timed(lambda: eng.state_trans(g0, thermo)))
+    guard("transposes", _transposes)
+    def _obs_chain():
+        # observation chain on the device: departure + QC, then filter / sort / gather
+        od = {kf: torch.as_tensor(np.ascontiguousarray(obs[kf], dtype=np.int32 if kf in ("elm", "typ") else np.float64), device=dev)
+              for kf in ("elm", "typ", "ri", "rj", "lev", "dat", "err", "val", "ensval")}
+        nobs, nensobs = od["ensval"].shape
+        hx = od["ensval"] + od["dat"][:, None]           # H(x_m) again (the generator stored perturbation-like rows)
+        qc = torch.zeros(nobs, dtype=torch.int32, device=dev)
+
+        def dep():
+            e = hx.clone()
+            q = qc.clone()
+            eng.obs_departure_qc_device(od["elm"], od["dat"], od["err"], q, e)
+        t_clone = timed(lambda: (hx.clone(), qc.clone()))
+        rec("obs_departure_qc_kernel", "departure + QC of set_letkf_obs (letkf_obs.f90:355-560)", 2 * nobs * nensobs * 8,
+            max(timed(dep) - t_clone, 1e-4), note="clone of the input subtracted; %d observations x %d" % (nobs, nensobs))
+        rec("set_obs_device (obs_prepare/compact/bucket_*/obs_gather kernels)", "qc filter + combined types + bucket sort + row gather "
+            "(letkf_obs.f90:308-342, 747-805)", nobs * (nensobs * 8 + (k + 6) * 8 + 6 * 8), timed(lambda: eng.set_letkf_obs_device(od, None)),
+            note="whole call incl. two small D2H synchronisations; latency-bound for %d observations" % nobs)
+    guard("obs_chain", _obs_chain)
     # stand-alone search at the grid points of one level (latency / L2 bound: reported for completeness)
     try:
         npt = min(nij, 65536)
