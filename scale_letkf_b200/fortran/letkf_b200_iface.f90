@@ -28,6 +28,9 @@ module letkf_b200_iface
   public :: letkf_b200_setup, letkf_b200_finalize
   public :: das_letkf_b200, letkf_core_b200
   public :: scatter_grd_b200_pack, gather_grd_b200_unpack
+  public :: letkf_b200_ipc, letkf_b200_radar_config, letkf_b200_thermo, letkf_b200_qc_config
+  public :: scatter_grd_b200_p2p, gather_grd_b200_p2p, c_peer_export, c_peer_open, c_set_obs_device, c_obsope_radar
+  public :: additive_inflation_b200, nobs_out_b200
 
   integer(c_int), parameter, public :: LETKF_B200_NOBTYPE = 24
   integer(c_int), parameter, public :: LETKF_B200_NID_VARLOCAL = 9
@@ -89,6 +92,20 @@ module letkf_b200_iface
     real(c_double)     :: Rdry, Rvap, CVdry, PRE00
     real(c_double)     :: TRACER_CV(LETKF_B200_MAX_NV)
     integer(c_int32_t) :: POSITIVE_DEFINITE_Q, POSITIVE_DEFINITE_QHYD
+  end type
+
+  ! struct letkf_b200_ipc (include/letkf_b200.h): CUDA IPC handle + offset of a device pointer, plain bytes to send to the peers
+  type, bind(C), public :: letkf_b200_ipc
+    integer(c_signed_char) :: handle(64)
+    integer(c_int64_t)     :: offset
+  end type
+
+  ! struct letkf_b200_radar_config (include/letkf_b200.h): PARAM_LETKF_RADAR switches + grid sizes + obs(iof)%meta(1:3)
+  type, bind(C), public :: letkf_b200_radar_config
+    integer(c_int32_t) :: METHOD_REF_CALC, USE_TERMINAL_VELOCITY
+    integer(c_int32_t) :: nlevh, nlonh, nlath, nlev, KHALO, nv3dd
+    real(c_double)     :: MIN_RADAR_REF_DBZ, LOW_REF_SHIFT, RADAR_ZMAX
+    real(c_double)     :: radar_lon, radar_lat, radar_z
   end type
 
   type(c_ptr), save :: handle = c_null_ptr
@@ -216,6 +233,60 @@ module letkf_b200_iface
       type(c_ptr), value :: h, bufr, v3dg, v2dg
       integer(c_int), value :: np
     end function
+    ! ---- one-pass transposes with the exchange inside (scatter/gather_grd_mpi_alltoall, common_mpi_scale.f90:1279-1396) ----
+    integer(c_int) function c_peer_export(h, devptr, ipc) bind(C, name='letkf_b200_peer_export')
+      import :: c_int, c_ptr, letkf_b200_ipc
+      type(c_ptr), value :: h, devptr
+      type(letkf_b200_ipc), intent(out) :: ipc
+    end function
+    integer(c_int) function c_peer_open(h, ipc, mapped) bind(C, name='letkf_b200_peer_open')
+      import :: c_int, c_ptr, letkf_b200_ipc
+      type(c_ptr), value :: h
+      type(letkf_b200_ipc), intent(in) :: ipc
+      type(c_ptr), intent(out) :: mapped
+    end function
+    integer(c_int) function c_scatter_grd_p2p(h, np, myrank_e, nens, mslot, t, v3dg, v2dg, peer_v3d, peer_v2d) &
+        bind(C, name='letkf_b200_scatter_grd_p2p')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, t, v3dg, v2dg          ! t: letkf_b200_thermo or c_null_ptr (no state_trans); device pointers
+      integer(c_int), value :: np, myrank_e, nens, mslot
+      type(c_ptr), intent(in) :: peer_v3d(*), peer_v2d(*)   ! device address of v3d / v2d on every rank (own + peer_open)
+    end function
+    integer(c_int) function c_gather_grd_p2p(h, np, myrank_e, nens, mstart, mend, t, v3d, v2d, peer_v3dg, peer_v2dg) &
+        bind(C, name='letkf_b200_gather_grd_p2p')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, t, v3d, v2d
+      integer(c_int), value :: np, myrank_e, nens, mstart, mend
+      type(c_ptr), intent(in) :: peer_v3dg(*), peer_v2dg(*)  ! member-major grids of members mstart..mend on their owners
+    end function
+    ! ---- device-resident observation chain (letkf_obs.f90:308-342, 747-805) and the radar operator (obsope_tools.f90:476-494) ----
+    integer(c_int) function c_set_obs_device(h, obs, qc, nkept) bind(C, name='letkf_b200_set_obs_device')
+      import :: c_int, c_ptr, c_int32_t, letkf_b200_obs
+      type(c_ptr), value :: h, qc                      ! qc: device int32 array or c_null_ptr
+      type(letkf_b200_obs), intent(in) :: obs          ! every pointer a DEVICE array
+      integer(c_int32_t), intent(out) :: nkept
+    end function
+    integer(c_int) function c_obsope_radar(h, r, nobs, elm, ril, rjl, lon, lat, lev, rotc, nmem, v3dgh, ld_out, yobs, qc, &
+                                           mem_space) bind(C, name='letkf_b200_obsope_radar')
+      import :: c_int, c_ptr, letkf_b200_radar_config
+      type(c_ptr), value :: h, elm, ril, rjl, lon, lat, lev, rotc, yobs, qc
+      type(letkf_b200_radar_config), intent(in) :: r
+      integer(c_int), value :: nobs, nmem, ld_out, mem_space
+      type(c_ptr), intent(in) :: v3dgh(*)              ! v3dgh(nlevh,nlonh,nlath,nv3dd) of every member
+    end function
+    ! ---- post-loop blocks of das_letkf ----
+    integer(c_int) function c_additive_inflation(h, infl_add, q_ratio, ref_only, ishuf, addi3d, addi2d, gues3d, anal3d, anal2d, &
+                                                 weight_out, mem_space) bind(C, name='letkf_b200_additive_inflation')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h, ishuf, addi3d, addi2d, gues3d, anal3d, anal2d, weight_out
+      real(c_double), value :: infl_add
+      integer(c_int), value :: q_ratio, ref_only, mem_space
+    end function
+    integer(c_int) function c_nobs_out(h, nvar, pmean, logp, out, mem_space) bind(C, name='letkf_b200_nobs_out')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, pmean, logp, out
+      integer(c_int), value :: nvar, mem_space
+    end function
   end interface
 
 contains
@@ -292,7 +363,7 @@ contains
 
     ! namelist switches whose post-processing (letkf_tools.f90:693-932) is outside this wrapper: refuse loudly rather
     ! than return a different analysis or silently skip an output file
-    if (INFL_ADD > 0.0d0) call unsupported('INFL_ADD > 0 (additive inflation, letkf_tools.f90:804-929)')
+    ! INFL_ADD > 0: call additive_inflation_b200 after das_letkf_b200 with the ensemble read_ens_mpi_addiinfl returns
     if (nv2d > 0 .and. (INFL_MUL <= 0.0d0 .or. INFL_MUL_ADAPTIVE)) &
       call unsupported('2-D variables with INFL_MUL <= 0 or INFL_MUL_ADAPTIVE (no 2-D inflation field in the interface)')
 
@@ -416,6 +487,73 @@ contains
     integer, intent(in) :: np
     type(c_ptr), intent(in) :: d_bufr, d_v3dg, d_v2dg
     call check(c_buf_to_grd(handle, int(np, c_int), d_bufr, d_v3dg, d_v2dg), 'buf_to_grd')
+  end subroutine
+
+  !-----------------------------------------------------------------------------
+  ! scatter_grd_mpi_alltoall / gather_grd_mpi_alltoall (common_mpi_scale.f90:1279-1396) in ONE pass with the exchange
+  ! inside the kernel: every rank reads its own DEVICE arrays and stores into the receiving ranks' arrays over NVLink.
+  ! peer_*(1:np): the device address of the destination array on every e-rank as seen from this GPU -- this rank's own
+  ! pointer at index myrank_e + 1, the others mapped ONCE with letkf_b200_peer_export on the owner (send the 72-byte
+  ! letkf_b200_ipc with MPI_ALLGATHER over MPI_COMM_e) and letkf_b200_peer_open here.  The MPI_BARRIER(MPI_COMM_e) the
+  ! caller places before (nobody still reads the destination) and after the call stands where MPI_ALLTOALL blocked.
+  ! thermo present: state_trans / state_trans_inv (common_scale.f90:1181-1280) are applied on the way.
+  !-----------------------------------------------------------------------------
+  subroutine scatter_grd_b200_p2p(np, myrank_e, nens, mslot, d_v3dg, d_v2dg, peer_v3d, peer_v2d, thermo)
+    integer, intent(in) :: np, myrank_e, nens, mslot          ! mslot: the member slot (1-based) this rank's grid fills
+    type(c_ptr), intent(in) :: d_v3dg, d_v2dg, peer_v3d(np), peer_v2d(np)
+    type(letkf_b200_thermo), intent(in), target, optional :: thermo
+    type(c_ptr) :: pt
+    pt = c_null_ptr
+    if (present(thermo)) pt = c_loc(thermo)
+    call check(c_scatter_grd_p2p(handle, int(np, c_int), int(myrank_e, c_int), int(nens, c_int), int(mslot, c_int), pt, &
+                                 d_v3dg, d_v2dg, peer_v3d, peer_v2d), 'scatter_grd_p2p')
+  end subroutine
+  subroutine gather_grd_b200_p2p(np, myrank_e, nens, mstart, mend, d_v3d, d_v2d, peer_v3dg, peer_v2dg, thermo)
+    integer, intent(in) :: np, myrank_e, nens, mstart, mend
+    type(c_ptr), intent(in) :: d_v3d, d_v2d, peer_v3dg(np), peer_v2dg(np)
+    type(letkf_b200_thermo), intent(in), target, optional :: thermo
+    type(c_ptr) :: pt
+    pt = c_null_ptr
+    if (present(thermo)) pt = c_loc(thermo)
+    call check(c_gather_grd_p2p(handle, int(np, c_int), int(myrank_e, c_int), int(nens, c_int), int(mstart, c_int), &
+                                int(mend, c_int), pt, d_v3d, d_v2d, peer_v3dg, peer_v2dg), 'gather_grd_p2p')
+  end subroutine
+
+  !-----------------------------------------------------------------------------
+  ! Additive inflation block of das_letkf (letkf_tools.f90:804-929): call after das_letkf_b200 when INFL_ADD > 0 with the
+  ! ensemble read_ens_mpi_addiinfl delivered (host arrays laid out like gues3d / gues2d; NOT modified), the background
+  ! array (its mean slot is read when INFL_ADD_Q_RATIO) and, with INFL_ADD_SHUFFLE, the permutation the caller drew with
+  ! Knuth_Shuffle and broadcast (:861-866).
+  !-----------------------------------------------------------------------------
+  subroutine additive_inflation_b200(addi3d, addi2d, gues3d, anal3d, anal2d, ishuf)
+    use common_nml, only: INFL_ADD, INFL_ADD_Q_RATIO, INFL_ADD_REF_ONLY, MEMBER
+    use common_scale, only: nlev, nv3d, nv2d
+    use common_mpi_scale, only: nij1, nens
+    real(c_double), intent(in), target :: addi3d(nij1,nlev,nens,nv3d), addi2d(nij1,nens,nv2d), gues3d(nij1,nlev,nens,nv3d)
+    real(c_double), intent(inout), target :: anal3d(nij1,nlev,nens,nv3d), anal2d(nij1,nens,nv2d)
+    integer(c_int32_t), intent(in), target, optional :: ishuf(MEMBER)
+    type(c_ptr) :: p_sh, p_a2, p_n2
+    p_sh = c_null_ptr; p_a2 = c_null_ptr; p_n2 = c_null_ptr
+    if (present(ishuf)) p_sh = c_loc(ishuf)
+    if (nv2d > 0) then
+      p_a2 = c_loc(addi2d); p_n2 = c_loc(anal2d)
+    end if
+    call check(c_additive_inflation(handle, INFL_ADD, merge(1_c_int, 0_c_int, INFL_ADD_Q_RATIO), &
+                                    merge(1_c_int, 0_c_int, INFL_ADD_REF_ONLY), p_sh, c_loc(addi3d), p_a2, c_loc(gues3d), &
+                                    c_loc(anal3d), p_n2, c_null_ptr, LETKF_B200_MEM_HOST), 'additive_inflation')
+  end subroutine
+
+  !-----------------------------------------------------------------------------
+  ! NOBS_OUT fields (letkf_tools.f90:440-447, 767-778): work3d(:,:,1:11) as the reference fills it before write_restart --
+  ! local observation counts of report types 1, 3, 4, 8, 22, of (REF | RE0 | VR, PHARAD), and their cut-off distances --
+  ! for the variable-localisation group of iv3d_t.  pmean = gues3d(:,:,mmean,iv3d_p) BEFORE das_letkf_b200 (which destroys it).
+  !-----------------------------------------------------------------------------
+  subroutine nobs_out_b200(pmean, work3d)
+    use common_scale, only: nlev, iv3d_t
+    use common_mpi_scale, only: nij1
+    real(c_double), intent(in), target :: pmean(nij1,nlev)
+    real(c_double), intent(out), target :: work3d(nij1,nlev,11)
+    call check(c_nobs_out(handle, int(iv3d_t, c_int), c_loc(pmean), c_null_ptr, c_loc(work3d), LETKF_B200_MEM_HOST), 'nobs_out')
   end subroutine
 
   subroutine unsupported(what)

@@ -124,10 +124,13 @@ def test_gpu_nobs_out_matches_oracle(oracle, space, max_nobs, criterion):
     assert np.array_equal(got[:, :, :8], want[:, :, :8])                   # counts: bit-exact
     ok = hits == 0
     assert ok.mean() > 0.8
-    assert np.array_equal(got[:, :, 8:][ok], want[:, :, 8:][ok])            # cut-off values: same arithmetic, bit-exact
+    if criterion == 1:
+        assert np.array_equal(got[:, :, 8:][ok], want[:, :, 8:][ok])        # cut-off distance: same arithmetic, bit-exact
+    else:                                                                   # rloc / rdiag carry exp(): CUDA vs libm, <= 1 ulp
+        assert np.allclose(got[:, :, 8:][ok], want[:, :, 8:][ok], rtol=1e-14, atol=0.0)
     # at exact hits the reference reports the last scanned observation: never farther / worse than the worst selected one
     if criterion in (1, 3):
-        assert (got[:, :, 8:][~ok] >= want[:, :, 8:][~ok]).all()
+        assert (got[:, :, 8:][~ok] >= want[:, :, 8:][~ok] * (1 - 1e-14)).all()
     else:
-        assert (got[:, :, 8:][~ok] <= want[:, :, 8:][~ok]).all()
+        assert (got[:, :, 8:][~ok] <= want[:, :, 8:][~ok] * (1 + 1e-14)).all()
     assert (want[:, :, 5] > 0).any()
