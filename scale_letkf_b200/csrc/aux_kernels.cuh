@@ -632,6 +632,87 @@ __global__ void __launch_bounds__(256) grd_ens_p2p_kernel(TransposeDims d, State
       }
   }
 }
+// The same transposes with the tile loaded by cp.async (LDGSTS: no register staging, 8-byte elements straight to their
+// transposed place in shared memory) and KT = 16 levels per tile: 48 KB of shared memory for 11 variables -> four CTAs
+// per SM whose load / transform / store phases overlap (the register-staged 32-level tile above: 128 registers, 93 KB,
+// two CTAs, 25 % warps active, latency-bound).  The level tiles of a column block are ADJACENT in launch order
+// (blockIdx.x = level tile), so the 64-byte DRAM granules two level tiles share at a 480-byte column's cut are fetched
+// once and hit L2 for the neighbour (ncu of the kernel above: 1.40x the algorithmic reads).
+__device__ __forceinline__ void p2p_cp_async8(double *smem, const double *gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+template <int KT>
+__global__ void __launch_bounds__(256) grd_ens_p2p_async_kernel(TransposeDims d, StateTransParams T, int trans, int dir, int myrank,
+                                                                int nens, int slot0, const double *__restrict__ src, PeerPtrs peers) {
+  extern __shared__ double tile[];   // [nv3d][32 columns][KT + 1]
+  constexpr int RS = KT + 1, TS = 32 * RS, NE = 32 * KT, PER = NE / 256;
+  static_assert(NE % 256 == 0, "whole passes of the 256 threads over a tile plane");
+  const int t = threadIdx.x;
+  const int k0 = blockIdx.x * KT, i0 = blockIdx.y * 32, z = blockIdx.z;
+  const int colrank = dir == 0 ? z : myrank;          // whose columns this CTA moves
+  const int nij1 = nij1_of(d, colrank);
+  if (i0 >= nij1) return;
+  const size_t npts = (size_t)d.nlev * d.nlon * d.nlat;
+  auto gcol = [&](int i) -> size_t {   // first level of column i of rank `colrank` in a member-major field
+    const int j = colrank + d.np * i;
+    const int ilon = j % d.nlon, ilat = j / d.nlon;
+    return (size_t)d.nlev * (ilon + (size_t)d.nlon * ilat);
+  };
+  const size_t estride_n = (size_t)nij1 * d.nlev * nens;   // v3d(nij1, nlev, nens, nv3d) of rank `colrank`: variable stride
+  auto eidx0 = [&](int i, int k, int slot) -> size_t { return (size_t)i + (size_t)nij1 * ((size_t)k + (size_t)d.nlev * slot); };
+  double *dst = peers.p3[z];
+  // ---- load: PER elements per thread and variable; member-major side: lanes along the levels, ensemble side: along i ----
+  size_t goff[PER];
+  int soff[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int e = t + 256 * q;
+    int c, l;
+    if (dir == 0) { l = e % KT; c = e / KT; } else { c = e & 31; l = e >> 5; }
+    soff[q] = c * RS + l;
+    const bool ok = i0 + c < nij1 && k0 + l < d.nlev;
+    goff[q] = !ok ? (size_t)-1 : dir == 0 ? gcol(i0 + c) + k0 + l : eidx0(i0 + c, k0 + l, slot0 + z);
+  }
+  const size_t gstride = dir == 0 ? npts : estride_n;
+  for (int n = 0; n < d.nv3d; ++n) {
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      if (goff[q] != (size_t)-1) p2p_cp_async8(&tile[n * TS + soff[q]], src + goff[q] + gstride * n);
+      else tile[n * TS + soff[q]] = 0.0;
+    }
+  }
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (trans) {
+    for (int e = t; e < NE; e += 256) {
+      const int ii = e / KT, kk = e % KT;
+      if (i0 + ii < nij1 && k0 + kk < d.nlev) state_trans_point(T, tile + ii * RS + kk, TS, dir);
+    }
+    __syncthreads();
+  }
+  // ---- store: ensemble side along i (256-byte rows), member-major side along the levels ----
+  if (dir == 0) {
+    const int tx = t & 31, ty = t >> 5;
+    if (i0 + tx < nij1)
+      for (int n = 0; n < d.nv3d; ++n)
+        for (int kk = ty; kk < KT; kk += 8)
+          if (k0 + kk < d.nlev) dst[eidx0(i0 + tx, k0 + kk, slot0) + estride_n * n] = tile[n * TS + tx * RS + kk];
+  } else {
+    size_t go[PER];
+    int so[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int e = t + 256 * q, l = e % KT, c = e / KT;
+      so[q] = c * RS + l;
+      go[q] = (i0 + c < nij1 && k0 + l < d.nlev) ? gcol(i0 + c) + k0 + l : (size_t)-1;
+    }
+    for (int n = 0; n < d.nv3d; ++n)
+#pragma unroll
+      for (int q = 0; q < PER; ++q)
+        if (go[q] != (size_t)-1) dst[go[q] + npts * n] = tile[n * TS + so[q]];
+  }
+}
 // 2-D variables of the one-pass transposes: v2dg(nlon,nlat,nv2d) <-> v2d(nij1,nens,nv2d)
 __global__ void grd_ens_p2p_2d_kernel(TransposeDims d, int dir, int myrank, int nens, int slot0, int npeers,
                                       const double *__restrict__ src, PeerPtrs peers) {

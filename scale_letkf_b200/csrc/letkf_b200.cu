@@ -1805,10 +1805,20 @@ static int grd_ens_p2p(letkf_b200_handle *h, int np, int myrank, int nens, int d
     pp.p3[i] = peer3[i];
     pp.p2[i] = (peer2 && c.nv2d > 0) ? peer2[i] : nullptr;
   }
-  const size_t smem = (size_t)c.nv3d * 32 * 33 * sizeof(double);
-  CK(cudaFuncSetAttribute(grd_ens_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 32 * 33 * (int)sizeof(double)));
-  const dim3 grid((unsigned)((d.nij1max + 31) / 32), (unsigned)((c.nlev + 31) / 32), (unsigned)npeers);
-  grd_ens_p2p_kernel<<<grid, dim3(32, 8), smem, h->stream>>>(d, P, t ? 1 : 0, dir, myrank, nens, slot0, src3, pp);
+  static const int variant = [] { const char *e = std::getenv("LETKF_B200_P2P_TILE"); return e ? std::atoi(e) : 16; }();
+  if (variant == 32) {   // A/B aid: the register-staged 32-level tile of the first version
+    const size_t smem = (size_t)c.nv3d * 32 * 33 * sizeof(double);
+    CK(cudaFuncSetAttribute(grd_ens_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 32 * 33 * (int)sizeof(double)));
+    const dim3 grid((unsigned)((d.nij1max + 31) / 32), (unsigned)((c.nlev + 31) / 32), (unsigned)npeers);
+    grd_ens_p2p_kernel<<<grid, dim3(32, 8), smem, h->stream>>>(d, P, t ? 1 : 0, dir, myrank, nens, slot0, src3, pp);
+  } else {
+    constexpr int KT = 16;
+    if ((d.nij1max + 31) / 32 > 65535) return fail(h, LETKF_B200_EINVAL, "p2p transposes: more than 2 M columns per rank");
+    const size_t smem = (size_t)c.nv3d * 32 * (KT + 1) * sizeof(double);
+    CK(cudaFuncSetAttribute(grd_ens_p2p_async_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 32 * (KT + 1) * (int)sizeof(double)));
+    const dim3 grid((unsigned)((c.nlev + KT - 1) / KT), (unsigned)((d.nij1max + 31) / 32), (unsigned)npeers);
+    grd_ens_p2p_async_kernel<KT><<<grid, 256, smem, h->stream>>>(d, P, t ? 1 : 0, dir, myrank, nens, slot0, src3, pp);
+  }
   if (c.nv2d > 0 && src2 && peer2)
     grd_ens_p2p_2d_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(d, dir, myrank, nens, slot0, npeers, src2, pp);
   CK(cudaGetLastError());
