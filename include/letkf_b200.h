@@ -379,6 +379,38 @@ int letkf_b200_obsope_radar(letkf_b200_handle *h, const letkf_b200_radar_config 
                             const double *lev, const double *rotc, int nmem, const double *const *v3dgh,
                             int ld_out, double *yobs, int32_t *qc, int mem_space);
 
+/* ---- conventional (prepbufr) observation operator ----------------------
+ * Twin of the obsfmt_prepbufr branch of obsope_cal (scale/obs/obsope_tools.f90:466-473) and of monit_obs (scale/common/
+ * common_obs_scale.f90:1530-1540): phys2ijk (:999-1110, pressure -> level index by linear interpolation in ln p; surface
+ * observations keep their height) and Trans_XtoY (:264-337: U, V with the map-projection rotation, T, Tv, Q, RH by tri-linear
+ * interpolation; PS from the 2-D fields with the height adjustment prsadj :600-617 and the PS_ADJUST_THRES test), for ALL
+ * members in one launch.  v3dgh[m] = v3dgh(nlevh,nlonh,nlath,nv3dd) of member m in the reference's history-variable order
+ * (u v w t p q qc qr qi qs qg rh hgt), v2dgh[m] = v2dgh(nlonh,nlath,nv2dd) (topo ps rain u10m v10m t2m q2m); ril/rjl: local
+ * grid coordinates (rij_g2l); rotc(nobs,2) = MPRJ_rotcoef of SCALE-RM's map projection at (lon, lat) -- carried as data,
+ * NULL = (1, 0).  yobs/qc (ld_out, nobs): member fastest.  qc codes of the reference (iqc_good 0, iqc_ps_ter 10,
+ * iqc_out_vhi 20, iqc_out_vlo 21, iqc_otype 90, iqc_out_h 98).  ln() is CUDA's (<= 1 ulp of the host's): tested at 1e-12. */
+typedef struct letkf_b200_conv_config {
+  int32_t nlevh, nlonh, nlath, nlev, KHALO, nv3dd, nv2dd;
+  int32_t stggrd;                 /* 1: u, v on the staggered grid (monit_obs calls Trans_XtoY with stggrd = 1) */
+  double PS_ADJUST_THRES;         /* common_nml.f90:148 */
+} letkf_b200_conv_config;
+void letkf_b200_conv_config_defaults(letkf_b200_conv_config *c);
+int letkf_b200_obsope_conv(letkf_b200_handle *h, const letkf_b200_conv_config *r, int nobs, const int32_t *elm, const double *ril,
+                           const double *rjl, const double *lev, const double *rotc, int nmem, const double *const *v3dgh,
+                           const double *const *v2dgh, int ld_out, double *yobs, int32_t *qc, int mem_space);
+
+/* ---- monit_obs twin (scale/common/common_obs_scale.f90:1370-1844), one observation set (file) per call ----------------
+ * H(x) of ONE state (the mean background / analysis as history variables v3dgh, v2dgh) at the observations of one input
+ * file -- conv != NULL: prepbufr format (phys2ijk + Trans_XtoY, the caller sets conv->stggrd = 1 like monit_obs);
+ * radar != NULL: radar format (phys2ijkz + Trans_XtoY_radar, iqc_ref_low counts as good, no RADAR_ZMAX test; skip the call
+ * when DEPARTURE_STAT_RADAR is off) -- then ohx = dat - H(x) where the operator's qc is good, undef elsewhere (:1566-1570).
+ * Observations with |dif| > t_range (DEPARTURE_STAT_T_RANGE > 0; dif may be NULL) keep oqc = -1.  The statistics over all
+ * sets are letkf_b200_monit_dep on the concatenated (elm, ohx, oqc) -- exactly the reference's last step (:1808). */
+int letkf_b200_monit_obs_set(letkf_b200_handle *h, const letkf_b200_conv_config *conv, const letkf_b200_radar_config *radar, int nobs,
+                             const int32_t *elm, const double *ril, const double *rjl, const double *lon, const double *lat,
+                             const double *lev, const double *dat, const double *dif, const double *rotc, double t_range,
+                             const double *v3dgh, const double *v2dgh, double *ohx, int32_t *oqc, int mem_space);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,6 +109,16 @@ void oracle_monit_dep(int nn, const int32_t *elm, const double *dep, const int32
                       double *bias, double *rmse);
 int oracle_max_threads(void);
 
+/* conventional observation operator for all members and the observation loop of monit_obs (oracle_conv.cpp): obsope_tools.f90:
+ * 466-473, common_obs_scale.f90:264-337, 600-617, 999-1110, 1516-1572; arguments as letkf_b200_obsope_conv /
+ * letkf_b200_monit_obs_set (host pointers) */
+void oracle_obsope_conv(const letkf_b200_conv_config *r, int nobs, const int32_t *elm, const double *ril, const double *rjl,
+                        const double *lev, const double *rotc, int nmem, const double *const *v3dgh, const double *const *v2dgh,
+                        int ld_out, double *yobs, int32_t *qc);
+void oracle_monit_obs_set(const letkf_b200_conv_config *conv, const letkf_b200_radar_config *radar, int nobs, const int32_t *elm,
+                          const double *ril, const double *rjl, const double *lon, const double *lat, const double *lev,
+                          const double *dat, const double *dif, const double *rotc, double t_range, const double *v3dgh,
+                          const double *v2dgh, double *ohx, int32_t *oqc);
 /* radar observation operator for all members (oracle_radar.cpp): obsope_tools.f90:476-494, common_obs_scale.f90:342-493,
  * 626-990, 1116-1237; arguments as letkf_b200_obsope_radar (host pointers) */
 void oracle_obsope_radar(const letkf_b200_radar_config *r, int nobs, const int32_t *elm, const double *ril, const double *rjl,

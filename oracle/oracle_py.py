@@ -340,6 +340,48 @@ def monit_dep(elm, dep, qc):
     return n, b, r
 
 
+def obsope_conv(ccfg, elm, ril, rjl, lev, grids3, grids2, rotc=None):
+    """oracle_conv.cpp: conventional observation operator (phys2ijk + Trans_XtoY) for all members; grids3 / grids2 = lists of
+    F-order v3dgh(nlevh,nlonh,nlath,nv3dd) / v2dgh(nlonh,nlath,nv2dd)"""
+    nobs, nmem = len(elm), len(grids3)
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    elm = np.ascontiguousarray(elm, dtype=np.int32)
+    ril, rjl, lev = f(ril), f(rjl), f(lev)
+    rotc = None if rotc is None else f(rotc)
+    p3 = (C.c_void_p * nmem)(*[g.ctypes.data for g in grids3])
+    p2 = (C.c_void_p * nmem)(*[g.ctypes.data for g in grids2])
+    y = np.zeros((nobs, nmem))
+    q = np.zeros((nobs, nmem), dtype=np.int32)
+    L = lib()
+    L.oracle_obsope_conv.restype = None
+    L.oracle_obsope_conv(C.byref(ccfg), nobs, _p(elm), _p(ril), _p(rjl), _p(lev), _p(rotc), nmem, p3, p2, nmem, _p(y), _p(q))
+    return y, q
+
+
+def monit_obs(sets, v3dgh, v2dgh, t_range=0.0):
+    """monit_obs (common_obs_scale.f90:1370-1844) over a list of observation sets (dicts as scale_letkf_b200.LETKF.monit_obs takes
+    them): per-set observation loop (oracle_conv.cpp) + monit_dep over the concatenation."""
+    f = lambda x: None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+    L = lib()
+    L.oracle_monit_obs_set.restype = None
+    L.oracle_monit_obs_set.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_double] + [C.c_void_p] * 4
+    elms, ohxs, oqcs = [], [], []
+    for st in sets:
+        cfg = st["cfg"]
+        conv = isinstance(cfg, capi.ConvConfig)
+        elm = np.ascontiguousarray(st["elm"], dtype=np.int32)
+        n = len(elm)
+        ohx, oqc = np.zeros(n), np.zeros(n, dtype=np.int32)
+        cp = C.cast(C.pointer(cfg), C.c_void_p)
+        L.oracle_monit_obs_set(cp if conv else None, None if conv else cp, n, _p(elm), _p(f(st["ril"])), _p(f(st["rjl"])),
+                               _p(f(st.get("lon"))), _p(f(st.get("lat"))), _p(f(st["lev"])), _p(f(st["dat"])), _p(f(st.get("dif"))),
+                               _p(f(st.get("rotc"))), float(t_range), _p(v3dgh), _p(v2dgh), _p(ohx), _p(oqc))
+        elms.append(elm); ohxs.append(ohx); oqcs.append(oqc)
+    elm, ohx, oqc = np.concatenate(elms), np.concatenate(ohxs), np.concatenate(oqcs)
+    nobs, bias, rmse = monit_dep(elm, ohx, oqc)
+    return dict(nobs=nobs, bias=bias, rmse=rmse, ohx=ohx, oqc=oqc, elm=elm)
+
+
 def obsope_radar(rcfg, elm, ril, rjl, lon, lat, lev, grids, rotc=None):
     """oracle_radar.cpp: radar observation operator for all members; grids = list of F-order v3dg(nlevh,nlonh,nlath,nv3dd)"""
     nobs, nmem = len(elm), len(grids)

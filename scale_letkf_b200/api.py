@@ -411,6 +411,64 @@ class LETKF:
                                                   _ptr(lat), _ptr(lev), _ptr(rotc), nmem, ptrs, nmem, _ptr(y), _ptr(q), space))
         return y, q
 
+    # ---- conventional observation operator, monit_obs ---------------------------------------------------
+    def conv_config_defaults(self):
+        r = capi.ConvConfig()
+        self.lib.letkf_b200_conv_config_defaults(C.byref(r))
+        return r
+
+    def obsope_conv(self, ccfg, elm, ril, rjl, lev, grids3, grids2, rotc=None):
+        """H(x_m) of conventional (prepbufr) observations for all members (obsope_tools.f90:466-473 twin: phys2ijk +
+        Trans_XtoY).  grids3 / grids2: per member v3dgh(nlevh,nlonh,nlath,nv3dd) / v2dgh(nlonh,nlath,nv2dd), numpy F-order
+        (host) or torch CUDA tensors.  Returns (yobs, qc), shape (nobs, nmem)."""
+        nobs, nmem = len(elm), len(grids3)
+        dev = _is_torch(grids3[0])
+        p3 = (C.c_void_p * nmem)(*[_ptr(g) for g in grids3])
+        p2 = (C.c_void_p * nmem)(*[_ptr(g) for g in grids2])
+        if dev:
+            import torch
+            d = grids3[0].device
+            t = lambda a, dt: a if _is_torch(a) else torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=d)
+            elm, ril, rjl, lev = t(elm, np.int32), t(ril, np.float64), t(rjl, np.float64), t(lev, np.float64)
+            rotc = None if rotc is None else t(rotc, np.float64)
+            y = torch.empty((nobs, nmem), dtype=torch.float64, device=d)
+            q = torch.empty((nobs, nmem), dtype=torch.int32, device=d)
+            space = capi.MEM_DEVICE
+        else:
+            f = lambda x: np.ascontiguousarray(x, dtype=np.float64)
+            elm = np.ascontiguousarray(elm, dtype=np.int32)
+            ril, rjl, lev = f(ril), f(rjl), f(lev)
+            rotc = None if rotc is None else f(rotc)
+            y = np.zeros((nobs, nmem))
+            q = np.zeros((nobs, nmem), dtype=np.int32)
+            space = capi.MEM_HOST
+        self._ck(self.lib.letkf_b200_obsope_conv(self.h, C.byref(ccfg), nobs, _ptr(elm), _ptr(ril), _ptr(rjl), _ptr(lev), _ptr(rotc),
+                                                 nmem, p3, p2, nmem, _ptr(y), _ptr(q), space))
+        return y, q
+
+    def monit_obs(self, sets, v3dgh, v2dgh, t_range=0.0):
+        """monit_obs (common_obs_scale.f90:1370-1844): departure statistics of ONE state (history variables v3dgh, v2dgh: numpy
+        F-order host arrays) against the observations of every input set.  sets: list of dicts with `cfg` (ConvConfig for the
+        prepbufr format, RadarConfig for the radar format), elm, ril, rjl, lev, dat and, optionally, lon, lat (radar), dif, rotc.
+        Returns dict(nobs[16], bias[16], rmse[16], ohx, oqc, elm): the per-observation arrays concatenated in set order."""
+        f = lambda x: None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+        elms, ohxs, oqcs = [], [], []
+        for st in sets:
+            cfg = st["cfg"]
+            conv = isinstance(cfg, capi.ConvConfig)
+            elm = np.ascontiguousarray(st["elm"], dtype=np.int32)
+            n = len(elm)
+            ohx, oqc = np.zeros(n), np.zeros(n, dtype=np.int32)
+            self._ck(self.lib.letkf_b200_monit_obs_set(
+                self.h, C.byref(cfg) if conv else None, None if conv else C.byref(cfg), n, _ptr(elm), _ptr(f(st["ril"])),
+                _ptr(f(st["rjl"])), _ptr(f(st.get("lon"))), _ptr(f(st.get("lat"))), _ptr(f(st["lev"])), _ptr(f(st["dat"])),
+                _ptr(f(st.get("dif"))), _ptr(f(st.get("rotc"))), float(t_range), _ptr(v3dgh), _ptr(v2dgh), _ptr(ohx), _ptr(oqc),
+                capi.MEM_HOST))
+            elms.append(elm); ohxs.append(ohx); oqcs.append(oqc)
+        elm, ohx, oqc = np.concatenate(elms), np.concatenate(ohxs), np.concatenate(oqcs)
+        nobs, bias, rmse = self.monit_dep(elm, ohx, oqc)
+        return dict(nobs=nobs, bias=bias, rmse=rmse, ohx=ohx, oqc=oqc, elm=elm)
+
     # ---- device-resident observation chain --------------------------------------------------------------
     def obs_departure_qc_device(self, elm, dat, err, qc, ensval, qcfg=None):
         """departure + QC (letkf_obs.f90:355-560) in place on torch CUDA tensors: ensval (nobs, nensobs) H(x_m) ->

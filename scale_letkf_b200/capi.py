@@ -107,6 +107,15 @@ class RadarConfig(C.Structure):
     ]
 
 
+class ConvConfig(C.Structure):
+    """letkf_b200_conv_config (conventional observation operator: grid sizes + PS_ADJUST_THRES, common_nml.f90:148)"""
+    _fields_ = [
+        ("nlevh", C.c_int32), ("nlonh", C.c_int32), ("nlath", C.c_int32), ("nlev", C.c_int32), ("KHALO", C.c_int32),
+        ("nv3dd", C.c_int32), ("nv2dd", C.c_int32), ("stggrd", C.c_int32),
+        ("PS_ADJUST_THRES", C.c_double),
+    ]
+
+
 class Ipc(C.Structure):
     """letkf_b200_ipc: CUDA IPC handle + offset of a device pointer (one-pass transposes over peer memory)."""
     _fields_ = [("handle", C.c_ubyte * 64), ("offset", C.c_uint64)]
@@ -175,6 +184,11 @@ PROTOTYPES = {
     "letkf_b200_set_obs_device": (_i, [_vp, C.POINTER(Obs), _vp, _ip]),
     "letkf_b200_get_kept_index": (_i, [_vp, _vp]),
     "letkf_b200_radar_config_defaults": (None, [C.POINTER(RadarConfig)]),
+    "letkf_b200_conv_config_defaults": (None, [C.POINTER(ConvConfig)]),
+    "letkf_b200_obsope_conv": (_i, [_vp, C.POINTER(ConvConfig), _i, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_vp), C.POINTER(_vp), _i,
+                                    _vp, _vp, _i]),
+    "letkf_b200_monit_obs_set": (_i, [_vp, C.POINTER(ConvConfig), C.POINTER(RadarConfig), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _i]),
     "letkf_b200_obsope_radar": (_i, [_vp, C.POINTER(RadarConfig), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_vp), _i,
                                      _vp, _vp, _i]),
     "letkf_b200_peer_export": (_i, [_vp, _vp, C.POINTER(Ipc)]),

@@ -1907,4 +1907,132 @@ int letkf_b200_obsope_radar(letkf_b200_handle *h, const letkf_b200_radar_config 
   return LETKF_B200_OK;
 }
 
+// ---- conventional observation operator and monit_obs ---------------------------------------------------------------
+void letkf_b200_conv_config_defaults(letkf_b200_conv_config *c) {
+  std::memset(c, 0, sizeof(*c));
+  c->KHALO = 2;
+  c->nv3dd = 13;
+  c->nv2dd = 7;
+  c->stggrd = 0;
+  c->PS_ADJUST_THRES = 100.0;   // common_nml.f90:148
+}
+
+int letkf_b200_obsope_conv(letkf_b200_handle *h, const letkf_b200_conv_config *r, int nobs, const int32_t *elm, const double *ril,
+                           const double *rjl, const double *lev, const double *rotc, int nmem, const double *const *v3dgh,
+                           const double *const *v2dgh, int ld_out, double *yobs, int32_t *qc, int mem_space) {
+  if (!h || !r || nobs < 0 || nmem < 1 || ld_out < nmem || !v3dgh || !v2dgh) return LETKF_B200_EINVAL;
+  if (nobs == 0) return LETKF_B200_OK;
+  if (!elm || !ril || !rjl || !lev || !yobs || !qc) return LETKF_B200_EINVAL;
+  if (r->nv3dd < 13 || r->nv2dd < 7 || r->nlev + 2 * r->KHALO > r->nlevh)
+    return fail(h, LETKF_B200_EINVAL, "obsope_conv: inconsistent grid sizes");
+  CK(cudaSetDevice(h->device));
+  const bool host = mem_space != LETKF_B200_MEM_DEVICE;
+  ConvParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.nobs = nobs; P.nmem = nmem; P.nlevh = r->nlevh; P.nlonh = r->nlonh; P.nlath = r->nlath; P.nlev = r->nlev; P.khalo = r->KHALO;
+  P.ld_out = ld_out; P.stggrd = r->stggrd; P.ps_thres = r->PS_ADJUST_THRES;
+  const size_t g3 = (size_t)r->nlevh * r->nlonh * r->nlath * r->nv3dd, g2 = (size_t)r->nlonh * r->nlath * r->nv2dd;
+  const size_t no = (size_t)nobs * ld_out;
+  DevBuf<double> d_geo, d_grid, d_y;
+  DevBuf<int> d_elm, d_qc;
+  DevBuf<const double *> d_ptr;
+  CK(d_ptr.ensure(2 * (size_t)nmem));
+  std::vector<const double *> ptrs(2 * (size_t)nmem);
+  if (host) {
+    CK(d_geo.ensure((size_t)nobs * 5)); CK(d_elm.ensure(nobs)); CK(d_y.ensure(no)); CK(d_qc.ensure(no));
+    CK(d_grid.ensure((g3 + g2) * nmem));
+    const double *src[3] = {ril, rjl, lev};
+    for (int i = 0; i < 3; ++i)
+      CK(cudaMemcpyAsync(d_geo.p + (size_t)i * nobs, src[i], sizeof(double) * nobs, cudaMemcpyHostToDevice, h->stream));
+    if (rotc) CK(cudaMemcpyAsync(d_geo.p + (size_t)3 * nobs, rotc, sizeof(double) * 2 * nobs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_elm.p, elm, sizeof(int) * nobs, cudaMemcpyHostToDevice, h->stream));
+    for (int m = 0; m < nmem; ++m) {
+      double *b3 = d_grid.p + (g3 + g2) * m, *b2 = b3 + g3;
+      CK(cudaMemcpyAsync(b3, v3dgh[m], sizeof(double) * g3, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(b2, v2dgh[m], sizeof(double) * g2, cudaMemcpyHostToDevice, h->stream));
+      ptrs[m] = b3;
+      ptrs[nmem + m] = b2;
+    }
+    P.ril = d_geo.p; P.rjl = d_geo.p + nobs; P.lev = d_geo.p + 2 * (size_t)nobs; P.rotc = rotc ? d_geo.p + 3 * (size_t)nobs : nullptr;
+    P.elm = d_elm.p; P.yobs = d_y.p; P.qc = d_qc.p;
+  } else {
+    for (int m = 0; m < nmem; ++m) {
+      ptrs[m] = v3dgh[m];
+      ptrs[nmem + m] = v2dgh[m];
+    }
+    P.ril = ril; P.rjl = rjl; P.lev = lev; P.rotc = rotc; P.elm = elm; P.yobs = yobs; P.qc = qc;
+  }
+  CK(cudaMemcpyAsync(d_ptr.p, ptrs.data(), sizeof(double *) * 2 * nmem, cudaMemcpyHostToDevice, h->stream));
+  P.v3dgh = d_ptr.p;
+  P.v2dgh = d_ptr.p + nmem;
+  obsope_conv_kernel<<<dim3((unsigned)((nobs + 127) / 128), (unsigned)nmem), 128, 0, h->stream>>>(P);
+  CK(cudaGetLastError());
+  if (host) {
+    CK(cudaMemcpyAsync(yobs, d_y.p, sizeof(double) * no, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(qc, d_qc.p, sizeof(int) * no, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  d_geo.release(); d_grid.release(); d_y.release(); d_elm.release(); d_qc.release(); d_ptr.release();
+  return LETKF_B200_OK;
+}
+
+int letkf_b200_monit_obs_set(letkf_b200_handle *h, const letkf_b200_conv_config *conv, const letkf_b200_radar_config *radar, int nobs,
+                             const int32_t *elm, const double *ril, const double *rjl, const double *lon, const double *lat,
+                             const double *lev, const double *dat, const double *dif, const double *rotc, double t_range,
+                             const double *v3dgh, const double *v2dgh, double *ohx, int32_t *oqc, int mem_space) {
+  if (!h || (!conv) == (!radar) || nobs < 0) return LETKF_B200_EINVAL;   // exactly one format
+  if (nobs == 0) return LETKF_B200_OK;
+  if (!elm || !ril || !rjl || !lev || !dat || !v3dgh || !ohx || !oqc || (conv && !v2dgh) || (radar && (!lon || !lat))) return LETKF_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const bool host = mem_space != LETKF_B200_MEM_DEVICE;
+  const int nlevh = conv ? conv->nlevh : radar->nlevh, nlonh = conv ? conv->nlonh : radar->nlonh, nlath = conv ? conv->nlath : radar->nlath;
+  const size_t g3 = (size_t)nlevh * nlonh * nlath * (conv ? conv->nv3dd : radar->nv3dd);
+  const size_t g2 = conv ? (size_t)nlonh * nlath * conv->nv2dd : 0;
+  // everything on the device: inputs are staged when they are host arrays, then the operators run in device mode
+  DevBuf<double> d_in, d_grid, d_y, d_ohx;
+  DevBuf<int> d_elm, d_q, d_oqc;
+  const double *p_ril = ril, *p_rjl = rjl, *p_lon = lon, *p_lat = lat, *p_lev = lev, *p_dat = dat, *p_dif = dif, *p_rotc = rotc;
+  const double *p_g3 = v3dgh, *p_g2 = v2dgh;
+  const int *p_elm = elm;
+  double *p_ohx = ohx;
+  int *p_oqc = oqc;
+  if (host) {
+    CK(d_in.ensure((size_t)nobs * 9)); CK(d_elm.ensure(nobs)); CK(d_grid.ensure(g3 + g2)); CK(d_ohx.ensure(nobs)); CK(d_oqc.ensure(nobs));
+    const double *src[7] = {ril, rjl, lon, lat, lev, dat, dif};
+    const double **dstp[7] = {&p_ril, &p_rjl, &p_lon, &p_lat, &p_lev, &p_dat, &p_dif};
+    for (int i = 0; i < 7; ++i) {
+      if (!src[i]) continue;
+      CK(cudaMemcpyAsync(d_in.p + (size_t)i * nobs, src[i], sizeof(double) * nobs, cudaMemcpyHostToDevice, h->stream));
+      *dstp[i] = d_in.p + (size_t)i * nobs;
+    }
+    if (rotc) {
+      CK(cudaMemcpyAsync(d_in.p + (size_t)7 * nobs, rotc, sizeof(double) * 2 * nobs, cudaMemcpyHostToDevice, h->stream));
+      p_rotc = d_in.p + (size_t)7 * nobs;
+    }
+    CK(cudaMemcpyAsync(d_elm.p, elm, sizeof(int) * nobs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_grid.p, v3dgh, sizeof(double) * g3, cudaMemcpyHostToDevice, h->stream));
+    if (g2) CK(cudaMemcpyAsync(d_grid.p + g3, v2dgh, sizeof(double) * g2, cudaMemcpyHostToDevice, h->stream));
+    p_elm = d_elm.p; p_g3 = d_grid.p; p_g2 = d_grid.p + g3; p_ohx = d_ohx.p; p_oqc = d_oqc.p;
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  CK(d_y.ensure(nobs)); CK(d_q.ensure(nobs));
+  int rc;
+  if (conv) {
+    rc = letkf_b200_obsope_conv(h, conv, nobs, p_elm, p_ril, p_rjl, p_lev, p_rotc, 1, &p_g3, &p_g2, 1, d_y.p, d_q.p, LETKF_B200_MEM_DEVICE);
+  } else {
+    letkf_b200_radar_config rr = *radar;
+    rr.RADAR_ZMAX = 1.0e300;   // monit_obs has no RADAR_ZMAX test (common_obs_scale.f90:1545-1555; obsope_cal has: obsope_tools.f90:476)
+    rc = letkf_b200_obsope_radar(h, &rr, nobs, p_elm, p_ril, p_rjl, p_lon, p_lat, p_lev, p_rotc, 1, &p_g3, 1, d_y.p, d_q.p, LETKF_B200_MEM_DEVICE);
+  }
+  if (rc != LETKF_B200_OK) return rc;
+  monit_ohx_kernel<<<(nobs + 255) / 256, 256, 0, h->stream>>>(nobs, p_dat, p_dif, t_range, d_y.p, d_q.p, p_ohx, p_oqc);
+  CK(cudaGetLastError());
+  if (host) {
+    CK(cudaMemcpyAsync(ohx, p_ohx, sizeof(double) * nobs, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(oqc, p_oqc, sizeof(int) * nobs, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return LETKF_B200_OK;
+}
+
 }  // extern "C"

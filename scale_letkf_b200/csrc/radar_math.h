@@ -93,6 +93,110 @@ LETKF_HD double com_gamma(double x) {   // common/common.f90:861-912 (x > 1, non
   return 1.0 / (gr * z) * r;
 }
 
+// ---- conventional (prepbufr) observation operator: itpl_2d :1295-1315, phys2ijk :999-1110, prsadj :600-617, Trans_XtoY
+// :264-337 of scale/common/common_obs_scale.f90 --------------------------------------------------------------------------------
+enum { IQC_PS_TER = 10 };
+enum { ID_U = 2819, ID_V = 2820, ID_T = 3073, ID_TV = 3074, ID_Q = 3330, ID_RH = 3331, ID_PS = 14593 };
+constexpr double kRv = 461.50, kFvirt = kRv / kRd - 1.0;   // common/common.f90:31, 34
+
+struct Grid2 {   // v2dgh(nlonh, nlath, nv2dd)
+  const double *v;
+  int nlonh, nlath;
+  LETKF_HD double at(int i, int j, int n) const { return v[(size_t)(i - 1) + (size_t)nlonh * ((size_t)(j - 1) + (size_t)nlath * n)]; }
+};
+
+LETKF_HD double itpl_2d(const Grid2 &g, int n, double ri, double rj) {
+  const int i = (int)ceil(ri), j = (int)ceil(rj);
+  const double ai = ri - (double)(i - 1), aj = rj - (double)(j - 1);
+  return g.at(i - 1, j - 1, n) * (1 - ai) * (1 - aj) + g.at(i, j - 1, n) * ai * (1 - aj) + g.at(i - 1, j, n) * (1 - ai) * aj +
+         g.at(i, j, n) * ai * aj;
+}
+
+// one level of itpl_2d_column(LOG(p_full)) (:1055-1056)
+LETKF_HD double lnpcol(const Grid &g, int n, int k, int i, int j, double ai, double aj) {
+  return log(g.at(k, i - 1, j - 1, n)) * (1 - ai) * (1 - aj) + log(g.at(k, i, j - 1, n)) * ai * (1 - aj) +
+         log(g.at(k, i - 1, j, n)) * (1 - ai) * aj + log(g.at(k, i, j, n)) * ai * aj;
+}
+
+// phys2ijk: pressure -> fractional level index (surface observations, elem > 9999, keep rlev); returns the QC flag
+LETKF_HD int phys2ijk(const Grid &g, int ip, int elem, int nlev, int khalo, double ri, double rj, double rlev, double &rk) {
+  rk = kUndef;
+  if (ri < 1.0 || ri > (double)g.nlonh || rj < 1.0 || rj > (double)g.nlath) return IQC_OUT_H;
+  if (elem > 9999) {
+    rk = rlev;
+    return IQC_GOOD;
+  }
+  const int i = (int)ceil(ri), j = (int)ceil(rj);
+  int ks = 1 + khalo;   // lowest valid level
+  for (int jj = j - 1; jj <= j; ++jj)
+    for (int ii = i - 1; ii <= i; ++ii) {
+      int k = 1 + khalo;
+      for (; k <= nlev + khalo; ++k)
+        if (g.at(k, ii, jj, ip) >= 0.0) break;
+      if (k > ks) ks = k;
+    }
+  const double ai = ri - (double)(i - 1), aj = rj - (double)(j - 1);
+  const double lr = log(rlev);
+  if (lr < lnpcol(g, ip, nlev + khalo, i, j, ai, aj)) return IQC_OUT_VHI;
+  if (lr > lnpcol(g, ip, ks, i, j, ai, aj)) return IQC_OUT_VLO;
+  int k = ks + 1;
+  double pk = 0.0;
+  for (; k <= nlev + khalo; ++k) {
+    pk = lnpcol(g, ip, k, i, j, ai, aj);
+    if (pk < lr) break;   // assuming descending order of plev
+  }
+  if (k > nlev + khalo) {   // lr == plev(top): the Fortran loop index runs one past the end
+    k = nlev + khalo;
+    pk = lnpcol(g, ip, k, i, j, ai, aj);
+  }
+  const double pkm = lnpcol(g, ip, k - 1, i, j, ai, aj);
+  rk = (double)(k - 1) + (lr - pkm) / (pk - pkm);
+  return IQC_GOOD;
+}
+
+LETKF_HD double prsadj(double p, double dz, double t, double q) {
+  const double gamma = 5.0e-3;
+  if (dz != 0.0) {
+    const double tv = t * (1.0 + 0.608 * q);
+    p = p * pow((-gamma * dz + tv) / tv, kGG / (gamma * kRd));
+  }
+  return p;
+}
+
+// Trans_XtoY; rot1/rot2 = MPRJ_rotcoef(lon, lat) of the observation (SCALE-RM's map projection: carried as data)
+LETKF_HD void trans_xtoy(int elm, double ri, double rj, double rk, double rot1, double rot2, const Grid &g3, const Grid2 &g2,
+                         int stggrd, double ps_adjust_thres, double &yobs, int &qc) {
+  yobs = kUndef;
+  qc = IQC_GOOD;
+  if (elm == ID_U || elm == ID_V) {
+    double u, v;
+    if (stggrd == 1) {
+      u = itpl_3d(g3, 0, rk, ri - 0.5, rj);
+      v = itpl_3d(g3, 1, rk, ri, rj - 0.5);
+    } else {
+      u = itpl_3d(g3, 0, rk, ri, rj);
+      v = itpl_3d(g3, 1, rk, ri, rj);
+    }
+    yobs = (elm == ID_U) ? u * rot1 - v * rot2 : u * rot2 + v * rot1;
+  } else if (elm == ID_T) {
+    yobs = itpl_3d(g3, 3, rk, ri, rj);
+  } else if (elm == ID_TV) {
+    yobs = itpl_3d(g3, 3, rk, ri, rj);
+    const double q = itpl_3d(g3, 5, rk, ri, rj);
+    yobs = yobs * (1.0 + kFvirt * q);
+  } else if (elm == ID_Q) {
+    yobs = itpl_3d(g3, 5, rk, ri, rj);
+  } else if (elm == ID_PS) {
+    const double t = itpl_2d(g2, 5, ri, rj), q = itpl_2d(g2, 6, ri, rj), topo = itpl_2d(g2, 0, ri, rj);
+    yobs = prsadj(itpl_2d(g2, 1, ri, rj), rk - topo, t, q);
+    if (fabs(rk - topo) > ps_adjust_thres) qc = IQC_PS_TER;
+  } else if (elm == ID_RH) {
+    yobs = itpl_3d(g3, 11, rk, ri, rj);
+  } else {
+    qc = IQC_OTYPE;
+  }
+}
+
 struct RadarCfg {
   int method, use_tv;
   double min_ref, min_ref_dbz, low_ref_shift;
