@@ -30,7 +30,7 @@ module letkf_b200_iface
   public :: scatter_grd_b200_pack, gather_grd_b200_unpack
   public :: letkf_b200_ipc, letkf_b200_radar_config, letkf_b200_thermo, letkf_b200_qc_config
   public :: scatter_grd_b200_p2p, gather_grd_b200_p2p, c_peer_export, c_peer_open, c_set_obs_device, c_obsope_radar
-  public :: additive_inflation_b200, nobs_out_b200
+  public :: additive_inflation_b200, nobs_out_b200, letkf_b200_conv_config, c_obsope_conv, c_monit_obs_set, c_monit_dep
 
   integer(c_int), parameter, public :: LETKF_B200_NOBTYPE = 24
   integer(c_int), parameter, public :: LETKF_B200_NID_VARLOCAL = 9
@@ -106,6 +106,12 @@ module letkf_b200_iface
     integer(c_int32_t) :: nlevh, nlonh, nlath, nlev, KHALO, nv3dd
     real(c_double)     :: MIN_RADAR_REF_DBZ, LOW_REF_SHIFT, RADAR_ZMAX
     real(c_double)     :: radar_lon, radar_lat, radar_z
+  end type
+
+  ! struct letkf_b200_conv_config (include/letkf_b200.h): grid sizes of the history variables + PS_ADJUST_THRES
+  type, bind(C), public :: letkf_b200_conv_config
+    integer(c_int32_t) :: nlevh, nlonh, nlath, nlev, KHALO, nv3dd, nv2dd, stggrd
+    real(c_double)     :: PS_ADJUST_THRES
   end type
 
   type(c_ptr), save :: handle = c_null_ptr
@@ -273,6 +279,23 @@ module letkf_b200_iface
       type(letkf_b200_radar_config), intent(in) :: r
       integer(c_int), value :: nobs, nmem, ld_out, mem_space
       type(c_ptr), intent(in) :: v3dgh(*)              ! v3dgh(nlevh,nlonh,nlath,nv3dd) of every member
+    end function
+    ! ---- conventional operator (obsope_tools.f90:466-473) and the observation loop of monit_obs (common_obs_scale.f90:1516-1572) ----
+    integer(c_int) function c_obsope_conv(h, r, nobs, elm, ril, rjl, lev, rotc, nmem, v3dgh, v2dgh, ld_out, yobs, qc, mem_space) &
+        bind(C, name='letkf_b200_obsope_conv')
+      import :: c_int, c_ptr, letkf_b200_conv_config
+      type(c_ptr), value :: h, elm, ril, rjl, lev, rotc, yobs, qc
+      type(letkf_b200_conv_config), intent(in) :: r
+      integer(c_int), value :: nobs, nmem, ld_out, mem_space
+      type(c_ptr), intent(in) :: v3dgh(*), v2dgh(*)    ! v3dgh(nlevh,nlonh,nlath,nv3dd), v2dgh(nlonh,nlath,nv2dd) of every member
+    end function
+    ! conv / radar: exactly one is a c_loc(config), the other c_null_ptr; then c_monit_dep over the concatenated (elm, ohx, oqc)
+    integer(c_int) function c_monit_obs_set(h, conv, radar, nobs, elm, ril, rjl, lon, lat, lev, dat, dif, rotc, t_range, v3dgh, v2dgh, &
+                                            ohx, oqc, mem_space) bind(C, name='letkf_b200_monit_obs_set')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h, conv, radar, elm, ril, rjl, lon, lat, lev, dat, dif, rotc, v3dgh, v2dgh, ohx, oqc
+      integer(c_int), value :: nobs, mem_space
+      real(c_double), value :: t_range
     end function
     ! ---- post-loop blocks of das_letkf ----
     integer(c_int) function c_additive_inflation(h, infl_add, q_ratio, ref_only, ishuf, addi3d, addi2d, gues3d, anal3d, anal2d, &
