@@ -512,6 +512,8 @@ def measure(name, ctx, args, steps, warmup, legs):
         "traffic_source": "ncu capture under profiles/ (bytes per point x points of this run), not measured in this run",
         "peak_source": fp64_src + "; MEASURED_PEAKS.json holds no FP64 figure",
         "kernel_ms_per_step": kms, "launches_per_step": int(launches / world),
+        "kernel_ms_per_launch": kms / max(int(launches / world), 1),
+        "traffic_per_launch": None if traffic is None else traffic / max(int(launches / world), 1),
         "algorithmic_flops_per_step": flops / world, "algorithmic_bytes_per_step": abytes / world,
         "hbm": {"achieved": ach_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "frac": ach_gbs / peaks.get("hbm_gbs"), "peak_source": peaks_src + " MEASURED_PEAKS.json"},
