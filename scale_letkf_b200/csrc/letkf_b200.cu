@@ -141,14 +141,15 @@ struct letkf_b200_handle {
   TiledBufs *tiled = nullptr;
   std::map<std::string, void *> ipc_open;   // peer allocations mapped by letkf_b200_peer_open (by handle bytes)
   bool attr_gemm_big = false, attr_gemm_small = false;   // dynamic-shared-memory opt-in done on this handle's device
-  // pre-search pipeline (presearch_kernel): two pools, chunk parity
+  // pre-search pipeline (presearch_kernel): three pools (chunk index mod 3), the search runs two chunks ahead of the solver
   cudaStream_t s_search = nullptr;
   std::vector<cudaEvent_t> ev_s;
-  DevBuf<int> pl_n[2], pl_iob[2], ps_l_iob;
-  DevBuf<long long> pl_off[2];
-  DevBuf<double> pl_rdiag[2], pl_rloc[2], ps_l_rdiag, ps_l_rloc, ps_l_cnd;
+  static constexpr int kPools = 3;   // pooled local lists of three level chunks: the search runs two chunks ahead of the solver
+  DevBuf<int> pl_n[kPools], pl_iob[kPools], ps_l_iob;
+  DevBuf<long long> pl_off[kPools];
+  DevBuf<double> pl_rdiag[kPools], pl_rloc[kPools], ps_l_rdiag, ps_l_rloc, ps_l_cnd;
   DevBuf<unsigned> ps_l_cpk;
-  DevBuf<unsigned long long> ps_counters;   // [0..15] work counter block, [16], [17] pool cursors
+  DevBuf<unsigned long long> ps_counters;   // [0..15] work counter block, [18] redo count, [20..22] pool cursors
   int ps_grid = 0;
   DevBuf<long long> redo_list;
   // scratch of set_obs
@@ -427,7 +428,7 @@ int letkf_b200_create(const letkf_b200_config *cfg, int device, letkf_b200_handl
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     cudaStreamCreateWithPriority(&h->s_search, cudaStreamNonBlocking, hi);
   }
-  if (h->counters.ensure(16) != cudaSuccess || h->ps_counters.ensure(20) != cudaSuccess) {
+  if (h->counters.ensure(16) != cudaSuccess || h->ps_counters.ensure(24) != cudaSuccess) {
     delete h;
     return LETKF_B200_ECUDA;
   }
@@ -448,7 +449,7 @@ int letkf_b200_destroy(letkf_b200_handle *h) {
   for (auto &b : h->cb) b.release();
   h->cb_i.release();
   if (h->tiled) { h->tiled->release(); delete h->tiled; h->tiled = nullptr; }
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < letkf_b200_handle::kPools; ++b) {
     h->pl_n[b].release(); h->pl_iob[b].release(); h->pl_off[b].release(); h->pl_rdiag[b].release(); h->pl_rloc[b].release();
   }
   h->ps_l_iob.release(); h->ps_l_rdiag.release(); h->ps_l_rloc.release(); h->ps_l_cnd.release(); h->ps_l_cpk.release();
@@ -1204,36 +1205,37 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
       size_t fr = 0, tot = 0;
       if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
         double held = 0.0;   // what the two pools already hold counts as free
-        for (int b = 0; b < 2; ++b) held += (double)h->pl_iob[b].n * 4.0 + (double)h->pl_rdiag[b].n * 8.0 + (double)h->pl_rloc[b].n * 8.0;
-        budget = std::max(budget, std::min(8192.0 * 1048576.0, 0.2 * ((double)fr + held) / 2.0));
+        for (int b = 0; b < letkf_b200_handle::kPools; ++b) held += (double)h->pl_iob[b].n * 4.0 + (double)h->pl_rdiag[b].n * 8.0 + (double)h->pl_rloc[b].n * 8.0;
+        budget = std::max(budget, std::min(8192.0 * 1048576.0, 0.2 * ((double)fr + held) / (double)letkf_b200_handle::kPools));
       }
     }
     const size_t per = c.INFL_MUL_ADAPTIVE ? 20 : 12;
     pl_cap = (long long)std::min<double>((double)pl_entries_max * (double)round_up(h->maxl, 4), budget / per);
     pl_cap = std::max<long long>(pl_cap, 4);
     CK(h->redo_list.ensure((size_t)maxlev * h->nij1));
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < letkf_b200_handle::kPools; ++b) {
       CK(h->pl_n[b].ensure(pl_entries_max)); CK(h->pl_off[b].ensure(pl_entries_max));
       CK(h->pl_iob[b].ensure((size_t)pl_cap)); CK(h->pl_rdiag[b].ensure((size_t)pl_cap));
       if (c.INFL_MUL_ADAPTIVE) CK(h->pl_rloc[b].ensure((size_t)pl_cap));
     }
   }
   auto launch_search = [&](int ch) -> int {
-    const int b = ch & 1, l0 = lev0(ch), l1 = lev0(ch + 1);
+    const int b = ch % letkf_b200_handle::kPools, l0 = lev0(ch), l1 = lev0(ch + 1);
     if (host) CK(cudaStreamWaitEvent(h->s_search, h->ev_in[ch], 0));
-    if (ch >= 2) CK(cudaStreamWaitEvent(h->s_search, h->ev_k1[ch - 2], 0));   // the pool of chunk ch-2 is free again
+    if (ch >= letkf_b200_handle::kPools)   // the pool of chunk ch - 3 is free again
+      CK(cudaStreamWaitEvent(h->s_search, h->ev_k1[ch - letkf_b200_handle::kPools], 0));
     DasParams Q = P;
     Q.point_begin = (long long)l0 * h->nij1;
     Q.point_end = (long long)l1 * h->nij1;
     Q.pl_base = Q.point_begin;
     Q.pl_cap = pl_cap;
     Q.pl_iob = h->pl_iob[b].p; Q.pl_rdiag = h->pl_rdiag[b].p; Q.pl_rloc = c.INFL_MUL_ADAPTIVE ? h->pl_rloc[b].p : nullptr;
-    Q.pl_cursor = h->ps_counters.p + 16 + b;
+    Q.pl_cursor = h->ps_counters.p + 20 + b;
     Q.counters = h->ps_counters.p;
     Q.l_iob = h->ps_l_iob.p; Q.l_rdiag = h->ps_l_rdiag.p; Q.l_rloc = h->ps_l_rloc.p; Q.l_cnd = h->ps_l_cnd.p; Q.l_cpk = h->ps_l_cpk.p;
     Q.ccap = h->ccap;
     CK(cudaMemsetAsync(h->ps_counters.p, 0, sizeof(unsigned long long), h->s_search));
-    CK(cudaMemsetAsync(h->ps_counters.p + 16 + b, 0, sizeof(unsigned long long), h->s_search));
+    CK(cudaMemsetAsync(h->ps_counters.p + 20 + b, 0, sizeof(unsigned long long), h->s_search));
     const long long npts = Q.point_end - Q.point_begin;
     presearch_kernel<<<(unsigned)std::min<long long>(h->ps_grid, std::max<long long>(npts, 1)), 128, 0, h->s_search>>>(
         Q, h->pl_n[b].p, h->pl_off[b].p);
@@ -1254,19 +1256,27 @@ int letkf_b200_das_letkf(letkf_b200_handle *h, const letkf_b200_das_args *a) {
     // obs tables) is done
     CK(cudaEventRecord(h->ev0, h->stream));
     CK(cudaStreamWaitEvent(h->s_search, h->ev0, 0));
+    // The search runs TWO chunks ahead: the search of chunk c + 2 becomes eligible when the solver of chunk c - 1 is done, i.e.
+    // together with the solver of chunk c -- whichever of the two gets the SMs first, the solver of chunk c + 1 finds its
+    // lists ready.  (One chunk ahead, two pools: when the persistent solver CTAs of chunk c won that race the search of
+    // chunk c + 1 only ran in their tail and the solver of chunk c + 1 waited for it: 1 - 5 ms per chunk, box to box.)
     r = launch_search(0);
     if (r != LETKF_B200_OK) return r;
+    if (nchunk > 1) {
+      r = launch_search(1);
+      if (r != LETKF_B200_OK) return r;
+    }
   }
   for (int ch = 0; ch < nchunk; ++ch) {
     const int l0 = lev0(ch), l1 = lev0(ch + 1);
-    if (pre && ch + 1 < nchunk) {
-      r = launch_search(ch + 1);
+    if (pre && ch + 2 < nchunk) {
+      r = launch_search(ch + 2);
       if (r != LETKF_B200_OK) return r;
     }
     if (host) CK(cudaStreamWaitEvent(h->stream, h->ev_in[ch], 0));
     if (pre) {
       CK(cudaStreamWaitEvent(h->stream, h->ev_s[ch], 0));
-      const int b = ch & 1;
+      const int b = ch % letkf_b200_handle::kPools;
       P.pl_n = h->pl_n[b].p; P.pl_off = h->pl_off[b].p; P.pl_iob = h->pl_iob[b].p; P.pl_rdiag = h->pl_rdiag[b].p;
       P.pl_rloc = c.INFL_MUL_ADAPTIVE ? h->pl_rloc[b].p : nullptr;
       P.pl_base = (long long)l0 * h->nij1;
@@ -1587,18 +1597,39 @@ int letkf_b200_additive_inflation(letkf_b200_handle *h, double infl_add, int q_r
     }
   }
   DevBuf<int> &d_sh = h->so_tmp;   // (scratch of set_obs, free between calls)
-  const int *d_ishuf = nullptr;
+  const int *d_ishuf = nullptr, *d_inv = nullptr;
+  std::vector<int> inv;             // destination member of source member ms (register-resident kernel); empty: not a permutation
   if (ishuf) {
-    CK(d_sh.ensure((size_t)k));
+    inv.assign((size_t)k, -1);
+    bool perm = true;
+    for (int m = 0; m < k; ++m) {
+      if (inv[ishuf[m] - 1] >= 0) perm = false;
+      inv[ishuf[m] - 1] = m;
+    }
+    if (!perm) inv.clear();
+    CK(d_sh.ensure(2 * (size_t)k));
     CK(cudaMemcpyAsync(d_sh.p, ishuf, sizeof(int) * k, cudaMemcpyHostToDevice, h->stream));
+    if (!inv.empty()) CK(cudaMemcpyAsync(d_sh.p + k, inv.data(), sizeof(int) * k, cudaMemcpyHostToDevice, h->stream));
     d_ishuf = d_sh.p;
+    d_inv = inv.empty() ? nullptr : d_sh.p + k;
   }
+  // register-resident variant (one read of the additive members): opt-in, LETKF_B200_ADDINFL_REG=1 -- at 158 registers its
+  // occupancy is too low to beat the two-pass kernel on B200 (measured), kept for the A/B
+  static const bool reg_opt = std::getenv("LETKF_B200_ADDINFL_REG") != nullptr;
+  const bool reg_path = k <= 64 && reg_opt && (!ishuf || d_inv);
   const int q_lo = c.iv3d_q - 1, q_hi = c.iv3d_qg - 1;   // (the moisture variables q, qc, qr, qi, qs, qg are contiguous)
   // background mean = slot MEMBER of gues3d on the device, or the nv3d planes staged above
   const double *d_gm = !q_ratio ? nullptr : host ? h->st_rtps.p : gues3d;
   const size_t gm_vs = host ? sl : sl * nens, gm_off = host ? 0 : (size_t)k * sl;
-  additive_inflation_kernel<<<(unsigned)((o3 + 255) / 256), 256, 0, h->stream>>>(k, nens, nij, sl, c.nv3d, d_add3, d_an3, d_gm, gm_vs, gm_off, d_w,
-                                                                                 d_ishuf, infl_add, q_lo, q_hi);
+  if (reg_path && k <= 32)
+    additive_inflation_reg_kernel<32><<<(unsigned)((o3 + 127) / 128), 128, 0, h->stream>>>(k, nens, nij, sl, c.nv3d, d_add3, d_an3, d_gm, gm_vs,
+                                                                                          gm_off, d_w, d_inv, infl_add, q_lo, q_hi);
+  else if (reg_path)
+    additive_inflation_reg_kernel<64><<<(unsigned)((o3 + 127) / 128), 128, 0, h->stream>>>(k, nens, nij, sl, c.nv3d, d_add3, d_an3, d_gm, gm_vs,
+                                                                                          gm_off, d_w, d_inv, infl_add, q_lo, q_hi);
+  else
+    additive_inflation_kernel<<<(unsigned)((o3 + 255) / 256), 256, 0, h->stream>>>(k, nens, nij, sl, c.nv3d, d_add3, d_an3, d_gm, gm_vs, gm_off, d_w,
+                                                                                   d_ishuf, infl_add, q_lo, q_hi);
   if (two)
     additive_inflation_kernel<<<(unsigned)(((size_t)nij * c.nv2d + 255) / 256), 256, 0, h->stream>>>(k, nens, nij, (size_t)nij, c.nv2d, d_add2, d_an2,
                                                                                                      nullptr, 0, 0, d_w, d_ishuf, infl_add, -1, -2);
