@@ -70,6 +70,10 @@ template <class T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;              // owns its allocation: function-local buffers are freed on every return path
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
   cudaError_t ensure(size_t count) {
     if (count <= n && p) return cudaSuccess;
     if (p) cudaFree(p);
