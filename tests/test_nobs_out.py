@@ -81,6 +81,56 @@ def test_oracle_nobs_out_matches_bruteforce(oracle, max_nobs):
     assert checked > 60 and (max_nobs == 0 or full > 5)
 
 
+@pytest.mark.parametrize("criterion", [2, 3])
+def test_oracle_nobs_out_criterion_2_3_matches_bruteforce(oracle, criterion):
+    """MAX_NOBS_PER_GRID_CRITERION 2 (largest localisation weights) / 3 (smallest localised error variances): counts and the
+    cut-off value (rloc / rdiag of the worst selected observation) against a brute-force numpy selection over ALL observations"""
+    max_nobs = 10
+    cfg, rig1, rjg1, hgt1, obs, gues = radar_case(member=6, nlon=24, nlat=24, nlev=5, max_nobs=max_nobs, seed=905, radius=5.0e3)
+    cfg.MAX_NOBS_PER_GRID_CRITERION = criterion
+    o = oracle.Oracle(cfg)
+    o.set_obs(obs)
+    o.set_grid(rig1, rjg1, hgt1)
+    pmean = np.asfortranarray(gues[:, :, cfg.MEMBER, cfg.iv3d_p - 1])
+    out, hits = o.nobs_out(4, pmean)
+    nij1, nlev = hgt1.shape
+    dzf, dzf2 = cfg.dist_zero_fac, cfg.dist_zero_fac_square
+    checked = full = 0
+    for il in range(nlev):
+        for ij in range(0, nij1, 11):
+            ri, rj, rz = rig1[ij], rjg1[ij], hgt1[ij, il]
+            got = out[ij, il, :]
+            if _beta(cfg, ri, rj, rz, True) == 0.0:
+                assert np.array_equal(got, np.zeros(11))
+                continue
+            want = np.zeros(11)
+            for grp, slot in (((REF, RE0), 0), ((VR,), 2)):
+                keys = []
+                for n in np.nonzero(np.isin(obs["elm"], grp) & (obs["typ"] == 22))[0]:
+                    e = obs["elm"][n]
+                    hl = cfg.HORI_LOCAL_RADAR_OBSNOREF if e == RE0 else cfg.HORI_LOCAL_RADAR_VR if e == VR else cfg.HORI_LOCAL[21]
+                    vl = cfg.VERT_LOCAL_RADAR_VR if e == VR else cfg.VERT_LOCAL[21]
+                    nd_v = abs(obs["lev"][n] - rz) / vl
+                    nd_h = np.sqrt(((ri - obs["ri"][n]) * cfg.DX) ** 2 + ((rj - obs["rj"][n]) * cfg.DY) ** 2) / hl
+                    nd = nd_h * nd_h + nd_v * nd_v
+                    if nd_v > dzf or nd_h > dzf or nd > dzf2:
+                        continue
+                    rloc = np.exp(-0.5 * nd)
+                    keys.append(-rloc if criterion == 2 else obs["err"][n] ** 2 / rloc)     # ascending = best first
+                keys.sort()
+                cnt = min(len(keys), max_nobs)
+                want[4] += cnt
+                want[5 + slot] = cnt
+                if cnt == max_nobs:
+                    want[8 + slot] = -keys[cnt - 1] if criterion == 2 else keys[cnt - 1]
+                    full += 1
+            assert np.array_equal(got[:8], want[:8]), (ij, il, got, want)
+            if hits[ij, il] == 0:
+                assert np.allclose(got[8:], want[8:], rtol=1e-13, atol=0.0), (ij, il, got[8:], want[8:])
+            checked += 1
+    assert checked > 30 and full > 5
+
+
 def test_oracle_nobs_out_sonde_types(oracle):
     """conventional report types: out(:,:,1) counts ADPUPA (type 1), nothing at the radar slots"""
     cfg, rig1, rjg1, hgt1, obs, gues = sonde_case(member=7, nlon=10, nlat=9, nlev=4)
